@@ -1,0 +1,209 @@
+/*
+ * pymodem_b200.h -- C ABI of libpymodem_b200.so, the B200 (sm_100a) engine for
+ * pymodem's demod_chain hot path.
+ *
+ * The reference (ninocarrillo/pymodem) is plain Python and has no FFI; the seam
+ * this library replaces is the per-chain process fan-out
+ *     pymodem.py:140-166      Process(target=multiprocess_chain, args=[chain, audio, queue])
+ *     chain_execute.py:6-52   modem.demod -> slicer.slice -> stream.stream_unscramble_8bit -> codec.decode
+ * and the entry points below are what a ctypes binding on the reference side
+ * calls instead (see INTEGRATION.md for the stub).  Conventions: plain pointers
+ * and sizes only, int return code (0 = ok, <0 = error; pm_last_error() gives the
+ * text), no exceptions cross the boundary, the caller owns every buffer it
+ * passes, the engine owns all device memory, one host thread per engine.
+ * There is NO CPU fallback: every entry point fails with PM_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef PYMODEM_B200_H
+#define PYMODEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK              0
+#define PM_ERR_ARG        -1
+#define PM_ERR_CUDA       -2
+#define PM_ERR_UNSUPPORTED -3
+#define PM_ERR_CAPACITY   -4
+#define PM_ERR_STATE      -5
+
+/* modem kinds -- chain_builder.py:17-38 */
+#define PM_MODEM_AFSK      1   /* afsk.py:13   AFSKModem  */
+#define PM_MODEM_FSK       2   /* fsk.py:15    FSKModem   */
+#define PM_MODEM_BPSK      3   /* psk.py:20    BPSKModem  */
+#define PM_MODEM_MPSK      4   /* psk.py:479   MPSKModem  */
+#define PM_MODEM_AFSK_PLL  5   /* afsk_pll.py:16 AFSKPLLModem */
+/* slicer kinds -- chain_builder.py:40-52 */
+#define PM_SLICER_BINARY     1 /* slicer.py:9   */
+#define PM_SLICER_QUADRATURE 2 /* slicer.py:109 */
+/* codec kinds -- chain_builder.py:62-69 */
+#define PM_CODEC_AX25      1   /* ax25.py:11  */
+#define PM_CODEC_IL2P      2   /* il2p.py:109 */
+
+/*
+ * One demod_chain = {modem, slicer, stream, codec} (pymodem.py:68-114), flattened
+ * to plain data.  All filter taps are the float64 vectors produced by the
+ * reference's own tune() arithmetic on the host (afsk.py:102-146, fsk.py:115-147,
+ * psk.py:111-160/640-703); the engine never re-derives them.
+ */
+typedef struct pm_chain_desc {
+	int32_t modem_kind;
+	int32_t slicer_kind;
+	int32_t codec_kind;
+	int32_t invert_soft;            /* fsk.py:153-154  audio = -audio */
+
+	/* --- modem FIR taps (numpy.convolve order, i.e. h[0] first) --- */
+	const double *bpf;              /* afsk.py:112 input_bpf / fsk.py:133 input_lpf / psk input_bpf */
+	int32_t n_bpf;
+	int32_t n_corr;                 /* afsk.py:134 correlator length */
+	const double *mark_i;           /* afsk.py:138 */
+	const double *mark_q;           /* afsk.py:139 */
+	const double *space_i;          /* afsk.py:143 (space_gain applied, as the reference convolves it) */
+	const double *space_q;          /* afsk.py:144 */
+	const double *space_unit_i;     /* cos/sin before space_gain: lets chains that differ only  */
+	const double *space_unit_q;     /* in space_gain share one correlator pass                  */
+	double space_gain;              /* afsk.py:143 */
+	const double *lpf;              /* afsk.py:122 output_lpf / psk.py rrc taps */
+	int32_t n_lpf;
+	int32_t reserved0;
+
+	/* --- slicer (slicer.py:49-56, 181-191) --- */
+	double slicer_sample_rate;      /* pymodem.py:86-90 */
+	double symbol_rate;
+	double lock_rate;
+	uint32_t state_mask;            /* quadrature */
+	uint32_t bits_per_symbol;       /* quadrature */
+	uint32_t demap[16];             /* quadrature */
+
+	/* --- stream (lfsr.py:10-20) --- */
+	uint64_t lfsr_poly;
+	int32_t lfsr_invert;
+
+	/* --- codec options (il2p.py:140-145) --- */
+	int32_t il2p_crc;
+	int32_t il2p_disable_rs;
+	int32_t il2p_min_dist;
+	int32_t il2p_sync_tol;
+	int32_t reserved1;
+
+	/* --- PSK / PLL loop constants (psk.py, afsk_pll.py); see pm_loop_desc --- */
+	const void *loop;               /* NULL unless modem_kind is BPSK/MPSK/AFSK_PLL */
+} pm_chain_desc;
+
+/* One decoded packet == one reference PacketMeta (packet_meta.py:178-208). */
+typedef struct pm_packet_rec {
+	uint32_t chain;                 /* index into the loaded chain table (SourceDecoder = its object_name) */
+	uint32_t len;                   /* len(PacketMeta.data) */
+	uint64_t offset;                /* offset of data[0] in the byte arena */
+	int64_t  streamaddress;         /* ax25.py:82 / il2p.py:364 */
+	uint32_t bytes_corrected;       /* il2p.py:200 */
+	uint16_t calculated_crc;        /* crc_functions.py:45-54  (PacketMeta.CalcCRC) */
+	uint16_t carried_crc;           /* crc_functions.py:44 */
+	uint8_t  valid_crc;             /* crc_functions.py:55-61 */
+	uint8_t  valid_header;          /* packet_meta.py:21-41 */
+	uint8_t  pad[6];
+} pm_packet_rec;
+
+/* Timings are CUDA-event milliseconds on the engine's own stream. */
+typedef struct pm_stats {
+	double total_ms;                /* first enqueue .. results on host */
+	double h2d_ms;                  /* sum of host->device audio copies (0 for run_device) */
+	double front_ms;                /* FIR front-end kernels (all launches) */
+	double fixup_ms;                /* FP64 guard-band re-evaluation */
+	double slicer_ms;               /* symbol-timing recovery + hand-off verification */
+	double bits_ms;                 /* gather + LFSR + codec kernels */
+	double d2h_ms;
+	int64_t kernel_launches;        /* kernels of this library launched by the last run */
+	int64_t front_launches;
+	int64_t guard_flagged;          /* samples re-evaluated in FP64 */
+	int64_t slicer_repairs;         /* segments re-run because the warm-up hand-off did not verify */
+	int64_t slicer_segments;
+	int64_t h2d_bytes;
+	int64_t d2h_bytes;
+	int64_t n_packets;
+	int64_t n_stream_bits;          /* sliced bits over all chains */
+} pm_stats;
+
+typedef struct pm_engine pm_engine;
+
+/* Create an engine bound to one CUDA device (one process per GPU). */
+int pm_engine_create(int device, pm_engine **out);
+void pm_engine_destroy(pm_engine *e);
+const char *pm_last_error(const pm_engine *e);
+
+/* Replaces building demod_stack (pymodem.py:58-114): copies the chain table and
+ * uploads taps.  Chains keep their index (= config order). */
+int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_chains);
+
+/* Tunables: "segment_len", "warmup_len", "guard_eps", "tile", "keep_soft",
+ * "h2d_chunk". */
+int pm_engine_set_option(pm_engine *e, const char *key, double value);
+
+/*
+ * Replaces the fan-out + gather of pymodem.py:140-166 for every loaded chain:
+ * demod -> slice -> unscramble -> decode over the whole recording.
+ * pm_engine_run:        audio in HOST memory (pinned preferred); the H2D copy is
+ *                       chunked and overlapped with the front-end kernels.
+ * pm_engine_run_device: audio already resident in device memory.
+ * Results stay in the engine until the next run; fetch with pm_engine_get_packets.
+ */
+int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples);
+int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples);
+
+/*
+ * Sharded form used by the multi-GPU host (one engine per rank; the recording
+ * is split on the sample axis).  sample_base = global index of audio[0];
+ * the caller passes the hand-off state of the previous rank (or NULL for the
+ * first shard) and reads this shard's end state for the next one.
+ */
+typedef struct pm_shard_state {
+	double   phase_clock;           /* slicer.py:50 */
+	uint32_t last_sign;             /* sign of slicer.py:56 last_sample (1: >= 0) */
+	uint32_t last_sign_q;
+	int64_t  bit_count;             /* bits emitted before this shard (byte alignment, slicer.py:92-97) */
+	uint32_t state_register;        /* quadrature slicer */
+	uint32_t valid;
+} pm_shard_state;
+
+int64_t pm_engine_num_packets(const pm_engine *e);
+int64_t pm_engine_arena_bytes(const pm_engine *e);
+/* Records are ordered by (chain, position in stream) == the order the
+ * reference's per-chain decode() lists have. */
+int pm_engine_get_packets(const pm_engine *e, pm_packet_rec *recs, int64_t rec_cap,
+                          uint8_t *arena, int64_t arena_cap);
+
+/* Intermediates for parity tests (need option keep_soft=1 for the soft values). */
+int64_t pm_engine_soft_len(const pm_engine *e, int32_t chain);
+int pm_engine_get_soft(const pm_engine *e, int32_t chain, int32_t component /*0=I/real,1=Q*/,
+                       float *out, int64_t cap);
+/* AddressedData streams: stage 0 = slicer output (slicer.py:97), 1 = after LFSR (lfsr.py:47-51). */
+int64_t pm_engine_stream_len(const pm_engine *e, int32_t chain);
+int pm_engine_get_stream(const pm_engine *e, int32_t chain, int32_t stage,
+                         uint8_t *bytes, int64_t *addresses, int64_t cap);
+
+int pm_engine_get_stats(const pm_engine *e, pm_stats *out);
+
+/* FP32 FFMA peak microbenchmark (roofline denominator for the FIR kernels):
+ * returns achieved TFLOP/s of a register-resident FFMA loop on the device. */
+int pm_measure_fp32_peak(int device, double *tflops);
+
+/* Executed FP32 multiply-adds per input sample over all loaded chains (after
+ * the sharing of common filter passes) and the tile length of a front-end
+ * launch group -- reported by bench.py next to the roofline. */
+double pm_engine_front_macs_per_sample(const pm_engine *e);
+int pm_engine_front_tile(const pm_engine *e, int group);
+
+/* Pinned host memory for callers that want the overlapped H2D path. */
+void *pm_host_alloc(size_t bytes);
+void pm_host_free(void *p);
+
+const char *pm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,637 @@
+// bits.cu -- bit-level stages over packed bitstreams (integer kernels).
+//
+//   gather : (sign, rollover mask) -> packed symbol bitstream + per-byte sample
+//            address  == the AddressedData list of slicer.py:92-97 / 209-224
+//   lfsr   : lfsr.py:22-52 as a GF(2) FIR over 32-bit words
+//   ax25   : ax25.py:25-93 -- stateless flag detection, then one thread per
+//            inter-flag gap replays the HDLC machine exactly
+//   crc    : crc_functions.py:9-61, packet_meta.py:21-41
+//
+// Stream bit g lives in word g>>5 at bit g&31 (LSB-first), so "earlier" bits
+// are at lower positions; the reference's bytes are MSB-first groups of 8.
+#include "pm_common.cuh"
+
+#define GB_WORDS 1024          // mask words per gather block (32768 samples)
+#define GB_THREADS 256
+
+
+
+__device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v)
+{
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned int t = __shfl_up_sync(0xffffffffu, v, d);
+		if ((threadIdx.x & 31) >= d) v += t;
+	}
+	return v;
+}
+
+// exclusive scan over the block (blockDim.x multiple of 32, <= 1024); returns
+// the exclusive prefix of v and the block total.
+__device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned int *s_warp, unsigned int &total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	unsigned int inc = warp_incl_scan(v);
+	if (lane == 31) s_warp[wid] = inc;
+	__syncthreads();
+	if (wid == 0) {
+		unsigned int t = (lane < nw) ? s_warp[lane] : 0;
+		unsigned int ti = warp_incl_scan(t);
+		s_warp[lane] = ti - t;
+		if (lane == 31) s_warp[32] = ti;
+	}
+	__syncthreads();
+	unsigned int ex = inc - v + s_warp[wid];
+	total = s_warp[32];
+	__syncthreads();
+	return ex;
+}
+
+__device__ __forceinline__ uint32_t valid_mask_word(uint32_t m, long long w, long long nout)
+{
+	const long long first = w << 5;
+	if (first >= nout) return 0;
+	const long long remain = nout - first;
+	return remain >= 32 ? m : (m & ((1u << (int)remain) - 1u));
+}
+
+// --- gather step 1: symbols per block of GB_WORDS mask words -----------------
+__global__ void __launch_bounds__(GB_THREADS)
+gather_count_kernel(const BitChain *__restrict__ chains, const uint32_t *__restrict__ mask, long long mask_stride,
+                    unsigned int *__restrict__ block_count, int n_blocks)
+{
+	__shared__ unsigned int s_warp[33];
+	const int ch = blockIdx.y;
+	const long long nout = chains[ch].nout;
+	const uint32_t *mk = mask + (long long)ch * mask_stride;
+	const long long w0 = (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
+	unsigned int cnt = 0;
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const long long w = w0 + q;
+		if ((w << 5) < nout) cnt += __popc(valid_mask_word(mk[w], w, nout));
+	}
+	unsigned int total;
+	block_excl_scan(cnt, s_warp, total);
+	if (threadIdx.x == 0) block_count[(long long)ch * n_blocks + blockIdx.x] = total;
+}
+
+// --- generic per-chain exclusive scan of a row of counters (one CTA per row) --
+__global__ void __launch_bounds__(1024)
+row_scan_kernel(const unsigned int *__restrict__ in, unsigned int *__restrict__ out, int n, int row_stride,
+                unsigned int *__restrict__ totals)
+{
+	__shared__ unsigned int s_warp[33];
+	const unsigned int *src = in + (long long)blockIdx.x * row_stride;
+	unsigned int *dst = out + (long long)blockIdx.x * row_stride;
+	unsigned int carry = 0;
+	for (int base = 0; base < n; base += 1024) {
+		const int i = base + threadIdx.x;
+		unsigned int v = (i < n) ? src[i] : 0;
+		unsigned int total;
+		unsigned int ex = block_excl_scan(v, s_warp, total);
+		if (i < n) dst[i] = carry + ex;
+		carry += total;
+	}
+	if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+// --- gather step 3: write bits + byte addresses ------------------------------
+// symbol_base: symbols emitted before this shard (byte alignment is global,
+// slicer.py:92-97); init_state: quadrature state_register before the shard.
+__global__ void __launch_bounds__(GB_THREADS)
+gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restrict__ sign, long long sign_stride,
+                    const uint32_t *__restrict__ mask, long long mask_stride,
+                    const unsigned int *__restrict__ block_base, int n_blocks,
+                    uint32_t *__restrict__ bits, long long bits_stride,
+                    uint32_t *__restrict__ byte_addr, long long addr_stride,
+                    const unsigned int *__restrict__ init_state)
+{
+	__shared__ unsigned int s_warp[33];
+	__shared__ uint32_t s_stage[2 * GB_WORDS + 2];
+	const int ch = blockIdx.y;
+	const BitChain C = chains[ch];
+	const uint32_t *mk = mask + (long long)ch * mask_stride;
+	const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
+	const uint32_t *sq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
+	uint32_t *out = bits + (long long)ch * bits_stride;
+	uint32_t *oaddr = byte_addr + (long long)ch * addr_stride;
+	const long long w0 = (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
+
+	uint32_t m[4];
+	unsigned int cnt = 0;
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const long long w = w0 + q;
+		m[q] = ((w << 5) < C.nout) ? valid_mask_word(mk[w], w, C.nout) : 0;
+		cnt += __popc(m[q]);
+	}
+	unsigned int total;
+	const unsigned int ex = block_excl_scan(cnt, s_warp, total);
+	const unsigned int sym_block = block_base[(long long)ch * n_blocks + blockIdx.x];   // symbols before block
+	const long long bit_block = (long long)sym_block * C.bps;                            // stream bits before block
+	const unsigned int nbits_block = total * C.bps;
+	const int stage_shift = (int)(bit_block & 31);
+	const unsigned int stage_words = (stage_shift + nbits_block + 31) >> 5;
+	for (unsigned int i = threadIdx.x; i < stage_words; i += GB_THREADS) s_stage[i] = 0;
+	__syncthreads();
+
+	if (cnt) {
+		// quadrature: IQ signs of the symbol before this thread's first one
+		unsigned int prev_cur = 0;
+		if (C.quadrature && C.state_mask > 3u) {
+			long long w = w0;
+			uint32_t mm = 0;
+			int steps = 0;
+			// search backwards for the previous symbol
+			while (true) {
+				w -= 1;
+				if (w < 0) break;
+				mm = mk[w];
+				if (mm) break;
+				if (++steps > (1 << 20)) break;
+			}
+			if (w >= 0 && mm) {
+				const int i = 31 - __clz(mm);
+				prev_cur = (((sg[w] >> i) & 1u) << 1) | ((sq[w] >> i) & 1u);
+			} else {
+				prev_cur = init_state ? (init_state[ch] & 3u) : 0u;
+			}
+		}
+		long long sym = (long long)sym_block + ex;          // shard-local symbol index
+		for (int q = 0; q < 4; q++) {
+			uint32_t mm = m[q];
+			const long long w = w0 + q;
+			const uint32_t s = mm ? sg[w] : 0;
+			const uint32_t sqw = (mm && sq) ? sq[w] : 0;
+			while (mm) {
+				const int i = __ffs(mm) - 1;
+				mm &= mm - 1;
+				unsigned int val;
+				if (C.quadrature) {
+					const unsigned int cur = (((s >> i) & 1u) << 1) | ((sqw >> i) & 1u);
+					const unsigned int state = ((prev_cur << 2) | cur) & C.state_mask;
+					val = C.demap[state];
+					prev_cur = cur;
+				} else {
+					val = (s >> i) & 1u;
+				}
+				// stream bits of this symbol, MSB of val first (slicer.py:215-216)
+				for (int t = 0; t < C.bps; t++) {
+					const long long g = sym * C.bps + t;
+					const unsigned int b = (val >> (C.bps - 1 - t)) & 1u;
+					const unsigned int sp = (unsigned int)(g - bit_block) + stage_shift;
+					if (b) atomicOr(&s_stage[sp >> 5], 1u << (sp & 31));
+					if ((g & 7) == 7) oaddr[g >> 3] = (uint32_t)((w << 5) + i + 1);   // 1-based (slicer.py:75)
+				}
+				sym++;
+			}
+		}
+	}
+	__syncthreads();
+	const long long word0 = bit_block >> 5;
+	for (unsigned int i = threadIdx.x; i < stage_words; i += GB_THREADS) {
+		const uint32_t v = s_stage[i];
+		if (i == 0 || i == stage_words - 1) {
+			if (v) atomicOr(&out[word0 + i], v);
+		} else {
+			out[word0 + i] = v;
+		}
+	}
+}
+
+// --- finalize per-chain counters ----------------------------------------------
+__global__ void finalize_counts_kernel(const BitChain *__restrict__ chains, const unsigned int *__restrict__ sym_totals,
+                                       ChainCounters *__restrict__ cc, int n_chains)
+{
+	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= n_chains) return;
+	const long long nbits = (long long)sym_totals[ch] * chains[ch].bps;
+	cc[ch].nbits = nbits;
+	cc[ch].nbytes = nbits >> 3;
+	cc[ch].nflags = 0;
+	cc[ch].seq_needed = 0;
+}
+
+// --- LFSR: out[g] = XOR_{k in poly} in[g-k], in[<0] = 0 (lfsr.py:22-52) ----------
+__global__ void __launch_bounds__(256)
+lfsr_kernel(const BitChain *__restrict__ chains, const ChainCounters *__restrict__ cc,
+            const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long bits_stride, int max_words)
+{
+	const int ch = blockIdx.y;
+	const long long nb = cc[ch].nbytes * 8;
+	const long long nw = (nb + 31) >> 5;
+	const uint32_t *src = in + (long long)ch * bits_stride;
+	uint32_t *dst = out + (long long)ch * bits_stride;
+	const unsigned long long poly = chains[ch].lfsr_poly;
+	const bool inv = chains[ch].lfsr_invert != 0;
+	for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < max_words;
+	     w += (long long)gridDim.x * blockDim.x) {
+		uint32_t acc = 0;
+		if (w < nw) {
+			unsigned long long p = poly;
+			while (p) {
+				const int k = __ffsll((long long)p) - 1;
+				p &= p - 1;
+				const int q = k >> 5, r = k & 31;
+				const long long wh = w - q;
+				const uint32_t hi = (wh >= 0) ? src[wh] : 0u;
+				const uint32_t lo = (wh - 1 >= 0) ? src[wh - 1] : 0u;
+				acc ^= r ? ((hi << r) | (lo >> (32 - r))) : hi;
+			}
+			if (inv) acc = ~acc;
+			const long long rem = nb - (w << 5);
+			if (rem < 32) acc &= (1u << (int)rem) - 1u;
+		}
+		dst[w] = acc;
+	}
+}
+
+// --- AX.25 flag detection -------------------------------------------------------
+// A flag event is a 0 that follows exactly six 1s (ax25.py:73): stream pattern
+// 0,1,1,1,1,1,1,0 ending at bit g (a virtual 0 precedes the stream: one_count
+// starts at 0).
+__device__ __forceinline__ uint32_t flag_word(const uint32_t *__restrict__ d, long long w, long long nb)
+{
+	const uint32_t cur = d[w];
+	const uint32_t prev = (w > 0) ? d[w - 1] : 0u;
+	const unsigned long long V = ((unsigned long long)cur << 32) | prev;
+	const unsigned long long A = V >> 25;
+	unsigned long long F = ~A & (A >> 1) & (A >> 2) & (A >> 3) & (A >> 4) & (A >> 5) & (A >> 6) & ~(A >> 7);
+	uint32_t f = (uint32_t)F;
+	const long long rem = nb - (w << 5);
+	if (rem <= 0) return 0;
+	if (rem < 32) f &= (1u << (int)rem) - 1u;
+	return f;
+}
+
+#define FL_WORDS 1024
+__global__ void __launch_bounds__(256)
+flag_count_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restrict__ d, long long bits_stride,
+                  unsigned int *__restrict__ block_count, int n_blocks)
+{
+	__shared__ unsigned int s_warp[33];
+	const int ch = blockIdx.y;
+	const long long nb = cc[ch].nbytes * 8;
+	const uint32_t *src = d + (long long)ch * bits_stride;
+	const long long w0 = (long long)blockIdx.x * FL_WORDS + threadIdx.x * 4;
+	unsigned int cnt = 0;
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const long long w = w0 + q;
+		if ((w << 5) < nb) cnt += __popc(flag_word(src, w, nb));
+	}
+	unsigned int total;
+	block_excl_scan(cnt, s_warp, total);
+	if (threadIdx.x == 0) block_count[(long long)ch * n_blocks + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+flag_write_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restrict__ d, long long bits_stride,
+                  const unsigned int *__restrict__ block_base, int n_blocks,
+                  unsigned int *__restrict__ flag_pos, long long flag_stride)
+{
+	__shared__ unsigned int s_warp[33];
+	const int ch = blockIdx.y;
+	const long long nb = cc[ch].nbytes * 8;
+	const uint32_t *src = d + (long long)ch * bits_stride;
+	unsigned int *fp = flag_pos + (long long)ch * flag_stride;
+	const long long w0 = (long long)blockIdx.x * FL_WORDS + threadIdx.x * 4;
+	uint32_t f[4];
+	unsigned int cnt = 0;
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const long long w = w0 + q;
+		f[q] = ((w << 5) < nb) ? flag_word(src, w, nb) : 0u;
+		cnt += __popc(f[q]);
+	}
+	unsigned int total;
+	unsigned int idx = block_excl_scan(cnt, s_warp, total) + block_base[(long long)ch * n_blocks + blockIdx.x];
+	for (int q = 0; q < 4; q++) {
+		uint32_t ff = f[q];
+		while (ff) {
+			const int i = __ffs(ff) - 1;
+			ff &= ff - 1;
+			fp[idx++] = (unsigned int)(((w0 + q) << 5) + i);
+		}
+	}
+}
+
+// --- AX.25 gap replay -----------------------------------------------------------
+
+__device__ __forceinline__ unsigned int crc16_x25_dev(const uint8_t *p, unsigned int n)
+{
+	unsigned int crc = 0xFFFF;
+	for (unsigned int k = 0; k < n; k++) {
+		crc ^= p[k];
+#pragma unroll
+		for (int i = 0; i < 8; i++) crc = (crc & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
+	}
+	return crc ^ 0xFFFFu;
+}
+
+// The HDLC machine of ax25.py:25-93 over stream bits [start, end]; `end` is a
+// flag position (or the last stream bit when closing == false).  Bytes are
+// appended to `dst`.  Returns true when a packet is emitted at the flag.
+__device__ bool ax25_replay(const uint32_t *__restrict__ d, long long start, long long end, uint8_t *dst,
+                            unsigned int &len_out, int &overflow)
+{
+	unsigned int wb = 0, one_count = 0, bit_index = 0, byte_index = 0, len = 0;
+	bool emit = false;
+	for (long long g = start; g <= end; g++) {
+		const unsigned int bit = (d[g >> 5] >> (g & 31)) & 1u;
+		if (bit) {
+			wb |= 0x80;
+			one_count++;
+			bit_index++;
+			if (one_count > 6) { bit_index = 0; byte_index = 0; }       // abort: data not cleared
+			if (bit_index == 8) {
+				bit_index = 0;
+				dst[len++] = (uint8_t)wb;
+				byte_index++;
+				if (byte_index > 1023) { byte_index = 0; one_count = 0; overflow = 1; }
+			}
+			wb >>= 1;
+		} else {
+			if (one_count < 5) {
+				bit_index++;
+				if (bit_index == 8) {
+					bit_index = 0;
+					dst[len++] = (uint8_t)wb;
+					byte_index++;
+					if (byte_index > 1023) byte_index = 0;
+				}
+				wb >>= 1;
+			} else if (one_count == 6) {
+				if (g == end) emit = (byte_index >= 18 && bit_index == 7);
+				// (a flag strictly inside the range cannot happen: ranges end at the first flag)
+				byte_index = 0;
+				bit_index = 0;
+			}
+			one_count = 0;
+		}
+	}
+	len_out = len;
+	return emit;
+}
+
+__global__ void __launch_bounds__(128)
+ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
+                const uint32_t *__restrict__ d, long long bits_stride,
+                const unsigned int *__restrict__ flag_pos, long long flag_stride,
+                const unsigned int *__restrict__ flag_totals,
+                const uint32_t *__restrict__ byte_addr, long long addr_stride,
+                uint8_t *__restrict__ scratch, long long scratch_stride,
+                GapRec *__restrict__ gaps, long long gap_stride)
+{
+	const int ch = blockIdx.y;
+	if (chains[ch].codec != 1) return;
+	const unsigned int nfl = flag_totals[ch];
+	const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j == 0 && threadIdx.x == 0) cc[ch].nflags = (int)nfl;
+	if (j >= nfl) return;
+	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
+	const long long end = fp[j];
+	const long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
+	GapRec r;
+	r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0;
+	// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0
+	if (end - start + 1 >= 18 * 8 + 8) {
+		int overflow = 0;
+		unsigned int len = 0;
+		const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
+			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow);
+		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
+		r.emit = emit ? 1u : 0u;
+		r.len = len;
+		r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
+	}
+	gaps[(long long)ch * gap_stride + j] = r;
+}
+
+// Sequential replay of one whole chain (only when a gap overflowed
+// max_packet_length, ax25.py:46-51, which can desynchronise the stateless flag
+// detector).  One thread per chain; rewrites the chain's gap records as a
+// compact list of emitted packets.
+__global__ void ax25_sequential_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
+                                       const uint32_t *__restrict__ dall, long long bits_stride,
+                                       const uint32_t *__restrict__ byte_addr, long long addr_stride,
+                                       uint8_t *__restrict__ scratch, long long scratch_stride,
+                                       GapRec *__restrict__ gaps, long long gap_stride)
+{
+	const int ch = blockIdx.x;
+	if (threadIdx.x != 0 || chains[ch].codec != 1 || !cc[ch].seq_needed) return;
+	const uint32_t *d = dall + (long long)ch * bits_stride;
+	uint8_t *dst = scratch + (long long)ch * scratch_stride;
+	GapRec *out = gaps + (long long)ch * gap_stride;
+	const long long nb = cc[ch].nbytes * 8;
+	unsigned int wb = 0, one_count = 0, bit_index = 0, byte_index = 0;
+	// bytes of the current working packet are written at `base`, which only
+	// moves forward when a new PacketMeta starts; appended bytes never outrun
+	// the stream position (each needs >= 8 stream bits).
+	long long base = 0, len = 0;
+	unsigned int nrec = 0;
+	for (long long g = 0; g < nb; g++) {
+		const unsigned int bit = (d[g >> 5] >> (g & 31)) & 1u;
+		if (bit) {
+			wb |= 0x80; one_count++; bit_index++;
+			if (one_count > 6) { bit_index = 0; byte_index = 0; }
+			if (bit_index == 8) {
+				bit_index = 0; dst[base + len++] = (uint8_t)wb; byte_index++;
+				if (byte_index > 1023) { byte_index = 0; one_count = 0; }
+			}
+			wb >>= 1;
+		} else {
+			if (one_count < 5) {
+				bit_index++;
+				if (bit_index == 8) {
+					bit_index = 0; dst[base + len++] = (uint8_t)wb; byte_index++;
+					if (byte_index > 1023) byte_index = 0;
+				}
+				wb >>= 1;
+			} else if (one_count == 6) {
+				if (byte_index >= 18 && bit_index == 7) {
+					GapRec r;
+					r.emit = 1; r.len = (unsigned int)len; r.scratch_off = (unsigned int)base;
+					r.addr = byte_addr[(long long)ch * addr_stride + (g >> 3)];
+					out[nrec++] = r;
+					base += len;
+				}
+				// new PacketMeta(): later bytes may overwrite a non-emitted packet's bytes
+				len = 0;
+				byte_index = 0; bit_index = 0;
+			}
+			one_count = 0;
+		}
+	}
+	cc[ch].nflags = (int)nrec;     // gap list now holds exactly the emitted packets
+}
+
+// --- compaction: gap records -> ordered packet records ---------------------------
+
+
+// one CTA; chains in order, gaps in order => records ordered like the
+// reference's per-chain decode() lists.
+__global__ void __launch_bounds__(1024)
+packet_index_kernel(const BitChain *__restrict__ chains, const ChainCounters *__restrict__ cc, int n_chains,
+                    const GapRec *__restrict__ gaps, long long gap_stride,
+                    PacketRecDev *__restrict__ recs, unsigned int *__restrict__ rec_src,
+                    unsigned long long rec_cap, PacketTotals *__restrict__ totals, long long sample_base)
+{
+	__shared__ unsigned int s_warp[33];
+	unsigned long long n_rec = totals->n_packets, n_bytes = totals->n_bytes;
+	for (int ch = 0; ch < n_chains; ch++) {
+		if (chains[ch].codec != 1) continue;
+		const int n = cc[ch].nflags;
+		const GapRec *g = gaps + (long long)ch * gap_stride;
+		for (int base = 0; base < n; base += 1024) {
+			const int j = base + threadIdx.x;
+			GapRec r;
+			r.emit = 0; r.len = 0; r.scratch_off = 0; r.addr = 0;
+			if (j < n) r = g[j];
+			unsigned int tot_e, tot_b;
+			const unsigned int ex_e = block_excl_scan(r.emit, s_warp, tot_e);
+			const unsigned int ex_b = block_excl_scan(r.emit ? r.len : 0u, s_warp, tot_b);
+			if (r.emit) {
+				const unsigned long long ri = n_rec + ex_e;
+				if (ri < rec_cap) {
+					PacketRecDev p;
+					p.chain = ch; p.len = r.len; p.offset = n_bytes + ex_b;
+					p.streamaddress = sample_base + (long long)r.addr;
+					p.bytes_corrected = 0; p.calculated_crc = 0; p.carried_crc = 0;
+					p.valid_crc = 0; p.valid_header = 0;
+					for (int q = 0; q < 6; q++) p.pad[q] = 0;
+					recs[ri] = p;
+					rec_src[ri] = r.scratch_off;
+				}
+			}
+			n_rec += tot_e;
+			n_bytes += tot_b;
+		}
+	}
+	if (threadIdx.x == 0) { totals->n_packets = n_rec; totals->n_bytes = n_bytes; }
+}
+
+// one warp per packet: copy its bytes into the arena, CRC + header check
+__global__ void __launch_bounds__(256)
+packet_copy_kernel(PacketRecDev *__restrict__ recs, const unsigned int *__restrict__ rec_src,
+                   const PacketTotals *__restrict__ totals, unsigned long long first_rec, unsigned long long rec_cap,
+                   const uint8_t *__restrict__ scratch, long long scratch_stride,
+                   uint8_t *__restrict__ arena, unsigned long long arena_cap)
+{
+	const unsigned long long n = min(totals->n_packets, rec_cap);
+	const int lane = threadIdx.x & 31;
+	for (unsigned long long ri = first_rec + (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	     ri < n; ri += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
+		PacketRecDev p = recs[ri];
+		if (p.offset + p.len > arena_cap) continue;
+		const uint8_t *src = scratch + (long long)p.chain * scratch_stride + rec_src[ri];
+		uint8_t *dst = arena + p.offset;
+		for (unsigned int i = lane; i < p.len; i += 32) dst[i] = src[i];
+		if (lane == 0) {
+			// PacketMeta.CalcCRC (packet_meta.py:197-203) + Validate (:205-208)
+			const unsigned int carried = (unsigned int)src[p.len - 1] * 256u + src[p.len - 2];
+			const unsigned int calc = crc16_x25_dev(src, p.len - 2);
+			bool hdr = p.len > 15;
+			if (hdr)
+				for (int i = 0; i < 7; i++) {
+					const unsigned int wc = src[i] >> 1;
+					if ((wc < 32 || wc > 126) && wc != 0) hdr = false;
+				}
+			recs[ri].calculated_crc = (unsigned short)calc;
+			recs[ri].carried_crc = (unsigned short)carried;
+			recs[ri].valid_crc = (calc == carried);
+			recs[ri].valid_header = hdr;
+		}
+	}
+}
+
+// --- export of AddressedData streams for parity tests ----------------------------
+__global__ void __launch_bounds__(256)
+stream_export_kernel(const ChainCounters *__restrict__ cc, int ch, const uint32_t *__restrict__ bits,
+                     long long bits_stride, const uint32_t *__restrict__ byte_addr, long long addr_stride,
+                     uint8_t *__restrict__ out_bytes, long long *__restrict__ out_addr, long long sample_base)
+{
+	const long long nbytes = cc[ch].nbytes;
+	const uint32_t *src = bits + (long long)ch * bits_stride;
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes;
+	     b += (long long)gridDim.x * blockDim.x) {
+		const unsigned int v = (src[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+		out_bytes[b] = (uint8_t)(__brev(v) >> 24);            // first stream bit is the byte's MSB
+		out_addr[b] = sample_base + (long long)byte_addr[(long long)ch * addr_stride + b];
+	}
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+cudaError_t pm_launch_gather(const BitChain *chains, int n_chains, ChainCounters *cc, const uint32_t *sign,
+	long long sign_stride, const uint32_t *mask, long long mask_stride, long long max_words,
+	unsigned int *blk_count, unsigned int *blk_base, unsigned int *sym_totals,
+	uint32_t *bits, long long bits_stride, uint32_t *byte_addr, long long addr_stride,
+	const unsigned int *init_state, cudaStream_t st)
+{
+	const int n_blocks = (int)((max_words + GB_WORDS - 1) / GB_WORDS);
+	dim3 grid(n_blocks, n_chains);
+	gather_count_kernel<<<grid, GB_THREADS, 0, st>>>(chains, mask, mask_stride, blk_count, n_blocks);
+	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, sym_totals);
+	finalize_counts_kernel<<<(n_chains + 31) / 32, 32, 0, st>>>(chains, sym_totals, cc, n_chains);
+	cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)bits_stride * n_chains, st);
+	gather_write_kernel<<<grid, GB_THREADS, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, blk_base,
+		n_blocks, bits, bits_stride, byte_addr, addr_stride, init_state);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_lfsr(const BitChain *chains, int n_chains, const ChainCounters *cc, const uint32_t *in,
+	uint32_t *out, long long bits_stride, cudaStream_t st)
+{
+	int bx = (int)((bits_stride + 255) / 256);
+	if (bx > 1024) bx = 1024;
+	dim3 grid(bx, n_chains);
+	lfsr_kernel<<<grid, 256, 0, st>>>(chains, cc, in, out, bits_stride, (int)bits_stride);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *cc, const uint32_t *d,
+	long long bits_stride, unsigned int *blk_count, unsigned int *blk_base, unsigned int *flag_totals,
+	unsigned int *flag_pos, long long flag_stride, const uint32_t *byte_addr, long long addr_stride,
+	uint8_t *scratch, long long scratch_stride, GapRec *gaps, long long gap_stride, cudaStream_t st)
+{
+	const int n_blocks = (int)((bits_stride + FL_WORDS - 1) / FL_WORDS);
+	dim3 grid(n_blocks, n_chains);
+	flag_count_kernel<<<grid, 256, 0, st>>>(cc, d, bits_stride, blk_count, n_blocks);
+	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, flag_totals);
+	flag_write_kernel<<<grid, 256, 0, st>>>(cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
+	// gaps: at most flag_stride per chain
+	dim3 ggrid((unsigned int)((flag_stride + 127) / 128), n_chains);
+	ax25_gap_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals,
+		byte_addr, addr_stride, scratch, scratch_stride, gaps, gap_stride);
+	ax25_sequential_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, byte_addr, addr_stride, scratch,
+		scratch_stride, gaps, gap_stride);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_packets(const BitChain *chains, int n_chains, const ChainCounters *cc, const GapRec *gaps,
+	long long gap_stride, PacketRecDev *recs, unsigned int *rec_src, unsigned long long rec_cap,
+	PacketTotals *totals, const uint8_t *scratch, long long scratch_stride, uint8_t *arena,
+	unsigned long long arena_cap, long long sample_base, cudaStream_t st)
+{
+	packet_index_kernel<<<1, 1024, 0, st>>>(chains, cc, n_chains, gaps, gap_stride, recs, rec_src, rec_cap, totals,
+		sample_base);
+	packet_copy_kernel<<<296, 256, 0, st>>>(recs, rec_src, totals, 0, rec_cap, scratch, scratch_stride, arena,
+		arena_cap);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_stream_export(const ChainCounters *cc, int ch, const uint32_t *bits, long long bits_stride,
+	const uint32_t *byte_addr, long long addr_stride, uint8_t *out_bytes, long long *out_addr,
+	long long sample_base, cudaStream_t st)
+{
+	stream_export_kernel<<<296, 256, 0, st>>>(cc, ch, bits, bits_stride, byte_addr, addr_stride, out_bytes, out_addr,
+		sample_base);
+	return cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,904 @@
+// engine.cu -- host side of libpymodem_b200.so: chain table -> launch plans,
+// device memory, the run pipeline, and the C ABI of include/pymodem_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pm_common.cuh"
+#include "../../include/pymodem_b200.h"
+
+static_assert(sizeof(pm_packet_rec) == 40 && sizeof(PacketRecDev) == 40, "pm_packet_rec layout");
+
+extern "C" {
+cudaError_t pm_launch_afsk_front(const AfskPlan *, size_t, const int16_t *, long long, long long, int, uint32_t *,
+	long long, float *, long long, GuardList, cudaStream_t);
+cudaError_t pm_launch_fir_front(const FirPlan *, size_t, const int16_t *, long long, long long, int, uint32_t *,
+	long long, float *, long long, GuardList, cudaStream_t);
+cudaError_t pm_launch_guard_fixup(const Fp64Chain *, int, const int16_t *, long long, uint32_t *, long long,
+	float *, long long, GuardList, int, cudaStream_t);
+cudaError_t pm_launch_ffma_peak(float *, int, int, cudaStream_t);
+cudaError_t pm_launch_slicer_segments(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
+	SegState *, SegState *, const SegState *, int, int, int, cudaStream_t);
+cudaError_t pm_launch_slicer_verify(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
+	SegState *, const SegState *, SegState *, const SegState *, int, int, unsigned int *, cudaStream_t);
+cudaError_t pm_launch_gather(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const uint32_t *,
+	long long, long long, unsigned int *, unsigned int *, unsigned int *, uint32_t *, long long, uint32_t *,
+	long long, const unsigned int *, cudaStream_t);
+cudaError_t pm_launch_lfsr(const BitChain *, int, const ChainCounters *, const uint32_t *, uint32_t *, long long,
+	cudaStream_t);
+cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_t *, long long, unsigned int *,
+	unsigned int *, unsigned int *, unsigned int *, long long, const uint32_t *, long long, uint8_t *, long long,
+	GapRec *, long long, cudaStream_t);
+cudaError_t pm_launch_packets(const BitChain *, int, const ChainCounters *, const GapRec *, long long,
+	pm_packet_rec *, unsigned int *, unsigned long long, PacketTotals *, const uint8_t *, long long, uint8_t *,
+	unsigned long long, long long, cudaStream_t);
+cudaError_t pm_launch_stream_export(const ChainCounters *, int, const uint32_t *, long long, const uint32_t *,
+	long long, uint8_t *, long long *, long long, cudaStream_t);
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	cudaError_t ensure(size_t want)
+	{
+		if (want <= n) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; n = 0;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e == cudaSuccess) n = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct HostChain {
+	pm_chain_desc d;
+	std::vector<double> bpf, mark_i, mark_q, space_i, space_q, space_ui, space_uq, lpf;
+	int trim = 0;             // samples lost to 'valid' convolutions
+	int group = -1;           // front-end launch group
+};
+
+struct FrontGroup {
+	int kind = 0;             // PM_MODEM_AFSK / PM_MODEM_FSK
+	std::vector<int> chains;  // engine chain ids
+	AfskPlan afsk;
+	FirPlan fir;
+	size_t smem = 0;
+	int tile = 0;
+	int trim_max = 0;
+	double macs_per_sample = 0;   // executed FP32 MACs per input sample (after sharing)
+};
+
+struct pm_engine {
+	int device = 0;
+	cudaStream_t st = nullptr, st_copy = nullptr;
+	std::string err;
+	std::vector<HostChain> chains;
+	std::vector<FrontGroup> groups;
+	// options
+	int opt_seg_words = 2048;     // 65536 samples
+	int opt_warm_words = 1024;    // 32768 samples
+	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
+	int opt_tile = 0;             // 0 = auto
+	int opt_keep_soft = 0;
+	long long opt_h2d_chunk = 8 << 20;
+	unsigned int guard_cap = 1u << 20;
+	// device tables
+	DevBuf<double> d_taps64;
+	DevBuf<Fp64Chain> d_fp64;
+	DevBuf<SlicerChain> d_slicer;
+	DevBuf<BitChain> d_bitchain;
+	DevBuf<ChainCounters> d_cc;
+	DevBuf<SegState> d_init;
+	// run buffers
+	DevBuf<int16_t> d_audio;
+	DevBuf<uint32_t> d_sign, d_mask, d_bits_raw, d_bits_lfsr, d_byte_addr;
+	DevBuf<float> d_soft;
+	DevBuf<unsigned long long> d_guard_entries;
+	DevBuf<unsigned int> d_counters;      // [0] guard count, [1] repairs
+	DevBuf<SegState> d_S, d_E0, d_E1;
+	DevBuf<unsigned int> d_blk_count, d_blk_base, d_sym_totals, d_flag_totals, d_flag_pos, d_rec_src;
+	DevBuf<uint8_t> d_scratch, d_arena;
+	DevBuf<GapRec> d_gaps;
+	DevBuf<pm_packet_rec> d_recs;
+	DevBuf<PacketTotals> d_totals;
+	unsigned int *h_counters = nullptr;   // pinned
+	PacketTotals *h_totals = nullptr;     // pinned
+	// geometry of the last run
+	long long n_samples = 0, sign_stride = 0, bits_stride = 0, addr_stride = 0, flag_stride = 0,
+	          scratch_stride = 0, soft_stride = 0;
+	int n_seg = 0;
+	int sign_rows = 0;
+	long long sample_base = 0;
+	std::vector<ChainCounters> h_cc;
+	std::vector<pm_packet_rec> h_recs;
+	std::vector<uint8_t> h_arena;
+	pm_stats stats;
+	cudaEvent_t ev[8] = {};
+	std::vector<cudaEvent_t> ev_chunks;
+	bool have_run = false;
+};
+
+static int fail(pm_engine *e, int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (e) e->err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                        \
+	do {                                                                                                \
+		cudaError_t _e = (call);                                                                        \
+		if (_e != cudaSuccess)                                                                          \
+			return fail(e, PM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+	} while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool same_taps(const std::vector<double> &a, const std::vector<double> &b)
+{
+	return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+}
+
+// reversed float taps, zero padded to a multiple of 4
+static int push_taps(float *dst, int &used, const std::vector<double> &h, int &n_padded)
+{
+	n_padded = round_up((int)h.size(), 4);
+	if (used + n_padded > PM_MAX_TAPS) return -1;
+	const int off = used;
+	const int M = (int)h.size();
+	for (int j = 0; j < n_padded; j++) dst[off + j] = (j < M) ? (float)h[M - 1 - j] : 0.f;
+	used += n_padded;
+	return off;
+}
+
+// ---- AFSK group geometry for a candidate tile ---------------------------------
+struct AfskGeom {
+	int U_x, U_m, U_l, a_len;
+	int s_x1_off, s_m_off, s_m_stride;
+	size_t smem;
+	double cost;
+};
+
+static AfskGeom afsk_geom(const AfskPlan &p, int tile)
+{
+	AfskGeom g;
+	int cmax = 0;
+	double corr_sum = 0;
+	for (int j = 0; j < p.n_mag; j++) { cmax = std::max(cmax, p.mag_n[j]); corr_sum += p.mag_n[j]; }
+	g.U_l = tile / 16;
+	g.U_m = (tile + p.n_lpf + 15) / 16;
+	g.U_x = (16 * g.U_m + cmax + 15) / 16;
+	g.a_len = round_up(16 * g.U_x + p.n_bpf, 8);
+	const int a_phys = round_up(pm_phys(g.a_len) + 4, 4);
+	const int x_phys = round_up(pm_phys(16 * g.U_x) + 4, 4);
+	g.s_m_stride = round_up(pm_phys(16 * g.U_m) + 4, 4);
+	g.s_x1_off = a_phys;
+	g.s_m_off = a_phys + x_phys;
+	g.smem = sizeof(float) * (size_t)(g.s_m_off + p.n_mag * g.s_m_stride);
+	// issue-slot cost per output sample (warp granular)
+	auto warps = [](int units) { return (units + 31) / 32 * 32; };
+	double c = (double)warps(g.U_x) * p.n_bpf;
+	// magnitude units are laid out stream after stream
+	c += (double)warps(p.n_mag * g.U_m) * 2.0 * (corr_sum / std::max(1, p.n_mag));
+	c += (double)warps(p.n_pair * g.U_l) * 2.0 * p.n_lpf;
+	g.cost = c / tile;
+	return g;
+}
+
+static int build_groups(pm_engine *e)
+{
+	e->groups.clear();
+	const int nc = (int)e->chains.size();
+	for (int c = 0; c < nc; c++) e->chains[c].group = -1;
+	for (int c = 0; c < nc; c++) {
+		HostChain &hc = e->chains[c];
+		if (hc.group >= 0) continue;
+		FrontGroup g;
+		g.kind = hc.d.modem_kind;
+		if (g.kind != PM_MODEM_AFSK && g.kind != PM_MODEM_FSK)
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, g.kind);
+		for (int k = c; k < nc; k++) {
+			HostChain &o = e->chains[k];
+			if (o.group >= 0 || o.d.modem_kind != g.kind) continue;
+			if (!same_taps(o.bpf, hc.bpf)) continue;
+			if (g.kind == PM_MODEM_AFSK && !same_taps(o.lpf, hc.lpf)) continue;
+			if ((int)g.chains.size() >= PM_MAX_GCH) break;
+			g.chains.push_back(k);
+		}
+		const int gi = (int)e->groups.size();
+		if (g.kind == PM_MODEM_AFSK) {
+			AfskPlan &p = g.afsk;
+			memset(&p, 0, sizeof(p));
+			int used = 0;
+			p.bpf_off = push_taps(p.taps, used, hc.bpf, p.n_bpf);
+			p.lpf_off = push_taps(p.taps, used, hc.lpf, p.n_lpf);
+			if (p.bpf_off < 0 || p.lpf_off < 0) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+			// tone sets (unit gain) -> magnitude streams; chains -> (mark, space) pairs
+			struct Tone { const std::vector<double> *i, *q; };
+			std::vector<Tone> tones;
+			auto tone_id = [&](const std::vector<double> &ti, const std::vector<double> &tq) -> int {
+				for (size_t t = 0; t < tones.size(); t++)
+					if (same_taps(*tones[t].i, ti) && same_taps(*tones[t].q, tq)) return (int)t;
+				if ((int)tones.size() >= PM_MAX_MAG) return -1;
+				tones.push_back({&ti, &tq});
+				return (int)tones.size() - 1;
+			};
+			std::vector<int> cm, cs;
+			std::vector<int> kept;
+			for (int k : g.chains) {
+				HostChain &o = e->chains[k];
+				const int m = tone_id(o.mark_i, o.mark_q);
+				const int s = tone_id(o.space_ui, o.space_uq);
+				if (m < 0 || s < 0) continue;      // left for another group
+				cm.push_back(m); cs.push_back(s); kept.push_back(k);
+			}
+			g.chains = kept;
+			p.n_mag = (int)tones.size();
+			for (int t = 0; t < p.n_mag; t++) {
+				int npad = 0, npad2 = 0;
+				p.mag_i_off[t] = push_taps(p.taps, used, *tones[t].i, npad);
+				p.mag_q_off[t] = push_taps(p.taps, used, *tones[t].q, npad2);
+				if (p.mag_i_off[t] < 0 || p.mag_q_off[t] < 0) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+				p.mag_n[t] = npad;
+			}
+			// pairs, chains sorted by pair
+			std::vector<std::pair<int, int>> pairs;
+			std::vector<int> chain_pair(kept.size());
+			for (size_t i = 0; i < kept.size(); i++) {
+				std::pair<int, int> pr(cm[i], cs[i]);
+				auto it = std::find(pairs.begin(), pairs.end(), pr);
+				if (it == pairs.end()) { pairs.push_back(pr); chain_pair[i] = (int)pairs.size() - 1; }
+				else chain_pair[i] = (int)(it - pairs.begin());
+			}
+			if ((int)pairs.size() > PM_MAX_PAIR) return fail(e, PM_ERR_CAPACITY, "too many tone pairs in a group");
+			p.n_pair = (int)pairs.size();
+			int ci = 0;
+			for (int pi = 0; pi < p.n_pair; pi++) {
+				p.pair_mark[pi] = pairs[pi].first;
+				p.pair_space[pi] = pairs[pi].second;
+				p.pair_first[pi] = ci;
+				for (size_t i = 0; i < kept.size(); i++)
+					if (chain_pair[i] == pi) {
+						p.chain_gid[ci] = kept[i];
+						p.chain_gain[ci] = (float)e->chains[kept[i]].d.space_gain;
+						ci++;
+					}
+			}
+			p.pair_first[p.n_pair] = ci;
+			p.n_chain = ci;
+			p.guard_eps = (float)e->opt_guard_eps;
+			// tile: cheapest issue-slot cost that still fits two CTAs per SM
+			int best = 0;
+			double best_cost = 1e300;
+			const size_t smem_2cta = 112 * 1024, smem_max = 226 * 1024;
+			for (int pass = 0; pass < 2 && !best; pass++)
+				for (int tile = 256; tile <= 16384; tile += 32) {
+					AfskGeom gg = afsk_geom(p, tile);
+					if (gg.smem > (pass == 0 ? smem_2cta : smem_max)) break;
+					if (gg.cost < best_cost) { best_cost = gg.cost; best = tile; }
+				}
+			if (e->opt_tile > 0) best = round_up(e->opt_tile, 32);
+			if (!best) return fail(e, PM_ERR_CAPACITY, "AFSK front end does not fit in shared memory");
+			AfskGeom gg = afsk_geom(p, best);
+			if (gg.smem > smem_max) return fail(e, PM_ERR_CAPACITY, "tile %d needs %zu B shared memory", best, gg.smem);
+			p.tile = best; p.U_x = gg.U_x; p.U_m = gg.U_m; p.U_l = gg.U_l; p.a_len = gg.a_len;
+			p.s_x1_off = gg.s_x1_off; p.s_m_off = gg.s_m_off; p.s_m_stride = gg.s_m_stride;
+			g.smem = gg.smem;
+			g.tile = best;
+			double macs = hc.bpf.size() + 2.0 * p.n_pair * hc.lpf.size();
+			for (int t = 0; t < p.n_mag; t++) macs += 2.0 * tones[t].i->size();
+			g.macs_per_sample = macs;
+		} else {
+			FirPlan &p = g.fir;
+			memset(&p, 0, sizeof(p));
+			int used = 0;
+			p.taps_off = push_taps(p.taps, used, hc.bpf, p.n_taps);
+			if (p.taps_off < 0) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+			p.n_chain = (int)g.chains.size();
+			double abs_sum = 0;
+			for (double v : hc.bpf) abs_sum += std::fabs(v);
+			for (int i = 0; i < p.n_chain; i++) {
+				p.chain_gid[i] = g.chains[i];
+				p.chain_neg[i] = e->chains[g.chains[i]].d.invert_soft;
+			}
+			p.guard_eps = (float)(e->opt_guard_eps * abs_sum);
+			int tile = e->opt_tile > 0 ? round_up(e->opt_tile, 32) : 4096;
+			p.tile = tile;
+			p.U_y = tile / 16;
+			p.a_len = round_up(tile + p.n_taps + 16, 8);
+			g.smem = sizeof(float) * (size_t)(pm_phys(p.a_len) + 8);
+			if (g.smem > 226 * 1024) return fail(e, PM_ERR_CAPACITY, "FIR front end does not fit in shared memory");
+			g.tile = tile;
+			g.macs_per_sample = (double)hc.bpf.size();
+		}
+		g.trim_max = 0;
+		for (int k : g.chains) {
+			e->chains[k].group = gi;
+			g.trim_max = std::max(g.trim_max, e->chains[k].trim);
+		}
+		e->groups.push_back(g);
+	}
+	return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" const char *pm_version(void) { return "pymodem_b200 0.1 (sm_100a)"; }
+
+extern "C" int pm_engine_create(int device, pm_engine **out)
+{
+	if (!out) return PM_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+		return PM_ERR_CUDA;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PM_ERR_CUDA;
+	if (prop.major != 10) return PM_ERR_CUDA;          // sm_100a code only: no fallback path
+	pm_engine *e = new pm_engine();
+	e->device = device;
+	memset(&e->stats, 0, sizeof(e->stats));
+	if (cudaSetDevice(device) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaHostAlloc((void **)&e->h_counters, 64, cudaHostAllocDefault) != cudaSuccess ||
+	    cudaHostAlloc((void **)&e->h_totals, sizeof(PacketTotals), cudaHostAllocDefault) != cudaSuccess) {
+		delete e;
+		return PM_ERR_CUDA;
+	}
+	for (auto &ev : e->ev) cudaEventCreate(&ev);
+	*out = e;
+	return PM_OK;
+}
+
+extern "C" void pm_engine_destroy(pm_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->st);
+	cudaStreamSynchronize(e->st_copy);
+	e->d_taps64.release(); e->d_fp64.release(); e->d_slicer.release(); e->d_bitchain.release();
+	e->d_cc.release(); e->d_init.release(); e->d_audio.release(); e->d_sign.release(); e->d_mask.release();
+	e->d_bits_raw.release(); e->d_bits_lfsr.release(); e->d_byte_addr.release(); e->d_soft.release();
+	e->d_guard_entries.release(); e->d_counters.release(); e->d_S.release(); e->d_E0.release();
+	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
+	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
+	e->d_arena.release(); e->d_gaps.release(); e->d_recs.release(); e->d_totals.release();
+	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
+	if (e->h_counters) cudaFreeHost(e->h_counters);
+	if (e->h_totals) cudaFreeHost(e->h_totals);
+	cudaStreamDestroy(e->st);
+	cudaStreamDestroy(e->st_copy);
+	delete e;
+}
+
+extern "C" const char *pm_last_error(const pm_engine *e) { return e ? e->err.c_str() : "no engine"; }
+
+static void copy_vec(std::vector<double> &dst, const double *src, int n)
+{
+	dst.clear();
+	if (src && n > 0) dst.assign(src, src + n);
+}
+
+extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, int32_t n)
+{
+	if (!e || !descs || n <= 0) return fail(e, PM_ERR_ARG, "load_chains: bad arguments");
+	if (n >= 65536) return fail(e, PM_ERR_ARG, "too many chains");
+	cudaSetDevice(e->device);
+	e->chains.clear();
+	e->have_run = false;
+	for (int c = 0; c < n; c++) {
+		HostChain hc;
+		hc.d = descs[c];
+		const pm_chain_desc &d = descs[c];
+		if (d.modem_kind == PM_MODEM_AFSK) {
+			if (!d.bpf || !d.mark_i || !d.mark_q || !d.space_i || !d.space_q || !d.space_unit_i ||
+			    !d.space_unit_q || !d.lpf || d.n_bpf <= 0 || d.n_corr <= 0 || d.n_lpf <= 0)
+				return fail(e, PM_ERR_ARG, "chain %d: AFSK needs bpf/mark/space/lpf taps", c);
+			copy_vec(hc.bpf, d.bpf, d.n_bpf);
+			copy_vec(hc.mark_i, d.mark_i, d.n_corr); copy_vec(hc.mark_q, d.mark_q, d.n_corr);
+			copy_vec(hc.space_i, d.space_i, d.n_corr); copy_vec(hc.space_q, d.space_q, d.n_corr);
+			copy_vec(hc.space_ui, d.space_unit_i, d.n_corr); copy_vec(hc.space_uq, d.space_unit_q, d.n_corr);
+			copy_vec(hc.lpf, d.lpf, d.n_lpf);
+			hc.trim = (d.n_bpf - 1) + (d.n_corr - 1) + (d.n_lpf - 1);
+		} else if (d.modem_kind == PM_MODEM_FSK) {
+			if (!d.bpf || d.n_bpf <= 0) return fail(e, PM_ERR_ARG, "chain %d: FSK needs input filter taps", c);
+			copy_vec(hc.bpf, d.bpf, d.n_bpf);
+			hc.trim = d.n_bpf - 1;
+		} else {
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, d.modem_kind);
+		}
+		if (d.slicer_kind != PM_SLICER_BINARY)
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: slicer kind %d not supported by this build", c, d.slicer_kind);
+		if (d.codec_kind != PM_CODEC_AX25)
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: codec kind %d not supported by this build", c, d.codec_kind);
+		if (!(d.symbol_rate > 0) || !(d.slicer_sample_rate / d.symbol_rate >= 3.0))
+			return fail(e, PM_ERR_ARG, "chain %d: needs >= 3 samples per symbol", c);
+		// pointers in the copy are not valid after this call
+		hc.d.bpf = hc.d.mark_i = hc.d.mark_q = hc.d.space_i = hc.d.space_q = nullptr;
+		hc.d.space_unit_i = hc.d.space_unit_q = hc.d.lpf = nullptr;
+		hc.d.loop = nullptr;
+		e->chains.push_back(std::move(hc));
+	}
+	int rc = build_groups(e);
+	if (rc != PM_OK) return rc;
+
+	// FP64 taps (reversed = correlation order) for the guard-band fix-up
+	std::vector<double> flat;
+	std::vector<Fp64Chain> f64(n);
+	std::vector<size_t> offs;
+	auto push = [&](const std::vector<double> &h) {
+		size_t off = flat.size();
+		for (size_t j = 0; j < h.size(); j++) flat.push_back(h[h.size() - 1 - j]);
+		return off;
+	};
+	struct Offs { size_t bpf, mi, mq, si, sq, lpf; };
+	std::vector<Offs> o(n);
+	for (int c = 0; c < n; c++) {
+		HostChain &hc = e->chains[c];
+		o[c].bpf = push(hc.bpf); o[c].mi = push(hc.mark_i); o[c].mq = push(hc.mark_q);
+		o[c].si = push(hc.space_i); o[c].sq = push(hc.space_q); o[c].lpf = push(hc.lpf);
+	}
+	CK(e->d_taps64.ensure(flat.size() + 1));
+	CK(cudaMemcpy(e->d_taps64.p, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+	for (int c = 0; c < n; c++) {
+		HostChain &hc = e->chains[c];
+		Fp64Chain &f = f64[c];
+		f.kind = hc.d.modem_kind;
+		f.n_bpf = (int)hc.bpf.size(); f.n_corr = (int)hc.mark_i.size(); f.n_lpf = (int)hc.lpf.size();
+		f.neg = hc.d.invert_soft;
+		f.bpf = e->d_taps64.p + o[c].bpf;
+		f.mark_i = e->d_taps64.p + o[c].mi; f.mark_q = e->d_taps64.p + o[c].mq;
+		f.space_i = e->d_taps64.p + o[c].si; f.space_q = e->d_taps64.p + o[c].sq;
+		f.lpf = e->d_taps64.p + o[c].lpf;
+	}
+	CK(e->d_fp64.ensure(n));
+	CK(cudaMemcpy(e->d_fp64.p, f64.data(), n * sizeof(Fp64Chain), cudaMemcpyHostToDevice));
+	CK(e->d_slicer.ensure(n));
+	CK(e->d_bitchain.ensure(n));
+	CK(e->d_cc.ensure(n));
+	CK(e->d_init.ensure(n));
+	CK(e->d_sym_totals.ensure(n));
+	CK(e->d_flag_totals.ensure(n));
+	CK(e->d_counters.ensure(16));
+	CK(e->d_totals.ensure(1));
+	return PM_OK;
+}
+
+extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
+{
+	if (!e || !key) return PM_ERR_ARG;
+	std::string k(key);
+	bool replan = false;
+	if (k == "segment_len") e->opt_seg_words = std::max(1, (int)(value / 32));
+	else if (k == "warmup_len") e->opt_warm_words = std::max(0, (int)((value + 31) / 32));
+	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
+	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
+	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
+	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
+	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
+	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);
+	if (replan && !e->chains.empty()) return build_groups(e);
+	return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int prepare_run(pm_engine *e, long long n)
+{
+	const int nc = (int)e->chains.size();
+	if (nc == 0) return fail(e, PM_ERR_STATE, "no chains loaded");
+	if (n <= 0 || n >= (1ll << 32) - (1 << 20)) return fail(e, PM_ERR_ARG, "n_samples out of range");
+	e->n_samples = n;
+	e->sign_rows = nc;
+	long long max_words = 0, max_bits = 0;
+	std::vector<SlicerChain> sl(nc);
+	std::vector<BitChain> bc(nc);
+	std::vector<SegState> init(nc);
+	long long rec_cap = 16, arena_cap = 64;
+	for (int c = 0; c < nc; c++) {
+		HostChain &hc = e->chains[c];
+		const long long nout = std::max<long long>(0, n - hc.trim);
+		const FrontGroup &g = e->groups[hc.group];
+		const long long tiles = (nout + g.tile - 1) / g.tile;
+		max_words = std::max(max_words, tiles * g.tile / 32);
+		SlicerChain &s = sl[c];
+		s.sps = hc.d.slicer_sample_rate / hc.d.symbol_rate;       // slicer.py:51
+		s.thr = (s.sps / 2.0) - 0.5;                              // slicer.py:52
+		s.lock = hc.d.lock_rate;
+		s.nout = nout;
+		s.quadrature = 0; s.sign_q_row = 0; s.sign_row = c; s.pad = 0;
+		BitChain &b = bc[c];
+		memset(&b, 0, sizeof(b));
+		b.nout = nout; b.sign_row = c; b.bps = 1; b.lfsr_poly = hc.d.lfsr_poly; b.lfsr_invert = hc.d.lfsr_invert;
+		b.codec = hc.d.codec_kind;
+		init[c].clock = 0.0; init[c].last = 1; init[c].last_q = 1;
+		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
+		const long long mb = nout / min_gap + 64;
+		max_bits = std::max(max_bits, mb);
+		rec_cap += mb / 152 + 4;
+		arena_cap += mb / 8 + 64;
+	}
+	const int seg_words = e->opt_seg_words;
+	max_words = round_up((int)max_words, 4) + 4;
+	e->sign_stride = max_words;
+	e->n_seg = (int)((max_words + seg_words - 1) / seg_words);
+	e->bits_stride = round_up((int)((max_bits + 31) / 32) + 8, 4);
+	e->addr_stride = max_bits / 8 + 16;
+	e->flag_stride = max_bits / 7 + 16;
+	e->scratch_stride = max_bits / 8 + 64;
+	CK(e->d_sign.ensure((size_t)e->sign_rows * e->sign_stride));
+	CK(e->d_mask.ensure((size_t)nc * e->sign_stride));
+	CK(e->d_S.ensure((size_t)nc * e->n_seg));
+	CK(e->d_E0.ensure((size_t)nc * e->n_seg));
+	CK(e->d_E1.ensure((size_t)nc * e->n_seg));
+	const long long n_gblk = std::max((max_words + 1023) / 1024, (e->bits_stride + 1023) / 1024) + 1;
+	CK(e->d_blk_count.ensure((size_t)nc * n_gblk));
+	CK(e->d_blk_base.ensure((size_t)nc * n_gblk));
+	CK(e->d_bits_raw.ensure((size_t)nc * e->bits_stride));
+	CK(e->d_bits_lfsr.ensure((size_t)nc * e->bits_stride));
+	CK(e->d_byte_addr.ensure((size_t)nc * e->addr_stride));
+	CK(e->d_flag_pos.ensure((size_t)nc * e->flag_stride));
+	CK(e->d_gaps.ensure((size_t)nc * e->flag_stride));
+	CK(e->d_scratch.ensure((size_t)nc * e->scratch_stride));
+	CK(e->d_recs.ensure((size_t)rec_cap));
+	CK(e->d_rec_src.ensure((size_t)rec_cap));
+	CK(e->d_arena.ensure((size_t)arena_cap));
+	CK(e->d_guard_entries.ensure(e->guard_cap));
+	if (e->opt_keep_soft) {
+		e->soft_stride = n;
+		CK(e->d_soft.ensure((size_t)nc * n));
+	}
+	CK(cudaMemcpyAsync(e->d_slicer.p, sl.data(), nc * sizeof(SlicerChain), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemcpyAsync(e->d_bitchain.p, bc.data(), nc * sizeof(BitChain), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemcpyAsync(e->d_init.p, init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemsetAsync(e->d_counters.p, 0, 16 * sizeof(unsigned int), e->st));
+	CK(cudaMemsetAsync(e->d_totals.p, 0, sizeof(PacketTotals), e->st));
+	CK(cudaStreamSynchronize(e->st));      // the staging vectors above go out of scope
+	for (auto &g : e->groups) {
+		if (g.kind == PM_MODEM_AFSK)
+			for (int i = 0; i < g.afsk.n_chain; i++)
+				g.afsk.chain_nout[i] = std::max<long long>(0, n - e->chains[g.afsk.chain_gid[i]].trim);
+		else
+			for (int i = 0; i < g.fir.n_chain; i++)
+				g.fir.chain_nout[i] = std::max<long long>(0, n - e->chains[g.fir.chain_gid[i]].trim);
+	}
+	return PM_OK;
+}
+
+static GuardList guard_of(pm_engine *e)
+{
+	GuardList g;
+	g.entries = e->d_guard_entries.p;
+	g.count = e->d_counters.p;
+	g.cap = e->guard_cap;
+	return g;
+}
+
+// launch the front-end tiles [t0, t1) of every group (tile indices are per group)
+static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long long avail_from, long long avail_to,
+                        bool last)
+{
+	// A tile of group g needs audio [t*tile, t*tile + a_len): launch every tile
+	// that became complete with the samples in [0, avail_to).
+	for (auto &g : e->groups) {
+		const int a_len = (g.kind == PM_MODEM_AFSK) ? g.afsk.a_len : g.fir.a_len;
+		long long nout_max = 0;
+		for (int k : g.chains) nout_max = std::max(nout_max, std::max<long long>(0, n - e->chains[k].trim));
+		const long long tiles_total = (nout_max + g.tile - 1) / g.tile;
+		auto ready = [&](long long upto, bool fin) -> long long {
+			if (fin) return tiles_total;
+			long long t = (upto - a_len) / g.tile + 1;      // tiles with t*tile + a_len <= upto
+			if (upto < a_len) t = 0;
+			return std::min(std::max<long long>(t, 0), tiles_total);
+		};
+		const long long t0 = ready(avail_from, false), t1 = ready(avail_to, last);
+		long long t = t0;
+		while (t < t1) {
+			const int cnt = (int)std::min<long long>(t1 - t, 1 << 30);
+			cudaError_t ce;
+			if (g.kind == PM_MODEM_AFSK)
+				ce = pm_launch_afsk_front(&g.afsk, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), e->st);
+			else
+				ce = pm_launch_fir_front(&g.fir, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), e->st);
+			if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "front-end launch failed: %s", cudaGetErrorString(ce));
+			e->stats.kernel_launches++;
+			e->stats.front_launches++;
+			t += cnt;
+		}
+	}
+	return PM_OK;
+}
+
+static int run_back(pm_engine *e, const int16_t *d_audio)
+{
+	const int nc = (int)e->chains.size();
+	const long long n = e->n_samples;
+	// FP64 guard-band fix-up
+	int max_sum = 8;
+	for (auto &hc : e->chains) max_sum = std::max(max_sum, (int)(hc.mark_i.size() + hc.lpf.size() + 2));
+	cudaError_t ce = pm_launch_guard_fixup(e->d_fp64.p, max_sum, d_audio, n, e->d_sign.p, e->sign_stride,
+		e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 8, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches++;
+	CK(cudaEventRecord(e->ev[2], e->st));
+
+	// slicer
+	ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+		e->d_S.p, e->d_E0.p, e->d_init.p, e->n_seg, e->opt_seg_words, e->opt_warm_words, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches++;
+	SegState *Ein = e->d_E0.p, *Eout = e->d_E1.p;
+	e->stats.slicer_repairs = 0;
+	e->stats.slicer_segments = (int64_t)nc * e->n_seg;
+	for (int pass = 0;; pass++) {
+		CK(cudaMemsetAsync(e->d_counters.p + 1, 0, sizeof(unsigned int), e->st));
+		ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+			e->d_S.p, Ein, Eout, e->d_init.p, e->n_seg, e->opt_seg_words, e->d_counters.p + 1, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+		std::swap(Ein, Eout);
+		CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
+		CK(cudaStreamSynchronize(e->st));
+		if (e->h_counters[0] > e->guard_cap) return PM_ERR_CAPACITY;    // caller grows the list and re-runs
+		if (e->h_counters[1] == 0) break;
+		e->stats.slicer_repairs += e->h_counters[1];
+		if (pass > e->n_seg + 2) return fail(e, PM_ERR_STATE, "slicer hand-off did not converge");
+	}
+	e->stats.guard_flagged = e->h_counters[0];
+	CK(cudaEventRecord(e->ev[3], e->st));
+
+	// bits: gather -> lfsr -> ax25 -> packets
+	ce = pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+		e->sign_stride, e->d_blk_count.p, e->d_blk_base.p, e->d_sym_totals.p, e->d_bits_raw.p, e->bits_stride,
+		e->d_byte_addr.p, e->addr_stride, nullptr, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "gather launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches += 4;
+	ce = pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "lfsr launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches++;
+	ce = pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p,
+		e->d_blk_base.p, e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride,
+		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "ax25 launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches += 5;
+	ce = pm_launch_packets(e->d_bitchain.p, nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p,
+		e->d_recs.n, e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base,
+		e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "packet launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches += 2;
+	CK(cudaEventRecord(e->ev[4], e->st));
+
+	// results to host
+	CK(cudaMemcpyAsync(e->h_totals, e->d_totals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, e->st));
+	e->h_cc.resize(nc);
+	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
+	CK(cudaStreamSynchronize(e->st));
+	const unsigned long long np = e->h_totals->n_packets, nb = e->h_totals->n_bytes;
+	if (np > e->d_recs.n || nb > e->d_arena.n)
+		return fail(e, PM_ERR_CAPACITY, "packet buffers too small (%llu records, %llu bytes)", np, nb);
+	e->h_recs.resize(np);
+	e->h_arena.resize(nb);
+	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
+	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, nb, cudaMemcpyDeviceToHost, e->st));
+	CK(cudaEventRecord(e->ev[5], e->st));
+	CK(cudaStreamSynchronize(e->st));
+	e->stats.d2h_bytes = (int64_t)(np * sizeof(pm_packet_rec) + nb + sizeof(PacketTotals) + nc * sizeof(ChainCounters) + 8);
+	e->stats.n_packets = (int64_t)np;
+	e->stats.n_stream_bits = 0;
+	for (auto &c : e->h_cc) e->stats.n_stream_bits += c.nbits;
+	return PM_OK;
+}
+
+static void finish_stats(pm_engine *e)
+{
+	float ms = 0;
+	auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, e->ev[a], e->ev[b]); return (double)ms; };
+	e->stats.total_ms = el(0, 5);
+	e->stats.front_ms = el(0, 1);
+	e->stats.fixup_ms = el(1, 2);
+	e->stats.slicer_ms = el(2, 3);
+	e->stats.bits_ms = el(3, 4);
+	e->stats.d2h_ms = el(4, 5);
+}
+
+static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host)
+{
+	if (!e) return PM_ERR_ARG;
+	if (!audio) return fail(e, PM_ERR_ARG, "audio is NULL");
+	cudaSetDevice(e->device);
+	for (int attempt = 0; attempt < 4; attempt++) {
+		memset(&e->stats, 0, sizeof(e->stats));
+		int rc = prepare_run(e, n);
+		if (rc != PM_OK) return rc;
+		const int16_t *d_audio = audio;
+		CK(cudaEventRecord(e->ev[0], e->st));
+		if (on_host) {
+			CK(e->d_audio.ensure((size_t)n + 64));
+			d_audio = e->d_audio.p;
+			const long long chunk = e->opt_h2d_chunk;
+			const int n_chunks = (int)((n + chunk - 1) / chunk);
+			while ((int)e->ev_chunks.size() < n_chunks) {
+				cudaEvent_t ev;
+				CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+				e->ev_chunks.push_back(ev);
+			}
+			// the copy stream must not start before the engine stream reached this point
+			CK(cudaEventRecord(e->ev[6], e->st));
+			CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
+			long long done = 0;
+			for (int i = 0; i < n_chunks; i++) {
+				const long long len = std::min(chunk, n - done);
+				CK(cudaMemcpyAsync(e->d_audio.p + done, audio + done, (size_t)len * sizeof(int16_t),
+					cudaMemcpyHostToDevice, e->st_copy));
+				CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
+				CK(cudaStreamWaitEvent(e->st, e->ev_chunks[i], 0));
+				rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1);
+				if (rc != PM_OK) return rc;
+				done += len;
+			}
+			e->stats.h2d_bytes = (int64_t)n * 2;
+		} else {
+			rc = launch_front(e, d_audio, n, 0, n, true);
+			if (rc != PM_OK) return rc;
+		}
+		CK(cudaEventRecord(e->ev[1], e->st));
+		rc = run_back(e, d_audio);
+		if (rc == PM_ERR_CAPACITY && e->h_counters[0] > e->guard_cap) {
+			// guard list overflowed: grow it and run again
+			e->guard_cap = e->h_counters[0] + e->h_counters[0] / 4 + 1024;
+			cudaStreamSynchronize(e->st);
+			continue;
+		}
+		if (rc != PM_OK) return rc;
+		finish_stats(e);
+		e->have_run = true;
+		return PM_OK;
+	}
+	return fail(e, PM_ERR_CAPACITY, "guard list kept overflowing");
+}
+
+extern "C" int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples)
+{
+	return run_impl(e, audio_host, n_samples, true);
+}
+
+extern "C" int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples)
+{
+	return run_impl(e, audio_dev, n_samples, false);
+}
+
+extern "C" int64_t pm_engine_num_packets(const pm_engine *e) { return (e && e->have_run) ? (int64_t)e->h_recs.size() : -1; }
+extern "C" int64_t pm_engine_arena_bytes(const pm_engine *e) { return (e && e->have_run) ? (int64_t)e->h_arena.size() : -1; }
+
+extern "C" int pm_engine_get_packets(const pm_engine *e, pm_packet_rec *recs, int64_t rec_cap, uint8_t *arena,
+                                     int64_t arena_cap)
+{
+	if (!e || !e->have_run) return PM_ERR_STATE;
+	if ((int64_t)e->h_recs.size() > rec_cap || (int64_t)e->h_arena.size() > arena_cap) return PM_ERR_CAPACITY;
+	if (!e->h_recs.empty()) memcpy(recs, e->h_recs.data(), e->h_recs.size() * sizeof(pm_packet_rec));
+	if (!e->h_arena.empty()) memcpy(arena, e->h_arena.data(), e->h_arena.size());
+	return PM_OK;
+}
+
+extern "C" int64_t pm_engine_soft_len(const pm_engine *e, int32_t chain)
+{
+	if (!e || !e->have_run || chain < 0 || chain >= (int)e->chains.size()) return -1;
+	return std::max<long long>(0, e->n_samples - e->chains[chain].trim);
+}
+
+extern "C" int pm_engine_get_soft(const pm_engine *ce, int32_t chain, int32_t component, float *out, int64_t cap)
+{
+	pm_engine *e = const_cast<pm_engine *>(ce);
+	if (!e || !e->have_run) return PM_ERR_STATE;
+	if (!e->opt_keep_soft || !e->d_soft.p) return fail(e, PM_ERR_STATE, "soft values were not kept (option keep_soft)");
+	if (component != 0) return fail(e, PM_ERR_ARG, "component %d not available", component);
+	const int64_t len = pm_engine_soft_len(e, chain);
+	if (len < 0 || cap < len) return PM_ERR_CAPACITY;
+	cudaSetDevice(e->device);
+	CK(cudaMemcpy(out, e->d_soft.p + (size_t)chain * e->soft_stride, (size_t)len * sizeof(float), cudaMemcpyDeviceToHost));
+	return PM_OK;
+}
+
+extern "C" int64_t pm_engine_stream_len(const pm_engine *e, int32_t chain)
+{
+	if (!e || !e->have_run || chain < 0 || chain >= (int)e->chains.size()) return -1;
+	return e->h_cc[chain].nbytes;
+}
+
+extern "C" int pm_engine_get_stream(const pm_engine *ce, int32_t chain, int32_t stage, uint8_t *bytes,
+                                    int64_t *addresses, int64_t cap)
+{
+	pm_engine *e = const_cast<pm_engine *>(ce);
+	if (!e || !e->have_run) return PM_ERR_STATE;
+	const int64_t len = pm_engine_stream_len(e, chain);
+	if (len < 0 || cap < len) return PM_ERR_CAPACITY;
+	if (len == 0) return PM_OK;
+	cudaSetDevice(e->device);
+	uint8_t *d_b = nullptr;
+	long long *d_a = nullptr;
+	CK(cudaMalloc((void **)&d_b, (size_t)len));
+	CK(cudaMalloc((void **)&d_a, (size_t)len * sizeof(long long)));
+	const uint32_t *src = (stage == 0) ? e->d_bits_raw.p : e->d_bits_lfsr.p;
+	cudaError_t c1 = pm_launch_stream_export(e->d_cc.p, chain, src, e->bits_stride, e->d_byte_addr.p, e->addr_stride,
+		d_b, d_a, e->sample_base, e->st);
+	cudaError_t c2 = cudaMemcpyAsync(bytes, d_b, (size_t)len, cudaMemcpyDeviceToHost, e->st);
+	cudaError_t c3 = cudaMemcpyAsync(addresses, d_a, (size_t)len * sizeof(long long), cudaMemcpyDeviceToHost, e->st);
+	cudaError_t c4 = cudaStreamSynchronize(e->st);
+	cudaFree(d_b);
+	cudaFree(d_a);
+	if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess)
+		return fail(e, PM_ERR_CUDA, "stream export failed");
+	return PM_OK;
+}
+
+extern "C" int pm_engine_get_stats(const pm_engine *e, pm_stats *out)
+{
+	if (!e || !out) return PM_ERR_ARG;
+	*out = e->stats;
+	return PM_OK;
+}
+
+// executed FP32 MACs per input sample (all chains, after sharing) -- used by
+// bench.py for the roofline
+extern "C" double pm_engine_front_macs_per_sample(const pm_engine *e)
+{
+	double m = 0;
+	if (e) for (auto &g : e->groups) m += g.macs_per_sample;
+	return m;
+}
+
+extern "C" int pm_engine_front_tile(const pm_engine *e, int group)
+{
+	if (!e || group < 0 || group >= (int)e->groups.size()) return -1;
+	return e->groups[group].tile;
+}
+
+extern "C" int pm_measure_fp32_peak(int device, double *tflops)
+{
+	if (!tflops) return PM_ERR_ARG;
+	if (cudaSetDevice(device) != cudaSuccess) return PM_ERR_CUDA;
+	float *d = nullptr;
+	if (cudaMalloc((void **)&d, 16) != cudaSuccess) return PM_ERR_CUDA;
+	cudaEvent_t a, b;
+	cudaEventCreate(&a); cudaEventCreate(&b);
+	const int blocks = 148 * 8, iters = 4096;
+	pm_launch_ffma_peak(d, blocks, 64, 0);
+	cudaDeviceSynchronize();
+	double best = 0;
+	for (int rep = 0; rep < 5; rep++) {
+		cudaEventRecord(a, 0);
+		pm_launch_ffma_peak(d, blocks, iters, 0);
+		cudaEventRecord(b, 0);
+		if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return PM_ERR_CUDA; }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, a, b);
+		const double flops = 2.0 * blocks * 256.0 * iters * 8 * 16;
+		best = std::max(best, flops / (ms * 1e-3) / 1e12);
+	}
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	cudaFree(d);
+	*tflops = best;
+	return PM_OK;
+}
+
+// pinned host memory for callers without torch
+extern "C" void *pm_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+	return p;
+}
+extern "C" void pm_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,420 @@
+// front.cu -- FIR front ends (FP32 FFMA, shared-memory staged, fused).
+//
+// AFSK (reference afsk.py:148-167):
+//     x1 = audio (*) BPF
+//     m_j = sqrt((x1 (*) tone_i)^2 + (x1 (*) tone_q)^2)      per tone set j
+//     y_c = (m_mark (*) LPF) - space_gain_c * (m_space (*) LPF)
+// All convolutions are numpy 'valid' (y[n] = sum_k h[k] x[n+M-1-k]); taps are
+// stored reversed so every stage is a correlation y[n] = sum_j hr[j] x[n+j].
+// The reference computes LPF(m_mark - m_space_gained); LPF is linear, so the
+// LPF of the unit-gain space magnitude is shared by every chain that differs
+// only in space_gain (afsk_1200_ax25_super_opt.json chains 2-8).
+//
+// Only the SIGN of y reaches the rest of the chain (slicer.py:85, 99-102), so
+// the kernel's product is one bit per chain-sample.  A sample whose |y| is
+// within guard_eps of the magnitude scale |L_mark| + g|L_space| is queued for
+// FP64 re-evaluation (guard_fixup_kernel) so that the sign matches the
+// reference's float64 arithmetic.
+#include "pm_common.cuh"
+
+__device__ __forceinline__ float4 lds4(const float *s, int i)
+{
+	return *reinterpret_cast<const float4 *>(s + pm_phys(i));
+}
+
+__device__ __forceinline__ void sts4(float *s, int i, float a, float b, float c, float d)
+{
+	*reinterpret_cast<float4 *>(s + pm_phys(i)) = make_float4(a, b, c, d);
+}
+
+// One thread = 16 consecutive outputs of one FIR (NSET = 1) or of two FIRs
+// that share their input window (NSET = 2: the I and Q correlators).
+// Register-blocked sliding window: 16 new inputs (4 x LDS.128) feed 256 (512)
+// FFMAs; taps come from the constant bank.
+template <int NSET>
+struct FirUnit {
+	float a[16];
+	float b[16];
+
+	__device__ __forceinline__ void run(const float *__restrict__ s, int base,
+	                                    const float *__restrict__ tA, const float *__restrict__ tB, int ntaps)
+	{
+		float w[32];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			float4 v = lds4(s, base + 4 * q);
+			w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+		}
+#pragma unroll
+		for (int r = 0; r < 16; r++) { a[r] = 0.f; b[r] = 0.f; }
+		int j0 = 0;
+		for (; j0 + 16 <= ntaps; j0 += 16) {
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				float4 v = lds4(s, base + j0 + 16 + 4 * q);
+				w[16 + 4 * q] = v.x; w[17 + 4 * q] = v.y; w[18 + 4 * q] = v.z; w[19 + 4 * q] = v.w;
+			}
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				float hA = tA[j0 + k];
+				float hB = (NSET == 2) ? tB[j0 + k] : 0.f;
+#pragma unroll
+				for (int r = 0; r < 16; r++) {
+					a[r] = fmaf(hA, w[r + k], a[r]);
+					if (NSET == 2) b[r] = fmaf(hB, w[r + k], b[r]);
+				}
+			}
+#pragma unroll
+			for (int r = 0; r < 16; r++) w[r] = w[r + 16];
+		}
+		for (; j0 < ntaps; j0 += 4) {
+			float4 v = lds4(s, base + j0 + 16);
+			w[16] = v.x; w[17] = v.y; w[18] = v.z; w[19] = v.w;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				float hA = tA[j0 + k];
+				float hB = (NSET == 2) ? tB[j0 + k] : 0.f;
+#pragma unroll
+				for (int r = 0; r < 16; r++) {
+					a[r] = fmaf(hA, w[r + k], a[r]);
+					if (NSET == 2) b[r] = fmaf(hB, w[r + k], b[r]);
+				}
+			}
+#pragma unroll
+			for (int r = 0; r < 16; r++) w[r] = w[r + 4];
+		}
+	}
+};
+
+// Stage a_len int16 samples starting at n0 into shared memory as floats
+// (zero beyond the end of the recording).
+__device__ __forceinline__ void stage_audio(float *s_a, const int16_t *__restrict__ audio,
+                                            long long n0, long long n_audio, int a_len)
+{
+	for (int i = threadIdx.x * 8; i < a_len; i += blockDim.x * 8) {
+		long long g = n0 + i;
+		float f[8];
+		if (g + 8 <= n_audio) {
+			uint4 v = __ldg(reinterpret_cast<const uint4 *>(audio + g));
+			unsigned int u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				f[2 * q] = (float)(short)(u[q] & 0xFFFFu);
+				f[2 * q + 1] = (float)(short)(u[q] >> 16);
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < 8; q++) f[q] = (g + q < n_audio) ? (float)audio[g + q] : 0.f;
+		}
+		sts4(s_a, i, f[0], f[1], f[2], f[3]);
+		sts4(s_a, i + 4, f[4], f[5], f[6], f[7]);
+	}
+}
+
+template <bool WRITE_SOFT>
+__global__ void __launch_bounds__(PM_FRONT_THREADS, 2)
+afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict__ audio, long long n_audio,
+                  long long tile_first, uint32_t *__restrict__ sign, long long sign_stride,
+                  float *__restrict__ soft, long long soft_stride, GuardList guard)
+{
+	extern __shared__ __align__(16) float smem[];
+	float *s_a = smem;
+	float *s_x1 = smem + P.s_x1_off;
+	float *s_m = smem + P.s_m_off;
+	const long long n0 = (tile_first + blockIdx.x) * (long long)P.tile;
+	const int tid = threadIdx.x;
+
+	stage_audio(s_a, audio, n0, n_audio, P.a_len);
+	__syncthreads();
+
+	// input band-pass (afsk.py:151)
+	for (int u = tid; u < P.U_x; u += PM_FRONT_THREADS) {
+		FirUnit<1> f;
+		f.run(s_a, 16 * u, P.taps + P.bpf_off, nullptr, P.n_bpf);
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+			sts4(s_x1, 16 * u + 4 * q, f.a[4 * q], f.a[4 * q + 1], f.a[4 * q + 2], f.a[4 * q + 3]);
+	}
+	__syncthreads();
+
+	// tone correlators and magnitudes (afsk.py:153-160)
+	for (int u = tid; u < P.n_mag * P.U_m; u += PM_FRONT_THREADS) {
+		const int j = u / P.U_m;
+		const int ui = u - j * P.U_m;
+		FirUnit<2> f;
+		f.run(s_x1, 16 * ui, P.taps + P.mag_i_off[j], P.taps + P.mag_q_off[j], P.mag_n[j]);
+		float *dst = s_m + j * P.s_m_stride;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			float m[4];
+#pragma unroll
+			for (int t = 0; t < 4; t++) {
+				const float ci = f.a[4 * q + t], cq = f.b[4 * q + t];
+				m[t] = sqrtf(fmaf(ci, ci, cq * cq));
+			}
+			sts4(dst, 16 * ui + 4 * q, m[0], m[1], m[2], m[3]);
+		}
+	}
+	__syncthreads();
+
+	// output low-pass of the mark and space magnitudes, per-chain combination,
+	// sign packing (afsk.py:162-166 -> slicer.py:85,99)
+	const int lane = tid & 31;
+	const int total = P.n_pair * P.U_l;
+	for (int ub = tid - lane; ub < total; ub += PM_FRONT_THREADS) {
+		const int u = ub + lane;
+		const bool active = u < total;
+		int p = 0, ui = 0;
+		FirUnit<1> fm, fs;
+		if (active) {
+			p = u / P.U_l;
+			ui = u - p * P.U_l;
+			fm.run(s_m + P.pair_mark[p] * P.s_m_stride, 16 * ui, P.taps + P.lpf_off, nullptr, P.n_lpf);
+			fs.run(s_m + P.pair_space[p] * P.s_m_stride, 16 * ui, P.taps + P.lpf_off, nullptr, P.n_lpf);
+		}
+		// chains are visited in lock-step by the whole warp (a warp may
+		// straddle two pairs; lanes of the shorter pair idle)
+		int cmax = 0;
+		if (active) cmax = P.pair_first[p + 1] - P.pair_first[p];
+		cmax = __reduce_max_sync(0xffffffffu, cmax);
+		const long long nbase = n0 + 16 * ui;
+		for (int ci = 0; ci < cmax; ci++) {
+			unsigned int half = 0;
+			int c = -1;
+			if (active && ci < P.pair_first[p + 1] - P.pair_first[p]) {
+				c = P.pair_first[p] + ci;
+				const float g = P.chain_gain[c];
+				const int gid = P.chain_gid[c];
+				const long long nout = P.chain_nout[c];
+#pragma unroll
+				for (int r = 0; r < 16; r++) {
+					const float lm = fm.a[r], ls = fs.a[r];
+					const float y = fmaf(-g, ls, lm);
+					if (y >= 0.f) half |= (1u << r);
+					const float scale = fabsf(lm) + g * fabsf(ls);
+					if (fabsf(y) < P.guard_eps * scale && nbase + r < nout) {
+						unsigned int slot = atomicAdd(guard.count, 1u);
+						if (slot < guard.cap)
+							guard.entries[slot] = ((unsigned long long)gid << 48) | (unsigned long long)(nbase + r);
+					}
+					if (WRITE_SOFT && nbase + r < nout) soft[gid * soft_stride + nbase + r] = y;
+				}
+			}
+			// lanes 2k / 2k+1 hold the low / high half of one 32-sample word
+			const unsigned int hi = __shfl_down_sync(0xffffffffu, half, 1);
+			if (c >= 0 && !(lane & 1)) {
+				const long long word = (nbase >> 5);
+				sign[P.chain_gid[c] * sign_stride + word] = half | (hi << 16);
+			}
+		}
+	}
+}
+
+// Single-FIR front end: fsk.py:149-159 (y = audio (*) input_lpf, optional negate).
+template <bool WRITE_SOFT>
+__global__ void __launch_bounds__(PM_FRONT_THREADS, 2)
+fir_front_kernel(const __grid_constant__ FirPlan P, const int16_t *__restrict__ audio, long long n_audio,
+                 long long tile_first, uint32_t *__restrict__ sign, long long sign_stride,
+                 float *__restrict__ soft, long long soft_stride, GuardList guard)
+{
+	extern __shared__ __align__(16) float smem[];
+	float *s_a = smem;
+	const long long n0 = (tile_first + blockIdx.x) * (long long)P.tile;
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+
+	stage_audio(s_a, audio, n0, n_audio, P.a_len);
+	__syncthreads();
+
+	for (int ub = tid - lane; ub < P.U_y; ub += PM_FRONT_THREADS) {
+		const int u = ub + lane;
+		const bool active = u < P.U_y;
+		FirUnit<1> f;
+		float scale = 0.f;
+		if (active) {
+			f.run(s_a, 16 * u, P.taps + P.taps_off, nullptr, P.n_taps);
+			// magnitude scale for the guard band: peak |x| of the unit's input
+			// window (guard_eps already carries sum|h|); conservative, and the
+			// FP64 re-evaluation of a single FIR output is cheap.
+			for (int j = 0; j < P.n_taps + 16; j += 4) {
+				const float4 v = lds4(s_a, 16 * u + j);
+				scale = fmaxf(scale, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+			}
+		}
+		const long long nbase = n0 + 16 * u;
+		for (int c = 0; c < P.n_chain; c++) {
+			unsigned int half = 0;
+			if (active) {
+				const int gid = P.chain_gid[c];
+				const long long nout = P.chain_nout[c];
+#pragma unroll
+				for (int r = 0; r < 16; r++) {
+					const float y = P.chain_neg[c] ? -f.a[r] : f.a[r];
+					if (y >= 0.f) half |= (1u << r);
+					if (fabsf(y) < P.guard_eps * scale && nbase + r < nout) {
+						unsigned int slot = atomicAdd(guard.count, 1u);
+						if (slot < guard.cap)
+							guard.entries[slot] = ((unsigned long long)gid << 48) | (unsigned long long)(nbase + r);
+					}
+					if (WRITE_SOFT && nbase + r < nout) soft[gid * soft_stride + nbase + r] = y;
+				}
+			}
+			const unsigned int hi = __shfl_down_sync(0xffffffffu, half, 1);
+			if (active && !(lane & 1))
+				sign[P.chain_gid[c] * sign_stride + (nbase >> 5)] = half | (hi << 16);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// FP64 guard-band fix-up.  One CTA per queued (chain, sample): re-evaluate the
+// reference's own float64 formula (its taps, its order of stages) for that one
+// output and overwrite the sign bit (and the soft value when kept).
+// ---------------------------------------------------------------------------
+
+#define PM_FIX_THREADS 128
+
+__global__ void __launch_bounds__(PM_FIX_THREADS)
+guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restrict__ audio, long long n_audio,
+                   uint32_t *__restrict__ sign, long long sign_stride, float *__restrict__ soft,
+                   long long soft_stride, GuardList guard)
+{
+	extern __shared__ __align__(16) double sm64[];
+	const unsigned int n_entries = min(*guard.count, guard.cap);
+	for (unsigned int e = blockIdx.x; e < n_entries; e += gridDim.x) {
+		const unsigned long long ent = guard.entries[e];
+		const int gid = (int)(ent >> 48);
+		const long long n = (long long)(ent & 0xFFFFFFFFFFFFull);
+		const Fp64Chain C = chains[gid];
+		double y;
+		if (C.kind == 2) {
+			// y[n] = sum_j hr[j] a[n+j]
+			double acc = 0.0;
+			for (int j = threadIdx.x; j < C.n_bpf; j += PM_FIX_THREADS)
+				acc += C.bpf[j] * (double)audio[n + j];
+			sm64[threadIdx.x] = acc;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				double t = 0.0;
+				for (int i = 0; i < PM_FIX_THREADS; i++) t += sm64[i];
+				sm64[PM_FIX_THREADS] = t;
+			}
+			__syncthreads();
+			y = sm64[PM_FIX_THREADS];
+			if (C.neg) y = -y;
+		} else {
+			double *x1 = sm64;                               // n_corr + n_lpf - 1 values
+			double *d = sm64 + (C.n_corr + C.n_lpf);          // n_lpf values
+			const int nx = C.n_corr + C.n_lpf - 1;
+			for (int i = threadIdx.x; i < nx; i += PM_FIX_THREADS) {
+				double acc = 0.0;
+				for (int j = 0; j < C.n_bpf; j++) acc += C.bpf[j] * (double)audio[n + i + j];
+				x1[i] = acc;
+			}
+			__syncthreads();
+			for (int i = threadIdx.x; i < C.n_lpf; i += PM_FIX_THREADS) {
+				double mi = 0.0, mq = 0.0, si = 0.0, sq = 0.0;
+				for (int j = 0; j < C.n_corr; j++) {
+					const double x = x1[i + j];
+					mi += C.mark_i[j] * x; mq += C.mark_q[j] * x;
+					si += C.space_i[j] * x; sq += C.space_q[j] * x;
+				}
+				d[i] = sqrt(mi * mi + mq * mq) - sqrt(si * si + sq * sq);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				double acc = 0.0;
+				for (int i = 0; i < C.n_lpf; i++) acc += C.lpf[i] * d[i];
+				d[C.n_lpf] = acc;
+			}
+			__syncthreads();
+			y = d[C.n_lpf];
+		}
+		if (threadIdx.x == 0) {
+			uint32_t *w = sign + gid * sign_stride + (n >> 5);
+			const uint32_t bit = 1u << (n & 31);
+			if (y >= 0.0) atomicOr(w, bit); else atomicAnd(w, ~bit);
+			if (soft) soft[gid * soft_stride + n] = (float)y;
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------
+// FP32 FFMA peak microbenchmark (roofline denominator for the kernels above).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, float x)
+{
+	float a[16];
+#pragma unroll
+	for (int r = 0; r < 16; r++) a[r] = threadIdx.x * 0.001f + r;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+#pragma unroll
+			for (int r = 0; r < 16; r++) a[r] = fmaf(a[r], x, 0.5f);
+	}
+	float s = 0.f;
+#pragma unroll
+	for (int r = 0; r < 16; r++) s += a[r];
+	if (s == 12345.678f) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers (called from engine.cu)
+// ---------------------------------------------------------------------------
+extern "C" cudaError_t pm_launch_afsk_front(const AfskPlan *plan, size_t smem_bytes, const int16_t *audio,
+	long long n_audio, long long tile_first, int n_tiles, uint32_t *sign, long long sign_stride,
+	float *soft, long long soft_stride, GuardList guard, cudaStream_t st)
+{
+	if (n_tiles <= 0) return cudaSuccess;
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaFuncSetAttribute(afsk_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+		cudaFuncSetAttribute(afsk_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+		attr_done = true;
+	}
+	if (soft)
+		afsk_front_kernel<true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard);
+	else
+		afsk_front_kernel<false><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_fir_front(const FirPlan *plan, size_t smem_bytes, const int16_t *audio,
+	long long n_audio, long long tile_first, int n_tiles, uint32_t *sign, long long sign_stride,
+	float *soft, long long soft_stride, GuardList guard, cudaStream_t st)
+{
+	if (n_tiles <= 0) return cudaSuccess;
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaFuncSetAttribute(fir_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+		cudaFuncSetAttribute(fir_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+		attr_done = true;
+	}
+	if (soft)
+		fir_front_kernel<true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard);
+	else
+		fir_front_kernel<false><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int max_taps_sum, const int16_t *audio,
+	long long n_audio, uint32_t *sign, long long sign_stride, float *soft, long long soft_stride,
+	GuardList guard, int grid, cudaStream_t st)
+{
+	size_t smem = sizeof(double) * (size_t)(2 * max_taps_sum + PM_FIX_THREADS + 8);
+	guard_fixup_kernel<<<grid, PM_FIX_THREADS, smem, st>>>(chains, audio, n_audio, sign, sign_stride, soft,
+		soft_stride, guard);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_ffma_peak(float *out, int blocks, int iters, cudaStream_t st)
+{
+	ffma_peak_kernel<<<blocks, 256, 0, st>>>(out, iters, 0.999f);
+	return cudaGetLastError();
+}

@@ -1,0 +1,135 @@
+// pm_common.cuh -- shared definitions for the sm_100a kernels of libpymodem_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PM_MAX_MAG     8      // tone-magnitude streams per AFSK front-end group
+#define PM_MAX_PAIR    8      // (mark stream, space stream) pairs per group
+#define PM_MAX_GCH     16     // chains per front-end group
+#define PM_MAX_TAPS    1536   // floats of FIR taps carried in the kernel parameter block
+#define PM_FRONT_THREADS 256
+
+// Shared-memory sample arrays use a padded layout: 4 floats of padding after
+// every 16.  A thread owns 16 consecutive outputs ("unit"), so unit bases are
+// 80 B apart instead of 64 B and the 128-bit window loads of the 8 lanes of a
+// quarter-warp fall into 8 different 16-byte bank groups (conflict-free).
+__host__ __device__ __forceinline__ int pm_phys(int i) { return i + ((i >> 4) << 2); }
+
+// Plan of one fused AFSK front-end launch (all chains that share the input
+// band-pass and output low-pass taps).  Passed as a __grid_constant__ kernel
+// parameter, so taps are read through the constant bank (uniform loads).
+struct AfskPlan {
+	int tile;                 // chain output samples per CTA (multiple of 32)
+	int U_x, U_m, U_l;        // 16-output units per CTA: BPF, magnitude, LPF
+	int a_len;                // audio samples staged per CTA
+	int n_bpf, bpf_off;       // input BPF (taps reversed, count multiple of 4)
+	int n_mag;
+	int mag_n[PM_MAX_MAG];    // correlator taps (multiple of 4)
+	int mag_i_off[PM_MAX_MAG];
+	int mag_q_off[PM_MAX_MAG];
+	int n_lpf, lpf_off;
+	int n_pair;
+	int pair_mark[PM_MAX_PAIR];
+	int pair_space[PM_MAX_PAIR];
+	int pair_first[PM_MAX_PAIR + 1];   // chains of pair p: chain_*[pair_first[p] .. pair_first[p+1])
+	int n_chain;
+	int chain_gid[PM_MAX_GCH];         // engine-wide chain index
+	float chain_gain[PM_MAX_GCH];      // space_gain (afsk.py:143)
+	long long chain_nout[PM_MAX_GCH];  // valid demod outputs of the chain (N - trim)
+	int s_x1_off, s_m_off, s_m_stride; // shared-memory carve-up, in floats
+	float guard_eps;
+	float taps[PM_MAX_TAPS];
+};
+
+// Plan of a single-FIR front end (FSK: fsk.py:149-159).
+struct FirPlan {
+	int tile;
+	int U_y;
+	int a_len;
+	int n_taps, taps_off;
+	int n_chain;
+	int chain_gid[PM_MAX_GCH];
+	int chain_neg[PM_MAX_GCH];         // fsk.py:153 invert
+	long long chain_nout[PM_MAX_GCH];
+	float guard_eps;
+	float taps[PM_MAX_TAPS];
+};
+
+// Samples whose FP32 soft value is too close to zero to trust its sign are
+// queued here and re-evaluated in FP64 by the fix-up kernel.
+struct GuardList {
+	unsigned long long *entries;       // (chain gid << 48) | sample index
+	unsigned int *count;
+	unsigned int cap;
+};
+
+// ---- tables shared by the kernels and the host engine -------------------------
+struct Fp64Chain {            // float64 taps for the guard-band fix-up
+	int kind;                 // PM_MODEM_AFSK (1) or PM_MODEM_FSK (2)
+	int n_bpf, n_corr, n_lpf;
+	int neg;
+	const double *bpf;        // reversed (correlation order)
+	const double *mark_i, *mark_q, *space_i, *space_q;
+	const double *lpf;
+};
+
+struct SlicerChain {
+	double sps;              // samples_per_symbol   slicer.py:51
+	double thr;              // rollover_threshold   slicer.py:52
+	double lock;             // lock_rate
+	long long nout;          // valid soft samples of the chain
+	int quadrature;          // zero crossings on I or Q (slicer.py:226-233)
+	int sign_q_row;          // row of the Q sign stream (quadrature)
+	int sign_row;            // row of the (I) sign stream
+	int pad;
+};
+
+struct SegState {
+	double clock;            // phase_clock
+	unsigned int last;       // sign bit of last_sample (1: >= 0.0); slicer.py:55 starts at 0.0
+	unsigned int last_q;
+};
+
+struct BitChain {
+	long long nout;            // valid soft samples
+	int sign_row, sign_q_row;
+	int quadrature;
+	int bps;                   // bits per symbol (1 binary / bpsk, 2 qpsk)
+	unsigned int state_mask;
+	unsigned int demap[16];
+	unsigned long long lfsr_poly;
+	int lfsr_invert;
+	int codec;                 // PM_CODEC_*
+};
+
+struct ChainCounters {
+	long long nbits;           // total sliced bits of the chain
+	long long nbytes;          // nbits / 8 (trailing partial byte dropped, slicer.py:95)
+	int nflags;
+	int seq_needed;            // ax25 max_packet_length overflow seen: replay sequentially
+};
+
+struct GapRec {
+	unsigned int emit;        // 1: a packet was emitted at the closing flag
+	unsigned int len;         // bytes appended since the previous flag event
+	unsigned int scratch_off; // where they are in the chain's scratch bytes
+	unsigned int addr;        // byte address of the closing flag's byte (ax25.py:82)
+};
+
+struct PacketRecDev {          // mirrors pm_packet_rec (include/pymodem_b200.h)
+	unsigned int chain;
+	unsigned int len;
+	unsigned long long offset;
+	long long streamaddress;
+	unsigned int bytes_corrected;
+	unsigned short calculated_crc;
+	unsigned short carried_crc;
+	unsigned char valid_crc;
+	unsigned char valid_header;
+	unsigned char pad[6];
+};
+
+struct PacketTotals {
+	unsigned long long n_packets;
+	unsigned long long n_bytes;
+};

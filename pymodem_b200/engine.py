@@ -1,0 +1,194 @@
+"""Python face of the CUDA engine: chain objects -> pm_chain_desc table ->
+pm_engine_run -> list[PacketMeta] per chain.
+
+No CPU fallback: everything here calls libpymodem_b200.so through ctypes and
+raises if the library or an sm_100 GPU is missing."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .modems_codecs.packet_meta import PacketMeta
+
+
+class EngineError(RuntimeError):
+	pass
+
+
+REC_DTYPE = np.dtype([
+	('chain', '<u4'), ('len', '<u4'), ('offset', '<u8'), ('streamaddress', '<i8'),
+	('bytes_corrected', '<u4'), ('calculated_crc', '<u2'), ('carried_crc', '<u2'),
+	('valid_crc', 'u1'), ('valid_header', 'u1'), ('pad', 'u1', (6,)),
+])
+assert REC_DTYPE.itemsize == ctypes.sizeof(_lib.PacketRec) == 40
+
+
+def describe_chain(chain, keep):
+	"""[object_name, modem, slicer, stream, codec] -> pm_chain_desc"""
+	_name, modem, slicer, stream, codec = chain
+	desc = _lib.ChainDesc()
+	for block, what in ((modem, 'modem'), (slicer, 'slicer'), (stream, 'stream'), (codec, 'codec')):
+		if block == [] or block is None:
+			# the reference degrades a bad slicer/stream/codec spec to [] and the
+			# chain then dies in its child process (pymodem.py:96-113)
+			raise EngineError(f"chain '{_name}': invalid or missing '{what}'")
+	modem.describe(desc, keep)
+	slicer.describe(desc)
+	stream.describe(desc)
+	codec.describe(desc)
+	return desc
+
+
+class Engine:
+	"""One engine = one GPU + one chain table (a demod_stack)."""
+
+	def __init__(self, demod_stack, device=0, **options):
+		self._lib = _lib.load()
+		self._h = ctypes.c_void_p()
+		self.names = [chain[0] for chain in demod_stack]
+		rc = self._lib.pm_engine_create(int(device), ctypes.byref(self._h))
+		if rc != _lib.PM_OK:
+			self._h = ctypes.c_void_p()
+			raise EngineError(
+				f"pm_engine_create(device={device}) failed ({rc}): a B200 (sm_100) GPU is required; "
+				"there is no CPU fallback")
+		for key, value in options.items():
+			self.set_option(key, value)
+		keep = []
+		descs = (_lib.ChainDesc * len(demod_stack))()
+		for i, chain in enumerate(demod_stack):
+			descs[i] = describe_chain(chain, keep)
+		self._check(self._lib.pm_engine_load_chains(self._h, descs, len(demod_stack)))
+		self.n_chains = len(demod_stack)
+
+	def _check(self, rc):
+		if rc != _lib.PM_OK:
+			msg = self._lib.pm_last_error(self._h)
+			raise EngineError(f"pymodem_b200 error {rc}: {msg.decode() if msg else ''}")
+
+	def close(self):
+		if getattr(self, '_h', None) and self._h.value:
+			self._lib.pm_engine_destroy(self._h)
+			self._h = ctypes.c_void_p()
+
+	def __del__(self):
+		try:
+			self.close()
+		except Exception:
+			pass
+
+	def set_option(self, key, value):
+		self._check(self._lib.pm_engine_set_option(self._h, key.encode(), float(value)))
+
+	# -- execution -------------------------------------------------------------
+	def run_raw(self, audio):
+		"""int16 host ndarray -> (records structured array, arena uint8 array).
+		This is the reference-facing C-ABI call with HOST buffers."""
+		audio = np.ascontiguousarray(audio, dtype=np.int16)
+		self._check(self._lib.pm_engine_run(self._h, audio.ctypes.data, audio.shape[0]))
+		return self.fetch()
+
+	def run_host_ptr(self, ptr, n):
+		self._check(self._lib.pm_engine_run(self._h, ptr, n))
+
+	def run_device_ptr(self, ptr, n):
+		"""audio already resident in device memory (e.g. a torch int16 tensor's data_ptr())."""
+		self._check(self._lib.pm_engine_run_device(self._h, ptr, n))
+
+	def fetch(self):
+		n = self._lib.pm_engine_num_packets(self._h)
+		nb = self._lib.pm_engine_arena_bytes(self._h)
+		if n < 0:
+			raise EngineError("no results: run the engine first")
+		recs = np.zeros(n, dtype=REC_DTYPE)
+		arena = np.zeros(max(nb, 1), dtype=np.uint8)
+		self._check(self._lib.pm_engine_get_packets(self._h, recs.ctypes.data, n, arena.ctypes.data, arena.shape[0]))
+		return recs, arena[:nb]
+
+	def packets(self, recs, arena):
+		"""records -> [list[PacketMeta]] per chain, in config order (the order the
+		reference's deterministic driver produces)."""
+		out = [[] for _ in range(self.n_chains)]
+		raw = arena.tobytes()
+		for r in recs:
+			p = PacketMeta()
+			off = int(r['offset'])
+			p.data = list(raw[off:off + int(r['len'])])
+			p.streamaddress = int(r['streamaddress'])
+			p.SourceDecoder = self.names[int(r['chain'])]
+			p.BytesCorrected = int(r['bytes_corrected'])
+			p.CalculatedCRC = int(r['calculated_crc'])
+			p.CarriedCRC = int(r['carried_crc'])
+			p.ValidCRC = bool(r['valid_crc'])
+			p.ValidHeader = bool(r['valid_header'])
+			p._device_checked = True
+			out[int(r['chain'])].append(p)
+		return out
+
+	def run(self, audio):
+		recs, arena = self.run_raw(audio)
+		return self.packets(recs, arena)
+
+	# -- intermediates (parity tests) -------------------------------------------
+	def soft(self, chain, component=0):
+		n = self._lib.pm_engine_soft_len(self._h, chain)
+		if n < 0:
+			raise EngineError("no soft values: run with keep_soft=1 first")
+		out = np.zeros(n, dtype=np.float32)
+		self._check(self._lib.pm_engine_get_soft(self._h, chain, component, out.ctypes.data, n))
+		return out
+
+	def stream(self, chain, stage):
+		"""AddressedData stream of a chain: stage 0 = slicer output, 1 = after LFSR.
+		-> (bytes uint8[n], addresses int64[n])"""
+		n = self._lib.pm_engine_stream_len(self._h, chain)
+		if n < 0:
+			raise EngineError("no stream: run the engine first")
+		b = np.zeros(max(n, 1), dtype=np.uint8)
+		a = np.zeros(max(n, 1), dtype=np.int64)
+		self._check(self._lib.pm_engine_get_stream(self._h, chain, stage, b.ctypes.data, a.ctypes.data, n))
+		return b[:n], a[:n]
+
+	def stats(self):
+		s = _lib.Stats()
+		self._check(self._lib.pm_engine_get_stats(self._h, ctypes.byref(s)))
+		return s.as_dict()
+
+	def front_macs_per_sample(self):
+		return self._lib.pm_engine_front_macs_per_sample(self._h)
+
+
+_cache = {}
+
+
+def engine_for(demod_stack, device=0, **options):
+	"""Engines are cached per (chain objects, device, options): building one uploads taps."""
+	key = (tuple(id(b) for chain in demod_stack for b in chain[1:]), device, tuple(sorted(options.items())))
+	eng = _cache.get(key)
+	if eng is None:
+		eng = Engine(demod_stack, device=device, **options)
+		_cache.clear()
+		_cache[key] = eng
+		eng._stack_ref = demod_stack      # keep ids alive
+	return eng
+
+
+def demod_only(modem, audio):
+	"""modem.demod(audio) on the GPU: float64 ndarray of soft values."""
+	from .modems_codecs import ax25, lfsr, slicer
+	s = slicer.BinarySlicer(sample_rate=getattr(modem, 'output_sample_rate', modem.sample_rate),
+		config=str(int(getattr(modem, 'symbol_rate', 1200))))
+	eng = Engine([["demod", modem, s, lfsr.LFSR(), ax25.AX25Codec()]], keep_soft=1)
+	try:
+		eng.run_raw(audio)
+		return eng.soft(0).astype(np.float64)
+	finally:
+		eng.close()
+
+
+def measure_fp32_peak(device=0):
+	t = ctypes.c_double()
+	rc = _lib.load().pm_measure_fp32_peak(device, ctypes.byref(t))
+	if rc != _lib.PM_OK:
+		raise EngineError(f"pm_measure_fp32_peak failed ({rc})")
+	return t.value

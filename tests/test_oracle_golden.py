@@ -1,0 +1,100 @@
+"""The CPU oracle against the fixtures produced by the live reference
+(tools/make_golden.py) and the known-answer vectors of SURVEY.md Appendix B.2.
+This is what pins the oracle; the GPU tests then compare the CUDA path to both."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLD, Golden
+
+CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k"]
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_packets_match_reference(oracle, tag):
+	g = Golden(tag)
+	got = oracle.run_config(g.sample_rate, g.lines, g.audio())
+	assert got == g.all_packets()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_chunked_equals_monolithic(oracle, tag):
+	g = Golden(tag)
+	got = oracle.run_config(g.sample_rate, g.lines, g.audio(), chunk=50001)
+	assert got == g.all_packets()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_stages_match_reference(oracle, tag):
+	g = Golden(tag)
+	audio = g.audio()
+	for ci, line in enumerate(g.chain_lines()):
+		if f"c{ci}_soft_dec" not in g.z:
+			continue
+		chain = oracle.Chain(g.sample_rate, line)
+		soft = chain.modem.demod(audio)
+		assert len(soft) == int(g.z[f"c{ci}_soft_len"])
+		# same numpy.convolve calls as the reference: bit-identical on this host
+		np.testing.assert_allclose(soft[::97], g.z[f"c{ci}_soft_dec"], rtol=0, atol=1e-9 * float(g.z[f"c{ci}_soft_rms"]))
+		b, a = chain.slicer.slice(soft)
+		np.testing.assert_array_equal(b, g.z[f"c{ci}_sl_bytes"])
+		np.testing.assert_array_equal(a, g.z[f"c{ci}_sl_addr"])
+		d, _ = chain.stream.stream_unscramble_8bit(b, a)
+		np.testing.assert_array_equal(d, g.z[f"c{ci}_ds_bytes"])
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_correlate_matches_reference(oracle, tag):
+	g = Golden(tag)
+	names = [l["object_name"] for l in g.chain_lines()]
+	uniq, bad = oracle.correlate(g.all_packets(), names, g.sample_rate / 40)
+	assert [u[0] for u in uniq] == list(g.z["uniq_addr"])
+	assert [u[2] for u in uniq] == list(g.z["uniq_crc"])
+	assert [len(u[3]) for u in uniq] == list(g.z["uniq_ndec"])
+	assert bad == int(g.z["bad_count"])
+
+
+def test_kats(oracle):
+	z = np.load(os.path.join(GOLD, "kats.npz"))
+	# CRC-16/X.25("123456789") = 0x906E  
+	pkt = bytes(z["crc_append_123456789"])
+	assert pkt[-2:] == bytes([0x6E, 0x90])
+	assert oracle.crc16(b"123456789") == 0x906E
+	assert oracle.check_crc(pkt) == [36974, 36974, True] == [int(x) for x in z["crc_check"]]
+	data = z["lfsr_in"]
+	for key in z.files:
+		if not key.startswith("lfsr_") or key == "lfsr_in":
+			continue
+		_, poly, inv = key.split("_")
+		l = oracle.LFSR({"poly": poly, "invert": "true" if inv == "1" else "false"})
+		out, _ = l.stream_unscramble_8bit(data, None)
+		np.testing.assert_array_equal(out, z[key])
+	# SURVEY.md B.2 LFSR vectors
+	l = oracle.LFSR({"poly": "0x3", "invert": "True"})
+	out, _ = l.stream_unscramble_8bit(np.array([0x00, 0xFF, 0xAA, 0x0F, 0x7E], dtype=np.uint8), None)
+	assert list(out) == [0xFF, 0x7F, 0x80, 0xF7, 0x3E]
+	l = oracle.LFSR({"poly": "0x63003", "invert": "True"})
+	out, _ = l.stream_unscramble_8bit(np.array([0x00, 0xFF, 0xAA, 0x0F, 0x7E, 0x12, 0x34], dtype=np.uint8), None)
+	assert list(out) == [0xFF, 0x7F, 0x88, 0xB0, 0xF1, 0xEC, 0xA0]
+
+
+def test_ax25_quirks(oracle):
+	"""Edge cases of ax25.py the GPU decoder must reproduce: abort does not clear
+	the accumulated bytes; minimum length 18; frames share flags."""
+	from pymodem_b200 import synth
+	frame = synth.ax25_ui_frame("MODEM", "NOISE", b"hello world, this is a test")
+	bits = list(synth.hdlc_bits(frame, preamble_flags=2, postamble_flags=1))
+	# junk + abort (8 ones) directly before the frame's opening flag: junk bytes stay in data
+	junk = [1, 0, 1, 1, 0, 0, 1, 0] * 3 + [1] * 8 + [0]
+	stream = [0] * 5 + junk + bits + [0] * 11
+	stream += [0] * ((-len(stream)) % 8)
+	by = np.packbits(np.array(stream, dtype=np.uint8))
+	addr = np.arange(1, len(by) + 1, dtype=np.int64) * 320
+	pk = oracle.AX25Codec("x").decode(by, addr)
+	assert len(pk) == 1 and pk[0][1] == frame
+	# a too-short frame (17 bytes) is dropped
+	short = list(synth.hdlc_bits(bytes(range(17)), preamble_flags=1, postamble_flags=1))
+	short += [0] * ((-len(short)) % 8)
+	by = np.packbits(np.array(short, dtype=np.uint8))
+	assert oracle.AX25Codec("x").decode(by, np.arange(len(by), dtype=np.int64)) == []

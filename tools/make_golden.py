@@ -1,0 +1,154 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, importable only in the build container) on deterministic
+synthetic audio.  The fixtures pin the oracle (tests/test_oracle_golden.py) and
+are compared directly with the CUDA path (tests/test_gpu_*.py).
+
+Usage: python tools/make_golden.py            (needs /root/reference)
+"""
+import contextlib
+import hashlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(0, REPO)
+
+from pymodem_b200 import synth  # noqa: E402
+
+import modems_codecs.chain_builder as cb  # noqa: E402  (the reference's)
+import modems_codecs.chain_execute as ce  # noqa: E402
+import modems_codecs.crc_functions as crcf  # noqa: E402
+import modems_codecs.lfsr as ref_lfsr  # noqa: E402
+from modems_codecs.data_classes import AddressedData  # noqa: E402
+from modems_codecs.packet_meta import PacketMetaArray  # noqa: E402
+
+GOLD = os.path.join(REPO, "tests", "golden")
+
+
+def quiet():
+	return contextlib.redirect_stdout(io.StringIO())
+
+
+def load_config(name):
+	with open(os.path.join(REF, "configs", name)) as f:
+		return [json.loads(line) for line in f]
+
+
+def build_ref_chain(sr, line):
+	with quiet():
+		m = cb.ModemConfigurator(sr, line['modem'])
+		try:
+			rate = m.output_sample_rate
+		except AttributeError:
+			rate = sr
+		s = cb.SlicerConfigurator(rate, line['slicer'])
+		st = cb.StreamConfigurator(line['stream'])
+		c = cb.CodecConfigurator(line['codec'], line['object_name'])
+	return [line['object_name'], m, s, st, c]
+
+
+def run_case(tag, config_name, lines, sr, audio, meta, stage_chains=(0,)):
+	"""Deterministic driver: chains in config order, fresh blocks."""
+	out = {"config_json": np.array(json.dumps(lines)), "sample_rate": np.array(sr),
+		"audio_sha256": np.array(hashlib.sha256(audio.tobytes()).hexdigest()),
+		"meta_json": np.array(json.dumps(meta))}
+	chains = [l for l in lines if l.get('object_type') == 'demod_chain']
+	all_packets = []
+	for ci, line in enumerate(chains):
+		chain = build_ref_chain(sr, line)
+		with quiet():
+			soft = chain[1].demod(audio)
+			sliced = chain[2].slice(soft)
+			descr = chain[3].stream_unscramble_8bit(sliced)
+			packets = chain[4].decode(descr)
+		all_packets.append(packets)
+		lens = np.array([len(p.data) for p in packets], dtype=np.int64)
+		out[f"c{ci}_addr"] = np.array([p.streamaddress for p in packets], dtype=np.int64)
+		out[f"c{ci}_len"] = lens
+		out[f"c{ci}_corr"] = np.array([p.BytesCorrected for p in packets], dtype=np.int64)
+		out[f"c{ci}_data"] = np.array([int(b) for p in packets for b in p.data], dtype=np.uint8)
+		if ci in stage_chains:
+			if hasattr(soft, 'i_data'):
+				soft_i, soft_q = np.asarray(soft.i_data, dtype=np.float64), np.asarray(soft.q_data, dtype=np.float64)
+				out[f"c{ci}_softq_dec"] = soft_q[::97]
+			else:
+				soft_i = np.asarray(soft, dtype=np.float64)
+			out[f"c{ci}_soft_len"] = np.array(len(soft_i))
+			out[f"c{ci}_soft_dec"] = soft_i[::97]                 # decimated soft values
+			out[f"c{ci}_soft_win"] = soft_i[10000:10000 + 8192]    # one full-rate window
+			out[f"c{ci}_soft_rms"] = np.array(np.sqrt(np.mean(soft_i ** 2)))
+			out[f"c{ci}_sl_bytes"] = np.array([int(d.data) for d in sliced], dtype=np.uint8)
+			out[f"c{ci}_sl_addr"] = np.array([int(d.address) for d in sliced], dtype=np.int64)
+			out[f"c{ci}_ds_bytes"] = np.array([int(d.data) for d in descr], dtype=np.uint8)
+	# CalcCRCs + Correlate (pymodem.py:170-175)
+	results = PacketMetaArray()
+	for p in all_packets:
+		results.add(p)
+	results.CalcCRCs()
+	results.Correlate(address_distance=sr / 40)
+	out["uniq_addr"] = np.array([p.streamaddress for p in results.unique_packet_array], dtype=np.int64)
+	out["uniq_crc"] = np.array([p.CalculatedCRC for p in results.unique_packet_array], dtype=np.int64)
+	out["uniq_ndec"] = np.array([len(p.CorrelatedDecoders) for p in results.unique_packet_array], dtype=np.int64)
+	out["bad_count"] = np.array(results.CountBad())
+	out["n_chains"] = np.array(len(chains))
+	path = os.path.join(GOLD, f"{tag}.npz")
+	np.savez_compressed(path, **out)
+	print(tag, "chains", len(chains), "packets", [len(p) for p in all_packets],
+		"unique", len(results.unique_packet_array), "bad", results.CountBad(),
+		f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def kats():
+	out = {}
+	pkt = list(b"123456789")
+	crcf.AppendCRC(pkt)
+	out["crc_append_123456789"] = np.array(pkt, dtype=np.uint8)
+	out["crc_check"] = np.array([int(x) for x in crcf.CheckCRC(pkt)], dtype=np.int64)
+	rng = np.random.default_rng(7)
+	data = rng.integers(0, 256, size=257, dtype=np.uint8)
+	for poly, inv in ((0x3, True), (0x63003, True), (0x1, False), (0x211, False), (0x21001, False)):
+		with quiet():
+			l = ref_lfsr.LFSR(poly=poly, invert=inv)
+			res = l.stream_unscramble_8bit([AddressedData(int(b), i) for i, b in enumerate(data)])
+		out[f"lfsr_{poly:x}_{int(inv)}"] = np.array([r.data for r in res], dtype=np.uint8)
+	out["lfsr_in"] = data
+	np.savez_compressed(os.path.join(GOLD, "kats.npz"), **out)
+	print("kats", list(out))
+
+
+def main():
+	os.makedirs(GOLD, exist_ok=True)
+	kats()
+	# (1) the headline config on 12 s of synthetic Bell-202 audio, noise ramp
+	meta = dict(gen="afsk1200_ax25", duration_s=12.0, sample_rate=48000, frame_interval_s=1.0,
+		noise_start=0.0, noise_end=1.4, seed=0, noise_seed=1, first_frame_s=0.3)
+	audio, _, _ = synth.afsk1200_ax25(**meta_args(meta))
+	run_case("afsk1200_superopt_48k", "afsk_1200_ax25_super_opt.json",
+		load_config("afsk_1200_ax25_super_opt.json"), 48000, audio, meta, stage_chains=(0, 1, 7))
+	# (2) same modulation at 44.1 kHz (non-integer samples/symbol: 36.75), AX.25 lines of afsk_1200.json
+	meta = dict(gen="afsk1200_ax25", duration_s=8.0, sample_rate=44100, frame_interval_s=1.0,
+		noise_start=0.0, noise_end=1.0, seed=2, noise_seed=3, first_frame_s=0.3)
+	audio, _, _ = synth.afsk1200_ax25(**meta_args(meta))
+	lines = [l for l in load_config("afsk_1200.json") if l.get('codec', {}).get('type') != 'il2p']
+	run_case("afsk1200_ax25_44k1", "afsk_1200.json", lines, 44100, audio, meta, stage_chains=(0, 1))
+	# (3) G3RUH FSK 9600 AX.25 (fsk_9600.json line 3: poly 0x63003 + invert)
+	meta = dict(gen="fsk9600_ax25", duration_s=4.0, sample_rate=48000, frame_interval_s=0.25,
+		noise_start=0.0, noise_end=0.7, seed=4, noise_seed=5, first_frame_s=0.05)
+	audio, _, _ = synth.fsk9600_ax25(**meta_args(meta))
+	lines = [l for l in load_config("fsk_9600.json") if l.get('codec', {}).get('type') == 'ax25'
+		or l.get('object_type') == 'report']
+	run_case("fsk9600_ax25_48k", "fsk_9600.json", lines, 48000, audio, meta, stage_chains=(0,))
+
+
+def meta_args(meta):
+	return {k: v for k, v in meta.items() if k != "gen"}
+
+
+if __name__ == "__main__":
+	main()
