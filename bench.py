@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- demod chain-samples/sec of the many-chain AFSK 1200 super-opt config
+(reference configs/afsk_1200_ax25_super_opt.json, 8 chains) on one hour of 48 kHz
+synthetic AWGN AX.25 audio per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--seconds S]
+
+A step = one pass of the whole hot path (FIR front end -> symbol-timing slicer ->
+NRZI/LFSR -> AX.25 HDLC + CRC -> packet records on the host) over one batch =
+`seconds` of audio x 8 chains on every rank.  `value` times it with the audio already
+resident in HBM (pm_engine_run_device); `e2e` times the reference-facing C-ABI call
+with HOST buffers (pm_engine_run: pinned host audio -> chunked H2D overlapped with the
+front-end kernels -> records D2H).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+	sys.path.insert(0, REPO)
+
+SAMPLE_RATE = 48000
+METRIC = "demod chain-samples/sec"
+UNIT = "chain-samples/s"
+# reference-equivalent (unshared) FP32 work of the AFSK front end
+REF_FLOP_PER_CHAIN_SAMPLE = 956.0
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+
+
+def make_audio(seconds, rank):
+	"""The workload of SURVEY.md 8(d): AX.25 UI frames every 3.1 s, Bell-202 AFSK, AWGN sigma
+	ramped 0 -> 1.6 x signal amplitude across the recording; seeds differ per rank."""
+	from pymodem_b200 import synth
+	return synth.afsk1200_ax25(duration_s=seconds, sample_rate=SAMPLE_RATE, frame_interval_s=3.1,
+		noise_start=0.0, noise_end=1.6, seed=1000 + 2 * rank, noise_seed=1001 + 2 * rank)[0]
+
+
+class ClockSampler:
+	"""nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+	Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+		"clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+	def __init__(self, gpu_index):
+		self.gpu = gpu_index
+		self.rows = []
+		self.proc = None
+
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+				"-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+		except OSError:
+			self.proc = None
+			return
+		self.thread = threading.Thread(target=self._read, daemon=True)
+		self.thread.start()
+
+	def _read(self):
+		for line in self.proc.stdout:
+			self.rows.append(line.strip())
+
+	def stop(self):
+		if not self.proc:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=5)
+		except subprocess.TimeoutExpired:
+			self.proc.kill()
+		sm, mx, reasons, power = [], [], set(), []
+		for row in self.rows:
+			f = [x.strip() for x in row.split(",")]
+			if len(f) < 9:
+				continue
+			try:
+				sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+			except ValueError:
+				continue
+			for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+				if val.lower().startswith("active"):
+					reasons.add(name)
+		return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+			"power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+	try:
+		with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+			return json.load(f), "measured (MEASURED_PEAKS.json)"
+	except (OSError, ValueError):
+		return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm, one process per chain (the
+# reference's own parallel model, pymodem.py:140-166)
+# ---------------------------------------------------------------------------------------
+def _cpu_chain_worker(args):
+	ci, audio = args
+	from oracle import oracle as orc
+	from pymodem_b200 import configs
+	line = configs.demod_chains(configs.afsk_1200_ax25_super_opt())[ci]
+	chain = orc.Chain(SAMPLE_RATE, line)
+	t0 = time.perf_counter()
+	pk = chain.process_chunked(audio, chunk=1 << 20)
+	return time.perf_counter() - t0, len(pk)
+
+
+def cpu_single_core(audio_sample):
+	"""All 8 chains sequentially on one core (the scalar port) -> chain-samples/s."""
+	t0 = time.perf_counter()
+	n = 0
+	for ci in range(8):
+		_, k = _cpu_chain_worker((ci, audio_sample))
+		n += k
+	dt = time.perf_counter() - t0
+	return 8 * len(audio_sample) / dt, dt, n
+
+
+def run_reference_arm(args):
+	"""--impl reference: the CPU implementation of the path (oracle port; the Python reference
+	cannot travel to the GPU box) with one process per chain, on a bounded sample per step."""
+	import multiprocessing as mp
+	rank = int(os.environ.get("RANK", "0"))
+	if rank != 0:
+		return
+	from oracle import oracle as orc
+	orc.build()
+	sample_s = args.cpu_seconds
+	audio = make_audio(sample_s, 0)
+	n_chains = 8
+	procs = min(n_chains, os.cpu_count() or 1)
+	ctx = mp.get_context("fork")
+	with ctx.Pool(procs) as pool:
+		def step():
+			t0 = time.perf_counter()
+			pool.map(_cpu_chain_worker, [(ci, audio) for ci in range(n_chains)])
+			return time.perf_counter() - t0
+		for _ in range(args.warmup):
+			step()
+		times = [step() for _ in range(args.steps)]
+	total = sum(times)
+	value = n_chains * len(audio) * args.steps / total
+	sample = (f"{sample_s:g} s of the 48 kHz workload x {n_chains} chains per step, chunked oracle port "
+		f"(numpy.convolve FIRs + C slicer/LFSR/AX.25), one process per chain")
+	line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+		"steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+		"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+		"config": {"workload": "afsk_1200_ax25_super_opt x 48 kHz synthetic AWGN AX.25 audio (bounded sample)",
+			"chains": n_chains, "sample_rate": SAMPLE_RATE, "seconds_per_step": sample_s},
+		"cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+		"gpu_launches": 0, "host_cpus": os.cpu_count()}
+	print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+def run_b200_arm(args):
+	import torch
+	import torch.distributed as dist
+	from pymodem_b200 import configs
+	from pymodem_b200.engine import Engine, measure_fp32_peak
+	from pymodem_b200.modems_codecs import chain_builder
+
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	rank = int(os.environ.get("RANK", "0"))
+	local = int(os.environ.get("LOCAL_RANK", "0"))
+	if not torch.cuda.is_available():
+		raise SystemExit("bench.py: no CUDA device -- the demod_chain engine has no CPU fallback")
+	torch.cuda.set_device(local)
+	if world > 1:
+		dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+	def barrier():
+		if world > 1:
+			dist.barrier()
+
+	lines = configs.afsk_1200_ax25_super_opt()
+	stack = [chain_builder.build_chain(SAMPLE_RATE, l) for l in configs.demod_chains(lines)]
+	n_chains = len(stack)
+	audio = make_audio(args.seconds, rank)
+	n = len(audio)
+	pinned = torch.from_numpy(audio).pin_memory()
+	dev_audio = pinned.cuda(non_blocking=False)
+	torch.cuda.synchronize()
+
+	eng = Engine(stack, device=local)
+	fp32_peak = measure_fp32_peak(local) if rank == 0 else None
+
+	def step_device():
+		eng.run_device_ptr(dev_audio.data_ptr(), n)
+		return eng.stats()
+
+	def step_host():
+		eng.run_host_ptr(pinned.data_ptr(), n)
+		return eng.stats()
+
+	def timed(step, k):
+		barrier()
+		torch.cuda.synchronize()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		e0.record()
+		t0 = time.perf_counter()
+		stats = [step() for _ in range(k)]          # every step ends with results on the host (stream sync)
+		e1.record()
+		torch.cuda.synchronize()
+		wall = time.perf_counter() - t0
+		ms = max(e0.elapsed_time(e1), 0.0)
+		ms = max(ms, 0.0)
+		t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+		if world > 1:
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		barrier()
+		return float(t[0]), float(t[1]), stats
+
+	for _ in range(args.warmup):
+		step_device()
+	sampler = ClockSampler(local)
+	if rank == 0:
+		sampler.start()
+	ev_ms, wall_ms, stats = timed(step_device, args.steps)
+	# e2e: the same metric through the C ABI with host buffers
+	for _ in range(min(args.warmup, 3)):
+		step_host()
+	e2e_ev_ms, e2e_wall_ms, e2e_stats = timed(step_host, args.steps)
+	clocks = sampler.stop() if rank == 0 else None
+
+	n_packets = stats[-1]["n_packets"]
+	launches = sum(s["kernel_launches"] for s in stats)
+	front_ms = statistics.mean(s["front_ms"] for s in stats)
+	front_launches = stats[-1]["front_launches"]
+	total_units = n_chains * n * world
+	ms_per_step = max(ev_ms, wall_ms) / args.steps
+	value = total_units / (ms_per_step * 1e-3)
+	e2e_ms = max(e2e_ev_ms, e2e_wall_ms) / args.steps
+	e2e_value = total_units / (e2e_ms * 1e-3)
+
+	if rank != 0:
+		eng.close()
+		if world > 1:
+			dist.destroy_process_group()
+		return
+
+	# roofline of the dominant kernel (afsk_front_kernel: FP32 FFMA bound)
+	macs = eng.front_macs_per_sample()
+	executed_flop = 2.0 * macs * n
+	t_front = front_ms * 1e-3 / max(front_launches, 1)
+	achieved = executed_flop / max(front_launches, 1) / t_front / 1e12
+	peaks, peaks_src = measured_peaks()
+	algo_bytes = 2.0 * n + n_chains * n / 8.0        # int16 audio in, 1 sign bit per chain-sample out
+	roofline = {"kernel": "afsk_front_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+		"unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+		"peak_source": "pm_measure_fp32_peak: register-resident FFMA loop timed in this run "
+			f"(nominal {FP32_NOMINAL_TFLOPS:.1f} at max clocks; MEASURED_PEAKS.json has no FP32 entry)",
+		"executed_mac_per_sample": macs,
+		"reference_equiv_tflops": REF_FLOP_PER_CHAIN_SAMPLE * n_chains * n / t_front / max(front_launches, 1) / 1e12,
+		"kernel_ms": front_ms / max(front_launches, 1), "launches_per_step": front_launches,
+		"hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / t_front / 1e9,
+			"peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src}}
+	stage_ms = {k: statistics.mean(s[k] for s in stats) for k in ("total_ms", "front_ms", "fixup_ms", "slicer_ms", "bits_ms", "d2h_ms")}
+
+	# CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+	cpu = None
+	if world == 1 and not args.no_cpu:
+		from oracle import oracle as orc
+		orc.build()
+		sample = audio[: int(args.cpu_seconds * SAMPLE_RATE)]
+		v, dt, _ = cpu_single_core(sample)
+		cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+			"sample": f"first {len(sample) / SAMPLE_RATE:g} s of this workload x {n_chains} chains, oracle port "
+				f"(numpy.convolve + C slicer/LFSR/AX.25) on one core, {dt:.1f} s"}
+
+	line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+		"ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+		"data": "synthetic",
+		"config": {"workload": f"afsk_1200_ax25_super_opt ({n_chains} chains) x {args.seconds:g} s of 48 kHz synthetic "
+			"AWGN AX.25 audio per GPU", "chains": n_chains, "sample_rate": SAMPLE_RATE, "samples_per_gpu": n,
+			"l2": "inputs larger than L2 (345.6 MB int16 audio per GPU per step)" if n * 2 > 126e6 else "input fits L2",
+			"parallelism": f"segments x chains on {world} GPU(s), one recording shard per rank"},
+		"e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+			"h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"]},
+		"gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+		"stage_ms": stage_ms, "packets_per_step": n_packets,
+		"slicer": {"segments": stats[-1]["slicer_segments"], "repairs": stats[-1]["slicer_repairs"],
+			"guard_flagged": stats[-1]["guard_flagged"]},
+		"timing": {"cuda_event_ms": ev_ms, "wall_ms": wall_ms, "e2e_cuda_event_ms": e2e_ev_ms, "e2e_wall_ms": e2e_wall_ms},
+		"host_cpus": os.cpu_count()}
+	print(json.dumps(line), flush=True)
+	eng.close()
+	if world > 1:
+		dist.destroy_process_group()
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--gpus", type=int, default=1)
+	ap.add_argument("--steps", type=int, default=20)
+	ap.add_argument("--warmup", type=int, default=3)
+	ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+	ap.add_argument("--seconds", type=float, default=3600.0, help="audio per GPU per step")
+	ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bounded sample for the CPU arm")
+	ap.add_argument("--no-cpu", action="store_true")
+	args = ap.parse_args()
+	args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+	if args.impl == "reference":
+		run_reference_arm(args)
+	else:
+		run_b200_arm(args)
+
+
+if __name__ == "__main__":
+	main()

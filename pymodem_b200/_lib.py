@@ -58,6 +58,14 @@ class Stats(ctypes.Structure):
 		return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ShardState(ctypes.Structure):
+	"""pm_shard_state"""
+	_fields_ = [
+		("phase_clock", ctypes.c_double), ("last_sign", ctypes.c_uint32), ("last_sign_q", ctypes.c_uint32),
+		("bit_count", ctypes.c_int64), ("state_register", ctypes.c_uint32), ("valid", ctypes.c_uint32),
+	]
+
+
 # every symbol include/pymodem_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_char_p
 PROTOTYPES = {
