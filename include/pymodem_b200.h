@@ -139,8 +139,8 @@ const char *pm_last_error(const pm_engine *e);
  * uploads taps.  Chains keep their index (= config order). */
 int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_chains);
 
-/* Tunables: "segment_len", "warmup_len", "guard_eps", "tile", "keep_soft",
- * "h2d_chunk". */
+/* Tunables: "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32),
+ * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap". */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
 
 /*
@@ -155,19 +155,53 @@ int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples);
 int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples);
 
 /*
- * Sharded form used by the multi-GPU host (one engine per rank; the recording
- * is split on the sample axis).  sample_base = global index of audio[0];
- * the caller passes the hand-off state of the previous rank (or NULL for the
- * first shard) and reads this shard's end state for the next one.
+ * Sharded form used by the multi-GPU host (one engine per rank; ONE recording is
+ * split on the sample axis; pymodem_b200/sharded.py drives it).  Positions are in
+ * soft samples (the demod output the slicer addresses, slicer.py:75): global soft
+ * sample = local + sample_base, and audio[i] is the recording's sample
+ * sample_base + i.  A rank owns soft samples [own_begin, own_begin + own_len) of
+ * its local buffer; the samples before own_begin are slicer warm-up (and FIR
+ * history), the ones after the own range let the last stream byte complete.
+ * own_begin and own_len must be multiples of the segment length (option
+ * "segment_len"), except own_len on the last shard.
+ *
+ *   begin   : front end + slicer over the local buffer, speculating the state at
+ *             own_begin from the warm-up (true start state on the first shard)
+ *   handoff : given the previous shard's state, verify the speculation bit for
+ *             bit and repair if it was wrong; *changed tells whether this shard's
+ *             own end state / symbol count changed (then the next shard has to
+ *             look again).  Repeat over all shards until nothing changes.
+ *   gather  : place the own bits at their global byte alignment
+ *             (symbols_before = symbols of all earlier shards, per chain) and
+ *             return the last tail_bits own bits of every chain
+ *   finish  : prepend the previous shard's tail, descramble, decode; a packet is
+ *             emitted by the shard that holds its closing bit
+ * PM_ERR_STATE from finish means a frame reached back past the hand-off tail
+ * (or needs the sequential AX.25 replay): run unsharded or with a longer tail.
  */
-typedef struct pm_shard_state {
-	double   phase_clock;           /* slicer.py:50 */
-	uint32_t last_sign;             /* sign of slicer.py:56 last_sample (1: >= 0) */
-	uint32_t last_sign_q;
-	int64_t  bit_count;             /* bits emitted before this shard (byte alignment, slicer.py:92-97) */
-	uint32_t state_register;        /* quadrature slicer */
-	uint32_t valid;
+typedef struct pm_shard_plan {
+	int64_t sample_base;
+	int64_t own_begin;
+	int64_t own_len;
+	int32_t first;                  /* shard holds the start of the recording */
+	int32_t last;                   /* shard holds the end of the recording */
+	int32_t tail_bits;              /* hand-off tail per chain, multiple of 32 */
+	int32_t reserved;
+} pm_shard_plan;
+
+typedef struct pm_shard_state {     /* one per chain */
+	double   start_clock;           /* slicer.py:50 phase_clock reached at own_begin */
+	double   end_clock;             /* ... at own_begin + own_len */
+	uint32_t start_last, start_last_q;   /* sign (1: >= 0) of slicer.py:56 last_sample at own_begin */
+	uint32_t end_last, end_last_q;
+	int64_t  n_symbols;             /* symbols taken inside the own range */
 } pm_shard_state;
+
+int pm_engine_shard_begin(pm_engine *e, const int16_t *audio, int64_t n_samples, int32_t audio_on_device,
+                          const pm_shard_plan *plan, pm_shard_state *out);
+int pm_engine_shard_handoff(pm_engine *e, const pm_shard_state *prev, pm_shard_state *out, int32_t *changed);
+int pm_engine_shard_gather(pm_engine *e, const int64_t *symbols_before, uint32_t *tail_out);
+int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in);
 
 int64_t pm_engine_num_packets(const pm_engine *e);
 int64_t pm_engine_arena_bytes(const pm_engine *e);

@@ -58,11 +58,20 @@ class Stats(ctypes.Structure):
 		return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ShardPlan(ctypes.Structure):
+	"""pm_shard_plan"""
+	_fields_ = [
+		("sample_base", ctypes.c_int64), ("own_begin", ctypes.c_int64), ("own_len", ctypes.c_int64),
+		("first", ctypes.c_int32), ("last", ctypes.c_int32), ("tail_bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
+	]
+
+
 class ShardState(ctypes.Structure):
 	"""pm_shard_state"""
 	_fields_ = [
-		("phase_clock", ctypes.c_double), ("last_sign", ctypes.c_uint32), ("last_sign_q", ctypes.c_uint32),
-		("bit_count", ctypes.c_int64), ("state_register", ctypes.c_uint32), ("valid", ctypes.c_uint32),
+		("start_clock", ctypes.c_double), ("end_clock", ctypes.c_double),
+		("start_last", ctypes.c_uint32), ("start_last_q", ctypes.c_uint32),
+		("end_last", ctypes.c_uint32), ("end_last_q", ctypes.c_uint32), ("n_symbols", ctypes.c_int64),
 	]
 
 
@@ -76,6 +85,10 @@ PROTOTYPES = {
 	"pm_engine_set_option": (ctypes.c_int, [_vp, _cp, ctypes.c_double]),
 	"pm_engine_run": (ctypes.c_int, [_vp, _vp, _i64]),
 	"pm_engine_run_device": (ctypes.c_int, [_vp, _vp, _i64]),
+	"pm_engine_shard_begin": (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.POINTER(ShardPlan), ctypes.POINTER(ShardState)]),
+	"pm_engine_shard_handoff": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState), ctypes.POINTER(ShardState), ctypes.POINTER(_i32)]),
+	"pm_engine_shard_gather": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _vp]),
+	"pm_engine_shard_finish": (ctypes.c_int, [_vp, _vp]),
 	"pm_engine_num_packets": (_i64, [_vp]),
 	"pm_engine_arena_bytes": (_i64, [_vp]),
 	"pm_engine_get_packets": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),

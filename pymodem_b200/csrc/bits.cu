@@ -58,13 +58,13 @@ __device__ __forceinline__ uint32_t valid_mask_word(uint32_t m, long long w, lon
 // --- gather step 1: symbols per block of GB_WORDS mask words -----------------
 __global__ void __launch_bounds__(GB_THREADS)
 gather_count_kernel(const BitChain *__restrict__ chains, const uint32_t *__restrict__ mask, long long mask_stride,
-                    unsigned int *__restrict__ block_count, int n_blocks)
+                    unsigned int *__restrict__ block_count, int n_blocks, long long w_origin)
 {
 	__shared__ unsigned int s_warp[33];
 	const int ch = blockIdx.y;
 	const long long nout = chains[ch].nout;
 	const uint32_t *mk = mask + (long long)ch * mask_stride;
-	const long long w0 = (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
+	const long long w0 = w_origin + (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
 	unsigned int cnt = 0;
 #pragma unroll
 	for (int q = 0; q < 4; q++) {
@@ -105,7 +105,8 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
                     const unsigned int *__restrict__ block_base, int n_blocks,
                     uint32_t *__restrict__ bits, long long bits_stride,
                     uint32_t *__restrict__ byte_addr, long long addr_stride,
-                    const unsigned int *__restrict__ init_state)
+                    const unsigned int *__restrict__ init_state, long long w_origin,
+                    const ShardBits *__restrict__ sb)
 {
 	__shared__ unsigned int s_warp[33];
 	__shared__ uint32_t s_stage[2 * GB_WORDS + 2];
@@ -116,7 +117,8 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 	const uint32_t *sq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
 	uint32_t *out = bits + (long long)ch * bits_stride;
 	uint32_t *oaddr = byte_addr + (long long)ch * addr_stride;
-	const long long w0 = (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
+	const long long w0 = w_origin + (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
+	const long long bit_off = sb[ch].bit_off;
 
 	uint32_t m[4];
 	unsigned int cnt = 0;
@@ -129,7 +131,7 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 	unsigned int total;
 	const unsigned int ex = block_excl_scan(cnt, s_warp, total);
 	const unsigned int sym_block = block_base[(long long)ch * n_blocks + blockIdx.x];   // symbols before block
-	const long long bit_block = (long long)sym_block * C.bps;                            // stream bits before block
+	const long long bit_block = (long long)sym_block * C.bps + bit_off;                  // stream bits before block
 	const unsigned int nbits_block = total * C.bps;
 	const int stage_shift = (int)(bit_block & 31);
 	const unsigned int stage_words = (stage_shift + nbits_block + 31) >> 5;
@@ -146,12 +148,12 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 			// search backwards for the previous symbol
 			while (true) {
 				w -= 1;
-				if (w < 0) break;
+				if (w < w_origin) break;
 				mm = mk[w];
 				if (mm) break;
 				if (++steps > (1 << 20)) break;
 			}
-			if (w >= 0 && mm) {
+			if (w >= w_origin && mm) {
 				const int i = 31 - __clz(mm);
 				prev_cur = (((sg[w] >> i) & 1u) << 1) | ((sq[w] >> i) & 1u);
 			} else {
@@ -178,7 +180,7 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 				}
 				// stream bits of this symbol, MSB of val first (slicer.py:215-216)
 				for (int t = 0; t < C.bps; t++) {
-					const long long g = sym * C.bps + t;
+					const long long g = sym * C.bps + t + bit_off;
 					const unsigned int b = (val >> (C.bps - 1 - t)) & 1u;
 					const unsigned int sp = (unsigned int)(g - bit_block) + stage_shift;
 					if (b) atomicOr(&s_stage[sp >> 5], 1u << (sp & 31));
@@ -202,15 +204,58 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 
 // --- finalize per-chain counters ----------------------------------------------
 __global__ void finalize_counts_kernel(const BitChain *__restrict__ chains, const unsigned int *__restrict__ sym_totals,
-                                       ChainCounters *__restrict__ cc, int n_chains)
+                                       ChainCounters *__restrict__ cc, int n_chains, const ShardBits *__restrict__ sb)
 {
 	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
 	if (ch >= n_chains) return;
-	const long long nbits = (long long)sym_totals[ch] * chains[ch].bps;
+	const long long nbits = (long long)sym_totals[ch] * chains[ch].bps + sb[ch].bit_off;
 	cc[ch].nbits = nbits;
 	cc[ch].nbytes = nbits >> 3;
 	cc[ch].nflags = 0;
 	cc[ch].seq_needed = 0;
+	cc[ch].tail_short = 0;
+	cc[ch].n_emit = 0;
+	cc[ch].n_emit_bytes = 0;
+}
+
+// --- hand-off tail between shards ---------------------------------------------------
+// extract: the last k_bits own bits of every chain (local positions [own_hi - k_bits, own_hi))
+// inject : the previous shard's tail into local positions [bit_off - k_bits, bit_off)
+__device__ __forceinline__ uint32_t read_bits32(const uint32_t *__restrict__ src, long long pos)
+{
+	const long long w = pos >> 5;
+	const int r = (int)(pos & 31);
+	const uint32_t lo = src[w];
+	if (r == 0) return lo;
+	return (lo >> r) | (src[w + 1] << (32 - r));
+}
+
+__global__ void __launch_bounds__(256)
+tail_extract_kernel(const uint32_t *__restrict__ bits, long long bits_stride, const ShardBits *__restrict__ sb,
+                    int k_words, uint32_t *__restrict__ out)
+{
+	const int ch = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= k_words) return;
+	const long long pos = sb[ch].own_hi - 32ll * k_words + 32ll * i;
+	out[(long long)ch * k_words + i] = (pos >= 0) ? read_bits32(bits + (long long)ch * bits_stride, pos) : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+tail_inject_kernel(uint32_t *__restrict__ bits, long long bits_stride, const ShardBits *__restrict__ sb,
+                   int k_words, const uint32_t *__restrict__ in)
+{
+	const int ch = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= k_words || sb[ch].first) return;
+	const uint32_t v = in[(long long)ch * k_words + i];
+	if (!v) return;
+	const long long pos = sb[ch].bit_off - 32ll * k_words + 32ll * i;     // >= 0 by construction
+	uint32_t *dst = bits + (long long)ch * bits_stride;
+	const long long w = pos >> 5;
+	const int r = (int)(pos & 31);
+	atomicOr(&dst[w], v << r);
+	if (r) atomicOr(&dst[w + 1], v >> (32 - r));
 }
 
 // --- LFSR: out[g] = XOR_{k in poly} in[g-k], in[<0] = 0 (lfsr.py:22-52) ----------
@@ -331,20 +376,31 @@ __device__ __forceinline__ unsigned int crc16_x25_dev(const uint8_t *p, unsigned
 }
 
 // The HDLC machine of ax25.py:25-93 over stream bits [start, end]; `end` is a
-// flag position (or the last stream bit when closing == false).  Bytes are
-// appended to `dst`.  Returns true when a packet is emitted at the flag.
+// flag position.  Bytes are appended to `dst`.  Returns true when a packet is
+// emitted at the flag.  `aborted` reports whether an abort (seven or more ones,
+// ax25.py:35-38) was seen, i.e. whether the emission decision is independent of
+// anything before `start`.
 __device__ bool ax25_replay(const uint32_t *__restrict__ d, long long start, long long end, uint8_t *dst,
-                            unsigned int &len_out, int &overflow)
+                            unsigned int &len_out, int &overflow, bool &aborted)
 {
 	unsigned int wb = 0, one_count = 0, bit_index = 0, byte_index = 0, len = 0;
 	bool emit = false;
+	aborted = false;
 	for (long long g = start; g <= end; g++) {
+		// inside a long run of ones nothing changes any more (bit_index = byte_index = 0,
+		// wb = 0x7F): skip whole all-ones words
+		if (one_count >= 8 && (g & 31) == 0) {
+			while (g + 32 <= end && d[g >> 5] == 0xFFFFFFFFu) {
+				g += 32;
+				if (one_count < (1u << 30)) one_count += 32;
+			}
+		}
 		const unsigned int bit = (d[g >> 5] >> (g & 31)) & 1u;
 		if (bit) {
 			wb |= 0x80;
 			one_count++;
 			bit_index++;
-			if (one_count > 6) { bit_index = 0; byte_index = 0; }       // abort: data not cleared
+			if (one_count > 6) { bit_index = 0; byte_index = 0; aborted = true; }   // abort: data not cleared
 			if (bit_index == 8) {
 				bit_index = 0;
 				dst[len++] = (uint8_t)wb;
@@ -382,7 +438,7 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
                 const unsigned int *__restrict__ flag_totals,
                 const uint32_t *__restrict__ byte_addr, long long addr_stride,
                 uint8_t *__restrict__ scratch, long long scratch_stride,
-                GapRec *__restrict__ gaps, long long gap_stride)
+                GapRec *__restrict__ gaps, long long gap_stride, const ShardBits *__restrict__ sb)
 {
 	const int ch = blockIdx.y;
 	if (chains[ch].codec != 1) return;
@@ -393,18 +449,29 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
 	const long long end = fp[j];
 	const long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
+	const ShardBits B = sb[ch];
 	GapRec r;
-	r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0;
-	// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0
-	if (end - start + 1 >= 18 * 8 + 8) {
+	r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
+	// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is
+	// emitted by the shard that holds its closing bit
+	const bool mine = end >= B.own_lo && end < B.own_hi;
+	const bool open_start = (j == 0) && !B.first;     // the gap reaches back past the hand-off tail
+	if (mine && (end - start + 1 >= 18 * 8 + 8 || open_start)) {
 		int overflow = 0;
 		unsigned int len = 0;
+		bool aborted = false;
 		const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
-			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow);
+			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
 		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
-		r.emit = emit ? 1u : 0u;
-		r.len = len;
-		r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
+		if (open_start && (emit || !aborted)) {
+			// either junk bytes from before the tail would be part of the frame, or the
+			// emission decision itself depends on bits we do not have
+			atomicExch(&cc[ch].tail_short, 1);
+		} else {
+			r.emit = emit ? 1u : 0u;
+			r.len = len;
+			r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
+		}
 	}
 	gaps[(long long)ch * gap_stride + j] = r;
 }
@@ -412,7 +479,8 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 // Sequential replay of one whole chain (only when a gap overflowed
 // max_packet_length, ax25.py:46-51, which can desynchronise the stateless flag
 // detector).  One thread per chain; rewrites the chain's gap records as a
-// compact list of emitted packets.
+// compact list of emitted packets.  (Unsharded runs only: the engine refuses a
+// sharded run that needs it.)
 __global__ void ax25_sequential_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
                                        const uint32_t *__restrict__ dall, long long bits_stride,
                                        const uint32_t *__restrict__ byte_addr, long long addr_stride,
@@ -454,6 +522,7 @@ __global__ void ax25_sequential_kernel(const BitChain *__restrict__ chains, Chai
 					GapRec r;
 					r.emit = 1; r.len = (unsigned int)len; r.scratch_off = (unsigned int)base;
 					r.addr = byte_addr[(long long)ch * addr_stride + (g >> 3)];
+					r.corrected = 0;
 					out[nrec++] = r;
 					base += len;
 				}
@@ -468,48 +537,70 @@ __global__ void ax25_sequential_kernel(const BitChain *__restrict__ chains, Chai
 }
 
 // --- compaction: gap records -> ordered packet records ---------------------------
-
-
-// one CTA; chains in order, gaps in order => records ordered like the
-// reference's per-chain decode() lists.
+// Chains in order, gaps in order => records ordered like the reference's
+// per-chain decode() lists.  Step 1: emitted packets / bytes per chain.
 __global__ void __launch_bounds__(1024)
-packet_index_kernel(const BitChain *__restrict__ chains, const ChainCounters *__restrict__ cc, int n_chains,
+packet_count_kernel(ChainCounters *__restrict__ cc, const GapRec *__restrict__ gaps, long long gap_stride)
+{
+	__shared__ unsigned int s_warp[33];
+	const int ch = blockIdx.x;
+	const int n = cc[ch].nflags;
+	const GapRec *g = gaps + (long long)ch * gap_stride;
+	unsigned int ne = 0, nb = 0;
+	for (int j = threadIdx.x; j < n; j += 1024) {
+		const GapRec r = g[j];
+		if (r.emit) { ne++; nb += r.len; }
+	}
+	unsigned int te, tb;
+	block_excl_scan(ne, s_warp, te);
+	block_excl_scan(nb, s_warp, tb);
+	if (threadIdx.x == 0) { cc[ch].n_emit = (int)te; cc[ch].n_emit_bytes = tb; }
+}
+
+// Step 2: one CTA per chain; its base is the sum over the chains before it.
+__global__ void __launch_bounds__(1024)
+packet_index_kernel(const ChainCounters *__restrict__ cc, int n_chains,
                     const GapRec *__restrict__ gaps, long long gap_stride,
                     PacketRecDev *__restrict__ recs, unsigned int *__restrict__ rec_src,
                     unsigned long long rec_cap, PacketTotals *__restrict__ totals, long long sample_base)
 {
 	__shared__ unsigned int s_warp[33];
-	unsigned long long n_rec = totals->n_packets, n_bytes = totals->n_bytes;
-	for (int ch = 0; ch < n_chains; ch++) {
-		if (chains[ch].codec != 1) continue;
-		const int n = cc[ch].nflags;
-		const GapRec *g = gaps + (long long)ch * gap_stride;
-		for (int base = 0; base < n; base += 1024) {
-			const int j = base + threadIdx.x;
-			GapRec r;
-			r.emit = 0; r.len = 0; r.scratch_off = 0; r.addr = 0;
-			if (j < n) r = g[j];
-			unsigned int tot_e, tot_b;
-			const unsigned int ex_e = block_excl_scan(r.emit, s_warp, tot_e);
-			const unsigned int ex_b = block_excl_scan(r.emit ? r.len : 0u, s_warp, tot_b);
-			if (r.emit) {
-				const unsigned long long ri = n_rec + ex_e;
-				if (ri < rec_cap) {
-					PacketRecDev p;
-					p.chain = ch; p.len = r.len; p.offset = n_bytes + ex_b;
-					p.streamaddress = sample_base + (long long)r.addr;
-					p.bytes_corrected = 0; p.calculated_crc = 0; p.carried_crc = 0;
-					p.valid_crc = 0; p.valid_header = 0;
-					for (int q = 0; q < 6; q++) p.pad[q] = 0;
-					recs[ri] = p;
-					rec_src[ri] = r.scratch_off;
-				}
-			}
-			n_rec += tot_e;
-			n_bytes += tot_b;
-		}
+	__shared__ unsigned long long s_base[2];
+	const int ch = blockIdx.x;
+	if (threadIdx.x == 0) {
+		unsigned long long r = 0, b = 0;
+		for (int c = 0; c < ch; c++) { r += (unsigned int)cc[c].n_emit; b += (unsigned long long)cc[c].n_emit_bytes; }
+		s_base[0] = r; s_base[1] = b;
 	}
-	if (threadIdx.x == 0) { totals->n_packets = n_rec; totals->n_bytes = n_bytes; }
+	__syncthreads();
+	unsigned long long n_rec = s_base[0], n_bytes = s_base[1];
+	const int n = cc[ch].nflags;
+	const GapRec *g = gaps + (long long)ch * gap_stride;
+	for (int base = 0; base < n; base += 1024) {
+		const int j = base + threadIdx.x;
+		GapRec r;
+		r.emit = 0; r.len = 0; r.scratch_off = 0; r.addr = 0; r.corrected = 0;
+		if (j < n) r = g[j];
+		unsigned int tot_e, tot_b;
+		const unsigned int ex_e = block_excl_scan(r.emit, s_warp, tot_e);
+		const unsigned int ex_b = block_excl_scan(r.emit ? r.len : 0u, s_warp, tot_b);
+		if (r.emit) {
+			const unsigned long long ri = n_rec + ex_e;
+			if (ri < rec_cap) {
+				PacketRecDev p;
+				p.chain = ch; p.len = r.len; p.offset = n_bytes + ex_b;
+				p.streamaddress = sample_base + (long long)r.addr;
+				p.bytes_corrected = r.corrected; p.calculated_crc = 0; p.carried_crc = 0;
+				p.valid_crc = 0; p.valid_header = 0;
+				for (int q = 0; q < 6; q++) p.pad[q] = 0;
+				recs[ri] = p;
+				rec_src[ri] = r.scratch_off;
+			}
+		}
+		n_rec += tot_e;
+		n_bytes += tot_b;
+	}
+	if (ch == n_chains - 1 && threadIdx.x == 0) { totals->n_packets = n_rec; totals->n_bytes = n_bytes; }
 }
 
 // one warp per packet: copy its bytes into the arena, CRC + header check
@@ -567,20 +658,37 @@ stream_export_kernel(const ChainCounters *__restrict__ cc, int ch, const uint32_
 // ---------------------------------------------------------------------------------
 extern "C" {
 
+// (sign, mask) words [w_origin, w_origin + n_words) -> packed bits placed at sb[ch].bit_off
 cudaError_t pm_launch_gather(const BitChain *chains, int n_chains, ChainCounters *cc, const uint32_t *sign,
-	long long sign_stride, const uint32_t *mask, long long mask_stride, long long max_words,
+	long long sign_stride, const uint32_t *mask, long long mask_stride, long long w_origin, long long n_words,
 	unsigned int *blk_count, unsigned int *blk_base, unsigned int *sym_totals,
 	uint32_t *bits, long long bits_stride, uint32_t *byte_addr, long long addr_stride,
-	const unsigned int *init_state, cudaStream_t st)
+	const unsigned int *init_state, const ShardBits *sb, cudaStream_t st)
 {
-	const int n_blocks = (int)((max_words + GB_WORDS - 1) / GB_WORDS);
+	const int n_blocks = (int)((n_words + GB_WORDS - 1) / GB_WORDS);
 	dim3 grid(n_blocks, n_chains);
-	gather_count_kernel<<<grid, GB_THREADS, 0, st>>>(chains, mask, mask_stride, blk_count, n_blocks);
+	gather_count_kernel<<<grid, GB_THREADS, 0, st>>>(chains, mask, mask_stride, blk_count, n_blocks, w_origin);
 	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, sym_totals);
-	finalize_counts_kernel<<<(n_chains + 31) / 32, 32, 0, st>>>(chains, sym_totals, cc, n_chains);
+	finalize_counts_kernel<<<(n_chains + 31) / 32, 32, 0, st>>>(chains, sym_totals, cc, n_chains, sb);
 	cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)bits_stride * n_chains, st);
 	gather_write_kernel<<<grid, GB_THREADS, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, blk_base,
-		n_blocks, bits, bits_stride, byte_addr, addr_stride, init_state);
+		n_blocks, bits, bits_stride, byte_addr, addr_stride, init_state, w_origin, sb);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_tail_extract(const uint32_t *bits, long long bits_stride, const ShardBits *sb, int n_chains,
+	int k_words, uint32_t *out, cudaStream_t st)
+{
+	dim3 grid((k_words + 255) / 256, n_chains);
+	tail_extract_kernel<<<grid, 256, 0, st>>>(bits, bits_stride, sb, k_words, out);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_launch_tail_inject(uint32_t *bits, long long bits_stride, const ShardBits *sb, int n_chains,
+	int k_words, const uint32_t *in, cudaStream_t st)
+{
+	dim3 grid((k_words + 255) / 256, n_chains);
+	tail_inject_kernel<<<grid, 256, 0, st>>>(bits, bits_stride, sb, k_words, in);
 	return cudaGetLastError();
 }
 
@@ -597,7 +705,8 @@ cudaError_t pm_launch_lfsr(const BitChain *chains, int n_chains, const ChainCoun
 cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *cc, const uint32_t *d,
 	long long bits_stride, unsigned int *blk_count, unsigned int *blk_base, unsigned int *flag_totals,
 	unsigned int *flag_pos, long long flag_stride, const uint32_t *byte_addr, long long addr_stride,
-	uint8_t *scratch, long long scratch_stride, GapRec *gaps, long long gap_stride, cudaStream_t st)
+	uint8_t *scratch, long long scratch_stride, GapRec *gaps, long long gap_stride, const ShardBits *sb,
+	int allow_sequential, cudaStream_t st)
 {
 	const int n_blocks = (int)((bits_stride + FL_WORDS - 1) / FL_WORDS);
 	dim3 grid(n_blocks, n_chains);
@@ -607,18 +716,20 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 	// gaps: at most flag_stride per chain
 	dim3 ggrid((unsigned int)((flag_stride + 127) / 128), n_chains);
 	ax25_gap_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals,
-		byte_addr, addr_stride, scratch, scratch_stride, gaps, gap_stride);
-	ax25_sequential_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, byte_addr, addr_stride, scratch,
-		scratch_stride, gaps, gap_stride);
+		byte_addr, addr_stride, scratch, scratch_stride, gaps, gap_stride, sb);
+	if (allow_sequential)
+		ax25_sequential_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, byte_addr, addr_stride, scratch,
+			scratch_stride, gaps, gap_stride);
 	return cudaGetLastError();
 }
 
-cudaError_t pm_launch_packets(const BitChain *chains, int n_chains, const ChainCounters *cc, const GapRec *gaps,
+cudaError_t pm_launch_packets(int n_chains, ChainCounters *cc, const GapRec *gaps,
 	long long gap_stride, PacketRecDev *recs, unsigned int *rec_src, unsigned long long rec_cap,
 	PacketTotals *totals, const uint8_t *scratch, long long scratch_stride, uint8_t *arena,
 	unsigned long long arena_cap, long long sample_base, cudaStream_t st)
 {
-	packet_index_kernel<<<1, 1024, 0, st>>>(chains, cc, n_chains, gaps, gap_stride, recs, rec_src, rec_cap, totals,
+	packet_count_kernel<<<n_chains, 1024, 0, st>>>(cc, gaps, gap_stride);
+	packet_index_kernel<<<n_chains, 1024, 0, st>>>(cc, n_chains, gaps, gap_stride, recs, rec_src, rec_cap, totals,
 		sample_base);
 	packet_copy_kernel<<<296, 256, 0, st>>>(recs, rec_src, totals, 0, rec_cap, scratch, scratch_stride, arena,
 		arena_cap);

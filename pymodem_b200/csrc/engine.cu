@@ -22,18 +22,24 @@ cudaError_t pm_launch_guard_fixup(const Fp64Chain *, int, const int16_t *, long 
 	float *, long long, GuardList, int, cudaStream_t);
 cudaError_t pm_launch_ffma_peak(float *, int, int, cudaStream_t);
 cudaError_t pm_launch_slicer_segments(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
-	SegState *, SegState *, const SegState *, int, int, int, cudaStream_t);
+	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, cudaStream_t);
 cudaError_t pm_launch_slicer_verify(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
-	SegState *, const SegState *, SegState *, const SegState *, int, int, unsigned int *, cudaStream_t);
+	SegState *, const SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *, cudaStream_t);
+cudaError_t pm_launch_slicer_sweep(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
+	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *, cudaStream_t);
+cudaError_t pm_launch_slicer_count(const SlicerChain *, int, const uint32_t *, long long, long long, long long,
+	unsigned long long *, cudaStream_t);
 cudaError_t pm_launch_gather(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const uint32_t *,
-	long long, long long, unsigned int *, unsigned int *, unsigned int *, uint32_t *, long long, uint32_t *,
-	long long, const unsigned int *, cudaStream_t);
+	long long, long long, long long, unsigned int *, unsigned int *, unsigned int *, uint32_t *, long long, uint32_t *,
+	long long, const unsigned int *, const ShardBits *, cudaStream_t);
+cudaError_t pm_launch_tail_extract(const uint32_t *, long long, const ShardBits *, int, int, uint32_t *, cudaStream_t);
+cudaError_t pm_launch_tail_inject(uint32_t *, long long, const ShardBits *, int, int, const uint32_t *, cudaStream_t);
 cudaError_t pm_launch_lfsr(const BitChain *, int, const ChainCounters *, const uint32_t *, uint32_t *, long long,
 	cudaStream_t);
 cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_t *, long long, unsigned int *,
 	unsigned int *, unsigned int *, unsigned int *, long long, const uint32_t *, long long, uint8_t *, long long,
-	GapRec *, long long, cudaStream_t);
-cudaError_t pm_launch_packets(const BitChain *, int, const ChainCounters *, const GapRec *, long long,
+	GapRec *, long long, const ShardBits *, int, cudaStream_t);
+cudaError_t pm_launch_packets(int, ChainCounters *, const GapRec *, long long,
 	pm_packet_rec *, unsigned int *, unsigned long long, PacketTotals *, const uint8_t *, long long, uint8_t *,
 	unsigned long long, long long, cudaStream_t);
 cudaError_t pm_launch_stream_export(const ChainCounters *, int, const uint32_t *, long long, const uint32_t *,
@@ -82,8 +88,10 @@ struct pm_engine {
 	std::vector<HostChain> chains;
 	std::vector<FrontGroup> groups;
 	// options
-	int opt_seg_words = 2048;     // 65536 samples
-	int opt_warm_words = 1024;    // 32768 samples
+	int opt_seg_words = 512;      // 16384 samples
+	int opt_warm_words = 256;     // 8192 samples
+	int opt_chk_words = 32;       // checkpoint every 1024 samples
+	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
@@ -102,7 +110,20 @@ struct pm_engine {
 	DevBuf<float> d_soft;
 	DevBuf<unsigned long long> d_guard_entries;
 	DevBuf<unsigned int> d_counters;      // [0] guard count, [1] repairs
-	DevBuf<SegState> d_S, d_E0, d_E1;
+	DevBuf<SegState> d_S, d_E0, d_E1, d_chk;
+	DevBuf<ShardBits> d_shardbits;
+	DevBuf<unsigned long long> d_symcount;
+	DevBuf<uint32_t> d_tail;
+	SegState *E_cur = nullptr, *E_alt = nullptr;
+	SlicerGeom geom;
+	pm_shard_plan plan;
+	bool sharded = false;
+	int phase = 0;                        // 0 idle, 1 begun (slicer converged locally), 2 gathered
+	const int16_t *run_audio = nullptr;   // device pointer of the current run's audio
+	long long own_w0 = 0, own_w1 = 0, end_w = 0;   // own range / processed range in words
+	int k_end = 0;                        // segment whose end state is the shard's end state
+	std::vector<pm_shard_state> shard_out;
+	std::vector<SegState> h_init;
 	DevBuf<unsigned int> d_blk_count, d_blk_base, d_sym_totals, d_flag_totals, d_flag_pos, d_rec_src;
 	DevBuf<uint8_t> d_scratch, d_arena;
 	DevBuf<GapRec> d_gaps;
@@ -370,6 +391,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_taps64.release(); e->d_fp64.release(); e->d_slicer.release(); e->d_bitchain.release();
 	e->d_cc.release(); e->d_init.release(); e->d_audio.release(); e->d_sign.release(); e->d_mask.release();
 	e->d_bits_raw.release(); e->d_bits_lfsr.release(); e->d_byte_addr.release(); e->d_soft.release();
+	e->d_chk.release(); e->d_shardbits.release(); e->d_symcount.release(); e->d_tail.release();
 	e->d_guard_entries.release(); e->d_counters.release(); e->d_S.release(); e->d_E0.release();
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
@@ -483,6 +505,8 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	bool replan = false;
 	if (k == "segment_len") e->opt_seg_words = std::max(1, (int)(value / 32));
 	else if (k == "warmup_len") e->opt_warm_words = std::max(0, (int)((value + 31) / 32));
+	else if (k == "checkpoint_len") e->opt_chk_words = std::max(1, (int)(value / 32));
+	else if (k == "verify_passes") e->opt_verify_passes = std::max(0, (int)value);
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
@@ -494,21 +518,41 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 }
 
 // ---------------------------------------------------------------------------
-static int prepare_run(pm_engine *e, long long n)
+// One run = begin (front end + slicer) -> [handoff]* -> gather -> finish.
+// An unsharded run is the same pipeline with "everything is mine".
+// ---------------------------------------------------------------------------
+static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, bool sharded)
 {
 	const int nc = (int)e->chains.size();
 	if (nc == 0) return fail(e, PM_ERR_STATE, "no chains loaded");
 	if (n <= 0 || n >= (1ll << 32) - (1 << 20)) return fail(e, PM_ERR_ARG, "n_samples out of range");
+	const int seg_words = e->opt_seg_words;
+	int chk_words = std::min(e->opt_chk_words, seg_words);
+	while (seg_words % chk_words) chk_words--;
+	const long long seg_len = 32ll * seg_words;
+	if (plan.own_begin < 0 || plan.own_begin % seg_len)
+		return fail(e, PM_ERR_ARG, "own_begin must be a multiple of segment_len (%lld)", seg_len);
+	if (!plan.last && (plan.own_len <= 0 || plan.own_len % seg_len))
+		return fail(e, PM_ERR_ARG, "own_len must be a multiple of segment_len (%lld) on all but the last shard", seg_len);
+	if (plan.first && (plan.own_begin != 0 || plan.sample_base != 0))
+		return fail(e, PM_ERR_ARG, "the first shard starts at sample 0");
+	if (plan.tail_bits < 0 || plan.tail_bits % 32) return fail(e, PM_ERR_ARG, "tail_bits must be a multiple of 32");
 	e->n_samples = n;
+	e->plan = plan;
+	e->sharded = sharded;
+	e->sample_base = plan.sample_base;
 	e->sign_rows = nc;
-	long long max_words = 0, max_bits = 0;
+	long long max_words = 0, max_bits = 0, max_nout = 0;
 	std::vector<SlicerChain> sl(nc);
 	std::vector<BitChain> bc(nc);
-	std::vector<SegState> init(nc);
+	e->h_init.assign(nc, SegState());
 	long long rec_cap = 16, arena_cap = 64;
 	for (int c = 0; c < nc; c++) {
 		HostChain &hc = e->chains[c];
+		if (sharded && hc.d.slicer_kind != PM_SLICER_BINARY)
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: only binary-slicer chains can be sharded", c);
 		const long long nout = std::max<long long>(0, n - hc.trim);
+		max_nout = std::max(max_nout, nout);
 		const FrontGroup &g = e->groups[hc.group];
 		const long long tiles = (nout + g.tile - 1) / g.tile;
 		max_words = std::max(max_words, tiles * g.tile / 32);
@@ -522,26 +566,44 @@ static int prepare_run(pm_engine *e, long long n)
 		memset(&b, 0, sizeof(b));
 		b.nout = nout; b.sign_row = c; b.bps = 1; b.lfsr_poly = hc.d.lfsr_poly; b.lfsr_invert = hc.d.lfsr_invert;
 		b.codec = hc.d.codec_kind;
-		init[c].clock = 0.0; init[c].last = 1; init[c].last_q = 1;
+		e->h_init[c].clock = 0.0; e->h_init[c].last = 1; e->h_init[c].last_q = 1;    // slicer.py:50,55
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
-		const long long mb = nout / min_gap + 64;
+		const long long mb = nout / min_gap + 64 + plan.tail_bits;
 		max_bits = std::max(max_bits, mb);
 		rec_cap += mb / 152 + 4;
 		arena_cap += mb / 8 + 64;
 	}
-	const int seg_words = e->opt_seg_words;
 	max_words = round_up((int)max_words, 4) + 4;
 	e->sign_stride = max_words;
-	e->n_seg = (int)((max_words + seg_words - 1) / seg_words);
+	// slicer geometry: segment 0 starts at own_begin
+	e->own_w0 = plan.own_begin / 32;
+	e->end_w = (max_nout + 31) / 32;
+	if (plan.last || plan.own_begin + plan.own_len >= max_nout) e->own_w1 = e->end_w;
+	else e->own_w1 = (plan.own_begin + plan.own_len) / 32;
+	if (e->own_w0 > e->end_w) e->own_w0 = e->end_w;
+	SlicerGeom &G = e->geom;
+	G.origin_w = e->own_w0;
+	G.seg_words = seg_words;
+	G.warm_words = e->opt_warm_words;
+	G.chk_words = chk_words;
+	G.n_chk = seg_words / chk_words;
+	G.n_seg = (int)std::max<long long>(1, (e->end_w - e->own_w0 + seg_words - 1) / seg_words);
+	G.true_start = plan.first ? 1 : 0;
+	e->k_end = (int)std::min<long long>(G.n_seg, std::max<long long>(1, (e->own_w1 - e->own_w0 + seg_words - 1) / seg_words));
+	e->n_seg = G.n_seg;
 	e->bits_stride = round_up((int)((max_bits + 31) / 32) + 8, 4);
 	e->addr_stride = max_bits / 8 + 16;
 	e->flag_stride = max_bits / 7 + 16;
 	e->scratch_stride = max_bits / 8 + 64;
 	CK(e->d_sign.ensure((size_t)e->sign_rows * e->sign_stride));
 	CK(e->d_mask.ensure((size_t)nc * e->sign_stride));
-	CK(e->d_S.ensure((size_t)nc * e->n_seg));
-	CK(e->d_E0.ensure((size_t)nc * e->n_seg));
-	CK(e->d_E1.ensure((size_t)nc * e->n_seg));
+	CK(e->d_S.ensure((size_t)nc * G.n_seg));
+	CK(e->d_E0.ensure((size_t)nc * G.n_seg));
+	CK(e->d_E1.ensure((size_t)nc * G.n_seg));
+	CK(e->d_chk.ensure((size_t)nc * G.n_seg * G.n_chk));
+	CK(e->d_shardbits.ensure(nc));
+	CK(e->d_symcount.ensure(nc));
+	CK(e->d_tail.ensure((size_t)nc * std::max(1, plan.tail_bits / 32)));
 	const long long n_gblk = std::max((max_words + 1023) / 1024, (e->bits_stride + 1023) / 1024) + 1;
 	CK(e->d_blk_count.ensure((size_t)nc * n_gblk));
 	CK(e->d_blk_base.ensure((size_t)nc * n_gblk));
@@ -561,7 +623,7 @@ static int prepare_run(pm_engine *e, long long n)
 	}
 	CK(cudaMemcpyAsync(e->d_slicer.p, sl.data(), nc * sizeof(SlicerChain), cudaMemcpyHostToDevice, e->st));
 	CK(cudaMemcpyAsync(e->d_bitchain.p, bc.data(), nc * sizeof(BitChain), cudaMemcpyHostToDevice, e->st));
-	CK(cudaMemcpyAsync(e->d_init.p, init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
 	CK(cudaMemsetAsync(e->d_counters.p, 0, 16 * sizeof(unsigned int), e->st));
 	CK(cudaMemsetAsync(e->d_totals.p, 0, sizeof(PacketTotals), e->st));
 	CK(cudaStreamSynchronize(e->st));      // the staging vectors above go out of scope
@@ -585,12 +647,11 @@ static GuardList guard_of(pm_engine *e)
 	return g;
 }
 
-// launch the front-end tiles [t0, t1) of every group (tile indices are per group)
+// launch the front-end tiles of every group that became complete with the
+// samples in [0, avail_to) and were not launched for [0, avail_from)
 static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long long avail_from, long long avail_to,
                         bool last)
 {
-	// A tile of group g needs audio [t*tile, t*tile + a_len): launch every tile
-	// that became complete with the samples in [0, avail_to).
 	for (auto &g : e->groups) {
 		const int a_len = (g.kind == PM_MODEM_AFSK) ? g.afsk.a_len : g.fir.a_len;
 		long long nout_max = 0;
@@ -622,10 +683,100 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 	return PM_OK;
 }
 
-static int run_back(pm_engine *e, const int16_t *d_audio)
+// Verify/repair until every hand-off inside the local buffer is bit-exact.
+static int slicer_converge(pm_engine *e)
 {
 	const int nc = (int)e->chains.size();
-	const long long n = e->n_samples;
+	cudaError_t ce;
+	for (int pass = 0;; pass++) {
+		CK(cudaMemsetAsync(e->d_counters.p + 1, 0, sizeof(unsigned int), e->st));
+		if (pass < e->opt_verify_passes) {
+			ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+				e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, e->st);
+			std::swap(e->E_cur, e->E_alt);
+		} else {
+			ce = pm_launch_slicer_sweep(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+				e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, e->st);
+		}
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+		CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
+		CK(cudaStreamSynchronize(e->st));
+		e->stats.slicer_repairs += e->h_counters[1];
+		if (pass >= e->opt_verify_passes) break;          // the sweep is exact by construction
+		if (e->h_counters[1] == 0) break;
+	}
+	return PM_OK;
+}
+
+// start state (S of segment 0), end state (E of segment k_end-1) and own symbol count of every chain
+static int read_shard_states(pm_engine *e)
+{
+	const int nc = (int)e->chains.size();
+	const int n_seg = e->geom.n_seg;
+	std::vector<SegState> s0(nc), e1(nc);
+	std::vector<unsigned long long> cnt(nc);
+	cudaError_t ce = pm_launch_slicer_count(e->d_slicer.p, nc, e->d_mask.p, e->sign_stride, e->own_w0, e->own_w1,
+		e->d_symcount.p, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "symbol count launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches++;
+	CK(cudaMemcpy2DAsync(s0.data(), sizeof(SegState), e->d_S.p, (size_t)n_seg * sizeof(SegState), sizeof(SegState), nc,
+		cudaMemcpyDeviceToHost, e->st));
+	CK(cudaMemcpy2DAsync(e1.data(), sizeof(SegState), e->E_cur + (e->k_end - 1), (size_t)n_seg * sizeof(SegState),
+		sizeof(SegState), nc, cudaMemcpyDeviceToHost, e->st));
+	CK(cudaMemcpyAsync(cnt.data(), e->d_symcount.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->st));
+	CK(cudaStreamSynchronize(e->st));
+	e->shard_out.resize(nc);
+	for (int c = 0; c < nc; c++) {
+		pm_shard_state &o = e->shard_out[c];
+		o.start_clock = s0[c].clock; o.start_last = s0[c].last; o.start_last_q = s0[c].last_q;
+		o.end_clock = e1[c].clock; o.end_last = e1[c].last; o.end_last_q = e1[c].last_q;
+		o.n_symbols = (int64_t)cnt[c];
+	}
+	return PM_OK;
+}
+
+static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
+                      bool sharded)
+{
+	const int nc = (int)e->chains.size();
+	memset(&e->stats, 0, sizeof(e->stats));
+	int rc = prepare_run(e, n, plan, sharded);
+	if (rc != PM_OK) return rc;
+	const int16_t *d_audio = audio;
+	CK(cudaEventRecord(e->ev[0], e->st));
+	if (on_host) {
+		CK(e->d_audio.ensure((size_t)n + 64));
+		d_audio = e->d_audio.p;
+		const long long chunk = e->opt_h2d_chunk;
+		const int n_chunks = (int)((n + chunk - 1) / chunk);
+		while ((int)e->ev_chunks.size() < n_chunks) {
+			cudaEvent_t ev;
+			CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			e->ev_chunks.push_back(ev);
+		}
+		// the copy stream must not start before the engine stream reached this point
+		CK(cudaEventRecord(e->ev[6], e->st));
+		CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
+		long long done = 0;
+		for (int i = 0; i < n_chunks; i++) {
+			const long long len = std::min(chunk, n - done);
+			CK(cudaMemcpyAsync(e->d_audio.p + done, audio + done, (size_t)len * sizeof(int16_t),
+				cudaMemcpyHostToDevice, e->st_copy));
+			CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
+			CK(cudaStreamWaitEvent(e->st, e->ev_chunks[i], 0));
+			rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1);
+			if (rc != PM_OK) return rc;
+			done += len;
+		}
+		e->stats.h2d_bytes = (int64_t)n * 2;
+	} else {
+		rc = launch_front(e, d_audio, n, 0, n, true);
+		if (rc != PM_OK) return rc;
+	}
+	e->run_audio = d_audio;
+	CK(cudaEventRecord(e->ev[1], e->st));
+
 	// FP64 guard-band fix-up
 	int max_sum = 8;
 	for (auto &hc : e->chains) max_sum = std::max(max_sum, (int)(hc.mark_i.size() + hc.lpf.size() + 2));
@@ -635,50 +786,134 @@ static int run_back(pm_engine *e, const int16_t *d_audio)
 	e->stats.kernel_launches++;
 	CK(cudaEventRecord(e->ev[2], e->st));
 
-	// slicer
+	// slicer: speculative segments, then verify/repair
+	e->E_cur = e->d_E0.p; e->E_alt = e->d_E1.p;
 	ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-		e->d_S.p, e->d_E0.p, e->d_init.p, e->n_seg, e->opt_seg_words, e->opt_warm_words, e->st);
+		e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches++;
-	SegState *Ein = e->d_E0.p, *Eout = e->d_E1.p;
-	e->stats.slicer_repairs = 0;
-	e->stats.slicer_segments = (int64_t)nc * e->n_seg;
-	for (int pass = 0;; pass++) {
-		CK(cudaMemsetAsync(e->d_counters.p + 1, 0, sizeof(unsigned int), e->st));
-		ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-			e->d_S.p, Ein, Eout, e->d_init.p, e->n_seg, e->opt_seg_words, e->d_counters.p + 1, e->st);
-		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
-		e->stats.kernel_launches++;
-		std::swap(Ein, Eout);
-		CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
-		CK(cudaStreamSynchronize(e->st));
-		if (e->h_counters[0] > e->guard_cap) return PM_ERR_CAPACITY;    // caller grows the list and re-runs
-		if (e->h_counters[1] == 0) break;
-		e->stats.slicer_repairs += e->h_counters[1];
-		if (pass > e->n_seg + 2) return fail(e, PM_ERR_STATE, "slicer hand-off did not converge");
+	e->stats.slicer_segments = (int64_t)nc * e->geom.n_seg;
+	if (!plan.first) {
+		// the state at own_begin is only speculated so far: take it as given until the hand-off
+		CK(cudaMemcpy2DAsync(e->d_init.p, sizeof(SegState), e->d_S.p, (size_t)e->geom.n_seg * sizeof(SegState),
+			sizeof(SegState), nc, cudaMemcpyDeviceToDevice, e->st));
 	}
+	rc = slicer_converge(e);
+	if (rc != PM_OK) return rc;
+	if (e->h_counters[0] > e->guard_cap) return PM_ERR_CAPACITY;    // caller grows the list and re-runs
 	e->stats.guard_flagged = e->h_counters[0];
 	CK(cudaEventRecord(e->ev[3], e->st));
+	return PM_OK;
+}
 
-	// bits: gather -> lfsr -> ax25 -> packets
-	ce = pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-		e->sign_stride, e->d_blk_count.p, e->d_blk_base.p, e->d_sym_totals.p, e->d_bits_raw.p, e->bits_stride,
-		e->d_byte_addr.p, e->addr_stride, nullptr, e->st);
+static int shard_begin_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
+                            bool sharded)
+{
+	if (!e) return PM_ERR_ARG;
+	if (!audio) return fail(e, PM_ERR_ARG, "audio is NULL");
+	cudaSetDevice(e->device);
+	e->phase = 0;
+	e->have_run = false;
+	for (int attempt = 0; attempt < 4; attempt++) {
+		int rc = begin_once(e, audio, n, on_host, plan, sharded);
+		if (rc == PM_ERR_CAPACITY && e->h_counters[0] > e->guard_cap) {
+			// guard list overflowed: grow it and run again
+			e->guard_cap = e->h_counters[0] + e->h_counters[0] / 4 + 1024;
+			cudaStreamSynchronize(e->st);
+			continue;
+		}
+		if (rc != PM_OK) return rc;
+		if (sharded) {
+			rc = read_shard_states(e);
+			if (rc != PM_OK) return rc;
+			if (!plan.first)       // what the device-side init[] holds now: the speculated start states
+				for (size_t c = 0; c < e->chains.size(); c++) {
+					e->h_init[c].clock = e->shard_out[c].start_clock;
+					e->h_init[c].last = e->shard_out[c].start_last;
+					e->h_init[c].last_q = e->shard_out[c].start_last_q;
+				}
+		}
+		e->phase = 1;
+		return PM_OK;
+	}
+	return fail(e, PM_ERR_CAPACITY, "guard list kept overflowing");
+}
+
+static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32_t *tail_out)
+{
+	if (!e || e->phase != 1) return fail(e, PM_ERR_STATE, "shard_gather: call shard_begin first");
+	const int nc = (int)e->chains.size();
+	const pm_shard_plan &plan = e->plan;
+	std::vector<ShardBits> sb(nc);
+	for (int c = 0; c < nc; c++) {
+		ShardBits &b = sb[c];
+		b.first = plan.first ? 1 : 0; b.pad = 0;
+		if (plan.first) {
+			b.bit_off = 0; b.own_lo = 0;
+		} else {
+			const long long P = symbols_before ? symbols_before[c] : 0;      // bps == 1: global bit index
+			if (P < plan.tail_bits)
+				return fail(e, PM_ERR_CAPACITY, "chain %d: earlier shards hold fewer bits (%lld) than the hand-off tail", c, P);
+			const long long A0 = ((P - plan.tail_bits) >> 3) << 3;              // global bit index of local bit 0
+			b.bit_off = P - A0;
+			b.own_lo = b.bit_off;
+		}
+		if (plan.last) b.own_hi = 0x7fffffffffffffffll;
+		else {
+			const long long n_own = e->sharded ? e->shard_out[c].n_symbols : 0;
+			if (n_own < plan.tail_bits)
+				return fail(e, PM_ERR_CAPACITY, "chain %d: shard holds fewer bits (%lld) than the hand-off tail", c, n_own);
+			b.own_hi = b.bit_off + n_own;
+		}
+	}
+	CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
+	cudaError_t ce = pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p,
+		e->sign_stride, e->own_w0, std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p,
+		e->d_sym_totals.p, e->d_bits_raw.p, e->bits_stride, e->d_byte_addr.p, e->addr_stride, nullptr,
+		e->d_shardbits.p, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "gather launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches += 4;
+	if (e->sharded && !plan.last && plan.tail_bits > 0 && tail_out) {
+		ce = pm_launch_tail_extract(e->d_bits_raw.p, e->bits_stride, e->d_shardbits.p, nc, plan.tail_bits / 32,
+			e->d_tail.p, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "tail extract launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+		CK(cudaMemcpyAsync(tail_out, e->d_tail.p, (size_t)nc * (plan.tail_bits / 32) * sizeof(uint32_t),
+			cudaMemcpyDeviceToHost, e->st));
+	}
+	CK(cudaStreamSynchronize(e->st));       // sb goes out of scope; tail_out is ready
+	e->phase = 2;
+	return PM_OK;
+}
+
+static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
+{
+	if (!e || e->phase != 2) return fail(e, PM_ERR_STATE, "shard_finish: call shard_gather first");
+	const int nc = (int)e->chains.size();
+	const pm_shard_plan &plan = e->plan;
+	cudaError_t ce;
+	if (e->sharded && !plan.first && plan.tail_bits > 0) {
+		if (!tail_in) return fail(e, PM_ERR_ARG, "shard_finish: the previous shard's tail is required");
+		CK(cudaMemcpyAsync(e->d_tail.p, tail_in, (size_t)nc * (plan.tail_bits / 32) * sizeof(uint32_t),
+			cudaMemcpyHostToDevice, e->st));
+		ce = pm_launch_tail_inject(e->d_bits_raw.p, e->bits_stride, e->d_shardbits.p, nc, plan.tail_bits / 32,
+			e->d_tail.p, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "tail inject launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+	}
 	ce = pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "lfsr launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches++;
 	ce = pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p,
 		e->d_blk_base.p, e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride,
-		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->st);
+		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->sharded ? 0 : 1, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "ax25 launch failed: %s", cudaGetErrorString(ce));
-	e->stats.kernel_launches += 5;
-	ce = pm_launch_packets(e->d_bitchain.p, nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p,
+	e->stats.kernel_launches += e->sharded ? 4 : 5;
+	ce = pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p,
 		e->d_recs.n, e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base,
 		e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "packet launch failed: %s", cudaGetErrorString(ce));
-	e->stats.kernel_launches += 2;
+	e->stats.kernel_launches += 3;
 	CK(cudaEventRecord(e->ev[4], e->st));
 
 	// results to host
@@ -686,6 +921,13 @@ static int run_back(pm_engine *e, const int16_t *d_audio)
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
 	CK(cudaStreamSynchronize(e->st));
+	for (int c = 0; c < nc; c++) {
+		if (e->h_cc[c].tail_short)
+			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
+				c, plan.tail_bits);
+		if (e->sharded && e->h_cc[c].seq_needed)
+			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (run unsharded)", c);
+	}
 	const unsigned long long np = e->h_totals->n_packets, nb = e->h_totals->n_bytes;
 	if (np > e->d_recs.n || nb > e->d_arena.n)
 		return fail(e, PM_ERR_CAPACITY, "packet buffers too small (%llu records, %llu bytes)", np, nb);
@@ -699,11 +941,6 @@ static int run_back(pm_engine *e, const int16_t *d_audio)
 	e->stats.n_packets = (int64_t)np;
 	e->stats.n_stream_bits = 0;
 	for (auto &c : e->h_cc) e->stats.n_stream_bits += c.nbits;
-	return PM_OK;
-}
-
-static void finish_stats(pm_engine *e)
-{
 	float ms = 0;
 	auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, e->ev[a], e->ev[b]); return (double)ms; };
 	e->stats.total_ms = el(0, 5);
@@ -712,62 +949,21 @@ static void finish_stats(pm_engine *e)
 	e->stats.slicer_ms = el(2, 3);
 	e->stats.bits_ms = el(3, 4);
 	e->stats.d2h_ms = el(4, 5);
+	e->phase = 0;
+	e->have_run = true;
+	return PM_OK;
 }
 
 static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host)
 {
-	if (!e) return PM_ERR_ARG;
-	if (!audio) return fail(e, PM_ERR_ARG, "audio is NULL");
-	cudaSetDevice(e->device);
-	for (int attempt = 0; attempt < 4; attempt++) {
-		memset(&e->stats, 0, sizeof(e->stats));
-		int rc = prepare_run(e, n);
-		if (rc != PM_OK) return rc;
-		const int16_t *d_audio = audio;
-		CK(cudaEventRecord(e->ev[0], e->st));
-		if (on_host) {
-			CK(e->d_audio.ensure((size_t)n + 64));
-			d_audio = e->d_audio.p;
-			const long long chunk = e->opt_h2d_chunk;
-			const int n_chunks = (int)((n + chunk - 1) / chunk);
-			while ((int)e->ev_chunks.size() < n_chunks) {
-				cudaEvent_t ev;
-				CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-				e->ev_chunks.push_back(ev);
-			}
-			// the copy stream must not start before the engine stream reached this point
-			CK(cudaEventRecord(e->ev[6], e->st));
-			CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
-			long long done = 0;
-			for (int i = 0; i < n_chunks; i++) {
-				const long long len = std::min(chunk, n - done);
-				CK(cudaMemcpyAsync(e->d_audio.p + done, audio + done, (size_t)len * sizeof(int16_t),
-					cudaMemcpyHostToDevice, e->st_copy));
-				CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
-				CK(cudaStreamWaitEvent(e->st, e->ev_chunks[i], 0));
-				rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1);
-				if (rc != PM_OK) return rc;
-				done += len;
-			}
-			e->stats.h2d_bytes = (int64_t)n * 2;
-		} else {
-			rc = launch_front(e, d_audio, n, 0, n, true);
-			if (rc != PM_OK) return rc;
-		}
-		CK(cudaEventRecord(e->ev[1], e->st));
-		rc = run_back(e, d_audio);
-		if (rc == PM_ERR_CAPACITY && e->h_counters[0] > e->guard_cap) {
-			// guard list overflowed: grow it and run again
-			e->guard_cap = e->h_counters[0] + e->h_counters[0] / 4 + 1024;
-			cudaStreamSynchronize(e->st);
-			continue;
-		}
-		if (rc != PM_OK) return rc;
-		finish_stats(e);
-		e->have_run = true;
-		return PM_OK;
-	}
-	return fail(e, PM_ERR_CAPACITY, "guard list kept overflowing");
+	pm_shard_plan plan;
+	memset(&plan, 0, sizeof(plan));
+	plan.first = plan.last = 1;
+	int rc = shard_begin_impl(e, audio, n, on_host, plan, false);
+	if (rc != PM_OK) return rc;
+	rc = shard_gather_impl(e, nullptr, nullptr);
+	if (rc != PM_OK) return rc;
+	return shard_finish_impl(e, nullptr);
 }
 
 extern "C" int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples)
@@ -778,6 +974,66 @@ extern "C" int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_
 extern "C" int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples)
 {
 	return run_impl(e, audio_dev, n_samples, false);
+}
+
+extern "C" int pm_engine_shard_begin(pm_engine *e, const int16_t *audio, int64_t n_samples, int32_t audio_on_device,
+                                     const pm_shard_plan *plan, pm_shard_state *out)
+{
+	if (!e || !plan || !out) return fail(e, PM_ERR_ARG, "shard_begin: bad arguments");
+	int rc = shard_begin_impl(e, audio, n_samples, !audio_on_device, *plan, true);
+	if (rc != PM_OK) return rc;
+	memcpy(out, e->shard_out.data(), e->shard_out.size() * sizeof(pm_shard_state));
+	return PM_OK;
+}
+
+extern "C" int pm_engine_shard_handoff(pm_engine *e, const pm_shard_state *prev, pm_shard_state *out, int32_t *changed)
+{
+	if (!e || !out || !changed) return fail(e, PM_ERR_ARG, "shard_handoff: bad arguments");
+	if (e->phase != 1 || !e->sharded) return fail(e, PM_ERR_STATE, "shard_handoff: call shard_begin first");
+	cudaSetDevice(e->device);
+	const int nc = (int)e->chains.size();
+	*changed = 0;
+	if (!e->plan.first) {
+		if (!prev) return fail(e, PM_ERR_ARG, "shard_handoff: the previous shard's state is required");
+		bool mismatch = false;
+		for (int c = 0; c < nc; c++) {
+			SegState want;
+			want.clock = prev[c].end_clock; want.last = prev[c].end_last; want.last_q = prev[c].end_last_q;
+			if (memcmp(&want.clock, &e->h_init[c].clock, sizeof(double)) || want.last != e->h_init[c].last ||
+			    want.last_q != e->h_init[c].last_q)
+				mismatch = true;
+			e->h_init[c] = want;
+		}
+		if (mismatch) {
+			const std::vector<pm_shard_state> before = e->shard_out;
+			CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+			int rc = slicer_converge(e);
+			if (rc != PM_OK) return rc;
+			rc = read_shard_states(e);
+			if (rc != PM_OK) return rc;
+			for (int c = 0; c < nc; c++)
+				if (memcmp(&before[c].end_clock, &e->shard_out[c].end_clock, sizeof(double)) ||
+				    before[c].end_last != e->shard_out[c].end_last || before[c].end_last_q != e->shard_out[c].end_last_q ||
+				    before[c].n_symbols != e->shard_out[c].n_symbols)
+					*changed = 1;
+		}
+	}
+	memcpy(out, e->shard_out.data(), e->shard_out.size() * sizeof(pm_shard_state));
+	return PM_OK;
+}
+
+extern "C" int pm_engine_shard_gather(pm_engine *e, const int64_t *symbols_before, uint32_t *tail_out)
+{
+	if (!e) return PM_ERR_ARG;
+	cudaSetDevice(e->device);
+	return shard_gather_impl(e, symbols_before, tail_out);
+}
+
+extern "C" int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in)
+{
+	if (!e) return PM_ERR_ARG;
+	cudaSetDevice(e->device);
+	return shard_finish_impl(e, tail_in);
 }
 
 extern "C" int64_t pm_engine_num_packets(const pm_engine *e) { return (e && e->have_run) ? (int64_t)e->h_recs.size() : -1; }

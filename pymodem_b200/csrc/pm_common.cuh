@@ -90,6 +90,27 @@ struct SegState {
 	unsigned int last_q;
 };
 
+// Geometry of one slicer pass over the local sign stream.
+struct SlicerGeom {
+	long long origin_w;      // first word of segment 0 (own range start / 32)
+	int n_seg;
+	int seg_words;
+	int warm_words;
+	int chk_words;           // checkpoint spacing (divides seg_words)
+	int n_chk;               // seg_words / chk_words
+	int true_start;          // local sample 0 is the true start of the recording
+};
+
+// Per-chain placement of the local bitstream when the recording is sharded on
+// the sample axis (all zero / "everything is mine" for an unsharded run).
+struct ShardBits {
+	long long bit_off;       // local stream position of the first own bit (tail bits + byte-alignment padding before it)
+	long long own_lo;        // packets are emitted by the shard that holds their closing bit: own_lo <= pos < own_hi
+	long long own_hi;
+	int first;               // first shard: the stream start is the true start
+	int pad;
+};
+
 struct BitChain {
 	long long nout;            // valid soft samples
 	int sign_row, sign_q_row;
@@ -103,10 +124,13 @@ struct BitChain {
 };
 
 struct ChainCounters {
-	long long nbits;           // total sliced bits of the chain
+	long long nbits;           // local stream bits of the chain (incl. hand-off tail and padding when sharded)
 	long long nbytes;          // nbits / 8 (trailing partial byte dropped, slicer.py:95)
 	int nflags;
 	int seq_needed;            // ax25 max_packet_length overflow seen: replay sequentially
+	int tail_short;            // sharded: a frame closing in the own range reaches back past the hand-off tail
+	int n_emit;                // packets emitted by this chain
+	long long n_emit_bytes;
 };
 
 struct GapRec {
@@ -114,6 +138,7 @@ struct GapRec {
 	unsigned int len;         // bytes appended since the previous flag event
 	unsigned int scratch_off; // where they are in the chain's scratch bytes
 	unsigned int addr;        // byte address of the closing flag's byte (ax25.py:82)
+	unsigned int corrected;   // BytesCorrected (IL2P; 0 for AX.25)
 };
 
 struct PacketRecDev {          // mirrors pm_packet_rec (include/pymodem_b200.h)

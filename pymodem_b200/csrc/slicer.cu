@@ -10,19 +10,19 @@
 // (chain, segment): it first runs the loop over `warm` samples before its
 // segment from a cold state -- every zero crossing contracts the clock error by
 // lock_rate, so the state converges to the true one -- and records the state it
-// reached at the segment start (S_k), then runs its segment and records the end
-// state (E_k).  A second kernel checks S_k == E_{k-1} BIT FOR BIT (IEEE double
-// pattern + last sign); a segment that fails is re-run from the true state.
-// By induction from segment 0 the result is exactly the sequential loop's.
-// All clock arithmetic is IEEE double, one rounding per operation, so it is
-// bit-identical to CPython's floats.
+// reached at the segment start (S_k), then runs its segment, recording a
+// checkpoint state every chk_words words and the end state (E_k).  A second
+// kernel checks S_k == E_{k-1} BIT FOR BIT (IEEE double pattern + last signs); a
+// segment that fails is re-run from the true state, but only until its state
+// equals a stored checkpoint again (from there on the first run was already
+// right).  By induction from segment 0 the result is exactly the sequential
+// loop's.  All clock arithmetic is IEEE double, one rounding per operation, so
+// it is bit-identical to CPython's floats.
 //
 // Output: one rollover mask bit per sample (bit i of word w = "a symbol was
 // taken at sample 32w+i"); bits and byte addresses are produced from
 // (sign, mask) by the gather kernels in bits.cu.
 #include "pm_common.cuh"
-
-
 
 __device__ __forceinline__ bool seg_state_equal(const SegState &a, const SegState &b)
 {
@@ -78,33 +78,42 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
 }
 
 // grid: (ceil(n_seg / 128), n_chains); block 128
+// Segment k covers words [origin_w + k*seg_words, origin_w + (k+1)*seg_words).
+// true_start != 0: local sample 0 is the true start of the recording, so a
+// warm-up window clipped at 0 starts from init[] (no speculation).
 __global__ void __launch_bounds__(128)
 slicer_segments_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ sign,
                        long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
-                       SegState *__restrict__ S, SegState *__restrict__ E, const SegState *__restrict__ init,
-                       int n_seg, int seg_words, int warm_words)
+                       SegState *__restrict__ S, SegState *__restrict__ E, SegState *__restrict__ chk,
+                       const SegState *__restrict__ init, SlicerGeom G)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int ch = blockIdx.y;
-	if (k >= n_seg) return;
+	if (k >= G.n_seg) return;
 	const SlicerChain C = chains[ch];
 	const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
 	const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
 	uint32_t *mk = mask + (long long)ch * mask_stride;
-	const long long w_begin = (long long)k * seg_words;
-	const long long w_end = w_begin + seg_words;
+	const long long w_begin = G.origin_w + (long long)k * G.seg_words;
 	SegState st;
-	long long w_warm = w_begin - warm_words;
-	if (w_warm <= 0) {
+	long long w_warm = w_begin - G.warm_words;
+	if (w_warm <= 0 && G.true_start) {
 		st = init[ch];                     // the true start state: no speculation
 		w_warm = 0;
 	} else {
+		if (w_warm < 0) w_warm = 0;
 		st.clock = 0.0; st.last = 1u; st.last_q = 1u;   // cold start (slicer.py:50,55)
 	}
 	run_words<false>(C, sg, sgq, mk, w_warm, w_begin, st);
-	S[(long long)ch * n_seg + k] = st;
-	run_words<true>(C, sg, sgq, mk, w_begin, w_end, st);
-	E[(long long)ch * n_seg + k] = st;
+	const long long idx = (long long)ch * G.n_seg + k;
+	S[idx] = st;
+	SegState *ck = chk + idx * G.n_chk;
+	for (int j = 0; j < G.n_chk; j++) {
+		const long long a = w_begin + (long long)j * G.chk_words;
+		run_words<true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+		ck[j] = st;
+	}
+	E[idx] = st;
 }
 
 // One verification / repair pass.  E_in -> E_out (double buffered so that a
@@ -113,12 +122,13 @@ __global__ void __launch_bounds__(128)
 slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ sign,
                      long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
                      SegState *__restrict__ S, const SegState *__restrict__ E_in, SegState *__restrict__ E_out,
-                     const SegState *__restrict__ init, int n_seg, int seg_words, unsigned int *repairs)
+                     SegState *__restrict__ chk, const SegState *__restrict__ init, SlicerGeom G,
+                     unsigned int *repairs)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int ch = blockIdx.y;
-	if (k >= n_seg) return;
-	const long long idx = (long long)ch * n_seg + k;
+	if (k >= G.n_seg) return;
+	const long long idx = (long long)ch * G.n_seg + k;
 	const SegState prev = (k == 0) ? init[ch] : E_in[idx - 1];
 	const SegState mine = S[idx];
 	if (seg_state_equal(prev, mine)) {
@@ -126,8 +136,9 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
 		return;
 	}
 	const SlicerChain C = chains[ch];
-	if ((long long)k * seg_words * 32 >= C.nout) {     // empty segment past the end
-		S[idx] = prev;
+	const long long w_begin = G.origin_w + (long long)k * G.seg_words;
+	S[idx] = prev;
+	if ((w_begin << 5) >= C.nout) {     // empty segment past the end
 		E_out[idx] = prev;
 		return;
 	}
@@ -136,27 +147,119 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
 	const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
 	uint32_t *mk = mask + (long long)ch * mask_stride;
 	SegState st = prev;
-	S[idx] = prev;
-	run_words<true>(C, sg, sgq, mk, (long long)k * seg_words, (long long)(k + 1) * seg_words, st);
+	SegState *ck = chk + idx * G.n_chk;
+	for (int j = 0; j < G.n_chk; j++) {
+		const long long a = w_begin + (long long)j * G.chk_words;
+		run_words<true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+		if (seg_state_equal(ck[j], st)) {          // merged with the first run: the rest is already right
+			E_out[idx] = E_in[idx];
+			return;
+		}
+		ck[j] = st;
+	}
 	E_out[idx] = st;
 }
 
-extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int n_chains, const uint32_t *sign,
-	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, SegState *E, const SegState *init,
-	int n_seg, int seg_words, int warm_words, cudaStream_t st)
+// Sequential fallback: one thread per chain walks its segments in order and repairs
+// every hand-off that does not verify.  Used when the parallel verify passes do not
+// converge quickly (stretches without zero crossings -- e.g. digital silence -- never
+// contract the state error, so every speculated start state in them is wrong).
+__global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ sign,
+                                    long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
+                                    SegState *__restrict__ S, SegState *__restrict__ E, SegState *__restrict__ chk,
+                                    const SegState *__restrict__ init, SlicerGeom G, unsigned int *repairs)
 {
-	dim3 grid((n_seg + 127) / 128, n_chains);
-	slicer_segments_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, init, n_seg,
-		seg_words, warm_words);
+	const int ch = blockIdx.x;
+	if (threadIdx.x != 0) return;
+	const SlicerChain C = chains[ch];
+	const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
+	const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
+	uint32_t *mk = mask + (long long)ch * mask_stride;
+	SegState prev = init[ch];
+	unsigned int fixed = 0;
+	for (int k = 0; k < G.n_seg; k++) {
+		const long long idx = (long long)ch * G.n_seg + k;
+		const long long w_begin = G.origin_w + (long long)k * G.seg_words;
+		if (!seg_state_equal(S[idx], prev)) {
+			S[idx] = prev;
+			if ((w_begin << 5) >= C.nout) {
+				E[idx] = prev;
+			} else {
+				fixed++;
+				SegState st = prev;
+				SegState *ck = chk + idx * G.n_chk;
+				bool merged = false;
+				for (int j = 0; j < G.n_chk && !merged; j++) {
+					const long long a = w_begin + (long long)j * G.chk_words;
+					run_words<true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+					if (seg_state_equal(ck[j], st)) merged = true; else ck[j] = st;
+				}
+				if (!merged) E[idx] = st;
+			}
+		}
+		prev = E[idx];
+	}
+	if (fixed) atomicAdd(repairs, fixed);
+}
+
+// Symbols (mask bits) of every chain in samples [w0*32, min(w1*32, nout)): one CTA per chain.
+__global__ void __launch_bounds__(256)
+slicer_count_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ mask, long long mask_stride,
+                    long long w0, long long w1, unsigned long long *__restrict__ out)
+{
+	__shared__ unsigned long long s_part[256];
+	const int ch = blockIdx.x;
+	const long long nout = chains[ch].nout;
+	const uint32_t *mk = mask + (long long)ch * mask_stride;
+	unsigned long long cnt = 0;
+	for (long long w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+		const long long first = w << 5;
+		if (first >= nout) break;
+		uint32_t m = mk[w];
+		const long long remain = nout - first;
+		if (remain < 32) m &= (1u << (int)remain) - 1u;
+		cnt += __popc(m);
+	}
+	s_part[threadIdx.x] = cnt;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if ((int)threadIdx.x < d) s_part[threadIdx.x] += s_part[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[ch] = s_part[0];
+}
+
+extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int n_chains, const uint32_t *sign,
+	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, SegState *E, SegState *chk,
+	const SegState *init, SlicerGeom G, cudaStream_t st)
+{
+	dim3 grid((G.n_seg + 127) / 128, n_chains);
+	slicer_segments_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, chk, init, G);
 	return cudaGetLastError();
 }
 
 extern "C" cudaError_t pm_launch_slicer_verify(const SlicerChain *chains, int n_chains, const uint32_t *sign,
 	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, const SegState *E_in,
-	SegState *E_out, const SegState *init, int n_seg, int seg_words, unsigned int *repairs, cudaStream_t st)
+	SegState *E_out, SegState *chk, const SegState *init, SlicerGeom G, unsigned int *repairs, cudaStream_t st)
 {
-	dim3 grid((n_seg + 127) / 128, n_chains);
-	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, init,
-		n_seg, seg_words, repairs);
+	dim3 grid((G.n_seg + 127) / 128, n_chains);
+	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, chk,
+		init, G, repairs);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_slicer_sweep(const SlicerChain *chains, int n_chains, const uint32_t *sign,
+	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, SegState *E, SegState *chk,
+	const SegState *init, SlicerGeom G, unsigned int *repairs, cudaStream_t st)
+{
+	slicer_sweep_kernel<<<n_chains, 32, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, chk, init, G,
+		repairs);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_slicer_count(const SlicerChain *chains, int n_chains, const uint32_t *mask,
+	long long mask_stride, long long w0, long long w1, unsigned long long *out, cudaStream_t st)
+{
+	slicer_count_kernel<<<n_chains, 256, 0, st>>>(chains, mask, mask_stride, w0, w1, out);
 	return cudaGetLastError();
 }

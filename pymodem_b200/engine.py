@@ -95,6 +95,38 @@ class Engine:
 		"""audio already resident in device memory (e.g. a torch int16 tensor's data_ptr())."""
 		self._check(self._lib.pm_engine_run_device(self._h, ptr, n))
 
+	# -- sharded execution (one recording split on the sample axis; see sharded.py) ------
+	def shard_begin(self, audio_ptr, n, plan, on_device=False):
+		"""plan: dict(sample_base, own_begin, own_len, first, last, tail_bits) -> ShardState array"""
+		p = _lib.ShardPlan(int(plan['sample_base']), int(plan['own_begin']), int(plan['own_len']),
+			int(bool(plan['first'])), int(bool(plan['last'])), int(plan['tail_bits']), 0)
+		self._tail_words = int(plan['tail_bits']) // 32
+		out = (_lib.ShardState * self.n_chains)()
+		self._check(self._lib.pm_engine_shard_begin(self._h, audio_ptr, int(n), int(bool(on_device)), ctypes.byref(p), out))
+		return out
+
+	def shard_handoff(self, prev_states):
+		"""prev_states: the previous shard's ShardState array (None on the first shard)
+		-> (this shard's ShardState array, changed)"""
+		out = (_lib.ShardState * self.n_chains)()
+		changed = ctypes.c_int32(0)
+		self._check(self._lib.pm_engine_shard_handoff(self._h, prev_states, out, ctypes.byref(changed)))
+		return out, bool(changed.value)
+
+	def shard_gather(self, symbols_before):
+		"""symbols_before: per-chain symbols of all earlier shards -> this shard's tail (uint32[n_chains, tail_words])"""
+		sb = (ctypes.c_int64 * self.n_chains)(*[int(x) for x in symbols_before])
+		tail = np.zeros((self.n_chains, max(self._tail_words, 1)), dtype=np.uint32)
+		self._check(self._lib.pm_engine_shard_gather(self._h, sb, tail.ctypes.data))
+		return tail[:, :self._tail_words]
+
+	def shard_finish(self, tail_in):
+		if tail_in is None:
+			self._check(self._lib.pm_engine_shard_finish(self._h, None))
+		else:
+			t = np.ascontiguousarray(tail_in, dtype=np.uint32)
+			self._check(self._lib.pm_engine_shard_finish(self._h, t.ctypes.data))
+
 	def fetch(self):
 		n = self._lib.pm_engine_num_packets(self._h)
 		nb = self._lib.pm_engine_arena_bytes(self._h)

@@ -1,0 +1,208 @@
+"""One recording sharded on the sample axis over several GPUs (one engine = one rank).
+
+The reference runs every chain over the whole file (pymodem.py:140-166).  Here chains stay
+together (they share the front end) and the *audio* is split: rank r owns the soft samples
+[B_r, B_{r+1}) and receives, besides its slice, the FIR history + slicer warm-up before it and
+a few symbols after it.  Three tiny exchanges make the result bit-identical to the unsharded
+run (all of them all-gathers of a few KB; NCCL on GPUs, gloo in the CPU tests):
+
+  1. slicer hand-off  -- every rank speculates its start state from the warm-up; the previous
+     rank's true end state is compared bit for bit and the shard is repaired when it differs
+     (repeated until no end state changes: at most `world` rounds, normally one);
+  2. symbol counts    -- stream bytes are cut every 8 bits counted from sample 0
+     (slicer.py:92-97), so a rank needs the number of symbols of all earlier ranks;
+  3. bit tails        -- the last `tail_bits` bits of every rank go to the next one, so a frame
+     that straddles a boundary is decoded by the rank that holds its closing flag.
+
+Finally the packet records of all ranks are gathered (rank order == stream order) for the
+existing streamaddress-based Correlate on the host (packet_meta.py:230-271).
+"""
+import ctypes
+import math
+import struct
+
+import numpy as np
+
+from . import _lib
+from .engine import REC_DTYPE
+
+
+def plan_shards(n_samples, world, segment_len=16384, warm_len=16384, trim_max=305, samples_per_symbol=40.0,
+		tail_bits=16384):
+	"""Split n_samples over `world` ranks.  Returns one dict per rank:
+	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields."""
+	if world < 1:
+		raise ValueError("world must be >= 1")
+	per = int(math.ceil(n_samples / world / segment_len)) * segment_len
+	if world > 1 and per * (world - 1) >= n_samples - trim_max:
+		raise ValueError(f"recording too short ({n_samples} samples) for {world} shards of segment_len {segment_len}")
+	back = int(math.ceil(warm_len / segment_len)) * segment_len
+	fwd = int(math.ceil(16 * samples_per_symbol / 32.0)) * 32 + 64
+	plans = []
+	for r in range(world):
+		b0 = r * per
+		base = max(0, b0 - back)
+		last = r == world - 1
+		a1 = n_samples if last else min(n_samples, b0 + per + fwd + trim_max)
+		plans.append(dict(rank=r, audio_begin=base, audio_end=a1, sample_base=base, own_begin=b0 - base,
+			own_len=per, first=(r == 0), last=last, tail_bits=tail_bits if world > 1 else 0))
+	return plans
+
+
+def _states_to_bytes(states):
+	return bytes(ctypes.string_at(ctypes.addressof(states), ctypes.sizeof(states)))
+
+
+def _states_from_bytes(blob, n_chains):
+	arr = (_lib.ShardState * n_chains)()
+	ctypes.memmove(ctypes.addressof(arr), blob, ctypes.sizeof(arr))
+	return arr
+
+
+class ShardWorker:
+	"""The per-rank side of the protocol; `engine` is a pymodem_b200.engine.Engine (or, in the
+	CPU tests, an object with the same shard_* / fetch methods)."""
+
+	def __init__(self, engine, plan, audio_ptr, n_local, on_device=False):
+		self.engine, self.plan, self.audio_ptr, self.n_local, self.on_device = engine, plan, audio_ptr, n_local, on_device
+		self.rank = plan['rank']
+		self.n_chains = engine.n_chains
+		self.rounds = 0
+
+	def begin(self):
+		self.states = self.engine.shard_begin(self.audio_ptr, self.n_local, self.plan, self.on_device)
+		return _states_to_bytes(self.states)
+
+	def handoff(self, all_blobs):
+		prev = _states_from_bytes(all_blobs[self.rank - 1], self.n_chains) if self.rank > 0 else None
+		self.states, changed = self.engine.shard_handoff(prev)
+		self.rounds += 1
+		return _states_to_bytes(self.states), changed
+
+	def gather(self, all_blobs):
+		before = [0] * self.n_chains
+		for q in range(self.rank):
+			st = _states_from_bytes(all_blobs[q], self.n_chains)
+			for c in range(self.n_chains):
+				before[c] += int(st[c].n_symbols)
+		tail = self.engine.shard_gather(before)
+		return np.ascontiguousarray(tail, dtype=np.uint32).tobytes()
+
+	def finish(self, all_tails):
+		tail_in = None
+		if self.rank > 0 and self.plan['tail_bits'] > 0:
+			tail_in = np.frombuffer(all_tails[self.rank - 1], dtype=np.uint32).reshape(self.n_chains, -1)
+		self.engine.shard_finish(tail_in)
+		recs, arena = self.engine.fetch()
+		return struct.pack("<qq", len(recs), len(arena)) + recs.tobytes() + arena.tobytes()
+
+
+def _unpack_result(blob):
+	n, nb = struct.unpack_from("<qq", blob, 0)
+	off = 16
+	recs = np.frombuffer(blob, dtype=REC_DTYPE, count=n, offset=off).copy()
+	arena = np.frombuffer(blob, dtype=np.uint8, count=nb, offset=off + n * REC_DTYPE.itemsize).copy()
+	return recs, arena
+
+
+def merge_results(blobs):
+	"""Per-rank (records, arena) blobs in rank order -> one (records, arena) ordered by
+	(chain, stream position), offsets rebased into the merged arena."""
+	parts = [_unpack_result(b) for b in blobs]
+	base, recs_all = 0, []
+	for recs, arena in parts:
+		recs = recs.copy()
+		recs['offset'] += base
+		base += len(arena)
+		recs_all.append(recs)
+	recs = np.concatenate(recs_all) if recs_all else np.zeros(0, dtype=REC_DTYPE)
+	arena = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, dtype=np.uint8)
+	order = np.argsort(recs['chain'], kind='stable')       # ranks are already in stream order within a chain
+	return recs[order], arena
+
+
+def run_protocol(workers, exchange, exchange_var=None):
+	"""Drive the shard protocol.  `workers` are the ShardWorkers living in this process (one per
+	rank under torch.distributed; all of them when several shards are emulated in one process).
+	exchange(list of equally long local blobs) -> the blobs of ALL ranks in rank order."""
+	exchange_var = exchange_var or exchange
+	blobs = exchange([w.begin() for w in workers])
+	while True:
+		outs = [w.handoff(blobs) for w in workers]
+		blobs = exchange([o[0] for o in outs])
+		flags = exchange([bytes([1 if o[1] else 0]) for o in outs])
+		if not any(f[0] for f in flags):
+			break
+	tails = exchange([w.gather(blobs) for w in workers])
+	results = exchange_var([w.finish(tails) for w in workers])
+	return merge_results(results)
+
+
+def local_exchange(blobs):
+	"""All shards live in this process (tests, single-GPU emulation)."""
+	return list(blobs)
+
+
+class TorchExchange:
+	"""All-gather of byte blobs over torch.distributed (NCCL with CUDA staging tensors, gloo on CPU)."""
+
+	def __init__(self, device):
+		import torch
+		import torch.distributed as dist
+		self.torch, self.dist, self.device = torch, dist, device
+		self.world = dist.get_world_size()
+
+	def __call__(self, blobs):
+		torch, dist = self.torch, self.dist
+		(blob,) = blobs
+		mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device) if len(blob) else \
+			torch.zeros(0, dtype=torch.uint8, device=self.device)
+		out = [torch.empty_like(mine) for _ in range(self.world)]
+		dist.all_gather(out, mine)
+		return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+	def var(self, blobs):
+		"""blobs of different lengths: gather the lengths first, pad to the longest."""
+		torch, dist = self.torch, self.dist
+		(blob,) = blobs
+		n = torch.tensor([len(blob)], dtype=torch.int64, device=self.device)
+		lens = [torch.zeros_like(n) for _ in range(self.world)]
+		dist.all_gather(lens, n)
+		lens = [int(x.item()) for x in lens]
+		padded = blob + bytes(max(lens) - len(blob))
+		return [b[:k] for b, k in zip(self([padded]), lens)]
+
+
+def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **options):
+	"""Emulate `world` ranks on ONE GPU (one engine per shard, run in lock step).  Used by the
+	GPU parity tests; the multi-GPU path (bench.py / run_sharded_distributed) runs the same
+	ShardWorker protocol with one process per GPU."""
+	from .engine import Engine
+	audio = np.ascontiguousarray(audio, dtype=np.int16)
+	seg = int(options.get('segment_len', 16384))
+	warm = int(options.get('warmup_len', 8192))
+	trim = max(_chain_trim(c) for c in demod_stack)
+	sps = max(float(c[2].sample_rate) / float(c[2].symbol_rate) for c in demod_stack)
+	plans = plan_shards(len(audio), world, segment_len=seg, warm_len=max(warm, seg), trim_max=trim,
+		samples_per_symbol=sps, tail_bits=tail_bits)
+	engines = [Engine(demod_stack, device=device, **options) for _ in plans]
+	try:
+		workers = []
+		for eng, plan in zip(engines, plans):
+			local = audio[plan['audio_begin']:plan['audio_end']]
+			workers.append(ShardWorker(eng, plan, local.ctypes.data, len(local)))
+			workers[-1]._keep = local
+		recs, arena = run_protocol(workers, local_exchange)
+		info = dict(rounds=[w.rounds for w in workers], plans=plans,
+			repairs=[e.stats()['slicer_repairs'] for e in engines])
+		return engines[0].packets(recs, arena), info
+	finally:
+		for e in engines:
+			e.close()
+
+
+def _chain_trim(chain):
+	modem = chain[1]
+	if hasattr(modem, 'mark_correlator_i'):
+		return (len(modem.input_bpf) - 1) + (len(modem.mark_correlator_i) - 1) + (len(modem.output_lpf) - 1)
+	return len(modem.input_lpf) - 1
