@@ -448,14 +448,18 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 	if (j >= nfl) return;
 	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
 	const long long end = fp[j];
-	const long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
+	long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
 	const ShardBits B = sb[ch];
 	GapRec r;
 	r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
 	// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is
 	// emitted by the shard that holds its closing bit
 	const bool mine = end >= B.own_lo && end < B.own_hi;
-	const bool open_start = (j == 0) && !B.first;     // the gap reaches back past the hand-off tail
+	// On a later shard the stream starts in the middle of the recording: a gap whose opening flag is
+	// not a reliably detected one (all 8 bits of its pattern at valid positions) reaches back past the
+	// hand-off tail.  It is replayed from the first valid bit with unknown history.
+	const bool open_start = !B.first && (j == 0 || (long long)fp[j - 1] < B.valid_from + 8);
+	if (open_start && start < B.valid_from) start = B.valid_from;
 	if (mine && (end - start + 1 >= 18 * 8 + 8 || open_start)) {
 		int overflow = 0;
 		unsigned int len = 0;
@@ -465,7 +469,8 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
 		if (open_start && (emit || !aborted)) {
 			// either junk bytes from before the tail would be part of the frame, or the
-			// emission decision itself depends on bits we do not have
+			// emission decision itself depends on bits we do not have (an abort -- seven ones, all
+			// of them valid bits -- resets the machine whatever came before)
 			atomicExch(&cc[ch].tail_short, 1);
 		} else {
 			r.emit = emit ? 1u : 0u;

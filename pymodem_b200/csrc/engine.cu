@@ -88,8 +88,8 @@ struct pm_engine {
 	std::vector<HostChain> chains;
 	std::vector<FrontGroup> groups;
 	// options
-	int opt_seg_words = 512;      // 16384 samples
-	int opt_warm_words = 256;     // 8192 samples
+	int opt_seg_words = 1024;     // 32768 samples  (profiles/r01_slicer_sweep.txt)
+	int opt_warm_words = 1024;    // 32768 samples
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
@@ -537,6 +537,8 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	if (plan.first && (plan.own_begin != 0 || plan.sample_base != 0))
 		return fail(e, PM_ERR_ARG, "the first shard starts at sample 0");
 	if (plan.tail_bits < 0 || plan.tail_bits % 32) return fail(e, PM_ERR_ARG, "tail_bits must be a multiple of 32");
+	if (sharded && !(plan.first && plan.last) && plan.tail_bits < 128)
+		return fail(e, PM_ERR_ARG, "tail_bits must be at least 128");
 	e->n_samples = n;
 	e->plan = plan;
 	e->sharded = sharded;
@@ -848,6 +850,7 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 	for (int c = 0; c < nc; c++) {
 		ShardBits &b = sb[c];
 		b.first = plan.first ? 1 : 0; b.pad = 0;
+		b.valid_from = 0;
 		if (plan.first) {
 			b.bit_off = 0; b.own_lo = 0;
 		} else {
@@ -857,6 +860,9 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 			const long long A0 = ((P - plan.tail_bits) >> 3) << 3;              // global bit index of local bit 0
 			b.bit_off = P - A0;
 			b.own_lo = b.bit_off;
+			int deg = 0;                                                        // LFSR history (lfsr.py:38-44)
+			for (unsigned long long q = e->chains[c].d.lfsr_poly; q > 1; q >>= 1) deg++;
+			b.valid_from = b.bit_off - plan.tail_bits + deg;
 		}
 		if (plan.last) b.own_hi = 0x7fffffffffffffffll;
 		else {

@@ -107,6 +107,8 @@ struct ShardBits {
 	long long bit_off;       // local stream position of the first own bit (tail bits + byte-alignment padding before it)
 	long long own_lo;        // packets are emitted by the shard that holds their closing bit: own_lo <= pos < own_hi
 	long long own_hi;
+	long long valid_from;    // first local position whose descrambled bit is known to be right: the bits before it are
+	                         // alignment padding or lack LFSR history (0 on the first shard)
 	int first;               // first shard: the stream start is the true start
 	int pad;
 };

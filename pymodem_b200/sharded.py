@@ -27,7 +27,7 @@ from . import _lib
 from .engine import REC_DTYPE
 
 
-def plan_shards(n_samples, world, segment_len=16384, warm_len=16384, trim_max=305, samples_per_symbol=40.0,
+def plan_shards(n_samples, world, segment_len=32768, warm_len=32768, trim_max=305, samples_per_symbol=40.0,
 		tail_bits=16384):
 	"""Split n_samples over `world` ranks.  Returns one dict per rank:
 	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields."""
@@ -179,8 +179,8 @@ def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **op
 	ShardWorker protocol with one process per GPU."""
 	from .engine import Engine
 	audio = np.ascontiguousarray(audio, dtype=np.int16)
-	seg = int(options.get('segment_len', 16384))
-	warm = int(options.get('warmup_len', 8192))
+	seg = int(options.get('segment_len', 32768))
+	warm = int(options.get('warmup_len', 32768))
 	trim = max(_chain_trim(c) for c in demod_stack)
 	sps = max(float(c[2].sample_rate) / float(c[2].symbol_rate) for c in demod_stack)
 	plans = plan_shards(len(audio), world, segment_len=seg, warm_len=max(warm, seg), trim_max=trim,

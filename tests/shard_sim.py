@@ -48,14 +48,16 @@ class _Chain:
 		return b[:n], a[:n]
 
 
-def _ax25_bits(bits):
-	"""ax25.py:25-93 over a bit array, reporting (closing bit position, data bytes) per emitted frame
-	and whether an abort was seen before the first flag."""
+def _ax25_bits(bits, valid_from=0):
+	"""ax25.py:25-93 over bits[valid_from:], reporting per flag (position, data bytes or None, whether a
+	reliable flag -- all 8 pattern bits valid -- came before, whether an abort was seen since the start)."""
 	out = []
 	wb = one = bit_index = byte_index = 0
 	data = []
 	first_flag_seen, abort_before_first = False, False
 	for g, bit in enumerate(bits):
+		if g < valid_from:
+			continue
 		if bit:
 			wb |= 0x80
 			one += 1
@@ -86,7 +88,8 @@ def _ax25_bits(bits):
 			elif one == 6:
 				emit = byte_index >= 18 and bit_index == 7
 				out.append((g, bytes(data) if emit else None, first_flag_seen, abort_before_first))
-				first_flag_seen = True
+				if g >= valid_from + 8:
+					first_flag_seen = True
 				data = []
 				byte_index = 0
 				bit_index = 0
@@ -168,6 +171,7 @@ class SimEngine:
 		K = self.plan['tail_bits']
 		recs, arena = [], bytearray()
 		for i, ch in enumerate(self.chains):
+			valid_from = 0
 			if self.plan['first']:
 				P, A0, bit_off, tail = 0, 0, 0, np.zeros(0, dtype=np.uint8)
 			else:
@@ -175,6 +179,7 @@ class SimEngine:
 				A0 = ((P - K) >> 3) << 3
 				bit_off = P - A0
 				tail = np.unpackbits(np.asarray(tail_in[i], dtype=np.uint32).view(np.uint8), bitorder='little')
+				valid_from = bit_off - K + max(ch.c.stream.polynomial.bit_length() - 1, 0)
 			stream = np.concatenate([np.zeros(bit_off - len(tail), dtype=np.uint8), tail, self.own_bits[i]])
 			stream = stream[:len(stream) // 8 * 8]
 			by = np.packbits(stream)
@@ -185,7 +190,7 @@ class SimEngine:
 			own_lo = bit_off
 			own_hi = len(dbits) + 1 if self.plan['last'] else bit_off + n_own
 			first_byte_global = P // 8 - A0 // 8           # local byte index of the first own byte
-			for (g, data, flag_before, abort_before) in _ax25_bits(dbits):
+			for (g, data, flag_before, abort_before) in _ax25_bits(dbits, valid_from):
 				if not (own_lo <= g < own_hi):
 					continue
 				if not flag_before and not self.plan['first'] and (data is not None or not abort_before):
