@@ -186,6 +186,7 @@ def run_b200_arm(args):
 	lines = configs.afsk_1200_ax25_super_opt()
 	stack = [chain_builder.build_chain(SAMPLE_RATE, l) for l in configs.demod_chains(lines)]
 	n_chains = len(stack)
+	phase_ms = {}
 	hour = make_audio(args.seconds, 0)
 	n_hour = len(hour)
 	eng = Engine(stack, device=local, **dict(kv.split("=") for kv in args.opt))
@@ -223,14 +224,17 @@ def run_b200_arm(args):
 		merged = {}
 
 		def step_device():
-			merged['r'] = run_protocol([ShardWorker(eng, plan, dev_audio.data_ptr(), n, on_device=True)], ex, ex.var)
+			merged['r'] = run_protocol([ShardWorker(eng, plan, dev_audio.data_ptr(), n, on_device=True)], ex, ex.var,
+				timing=phase_ms)
 			return eng.stats()
 
 		def step_host():
-			merged['r'] = run_protocol([ShardWorker(eng, plan, pinned.data_ptr(), n, on_device=False)], ex, ex.var)
+			merged['r'] = run_protocol([ShardWorker(eng, plan, pinned.data_ptr(), n, on_device=False)], ex, ex.var,
+				timing=phase_ms)
 			return eng.stats()
 
 	def timed(step, k):
+		phase_ms.clear()
 		barrier()
 		torch.cuda.synchronize()
 		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,6 +258,7 @@ def run_b200_arm(args):
 	if rank == 0:
 		sampler.start()
 	ev_ms, wall_ms, stats = timed(step_device, args.steps)
+	shard_phase = {k: v / args.steps for k, v in phase_ms.items()}
 	# e2e: the same metric through the C ABI with host buffers
 	for _ in range(min(args.warmup, 3)):
 		step_host()
@@ -317,7 +322,7 @@ def run_b200_arm(args):
 		"e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
 			"h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"]},
 		"gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-		"stage_ms": stage_ms, "packets_per_step": n_packets,
+		"stage_ms": stage_ms, "shard_phase_ms_rank0": shard_phase, "packets_per_step": n_packets,
 		"slicer": {"segments": stats[-1]["slicer_segments"], "repairs": stats[-1]["slicer_repairs"],
 			"guard_flagged": stats[-1]["guard_flagged"]},
 		"timing": {"cuda_event_ms": ev_ms, "wall_ms": wall_ms, "e2e_cuda_event_ms": e2e_ev_ms, "e2e_wall_ms": e2e_wall_ms},

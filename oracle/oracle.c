@@ -319,3 +319,437 @@ ORC_API int64_t orc_ax25_decode(orc_ax25 *a, const uint8_t *bytes, const int64_t
 	}
 	return nrec;
 }
+
+/* ------------------------------------------------------------------------ */
+/* GF(2^8) tables -- gf_functions.py:47-74 (initialize), :18-24 (mul)        */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+	int order;               /* 2**power */
+	int table[256];          /* antilog, order-1 entries used (gf_functions.py:52-54) */
+	int index[256];          /* log; index[0] stays 0 */
+	int inverse[256];
+} orc_gf;
+
+static int gf_mul(const orc_gf *gf, int a, int b)
+{
+	if (a == 0 || b == 0) return 0;                                 /* :19-20 */
+	int result = gf->index[a] + gf->index[b];
+	while (result > gf->order - 2) result -= gf->order - 1;         /* :22-23 */
+	return gf->table[result];
+}
+
+static void gf_init(orc_gf *gf, int power, int genpoly)
+{
+	memset(gf, 0, sizeof(*gf));
+	gf->order = 1 << power;
+	int lfsr = 1;                                                   /* :62 a^0 */
+	for (int i = gf->order - 2; i >= 0; i--) {                      /* :63-66 */
+		int feedback = lfsr & 1;                                    /* lfsr_step :7-16 */
+		lfsr >>= 1;
+		if (feedback) lfsr ^= genpoly >> 1;
+		gf->table[i] = lfsr;
+		gf->index[lfsr] = i;
+	}
+	for (int i = 1; i < gf->order; i++) {                           /* :70-74 brute-force inverse */
+		int j = 1;
+		while (gf_mul(gf, i, j) != 1) j++;
+		gf->inverse[i] = j;
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* Reed-Solomon -- rs_functions.py:9-31 (initialize), :33-150 (decode)       */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+	orc_gf gf;
+	int first_root, num_roots;
+	int genpoly[64];
+} orc_rs;
+
+static void rs_init(orc_rs *rs, int first_root, int num_roots, int gf_power, int gf_poly)
+{
+	gf_init(&rs->gf, gf_power, gf_poly);
+	rs->first_root = first_root;
+	rs->num_roots = num_roots;
+	memset(rs->genpoly, 0, sizeof(rs->genpoly));
+	rs->genpoly[0] = rs->gf.table[first_root];                      /* :19 */
+	rs->genpoly[1] = 1;
+	int len = 2;
+	for (int i = first_root + 1; i < first_root + num_roots; i++) { /* :22-30: multiply by (x + a^i) */
+		int f0 = rs->gf.table[i];
+		int res[64] = {0};
+		for (int a = 0; a < len; a++) {                             /* gf_functions.convolve :36-45 */
+			res[a] ^= gf_mul(&rs->gf, rs->genpoly[a], f0);
+			res[a + 1] ^= gf_mul(&rs->gf, rs->genpoly[a], 1);
+		}
+		len += 1;
+		memcpy(rs->genpoly, res, sizeof(int) * (size_t)len);
+	}
+}
+
+/* returns number of corrected bytes, or -1; corrects data in place */
+static int rs_decode(const orc_rs *rs, int *data, int block_size, int min_distance)
+{
+	const orc_gf *gf = &rs->gf;
+	const int nr = rs->num_roots;
+	int syndromes[32], error_locator[32], next_error_locator[32], error_locations[32], error_magnitudes[32];
+	int correction_poly[33];
+	int error_count = 0;
+	for (int i = 0; i < nr; i++) {                                  /* :36-42 */
+		syndromes[i] = 0;
+		int x = gf->table[rs->first_root + i];
+		for (int j = 0; j < block_size - 1; j++) syndromes[i] = gf_mul(gf, syndromes[i] ^ data[j], x);
+		syndromes[i] ^= data[block_size - 1];
+	}
+	for (int i = 0; i < nr; i++) {                                  /* :50-56 */
+		error_locator[i] = 0; next_error_locator[i] = 0; error_locations[i] = 0; error_magnitudes[i] = 0;
+	}
+	for (int i = 0; i < nr + 1; i++) correction_poly[i] = 0;
+	error_locator[0] = 1;
+	correction_poly[1] = 1;
+	int order_tracker = 0;
+	for (int step_factor = 1; step_factor <= nr; step_factor++) {   /* :60-82 Berlekamp */
+		int y = step_factor - 1;
+		int e = syndromes[y];
+		for (int i = 1; i <= order_tracker; i++) {
+			int x = y - i;
+			e ^= gf_mul(gf, error_locator[i], syndromes[x]);
+		}
+		if (e != 0) {
+			for (int i = 0; i <= order_tracker; i++)
+				next_error_locator[i] = error_locator[i] ^ gf_mul(gf, e, correction_poly[i]);
+			e = gf->inverse[e];
+			for (int i = 0; i < nr / 2 + 1; i++) correction_poly[i] = gf_mul(gf, error_locator[i], e);
+			for (int i = 0; i < nr / 2 + 1; i++) error_locator[i] = next_error_locator[i];
+		}
+		if (2 * order_tracker < step_factor) order_tracker = step_factor - order_tracker;
+		for (int i = nr; i > 0; i--) correction_poly[i] = correction_poly[i - 1];
+		correction_poly[0] = 0;
+	}
+	for (int j = 0; j < block_size; j++) {                          /* :85-98 Chien search */
+		int x = 0;
+		int y = j + gf->order - block_size;
+		for (int i = 1; i < nr / 2 + 1; i++) {
+			if (error_locator[i]) {
+				int z = y * i + gf->index[error_locator[i]];
+				while (z > gf->order - 2) z -= gf->order - 1;
+				x ^= gf->table[z];
+			}
+		}
+		x ^= error_locator[0];
+		if (x == 0) {
+			error_locations[error_count] = j;
+			error_count++;
+		}
+	}
+	if (error_count <= nr / 2 - min_distance) {                     /* :99 */
+		for (int i = 0; i < error_count; i++) {                     /* :101-108 Forney */
+			correction_poly[i] = syndromes[rs->first_root + i];
+			for (int j = 1; j <= i; j++)
+				correction_poly[i] ^= gf_mul(gf, syndromes[rs->first_root + i - j], error_locator[j]);
+		}
+		for (int i = 0; i < error_count; i++) {
+			int e = block_size - error_locations[i] - 1;
+			int z = correction_poly[0];
+			for (int j = 1; j < error_count; j++) {                 /* :112-122 */
+				int x = e * j;
+				while (x > gf->order - 2) x -= gf->order - 1;
+				x = gf->order - x - 1;
+				while (x > gf->order - 2) x -= gf->order - 1;
+				z ^= gf_mul(gf, correction_poly[j], gf->table[x]);
+			}
+			z = gf_mul(gf, z, gf->table[e]);
+			int y = error_locator[1];
+			for (int j = 3; j < nr / 2 + 1; j += 2) {               /* :125-132 */
+				int x = e * (j - 1);
+				while (x > gf->order - 2) x -= gf->order - 1;
+				x = gf->order - x - 1;
+				while (x > gf->order - 2) x -= gf->order - 1;
+				y ^= gf_mul(gf, error_locator[j], gf->table[x]);
+			}
+			y = gf->index[y];
+			y = gf->order - y - 1;
+			if (y == gf->order - 1) y = 0;
+			y = gf->table[y];
+			error_magnitudes[i] = gf_mul(gf, y, z);
+			data[error_locations[i]] ^= error_magnitudes[i];
+		}
+	}
+	for (int i = 0; i < nr; i++) {                                  /* :142-149 re-check */
+		syndromes[i] = 0;
+		int x = gf->table[rs->first_root + i];
+		for (int j = 0; j < block_size - 1; j++) syndromes[i] = gf_mul(gf, syndromes[i] ^ data[j], x);
+		syndromes[i] ^= data[block_size - 1];
+		if (syndromes[i] != 0) return -1;
+	}
+	return error_count;
+}
+
+/* KAT access for the tests */
+ORC_API void orc_gf_tables(int *table, int *index, int *inverse)
+{
+	orc_gf gf;
+	gf_init(&gf, 8, 0x11D);
+	memcpy(table, gf.table, sizeof(int) * 255);
+	memcpy(index, gf.index, sizeof(int) * 256);
+	memcpy(inverse, gf.inverse, sizeof(int) * 256);
+}
+
+ORC_API int orc_rs_genpoly(int num_roots, int *out)
+{
+	orc_rs rs;
+	rs_init(&rs, 0, num_roots, 8, 0x11D);
+	memcpy(out, rs.genpoly, sizeof(int) * (size_t)(num_roots + 1));
+	return num_roots + 1;
+}
+
+ORC_API int orc_rs_decode(int num_roots, uint8_t *data, int block_size, int min_distance)
+{
+	orc_rs rs;
+	int buf[256];
+	rs_init(&rs, 0, num_roots, 8, 0x11D);
+	for (int i = 0; i < block_size; i++) buf[i] = data[i];
+	int r = rs_decode(&rs, buf, block_size, min_distance);
+	for (int i = 0; i < block_size; i++) data[i] = (uint8_t)buf[i];
+	return r;
+}
+
+/* ------------------------------------------------------------------------ */
+/* IL2P -- il2p.py                                                           */
+/* ------------------------------------------------------------------------ */
+static const uint8_t hamming_decode_table[128] = {                  /* il2p.py:19-42 */
+	0x0, 0x0, 0x0, 0x3, 0x0, 0x5, 0xe, 0x7, 0x0, 0x9, 0xe, 0xb, 0xe, 0xd, 0xe, 0xe,
+	0x0, 0x3, 0x3, 0x3, 0x4, 0xd, 0x6, 0x3, 0x8, 0xd, 0xa, 0x3, 0xd, 0xd, 0xe, 0xd,
+	0x0, 0x5, 0x2, 0xb, 0x5, 0x5, 0x6, 0x5, 0x8, 0xb, 0xb, 0xb, 0xc, 0x5, 0xe, 0xb,
+	0x8, 0x1, 0x6, 0x3, 0x6, 0x5, 0x6, 0x6, 0x8, 0x8, 0x8, 0xb, 0x8, 0xd, 0x6, 0xf,
+	0x0, 0x9, 0x2, 0x7, 0x4, 0x7, 0x7, 0x7, 0x9, 0x9, 0xa, 0x9, 0xc, 0x9, 0xe, 0x7,
+	0x4, 0x1, 0xa, 0x3, 0x4, 0x4, 0x4, 0x7, 0xa, 0x9, 0xa, 0xa, 0x4, 0xd, 0xa, 0xf,
+	0x2, 0x1, 0x2, 0x2, 0xc, 0x5, 0x2, 0x7, 0xc, 0x9, 0x2, 0xb, 0xc, 0xc, 0xc, 0xf,
+	0x1, 0x1, 0x2, 0x1, 0x4, 0x1, 0x6, 0xf, 0x8, 0x1, 0xa, 0xf, 0xc, 0xf, 0xf, 0xf
+};
+
+static int bit_distance_32(uint32_t a, uint32_t b)                 /* il2p.py:44-86 == popcount(a ^ b) */
+{
+	return __builtin_popcount(a ^ b);
+}
+
+typedef struct {
+	/* options (il2p.py:111-116, 140-145) */
+	int collect_trailing_crc, min_distance, disable_rs, sync_tolerance;
+	/* state (il2p.py:118-138) */
+	int state;                      /* 0 sync_search, 1 rx_header, 2 rx_bigblocks, 3 rx_smallblocks, 4 rx_trailing_crc */
+	uint32_t working_word;
+	int buffer[255];
+	int bit_index, byte_index_a, block_index;
+	int bytes_corrected, block_fail;
+	int block_count, block_size, big_blocks;
+	int count_subfield;
+	orc_rs header_rs, block_rs;
+	uint8_t *data;                  /* working_packet.data */
+	int64_t len, cap;
+} orc_il2p;
+
+ORC_API orc_il2p *orc_il2p_new(int crc, int disable_rs, int min_dist, int sync_tol)
+{
+	orc_il2p *c = (orc_il2p *)calloc(1, sizeof(orc_il2p));
+	c->collect_trailing_crc = crc;
+	c->disable_rs = disable_rs;
+	c->min_distance = min_dist;
+	c->sync_tolerance = sync_tol;
+	c->state = 0;
+	c->working_word = 0xFFFFFF;                                     /* :119 */
+	rs_init(&c->header_rs, 0, 2, 8, 0x11D);                         /* :130-135 */
+	rs_init(&c->block_rs, 0, 16, 8, 0x11D);
+	c->cap = 4096;
+	c->data = (uint8_t *)malloc((size_t)c->cap);
+	return c;
+}
+
+ORC_API void orc_il2p_free(orc_il2p *c) { free(c->data); free(c); }
+
+static void il2p_append(orc_il2p *c, int b)
+{
+	if (c->len == c->cap) {
+		c->cap *= 2;
+		c->data = (uint8_t *)realloc(c->data, (size_t)c->cap);
+	}
+	c->data[c->len++] = (uint8_t)b;
+}
+
+/* block_unscramble :160-163 with LFSRnoaddr.stream_unscramble_8bit lfsr.py:62-92 (poly 0x211, no invert) */
+static void il2p_block_unscramble(orc_il2p *c)
+{
+	uint32_t sr = 0x1F0;
+	uint32_t working_byte = 0;
+	for (int k = 0; k < c->byte_index_a; k++) {
+		uint32_t input_byte = (uint32_t)c->buffer[k];
+		for (int b = 0; b < 8; b++) {
+			working_byte <<= 1;
+			working_byte &= 0xFE;
+			if (input_byte & 0x80) sr ^= 0x211;
+			working_byte |= sr & 1;
+			input_byte <<= 1;
+			sr >>= 1;
+		}
+		c->buffer[k] = (int)working_byte;
+	}
+}
+
+static void il2p_rs(orc_il2p *c, const orc_rs *rs)                  /* :170-207 */
+{
+	int r = c->disable_rs ? 0 : rs_decode(rs, c->buffer, c->byte_index_a, c->min_distance);
+	if (r < 0) c->block_fail = 1;
+	else c->bytes_corrected += r;
+}
+
+static void il2p_append_crc(orc_il2p *c)                            /* crc_functions.py:63-76 */
+{
+	uint32_t crc = crc16_x25(c->data, c->len);
+	il2p_append(c, (int)(crc & 0xFF));
+	il2p_append(c, (int)(crc >> 8));
+}
+
+/* unpack_il2p_header :214-290 + construct_ax25_header :292-344 + reform_control_byte :89-107 */
+static void il2p_header_to_ax25(orc_il2p *c)
+{
+	const int *b = c->buffer;
+	int type_subfield = (b[1] & 0x80) >> 7;
+	int count = 0, pid = 0, control = 0;
+	for (int i = 0; i < 10; i++) if (b[i + 2] & 0x80) count |= 0x200 >> i;
+	for (int i = 0; i < 4; i++) if (b[i + 1] & 0x40) pid |= 0x8 >> i;
+	for (int i = 0; i < 7; i++) if (b[i + 5] & 0x40) control |= 0x40 >> i;
+	c->count_subfield = count;
+	int dest[7], source[7];
+	for (int i = 0; i < 6; i++) dest[i] = (b[i] & 0x3F) + 0x20;
+	dest[6] = b[12] >> 4;
+	for (int i = 0; i < 6; i++) source[i] = (b[i + 6] & 0x3F) + 0x20;
+	source[6] = b[12] & 0xF;
+	enum { T_UI, T_S, T_U, T_I } type;
+	if (b[0] & 0x40) type = T_UI;
+	else if (pid == 0x0) type = T_S;
+	else if (pid == 0x1) type = T_U;
+	else type = T_I;
+	static const int pid_table[16] = {0, 0, 0x10, 0x01, 0x06, 0x07, 0x08, 0xC3, 0xC4, 0xCA, 0xCB, 0xCC, 0xCD, 0xCE, 0xCF, 0xF0};
+	int pid_byte = pid_table[pid];
+	int pf = (control & 0x40) != 0, cbit = 0, nr = 0, ns = 0, opcode = 0;
+	if (type == T_I) { ns = control & 0x7; nr = (control >> 3) & 0x7; cbit = 1; }
+	else if (type == T_S) { nr = (control >> 3) & 0x7; if (control & 0x4) cbit = 1; opcode = control & 0x3; }
+	else { if (control & 0x4) cbit = 1; opcode = (control >> 3) & 0x7; }
+	if (type_subfield != 1) return;                                 /* transparent: nothing reconstructed (:342) */
+	for (int i = 0; i < 6; i++) il2p_append(c, dest[i] << 1);
+	int v = (dest[6] << 1) + 0x60;
+	if (cbit) v += 0x80;
+	il2p_append(c, v);
+	for (int i = 0; i < 6; i++) il2p_append(c, source[i] << 1);
+	v = (source[6] << 1) + 0x60;
+	if (!cbit) v += 0x80;
+	v += 1;
+	il2p_append(c, v);
+	static const int u_control[8] = {0x2F, 0x43, 0x0F, 0x63, 0x87, 0x03, 0xAF, 0xE3};
+	int cb = 0;
+	if (type == T_U || type == T_UI) { cb = u_control[opcode]; if (pf) cb |= 0x10; }
+	else if (type == T_S) { cb = 0x1 | (opcode << 2) | (nr << 5); if (pf) cb |= 0x10; }
+	else { cb = (ns << 1) | (nr << 5); if (pf) cb |= 0x10; }
+	il2p_append(c, cb);
+	if (pid_byte != 0) il2p_append(c, pid_byte);
+}
+
+/*
+ * IL2PCodec.decode -- il2p.py:360-519.  Records as in orc_ax25_decode plus rec_corr[]
+ * (PacketMeta.BytesCorrected).  Every value the reference appends to working_packet.data fits a
+ * byte (callsign characters <= 0x5F << 1, SSID bytes <= 30 + 0x60 + 0x80 + 1).
+ */
+ORC_API int64_t orc_il2p_decode(orc_il2p *c, const uint8_t *bytes, const int64_t *addr, int64_t n,
+                                int64_t *rec_addr, int64_t *rec_off, int64_t *rec_len, int64_t *rec_corr,
+                                int64_t rec_cap, uint8_t *arena, int64_t arena_cap, int64_t *arena_used)
+{
+	int64_t nrec = 0;
+#define WRITE_N_SEARCH()                                                          \
+	do {                                                                          \
+		if (nrec < rec_cap && *arena_used + c->len <= arena_cap) {                \
+			rec_addr[nrec] = addr[k]; rec_off[nrec] = *arena_used;                \
+			rec_len[nrec] = c->len; rec_corr[nrec] = c->bytes_corrected;          \
+			memcpy(arena + *arena_used, c->data, (size_t)c->len);                 \
+		}                                                                         \
+		*arena_used += c->len; nrec++;                                            \
+		c->bytes_corrected = 0; c->len = 0; c->state = 0;                         \
+	} while (0)
+	for (int64_t k = 0; k < n; k++) {
+		uint32_t input_byte = bytes[k];
+		for (int ib = 0; ib < 8; ib++) {
+			uint32_t mask = (c->state == 0) ? 0xFFFFFFFFu : 0xFFu;  /* get_a_bit :147-153 */
+			c->working_word = (c->working_word << 1) & mask;
+			if (input_byte & 0x80) c->working_word |= 1;
+			input_byte <<= 1;
+			c->bit_index += 1;
+			if (c->state == 0) {                                    /* :367-376 */
+				if (bit_distance_32(c->working_word & 0xFFFFFF, 0xF15E48) <= c->sync_tolerance ||
+				    bit_distance_32(c->working_word, 0x5D57DF7F) <= c->sync_tolerance) {
+					c->bit_index = 0;
+					c->state = 1;
+				}
+				continue;
+			}
+			if (c->bit_index != 8) continue;
+			c->bit_index = 0;
+			c->buffer[c->byte_index_a] = (int)c->working_word;
+			c->byte_index_a += 1;
+			if (c->state == 1) {                                    /* rx_header :377-434 */
+				if (c->byte_index_a != 15) continue;
+				il2p_rs(c, &c->header_rs);
+				c->byte_index_a = 13;
+				il2p_block_unscramble(c);
+				c->byte_index_a = 0;
+				c->block_index = 0;
+				il2p_header_to_ax25(c);
+				if (c->block_fail) {
+					c->block_fail = 0;
+					c->state = 0;
+					c->len = 0;
+				} else if (c->count_subfield > 0) {
+					int cnt = c->count_subfield;                    /* calc_big_small_blocks :346-358 */
+					c->block_count = (cnt + 238) / 239;
+					c->block_size = cnt / c->block_count;
+					c->big_blocks = cnt - c->block_count * c->block_size;
+					if (c->big_blocks > 0) { c->block_size += 1; c->state = 2; }
+					else c->state = 3;
+					c->bit_index = 0;
+				} else if (c->collect_trailing_crc) {
+					c->state = 4;
+				} else {
+					il2p_append_crc(c);
+					WRITE_N_SEARCH();
+				}
+			} else if (c->state == 2 || c->state == 3) {            /* :436-501 */
+				if (c->byte_index_a != c->block_size + 16) continue;
+				il2p_rs(c, &c->block_rs);
+				il2p_block_unscramble(c);
+				for (int i = 0; i < c->block_size; i++) il2p_append(c, c->buffer[i]);
+				c->block_index += 1;
+				c->byte_index_a = 0;
+				if (c->block_fail) {
+					c->block_fail = 0;
+					c->len = 0;
+					c->state = 0;
+				} else if (c->state == 2 && c->block_index == c->big_blocks) {
+					if (c->block_count > c->block_index) { c->block_size -= 1; c->state = 3; }
+					else if (c->collect_trailing_crc) c->state = 4;
+					else { il2p_append_crc(c); WRITE_N_SEARCH(); }
+				} else if (c->state == 3 && c->block_index == c->block_count) {
+					if (c->collect_trailing_crc) c->state = 4;
+					else { il2p_append_crc(c); WRITE_N_SEARCH(); }
+				}
+			} else if (c->state == 4) {                             /* rx_trailing_crc :502-518 */
+				if (c->byte_index_a != 4) continue;
+				c->byte_index_a = 0;
+				int trailing_crc = 0;
+				for (int i = 0; i < 4; i++) trailing_crc += hamming_decode_table[c->buffer[i] & 0x7F] << (12 - i * 4);
+				il2p_append(c, trailing_crc & 0xFF);
+				il2p_append(c, trailing_crc >> 8);
+				WRITE_N_SEARCH();
+			}
+		}
+	}
+#undef WRITE_N_SEARCH
+	return nrec;
+}

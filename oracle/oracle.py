@@ -89,6 +89,18 @@ def lib():
 		L.orc_ax25_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
 			ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
 			ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+		L.orc_gf_tables.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+		L.orc_rs_genpoly.restype = ctypes.c_int
+		L.orc_rs_genpoly.argtypes = [ctypes.c_int, ctypes.c_void_p]
+		L.orc_rs_decode.restype = ctypes.c_int
+		L.orc_rs_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+		L.orc_il2p_new.restype = ctypes.c_void_p
+		L.orc_il2p_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+		L.orc_il2p_free.argtypes = [ctypes.c_void_p]
+		L.orc_il2p_decode.restype = ctypes.c_int64
+		L.orc_il2p_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+			ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+			ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
 		_lib = L
 	return _lib
 
@@ -312,6 +324,66 @@ class AX25Codec:
 		return [(int(rec_addr[r]), bytes(arena[rec_off[r]:rec_off[r] + rec_len[r]]), 0) for r in range(nrec)]
 
 
+class IL2PCodec:
+	"""il2p.py:109-519.  decode() returns [(streamaddress, bytes, BytesCorrected), ...]"""
+
+	def __init__(self, ident, options=None):
+		options = options or {}
+		self.identifier = ident
+		# il2p.py:140-145 StringOptionsRetune (chain_builder.py:66 always calls it)
+		self.collect_trailing_crc = check_boolean(options.get('crc', 'yes'))
+		self.disable_rs = check_boolean(options.get('disable_rs', 'no'))
+		self.min_distance = int(options.get('min_dist', 0))
+		self.sync_tolerance = int(options.get('sync_tol', 0))
+		self._h = lib().orc_il2p_new(int(self.collect_trailing_crc), int(self.disable_rs), self.min_distance,
+			self.sync_tolerance)
+
+	def __del__(self):
+		try:
+			lib().orc_il2p_free(self._h)
+		except Exception:
+			pass
+
+	def decode(self, data, addr):
+		data = np.ascontiguousarray(data, dtype=np.uint8)
+		addr = np.ascontiguousarray(addr, dtype=np.int64)
+		n = len(data)
+		rec_cap = n // 19 + 16
+		arena_cap = 2 * n + (1 << 16)
+		rec_addr = np.empty(rec_cap, dtype=np.int64)
+		rec_off = np.empty(rec_cap, dtype=np.int64)
+		rec_len = np.empty(rec_cap, dtype=np.int64)
+		rec_corr = np.empty(rec_cap, dtype=np.int64)
+		arena = np.empty(arena_cap, dtype=np.uint8)
+		used = ctypes.c_int64(0)
+		nrec = lib().orc_il2p_decode(self._h, _ptr(data), _ptr(addr), n, _ptr(rec_addr), _ptr(rec_off), _ptr(rec_len),
+			_ptr(rec_corr), rec_cap, _ptr(arena), arena_cap, ctypes.byref(used))
+		if nrec > rec_cap or used.value > arena_cap:
+			raise RuntimeError("oracle IL2P buffers too small")
+		return [(int(rec_addr[r]), bytes(arena[rec_off[r]:rec_off[r] + rec_len[r]]), int(rec_corr[r])) for r in range(nrec)]
+
+
+def gf_tables():
+	"""gf_functions.initialize(8, 0x11D) -> (table[255], index[256], inverse[256])"""
+	t, i, v = np.zeros(255, dtype=np.int32), np.zeros(256, dtype=np.int32), np.zeros(256, dtype=np.int32)
+	lib().orc_gf_tables(_ptr(t), _ptr(i), _ptr(v))
+	return t, i, v
+
+
+def rs_genpoly(num_roots):
+	"""rs_functions.initialize(0, num_roots, 8, 0x11D)['genpoly']"""
+	out = np.zeros(num_roots + 1, dtype=np.int32)
+	lib().orc_rs_genpoly(num_roots, _ptr(out))
+	return [int(x) for x in out]
+
+
+def rs_decode(num_roots, data, min_distance=0):
+	"""rs_functions.decode -> (result, corrected data)"""
+	buf = np.array(list(data), dtype=np.uint8)
+	r = lib().orc_rs_decode(num_roots, _ptr(buf), len(buf), min_distance)
+	return int(r), bytes(buf)
+
+
 def check_crc(data):
 	"""crc_functions.py:9-61 -> [carried, calculated, valid]"""
 	a = np.frombuffer(bytes(data), dtype=np.uint8)
@@ -356,6 +428,8 @@ class Chain:
 		c = line['codec']
 		if c['type'].lower() == 'ax25':
 			self.codec = AX25Codec(self.name)
+		elif c['type'].lower() == 'il2p':
+			self.codec = IL2PCodec(self.name, c.get('options', {}))      # chain_builder.py:64-66
 		else:
 			raise NotImplementedError(f"oracle codec type {c['type']}")
 

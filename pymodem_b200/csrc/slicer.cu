@@ -202,17 +202,16 @@ __global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, cons
 	if (fixed) atomicAdd(repairs, fixed);
 }
 
-// Symbols (mask bits) of every chain in samples [w0*32, min(w1*32, nout)): one CTA per chain.
+// Symbols (mask bits) of every chain in samples [w0*32, min(w1*32, nout)); out[] must be zeroed.
 __global__ void __launch_bounds__(256)
 slicer_count_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ mask, long long mask_stride,
                     long long w0, long long w1, unsigned long long *__restrict__ out)
 {
-	__shared__ unsigned long long s_part[256];
-	const int ch = blockIdx.x;
+	const int ch = blockIdx.y;
 	const long long nout = chains[ch].nout;
 	const uint32_t *mk = mask + (long long)ch * mask_stride;
-	unsigned long long cnt = 0;
-	for (long long w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+	unsigned int cnt = 0;
+	for (long long w = w0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += (long long)gridDim.x * blockDim.x) {
 		const long long first = w << 5;
 		if (first >= nout) break;
 		uint32_t m = mk[w];
@@ -220,13 +219,8 @@ slicer_count_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__re
 		if (remain < 32) m &= (1u << (int)remain) - 1u;
 		cnt += __popc(m);
 	}
-	s_part[threadIdx.x] = cnt;
-	__syncthreads();
-	for (int d = 128; d > 0; d >>= 1) {
-		if ((int)threadIdx.x < d) s_part[threadIdx.x] += s_part[threadIdx.x + d];
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) out[ch] = s_part[0];
+	cnt = __reduce_add_sync(0xffffffffu, cnt);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&out[ch], (unsigned long long)cnt);
 }
 
 extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int n_chains, const uint32_t *sign,
@@ -260,6 +254,11 @@ extern "C" cudaError_t pm_launch_slicer_sweep(const SlicerChain *chains, int n_c
 extern "C" cudaError_t pm_launch_slicer_count(const SlicerChain *chains, int n_chains, const uint32_t *mask,
 	long long mask_stride, long long w0, long long w1, unsigned long long *out, cudaStream_t st)
 {
-	slicer_count_kernel<<<n_chains, 256, 0, st>>>(chains, mask, mask_stride, w0, w1, out);
+	cudaMemsetAsync(out, 0, sizeof(unsigned long long) * n_chains, st);
+	long long nb = (w1 - w0 + 256 * 16 - 1) / (256 * 16);
+	if (nb < 1) nb = 1;
+	if (nb > 1184) nb = 1184;
+	dim3 grid((unsigned int)nb, n_chains);
+	slicer_count_kernel<<<grid, 256, 0, st>>>(chains, mask, mask_stride, w0, w1, out);
 	return cudaGetLastError();
 }

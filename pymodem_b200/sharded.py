@@ -121,20 +121,40 @@ def merge_results(blobs):
 	return recs[order], arena
 
 
-def run_protocol(workers, exchange, exchange_var=None):
+def run_protocol(workers, exchange, exchange_var=None, timing=None):
 	"""Drive the shard protocol.  `workers` are the ShardWorkers living in this process (one per
 	rank under torch.distributed; all of them when several shards are emulated in one process).
-	exchange(list of equally long local blobs) -> the blobs of ALL ranks in rank order."""
+	exchange(list of equally long local blobs) -> the blobs of ALL ranks in rank order.
+	Four collectives per run when every speculated hand-off verifies (the normal case)."""
+	import time
 	exchange_var = exchange_var or exchange
-	blobs = exchange([w.begin() for w in workers])
+	t = [time.perf_counter()]
+
+	def lap(name):
+		t.append(time.perf_counter())
+		if timing is not None:
+			timing[name] = timing.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
+	blobs = [w.begin() for w in workers]
+	lap("begin")
+	blobs = exchange([b + b"\x01" for b in blobs])
+	lap("exchange")
 	while True:
+		blobs = [b[:-1] for b in blobs]
 		outs = [w.handoff(blobs) for w in workers]
-		blobs = exchange([o[0] for o in outs])
-		flags = exchange([bytes([1 if o[1] else 0]) for o in outs])
-		if not any(f[0] for f in flags):
+		lap("handoff")
+		blobs = exchange([o[0] + (b"\x01" if o[1] else b"\x00") for o in outs])      # states + "changed" flag
+		lap("exchange")
+		if not any(b[-1] for b in blobs):
 			break
-	tails = exchange([w.gather(blobs) for w in workers])
-	results = exchange_var([w.finish(tails) for w in workers])
+	blobs = [b[:-1] for b in blobs]
+	tails = [w.gather(blobs) for w in workers]
+	lap("gather")
+	tails = exchange(tails)
+	lap("exchange")
+	results = [w.finish(tails) for w in workers]
+	lap("finish")
+	results = exchange_var(results)
+	lap("exchange")
 	return merge_results(results)
 
 
@@ -144,33 +164,59 @@ def local_exchange(blobs):
 
 
 class TorchExchange:
-	"""All-gather of byte blobs over torch.distributed (NCCL with CUDA staging tensors, gloo on CPU)."""
+	"""All-gather of byte blobs over torch.distributed (NCCL through pinned/CUDA staging tensors,
+	gloo on CPU tensors).  Staging buffers are cached per blob size."""
 
 	def __init__(self, device):
 		import torch
 		import torch.distributed as dist
-		self.torch, self.dist, self.device = torch, dist, device
+		self.torch, self.dist, self.device = torch, dist, torch.device(device)
 		self.world = dist.get_world_size()
+		self.cuda = self.device.type == "cuda"
+		self._bufs = {}
+		self._cap = 1 << 16
+
+	def _staging(self, n):
+		torch = self.torch
+		if n not in self._bufs:
+			h_in = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=self.cuda)
+			h_out = torch.empty(max(n, 1) * self.world, dtype=torch.uint8, pin_memory=self.cuda)
+			d_in = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device) if self.cuda else h_in
+			d_out = torch.empty(max(n, 1) * self.world, dtype=torch.uint8, device=self.device) if self.cuda else h_out
+			self._bufs[n] = (h_in, h_out, d_in, d_out)
+		return self._bufs[n]
 
 	def __call__(self, blobs):
 		torch, dist = self.torch, self.dist
 		(blob,) = blobs
-		mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device) if len(blob) else \
-			torch.zeros(0, dtype=torch.uint8, device=self.device)
-		out = [torch.empty_like(mine) for _ in range(self.world)]
-		dist.all_gather(out, mine)
-		return [bytes(t.cpu().numpy().tobytes()) for t in out]
+		n = len(blob)
+		h_in, h_out, d_in, d_out = self._staging(n)
+		if n:
+			h_in[:n].copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+		if self.cuda:
+			d_in.copy_(h_in, non_blocking=True)
+			dist.all_gather_into_tensor(d_out, d_in)
+			h_out.copy_(d_out, non_blocking=True)
+			torch.cuda.current_stream().synchronize()
+		else:
+			dist.all_gather_into_tensor(d_out, d_in)
+		raw = h_out.numpy().tobytes()
+		m = max(n, 1)
+		return [raw[r * m:r * m + n] for r in range(self.world)]
 
 	def var(self, blobs):
-		"""blobs of different lengths: gather the lengths first, pad to the longest."""
-		torch, dist = self.torch, self.dist
+		"""Blobs of different lengths in ONE collective: every rank sends a length header + its blob
+		padded to a common capacity (grown, by all ranks alike, when some blob did not fit)."""
 		(blob,) = blobs
-		n = torch.tensor([len(blob)], dtype=torch.int64, device=self.device)
-		lens = [torch.zeros_like(n) for _ in range(self.world)]
-		dist.all_gather(lens, n)
-		lens = [int(x.item()) for x in lens]
-		padded = blob + bytes(max(lens) - len(blob))
-		return [b[:k] for b, k in zip(self([padded]), lens)]
+		while True:
+			cap = self._cap
+			head = struct.pack("<q", len(blob))
+			out = self([head + (blob[:cap] if len(blob) <= cap else b"") .ljust(cap, b"\0")])
+			lens = [struct.unpack_from("<q", o, 0)[0] for o in out]
+			if max(lens) <= cap:
+				return [o[8:8 + k] for o, k in zip(out, lens)]
+			while self._cap < max(lens):
+				self._cap *= 2
 
 
 def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **options):

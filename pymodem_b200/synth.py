@@ -163,3 +163,211 @@ def fsk9600_ax25(duration_s, sample_rate=48000, frame_interval_s=0.5, amplitude=
 	x = sig + ramp * nrng.standard_normal(n, dtype=np.float32)
 	x = np.clip(x * (32767.0 * amplitude), -32768, 32767)
 	return np.rint(x).astype(np.int16), frames, starts
+
+
+# ---------------------------------------------------------------------------------------
+# IL2P transmitter (the reference only decodes, il2p.py).  Written as the inverse of the
+# reference's receiver: header packing inverts unpack_il2p_header (il2p.py:214-290), the
+# scrambler inverts block_unscramble (il2p.py:160-163: LFSR 0x211, receiver state 0x1F0), parity
+# is the remainder modulo the RS generator (first root 0, GF(2^8)/0x11D; rs_functions.py:9-31).
+# ---------------------------------------------------------------------------------------
+_GF_EXP = [0] * 512
+_GF_LOG = [0] * 256
+
+
+def _gf_setup():
+	x = 1
+	for i in range(255):
+		_GF_EXP[i] = x
+		_GF_LOG[x] = i
+		x <<= 1
+		if x & 0x100:
+			x ^= 0x11D
+	for i in range(255, 512):
+		_GF_EXP[i] = _GF_EXP[i - 255]
+
+
+_gf_setup()
+
+
+def _gf_mul(a, b):
+	return 0 if a == 0 or b == 0 else _GF_EXP[_GF_LOG[a] + _GF_LOG[b]]
+
+
+def rs_parity(data, num_roots):
+	"""Systematic RS parity: remainder of data(x) * x^r modulo prod_{i<r}(x + a^i); data[0] is the
+	highest-order coefficient (the receiver's Horner syndromes, rs_functions.py:36-42)."""
+	gen = [1]
+	for i in range(num_roots):
+		nxt = [0] * (len(gen) + 1)
+		for j, g in enumerate(gen):          # gen is highest-order first
+			nxt[j] ^= g
+			nxt[j + 1] ^= _gf_mul(g, _GF_EXP[i])
+		gen = nxt
+	rem = [0] * num_roots
+	for d in data:
+		fb = d ^ rem[0]
+		rem = rem[1:] + [0]
+		if fb:
+			for j in range(num_roots):
+				rem[j] ^= _gf_mul(gen[j + 1], fb)
+	return rem
+
+
+def il2p_scramble(block):
+	"""Transmit side of the receiver's per-block descrambler (state 0x1F0, poly 0x211)."""
+	sr = 0x1F0
+	out = []
+	for byte in block:
+		o = 0
+		for i in range(8):
+			d = (byte >> (7 - i)) & 1
+			s = d ^ (sr & 1)
+			if s:
+				sr ^= 0x211
+			sr >>= 1
+			o = (o << 1) | s
+		out.append(o)
+	return out
+
+
+_HAMMING_ENCODE = [0x0, 0x71, 0x62, 0x13, 0x54, 0x25, 0x36, 0x47, 0x38, 0x49, 0x5a, 0x2b, 0x6c, 0x1d, 0x0e, 0x7f]
+
+
+def il2p_frame(dest, src, payload, dest_ssid=0, src_ssid=0, command=True, trailing_crc=True):
+	"""IL2P type-1 (translated AX.25 UI, PID 0xF0) frame -> (bytes on the air after the sync word,
+	the AX.25 frame incl. FCS that the reference's decoder reconstructs)."""
+	payload = list(payload)
+	count = len(payload)
+	if count > 1023:
+		raise ValueError("IL2P payload is at most 1023 bytes")
+	dcall = [ord(c) for c in dest.ljust(6)[:6]]
+	scall = [ord(c) for c in src.ljust(6)[:6]]
+	hdr = [(c - 0x20) & 0x3F for c in dcall] + [(c - 0x20) & 0x3F for c in scall] + [((dest_ssid & 0xF) << 4) | (src_ssid & 0xF)]
+	hdr[0] |= 0x40                                   # UI
+	hdr[1] |= 0x80                                   # header type 1
+	for i in range(10):
+		if count & (0x200 >> i):
+			hdr[i + 2] |= 0x80
+	pid_field = 0xF                                  # AX.25 PID 0xF0
+	for i in range(4):
+		if pid_field & (0x8 >> i):
+			hdr[i + 1] |= 0x40
+	control = (5 << 3) | (0x4 if command else 0)     # UI opcode 5 (control byte 0x03), C bit
+	for i in range(7):
+		if control & (0x40 >> i):
+			hdr[i + 5] |= 0x40
+	sh = il2p_scramble(hdr)
+	air = sh + rs_parity(sh, 2)
+	if count:
+		n_blocks = -(-count // 239)
+		small = count // n_blocks
+		big = count - n_blocks * small
+		pos = 0
+		for b in range(n_blocks):
+			size = small + 1 if b < big else small
+			sb = il2p_scramble(payload[pos:pos + size])
+			air += sb + rs_parity(sb, 16)
+			pos += size
+	# what the receiver rebuilds (il2p.py:292-344)
+	ax = [c << 1 for c in dcall] + [((dest_ssid & 0xF) << 1) + 0x60 + (0x80 if command else 0)]
+	ax += [c << 1 for c in scall] + [((src_ssid & 0xF) << 1) + 0x60 + (0 if command else 0x80) + 1]
+	ax += [0x03, 0xF0] + payload
+	fcs = crc16_x25(ax)
+	if trailing_crc:
+		air += [_HAMMING_ENCODE[(fcs >> (12 - 4 * i)) & 0xF] for i in range(4)]
+	return bytes(air), bytes(ax + [fcs & 0xFF, fcs >> 8])
+
+
+def il2p_bits(air, preamble_bytes=12, postamble_bytes=2):
+	"""0x55 preamble + sync word 0xF15E48 + frame, MSB first -> uint8 array of bits."""
+	by = [0x55] * preamble_bytes + [0xF1, 0x5E, 0x48] + list(air) + [0x55] * postamble_bytes
+	return np.unpackbits(np.array(by, dtype=np.uint8))
+
+
+def _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed):
+	n = len(sig)
+	out = np.empty(n, dtype=np.int16)
+	nrng = np.random.default_rng(noise_seed)
+	chunk = 1 << 22
+	fs = 32767.0 * amplitude
+	for pos in range(0, n, chunk):
+		m = min(chunk, n - pos)
+		ramp = noise_start + (noise_end - noise_start) * (np.arange(pos, pos + m, dtype=np.float32) / max(n - 1, 1))
+		x = sig[pos:pos + m] + ramp * nrng.standard_normal(m, dtype=np.float32)
+		np.clip(x * fs, -32768, 32767, out=x)
+		out[pos:pos + m] = np.rint(x).astype(np.int16)
+	return out
+
+
+def _il2p_payloads(k, rng, payload_len):
+	if payload_len is None:
+		return _default_payload(k, rng)
+	return bytes(int(c) for c in rng.integers(0, 256, size=payload_len))
+
+
+def afsk1200_il2p(duration_s, sample_rate=48000, frame_interval_s=1.0, amplitude=0.5, noise_start=0.0,
+		noise_end=1.0, seed=0, noise_seed=1, mark=1200.0, space=2200.0, baud=1200.0, first_frame_s=0.3,
+		payload_len=None, invert=False):
+	"""IL2P+CRC frames as plain (non-NRZI) Bell-202 AFSK: bit 1 = mark tone (afsk.py:162 mark - space >= 0).
+	Returns (audio, [reconstructed AX.25 frames], starts)."""
+	rng = np.random.default_rng(seed)
+	n = int(round(duration_s * sample_rate))
+	sig = np.zeros(n, dtype=np.float32)
+	frames, starts = [], []
+	sps = sample_rate / baud
+	t, k = first_frame_s, 0
+	while True:
+		start = int(round(t * sample_rate))
+		plen = payload_len[k % len(payload_len)] if isinstance(payload_len, (list, tuple)) else payload_len
+		air, ax = il2p_frame("MODEM", "NOISE", _il2p_payloads(k, rng, plen))
+		line = il2p_bits(air)
+		if invert:
+			line = 1 - line
+		nsamp = int(np.floor(len(line) * sps))
+		if start + nsamp >= n:
+			break
+		idx = np.minimum((np.arange(nsamp) / sps).astype(np.int64), len(line) - 1)
+		freq = np.where(line[idx] == 1, mark, space)
+		sig[start:start + nsamp] = np.sin(2.0 * np.pi * np.cumsum(freq) / sample_rate).astype(np.float32)
+		frames.append(ax)
+		starts.append(start)
+		k += 1
+		t += max(frame_interval_s, nsamp / sample_rate + 0.1)
+	return _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed), frames, starts
+
+
+def fsk9600_il2p(duration_s, sample_rate=48000, frame_interval_s=0.25, amplitude=0.5, noise_start=0.0,
+		noise_end=0.7, seed=0, noise_seed=1, baud=9600.0, first_frame_s=0.05, payload_len=None):
+	"""IL2P+CRC frames as a two-level baseband waveform (bit 1 = positive), idle = 0x55 pattern."""
+	rng = np.random.default_rng(seed)
+	n = int(round(duration_s * sample_rate))
+	sps = sample_rate / baud
+	nbits = int(n / sps)
+	bits = np.tile(np.array([0, 1], dtype=np.uint8), nbits // 2 + 1)[:nbits]
+	frames, starts = [], []
+	t, k = first_frame_s, 0
+	while True:
+		b0 = int(round(t * baud))
+		plen = payload_len[k % len(payload_len)] if isinstance(payload_len, (list, tuple)) else payload_len
+		air, ax = il2p_frame("MODEM", "NOISE", _il2p_payloads(k, rng, plen))
+		fb = il2p_bits(air, preamble_bytes=4, postamble_bytes=1)
+		if b0 + len(fb) + 64 >= nbits:
+			break
+		bits[b0:b0 + len(fb)] = fb
+		frames.append(ax)
+		starts.append(int(b0 * sps))
+		k += 1
+		t += max(frame_interval_s, len(fb) / baud + 0.02)
+	idx = np.minimum((np.arange(n) / sps).astype(np.int64), nbits - 1)
+	sig = bits[idx].astype(np.float32) * 2.0 - 1.0
+	sig = np.convolve(sig, np.array([0.25, 0.5, 0.25], dtype=np.float32), 'same').astype(np.float32)
+	return _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed), frames, starts
+
+
+def wav_excerpt(name):
+	"""A committed excerpt of real audio (tests/golden/<name>.npz, made by tools/make_golden.py)."""
+	import os
+	path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", name + ".npz")
+	z = np.load(path)
+	return np.ascontiguousarray(z["audio"], dtype=np.int16), [], []

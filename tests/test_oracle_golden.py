@@ -8,7 +8,8 @@ import pytest
 
 from util import GOLD, Golden
 
-CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k"]
+CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
+	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k"]
 
 
 @pytest.mark.parametrize("tag", CASES)
@@ -77,6 +78,57 @@ def test_kats(oracle):
 	l = oracle.LFSR({"poly": "0x63003", "invert": "True"})
 	out, _ = l.stream_unscramble_8bit(np.array([0x00, 0xFF, 0xAA, 0x0F, 0x7E, 0x12, 0x34], dtype=np.uint8), None)
 	assert list(out) == [0xFF, 0x7F, 0x88, 0xB0, 0xF1, 0xEC, 0xA0]
+
+
+def test_gf_rs_kats(oracle):
+	"""GF(2^8)/0x11D tables, RS generator polynomials, RS decode."""
+	table, index, inverse = oracle.gf_tables()
+	assert list(table[:10]) == [1, 2, 4, 8, 16, 32, 64, 128, 29, 58]
+	assert list(index[1:9]) == [0, 1, 25, 2, 50, 26, 198, 3]
+	assert inverse[2] == 142 and inverse[0x53] == 140
+	assert oracle.rs_genpoly(2) == [2, 3, 1]
+	assert oracle.rs_genpoly(16) == [59, 36, 50, 98, 229, 41, 65, 163, 8, 30, 209, 68, 189, 104, 13, 59, 1]
+	block = bytearray(32)
+	block[3], block[10] = 0x55, 0xAA
+	assert oracle.rs_decode(16, block) == (2, bytes(32))
+	block = bytearray(32)
+	for k in range(9):
+		block[3 * k] = k + 1
+	assert oracle.rs_decode(16, block)[0] == -1
+
+
+def test_il2p_encoder_roundtrip(oracle):
+	"""synth.il2p_frame (the transmitter written as the inverse of the reference's receiver) through
+	the oracle's IL2P decoder: clean frames come back as the reconstructed AX.25 frames; up to 8 byte
+	errors per block and 1 in the header are corrected and counted; more fail."""
+	from pymodem_b200 import synth
+	rng = np.random.default_rng(3)
+	for plen in (0, 1, 40, 239, 240, 477, 1023):
+		payload = bytes(int(x) for x in rng.integers(0, 256, plen))
+		air, ax = synth.il2p_frame("MODEM", "NOISE", payload, dest_ssid=3, src_ssid=11)
+		bits = synth.il2p_bits(air, preamble_bytes=3, postamble_bytes=3)
+		bits = np.concatenate([bits, np.zeros((-len(bits)) % 8, dtype=np.uint8)])
+		by = np.packbits(bits)
+		got = oracle.IL2PCodec("x", {"sync_tol": "0"}).decode(by, np.arange(len(by), dtype=np.int64))
+		assert [(g[1], g[2]) for g in got] == [(ax, 0)]
+		assert oracle.check_crc(got[0][1])[2]
+		# corrupt 1 header byte + 8 bytes of the first block
+		bad = bytearray(by)
+		first = 3 + 3                                   # preamble + sync word
+		bad[first + 2] ^= 0x5A
+		n_err = 1
+		if plen >= 40:
+			for j in range(8):
+				bad[first + 15 + 2 * j] ^= 0x11 * (j + 1)
+			n_err += 8
+		got = oracle.IL2PCodec("x", {"sync_tol": "0"}).decode(np.frombuffer(bytes(bad), dtype=np.uint8),
+			np.arange(len(by), dtype=np.int64))
+		assert [(g[1], g[2]) for g in got] == [(ax, n_err)]
+		if plen >= 40:
+			bad[first + 15 + 17] ^= 0x77                    # a ninth error: the block fails, the packet is dropped
+			got = oracle.IL2PCodec("x", {"sync_tol": "0"}).decode(np.frombuffer(bytes(bad), dtype=np.uint8),
+				np.arange(len(by), dtype=np.int64))
+			assert got == []
 
 
 def test_ax25_quirks(oracle):

@@ -144,6 +144,30 @@ def main():
 	lines = [l for l in load_config("fsk_9600.json") if l.get('codec', {}).get('type') == 'ax25'
 		or l.get('object_type') == 'report']
 	run_case("fsk9600_ax25_48k", "fsk_9600.json", lines, 48000, audio, meta, stage_chains=(0,))
+	more_cases()
+
+
+def more_cases():
+	# (4) afsk_1200.json as shipped (2 AX.25 + 2 IL2P+CRC chains) on IL2P audio: RS corrections, failed
+	#     headers/blocks, multi-block payloads, header-only frames
+	meta = dict(gen="afsk1200_il2p", duration_s=14.0, sample_rate=48000, frame_interval_s=0.5, noise_start=0.3,
+		noise_end=1.3, seed=6, noise_seed=7, first_frame_s=0.3, payload_len=[None, 300, 10, 0, 240, 60])
+	audio, _, _ = synth.afsk1200_il2p(**meta_args(meta))
+	run_case("afsk1200_il2p_48k", "afsk_1200.json", load_config("afsk_1200.json"), 48000, audio, meta, stage_chains=(2, 3))
+	# (5) fsk_9600.json as shipped (IL2P+CRC, IL2P+CRC inverted, G3RUH AX.25) on IL2P baseband audio
+	meta = dict(gen="fsk9600_il2p", duration_s=5.0, sample_rate=48000, frame_interval_s=0.25, noise_start=0.2,
+		noise_end=0.9, seed=8, noise_seed=9, first_frame_s=0.05, payload_len=[None, 300, 10, 0, 240, 60])
+	audio, _, _ = synth.fsk9600_il2p(**meta_args(meta))
+	run_case("fsk9600_il2p_48k", "fsk_9600.json", load_config("fsk_9600.json"), 48000, audio, meta, stage_chains=(0, 1))
+	# (6) the one audio file the reference ships: audio_samples/afsk_300_il2pc_noise.wav (8 kHz), first 80 s,
+	#     with the correlator chains of afsk_300.json (lines 1, 4, 5; the afsk_pll lines are a different modem)
+	from scipy.io.wavfile import read as readwav
+	sr, wav = readwav(os.path.join(REF, "audio_samples", "afsk_300_il2pc_noise.wav"))
+	wav = np.ascontiguousarray(wav[:80 * sr])
+	np.savez_compressed(os.path.join(GOLD, "afsk300_wav_excerpt.npz"), audio=wav, sample_rate=np.array(sr))
+	lines = [l for l in load_config("afsk_300.json") if l.get('object_type') == 'report' or l['modem']['type'] == 'afsk']
+	meta = dict(gen="wav_excerpt", name="afsk300_wav_excerpt")
+	run_case("afsk300_real_8k", "afsk_300.json", lines, int(sr), wav, meta, stage_chains=(0, 1))
 
 
 def meta_args(meta):
@@ -151,4 +175,7 @@ def meta_args(meta):
 
 
 if __name__ == "__main__":
-	main()
+	if "--more" in sys.argv:
+		more_cases()
+	else:
+		main()
