@@ -753,3 +753,190 @@ ORC_API int64_t orc_il2p_decode(orc_il2p *c, const uint8_t *bytes, const int64_t
 #undef WRITE_N_SEARCH
 	return nrec;
 }
+
+/* ------------------------------------------------------------------------ */
+/* PSK / PLL recursive loops: agc.py, nco.py, iir.py, pi_control.py,          */
+/* phase_detector.py, complexmath.py, psk.py:162-195 / 705-773,              */
+/* afsk_pll.py:140-170.  Every double operation rounds separately            */
+/* (-ffp-contract=off), in the reference's evaluation order.                 */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+	/* AGC -- agc.py:8-24 */
+	double agc_scaled_attack;      /* attack_rate / sample_rate          agc.py:15 */
+	double agc_scaled_decay;       /* decay_rate / sample_rate           agc.py:16 */
+	double agc_sustain_time;
+	double agc_sustain_increment;  /* 1 / sample_rate                    agc.py:17 */
+	double agc_target;
+	/* NCO -- nco.py:14-32 */
+	double nco_phase_scale;        /* 2.0 * pi / sample_rate             nco.py:30 */
+	double nco_index_scale;        /* wavetable_size / (2.0 * pi)        nco.py:28 */
+	double nco_set_frequency;
+	double nco_two_pi;             /* 2.0 * pi */
+	double nco_quarter;            /* wavetable_size / 4.0               nco.py:46 */
+	const double *nco_wavetable;   /* amplitude * sin(i * 2.0 * pi / size), built by the caller with math.sin */
+	int64_t nco_size;
+	/* IIR_1 -- iir.py:15-29 */
+	double iir_b0, iir_b1, iir_a1;
+	/* PI_control -- pi_control.py:8-13 */
+	double pi_gain, pi_p, pi_i, pi_limit, pi_integral0;
+	/* PhaseDetector.qpsk_error_table -- phase_detector.py:34-45, granularity x granularity ints */
+	const int32_t *pd_table;
+	int64_t pd_granularity;
+} orc_loop;
+
+typedef struct {
+	double envelope, sustain_count, normal;                         /* agc.py:18-24 */
+	double phase, control, sine, cosine;                            /* nco.py:22-26 */
+	double x1, y1;                                                  /* iir.py:33-34 */
+	double integral, proportional;                                  /* pi_control.py:12-13 */
+} orc_loop_state;
+
+static void loop_state_init(const orc_loop *L, orc_loop_state *s, double normal)
+{
+	memset(s, 0, sizeof(*s));
+	s->normal = normal;
+	s->integral = L->pi_integral0;
+}
+
+/* AGC.peak_detect + the scaling line of AGC.apply -- agc.py:26-37, 72-76 */
+static double agc_step(const orc_loop *L, orc_loop_state *s, double sample)
+{
+	double compare_value = fabs(sample);
+	if (compare_value > s->envelope) {
+		s->envelope += (L->agc_scaled_attack * s->normal);
+		if (s->envelope > compare_value) s->envelope = compare_value;
+		s->sustain_count = 0.0;
+	}
+	if (s->sustain_count >= L->agc_sustain_time) {
+		s->envelope -= (L->agc_scaled_decay * s->normal);
+		if (s->envelope < 0) s->envelope = 0;
+	}
+	s->sustain_count += L->agc_sustain_increment;
+	if (s->envelope != 0) return L->agc_target * sample / s->envelope;
+	return sample;
+}
+
+/* NCO.update -- nco.py:34-53 */
+static void nco_step(const orc_loop *L, orc_loop_state *s)
+{
+	s->phase += (L->nco_phase_scale * (L->nco_set_frequency + s->control));
+	while (s->phase >= L->nco_two_pi) s->phase = s->phase - L->nco_two_pi;
+	while (s->phase < 0) s->phase = s->phase + L->nco_two_pi;
+	int64_t sine_index = (int64_t)(s->phase * L->nco_index_scale);
+	if (sine_index < L->nco_size) s->sine = L->nco_wavetable[sine_index];   /* IndexError keeps the old value :41-45 */
+	int64_t cosine_index = (int64_t)((double)sine_index + L->nco_quarter);
+	while (cosine_index >= L->nco_size) cosine_index -= L->nco_size;
+	while (cosine_index < 0) cosine_index += L->nco_size;
+	s->cosine = L->nco_wavetable[cosine_index];
+}
+
+/* IIR_1.update -- iir.py:38-54 (order 1) */
+static double iir_step(const orc_loop *L, orc_loop_state *s, double sample)
+{
+	double v = 0;
+	v += (sample * L->iir_b0);
+	v += (s->x1 * L->iir_b1);
+	v += (s->y1 * L->iir_a1);
+	s->x1 = sample;
+	s->y1 = v;
+	return v;
+}
+
+/* PI_control.update_saturate -- pi_control.py:25-33 */
+static double pi_step(const orc_loop *L, orc_loop_state *s, double sample)
+{
+	s->proportional = L->pi_gain * L->pi_p * sample;
+	s->integral += L->pi_gain * (L->pi_i * sample);
+	if (s->integral > L->pi_limit) s->integral = L->pi_limit;
+	if (s->integral < -L->pi_limit) s->integral = -L->pi_limit;
+	return s->proportional + s->integral;
+}
+
+/* max(buffer) -- agc.py:67 (python max over a float64 ndarray: first maximal element, NaN-free input) */
+ORC_API double orc_buffer_max(const double *x, int64_t n)
+{
+	double m = x[0];
+	for (int64_t i = 1; i < n; i++) if (x[i] > m) m = x[i];
+	return m;
+}
+
+/* AGC.apply -- agc.py:61-80, in place */
+ORC_API void orc_agc_apply(const orc_loop *L, double *x, int64_t n)
+{
+	orc_loop_state s;
+	if (n <= 0) return;
+	loop_state_init(L, &s, orc_buffer_max(x, n));
+	for (int64_t i = 0; i < n; i++) x[i] = agc_step(L, &s, x[i]);
+}
+
+/* BPSKModem.demod, the Costas loop -- psk.py:170-189; x is the AGC'd buffer; out = i_mixer */
+ORC_API void orc_bpsk_loop(const orc_loop *L, const double *x, int64_t n, double *out)
+{
+	orc_loop_state s;
+	loop_state_init(L, &s, 0.0);
+	for (int64_t k = 0; k < n; k++) {
+		double sample = x[k];
+		nco_step(L, &s);
+		double i_mixer = sample * s.cosine;                         /* ComplexOutput.real = cosine  nco.py:52 */
+		double q_mixer = sample * (-s.sine);                        /* ComplexOutput.imag = -sine   nco.py:53 */
+		double loop_mixer = i_mixer * q_mixer;
+		double f = iir_step(L, &s, loop_mixer);
+		s.control = pi_step(L, &s, f);
+		out[k] = i_mixer;
+	}
+}
+
+/* AFSKPLLModem.demod, the PLL -- afsk_pll.py:152-165; out = PI proportional term */
+ORC_API void orc_pll_loop(const orc_loop *L, const double *x, int64_t n, double *out)
+{
+	orc_loop_state s;
+	loop_state_init(L, &s, 0.0);
+	for (int64_t k = 0; k < n; k++) {
+		nco_step(L, &s);
+		double mixer = x[k] * s.sine;
+		double f = iir_step(L, &s, mixer);
+		s.control = pi_step(L, &s, f);
+		out[k] = s.proportional;
+	}
+}
+
+/* PhaseDetector.get_qpsk_angle_error -- phase_detector.py:124-149 */
+static int32_t pd_qpsk_error(const orc_loop *L, double re, double im)
+{
+	const int64_t g = L->pd_granularity;
+	double fr = floor(re * (double)g * 0.5), fi = floor(im * (double)g * 0.5);
+	if (fr > 1e9) fr = 1e9;
+	if (fr < -1e9) fr = -1e9;
+	if (fi > 1e9) fi = 1e9;
+	if (fi < -1e9) fi = -1e9;
+	int64_t real = (int64_t)fr, imag = (int64_t)fi;
+	if (real >= g) real = g - 1;
+	if (imag >= g) imag = g - 1;
+	if (real <= -g) real = -(g - 1);
+	if (imag <= -g) imag = -(g - 1);
+	if (real >= 0) {
+		if (imag >= 0) return L->pd_table[real * g + imag];
+		return L->pd_table[(-imag) * g + real];
+	}
+	if (imag >= 0) return L->pd_table[imag * g + (-real)];
+	return L->pd_table[(-real) * g + (-imag)];
+}
+
+/* MPSKModem.demod, the decision-directed loop -- psk.py:733-746; outputs the rotated I/Q samples */
+ORC_API void orc_mpsk_loop(const orc_loop *L, const double *re, const double *im, int64_t n,
+                           double *out_i, double *out_q)
+{
+	orc_loop_state s;
+	loop_state_init(L, &s, 0.0);
+	for (int64_t k = 0; k < n; k++) {
+		nco_step(L, &s);
+		const double c_re = s.cosine, c_im = -s.sine;
+		/* ComplexNumber.multiply -- complexmath.py:15-19 */
+		double real = (re[k] * c_re) - (im[k] * c_im);
+		double imag = (c_re * im[k]) + (re[k] * c_im);
+		double f = iir_step(L, &s, (double)pd_qpsk_error(L, real, imag));
+		s.control = nearbyint(pi_step(L, &s, f));                   /* python round(): half to even */
+		out_i[k] = real;
+		out_q[k] = imag;
+	}
+}

@@ -61,6 +61,18 @@ class _Lfsr(ctypes.Structure):
 	]
 
 
+class _Loop(ctypes.Structure):
+	"""orc_loop"""
+	_fields_ = [(n, ctypes.c_double) for n in (
+		"agc_scaled_attack", "agc_scaled_decay", "agc_sustain_time", "agc_sustain_increment", "agc_target",
+		"nco_phase_scale", "nco_index_scale", "nco_set_frequency", "nco_two_pi", "nco_quarter")] + [
+		("nco_wavetable", ctypes.c_void_p), ("nco_size", ctypes.c_int64),
+		("iir_b0", ctypes.c_double), ("iir_b1", ctypes.c_double), ("iir_a1", ctypes.c_double),
+		("pi_gain", ctypes.c_double), ("pi_p", ctypes.c_double), ("pi_i", ctypes.c_double),
+		("pi_limit", ctypes.c_double), ("pi_integral0", ctypes.c_double),
+		("pd_table", ctypes.c_void_p), ("pd_granularity", ctypes.c_int64)]
+
+
 def lib():
 	global _lib
 	if _lib is None:
@@ -101,6 +113,13 @@ def lib():
 		L.orc_il2p_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
 			ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
 			ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+		L.orc_buffer_max.restype = ctypes.c_double
+		L.orc_buffer_max.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+		L.orc_agc_apply.argtypes = [P(_Loop), ctypes.c_void_p, ctypes.c_int64]
+		L.orc_bpsk_loop.argtypes = [P(_Loop), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+		L.orc_pll_loop.argtypes = [P(_Loop), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+		L.orc_mpsk_loop.argtypes = [P(_Loop), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+			ctypes.c_void_p, ctypes.c_void_p]
 		_lib = L
 	return _lib
 
@@ -238,6 +257,227 @@ def rrc_taps(sample_rate, symbol_rate, symbol_span, rolloff_rate):
 			taps.append(numerator / (denominator * symbol_time))
 	taps = taps / np.linalg.norm(taps)
 	return np.multiply(taps, [1] * len(taps))
+
+
+# ----------------------------------------------------------------------------
+# PSK / PLL modems: FIRs in NumPy, AGC and the carrier loops in C
+# ----------------------------------------------------------------------------
+def _loop_desc(sample_rate, agc, carrier_freq, iir_cutoff, iir_gain, pi_p, pi_i, pi_limit, pi_gain,
+		integral0=0.0, with_pd=False, keep=None):
+	"""Constants of agc.py:8-24, nco.py:14-32, iir.py:15-29, pi_control.py:8-13, phase_detector.py:12-45
+	computed with the reference's own expressions (math.sin / math.tan / atan2 of the host libm)."""
+	from math import atan2, pi, sin, sqrt, tan
+	L = _Loop()
+	attack_rate, sustain_time, decay_rate, target = agc
+	L.agc_scaled_attack = attack_rate / sample_rate
+	L.agc_scaled_decay = decay_rate / sample_rate
+	L.agc_sustain_time = sustain_time
+	L.agc_sustain_increment = 1 / sample_rate
+	L.agc_target = target
+	size = 256
+	amplitude = 1.0
+	wavetable = np.array([amplitude * sin(i * 2.0 * pi / size) for i in range(size)], dtype=np.float64)
+	keep.append(wavetable)
+	L.nco_wavetable = wavetable.ctypes.data
+	L.nco_size = size
+	L.nco_index_scale = size / (2.0 * pi)
+	L.nco_phase_scale = 2.0 * pi / sample_rate
+	L.nco_set_frequency = carrier_freq
+	L.nco_two_pi = 2.0 * pi
+	L.nco_quarter = size / 4.0
+	radian_cutoff = 2.0 * pi * iir_cutoff                       # iir.py:15-26
+	warp_cutoff = 2.0 * sample_rate * tan(radian_cutoff / (2.0 * sample_rate))
+	omega_T = warp_cutoff / sample_rate
+	a1 = (2.0 - omega_T) / (2.0 + omega_T)
+	b0 = omega_T / (2.0 + omega_T)
+	L.iir_b0, L.iir_b1, L.iir_a1 = iir_gain * b0, iir_gain * b0, a1
+	L.pi_gain, L.pi_p, L.pi_i, L.pi_limit, L.pi_integral0 = pi_gain, pi_p, pi_i, pi_limit, integral0
+	if with_pd:                                                 # phase_detector.py:12-45 ('qpsk', 64, 32)
+		g, gain = 64, 32
+		min_mag, max_mag = g * .15, g * .76
+		table = np.zeros((g, g), dtype=np.int32)
+		for real in range(g):
+			for imag in range(g):
+				mag = sqrt((real**2) + (imag**2))
+				if mag >= min_mag and mag <= max_mag:
+					table[real, imag] = round(gain * ((atan2(imag, real) * 180 / pi) - 45))
+		keep.append(table)
+		L.pd_table = table.ctypes.data
+		L.pd_granularity = g
+	return L
+
+
+def hilbert_taps(tap_count):
+	"""hilbert.py:9-34 (hann window) -> (taps, delay)"""
+	from math import pi, sin
+	delay = tap_count // 2
+	taps = []
+	for n in range(-delay, -delay + tap_count):
+		taps.append(2 / (pi * n) if n % 2 else 0)
+	N = tap_count - 1
+	return np.array([taps[i] * sin(pi * i / N)**2 for i in range(tap_count)], dtype=np.float64), delay
+
+
+class BPSKModem:
+	"""psk.py:20-195"""
+
+	def __init__(self, sample_rate, config, options):
+		if config == '1200':                        # psk.py:56-88
+			p = dict(symbol_rate=1200.0, input_bpf_low_cutoff=200.0, input_bpf_high_cutoff=2800.0, input_bpf_span=4.80,
+				carrier_freq=1500.0)
+			self.max_freq_offset, self.rrc_rolloff_rate, self.rrc_span = 50 * 1.25, 0.9, 6
+			self.iir_cutoff, pi_p, self.pi_gain = 250.0, 0.4, 1800
+		else:                                       # '300', psk.py:26-55
+			p = dict(symbol_rate=300.0, input_bpf_low_cutoff=1200.0, input_bpf_high_cutoff=1800.0, input_bpf_span=1.5,
+				carrier_freq=1500.0)
+			self.max_freq_offset, self.rrc_rolloff_rate, self.rrc_span = 25 * 1.25, 0.6, 6
+			self.iir_cutoff, pi_p, self.pi_gain = 250.0, 0.06, 7200
+		self.pi_p, self.pi_i = pi_p, pi_p / 1000
+		p['sample_rate'] = sample_rate
+		for key in list(p):                         # psk.py:102-109
+			p[key] = float(options.get(key, p[key]))
+		self.__dict__.update(p)
+		self.tune()
+
+	def tune(self):                                 # psk.py:111-160
+		self.input_bpf_tap_count = round(self.sample_rate * self.input_bpf_span / self.symbol_rate)
+		self.input_bpf = firwin(self.input_bpf_tap_count, [self.input_bpf_low_cutoff, self.input_bpf_high_cutoff],
+			pass_zero='bandpass', fs=self.sample_rate, scale=True)
+		self.rrc = rrc_taps(self.sample_rate, self.symbol_rate, self.rrc_span, self.rrc_rolloff_rate)
+		self._keep = []
+		self.loop = _loop_desc(self.sample_rate, (500.0, 1.0, 50.0, 1.0), self.carrier_freq, self.iir_cutoff, 1.0,
+			self.pi_p, self.pi_i, self.max_freq_offset, self.pi_gain, keep=self._keep)
+		self.output_sample_rate = self.sample_rate
+
+	def demod(self, input_audio):                   # psk.py:162-195
+		audio = np.ascontiguousarray(np.convolve(input_audio, self.input_bpf, 'valid'), dtype=np.float64)
+		lib().orc_agc_apply(ctypes.byref(self.loop), _ptr(audio), len(audio))
+		demod_audio = np.empty_like(audio)
+		lib().orc_bpsk_loop(ctypes.byref(self.loop), _ptr(audio), len(audio), _ptr(demod_audio))
+		self.loop_input = audio
+		self.loop_out = demod_audio
+		return np.convolve(demod_audio, self.rrc, 'valid')
+
+
+class AFSKPLLModem:
+	"""afsk_pll.py:16-170"""
+
+	def __init__(self, sample_rate, config, options):
+		p = dict(symbol_rate=300.0, input_bpf_low_cutoff=1500.0, input_bpf_high_cutoff=1900.0, input_bpf_span=7.0,
+			output_lpf_cutoff=240.0, output_lpf_span=5, carrier_freq=1700.0)     # afsk_pll.py:22-50
+		p['sample_rate'] = sample_rate
+		for key in list(p):                         # afsk_pll.py:70-79
+			p[key] = float(options.get(key, p[key]))
+		self.__dict__.update(p)
+		self.tune()
+
+	def tune(self):                                 # afsk_pll.py:81-138
+		self.input_bpf_tap_count = round(self.sample_rate * self.input_bpf_span / self.symbol_rate)
+		self.output_lpf_tap_count = round(self.sample_rate * self.output_lpf_span / self.symbol_rate)
+		self.input_bpf = firwin(self.input_bpf_tap_count, [self.input_bpf_low_cutoff, self.input_bpf_high_cutoff],
+			pass_zero='bandpass', fs=self.sample_rate, scale=True)
+		self.output_lpf = firwin(self.output_lpf_tap_count, self.output_lpf_cutoff, fs=self.sample_rate, scale=True)
+		self._keep = []
+		pi_p = 0.6
+		self.loop = _loop_desc(self.sample_rate, (500.0, 1.0, 50.0, 1.0), self.carrier_freq, 150.0, 1.0,
+			pi_p, pi_p / 6000, 50, 900, keep=self._keep)
+		self.output_sample_rate = self.sample_rate
+
+	def demod(self, input_audio):                   # afsk_pll.py:140-170
+		audio = np.ascontiguousarray(np.convolve(input_audio, self.input_bpf, 'valid'), dtype=np.float64)
+		lib().orc_agc_apply(ctypes.byref(self.loop), _ptr(audio), len(audio))
+		demod_audio = np.empty_like(audio)
+		lib().orc_pll_loop(ctypes.byref(self.loop), _ptr(audio), len(audio), _ptr(demod_audio))
+		self.loop_input = audio
+		self.loop_out = demod_audio
+		return np.convolve(demod_audio, self.output_lpf, 'valid')
+
+
+class MPSKModem:
+	"""psk.py:479-773; demod() returns (i_data, q_data)"""
+	# config -> (agc attack, sustain, symbol_rate, bpf low, high, bpf span ms, hilbert span ms, carrier,
+	#            max_freq_offset, rrc rolloff, iir cutoff, pi_p, pi_i divisor, pi gain)   psk.py:485-629
+	_PRESETS = {
+		'qpsk_3600': (5000.0, 0.1, 1800, 300.0, 3000.0, 2, 4.5, 1650.0, 12.5 * 1.25, 0.3, 250.0, 0.15, 1000, (14400 / 65536)),
+		'qpsk_600': (500.0, 1, 300, 1200.0, 1800.0, 4, 3.4, 1500.0, 25, 0.6, 150, 0.1, 1000, (7200 / 65536)),
+		'qpsk_2400': (500.0, 1, 1200, 200.0, 2800.0, 2.7, 3.4, 1500.0, 25 * 1.25, 0.9, 250.0, 0.3, 2000, (14400 / 65536)),
+		'bpsk_300': (500.0, 1, 300, 1200.0, 1800.0, 2.7, 2.7, 1500.0, 50, 0.6, 250.0, 0.15, 1000, 1.5 * (500)),
+		'bpsk_1200': (500.0, 1, 1200, 200.0, 2800.0, 4.8, 2, 1500.0, 87.5, 0.9, 200.0, 0.15, 1000, 5),
+	}
+
+	def __init__(self, sample_rate, config, options):
+		(self.agc_attack_rate, self.agc_sustain_time, symbol_rate, self.input_bpf_low_cutoff, self.input_bpf_high_cutoff,
+			self.input_bpf_span, self.hilbert_span, carrier_freq, self.max_freq_offset, self.rrc_rolloff_rate,
+			self.iir_cutoff, self.pi_p, pi_div, self.pi_gain) = self._PRESETS[config]
+		self.pi_i = self.pi_p / pi_div
+		self.rrc_span = 6
+		# psk.py:634-638
+		self.symbol_rate = float(options.get('symbol_rate', symbol_rate))
+		self.sample_rate = float(options.get('sample_rate', sample_rate))
+		self.carrier_freq = float(options.get('carrier_freq', carrier_freq))
+		self.tune()
+
+	def tune(self):                                 # psk.py:640-703
+		self.input_bpf_tap_count = round(self.sample_rate * self.input_bpf_span / 1000)
+		self.hilbert_tap_count = round(self.sample_rate * self.hilbert_span / 1000)
+		self.input_bpf = firwin(self.input_bpf_tap_count, [self.input_bpf_low_cutoff, self.input_bpf_high_cutoff],
+			pass_zero='bandpass', fs=self.sample_rate, scale=True)
+		if self.hilbert_tap_count % 2 == 0:
+			self.hilbert_tap_count += 1
+		self.hilbert, self.hilbert_delay = hilbert_taps(self.hilbert_tap_count)
+		self.rrc = rrc_taps(self.sample_rate, self.symbol_rate, self.rrc_span, self.rrc_rolloff_rate)
+		self._keep = []
+		self.loop = _loop_desc(self.sample_rate, (self.agc_attack_rate, self.agc_sustain_time, 50.0, 1.0), self.carrier_freq,
+			self.iir_cutoff, 1.0, self.pi_p, self.pi_i, self.max_freq_offset, self.pi_gain,
+			integral0=-self.max_freq_offset, with_pd=True, keep=self._keep)      # psk.py:703
+		self.output_sample_rate = self.sample_rate
+
+	def demod(self, input_audio):                   # psk.py:705-773
+		audio = np.ascontiguousarray(np.convolve(input_audio, self.input_bpf, 'valid'), dtype=np.float64)
+		lib().orc_agc_apply(ctypes.byref(self.loop), _ptr(audio), len(audio))
+		imag_audio = np.ascontiguousarray(np.convolve(audio, self.hilbert, 'valid'))
+		delay_taps = [0] * (self.hilbert_delay + 1)
+		delay_taps[0] = 1
+		real_audio = np.convolve(audio, delay_taps, 'valid')
+		real_audio = np.ascontiguousarray(real_audio[:-self.hilbert_delay])
+		n = min(len(real_audio), len(imag_audio))
+		i_data = np.empty(n, dtype=np.float64)
+		q_data = np.empty(n, dtype=np.float64)
+		lib().orc_mpsk_loop(ctypes.byref(self.loop), _ptr(real_audio), _ptr(imag_audio), n, _ptr(i_data), _ptr(q_data))
+		self.loop_out = (i_data, q_data)
+		return np.convolve(i_data, self.rrc, 'valid'), np.convolve(q_data, self.rrc, 'valid')
+
+
+_QPSK_DEMAP = [3, 1, 2, 0, 2, 3, 0, 1, 1, 0, 3, 2, 0, 2, 1, 3]
+_BPSK_DEMAP = [0, 0, 1, 1]
+
+
+class QuadratureSlicer:
+	"""slicer.py:109-242"""
+	_PRESETS = {                                    # slicer.py:124-165
+		'qpsk_600': (0xF, 2, _QPSK_DEMAP, 300, 0.815), 'bpsk_300': (0x3, 1, _BPSK_DEMAP, 300, 0.815),
+		'bpsk_1200': (0x3, 1, _BPSK_DEMAP, 1200, 0.9), 'qpsk_2400': (0xF, 2, _QPSK_DEMAP, 1200, 0.9),
+		'qpsk_4800': (0xF, 2, _QPSK_DEMAP, 2400, 0.99), 'qpsk_3600': (0xF, 2, _QPSK_DEMAP, 1800, 0.99),
+	}
+
+	def __init__(self, sample_rate, config, options):
+		mask, bps, demap, symbol_rate, lock_rate = self._PRESETS.get(config, (0xF, 2, _QPSK_DEMAP, 1200, 0.9))
+		lock_rate = float(options.get('lock_rate', lock_rate))      # slicer.py:176-180
+		self.state = _Slicer()
+		d = (ctypes.c_uint32 * 16)(*demap)
+		lib().orc_qslicer_init(ctypes.byref(self.state), float(sample_rate), float(symbol_rate), lock_rate, mask, bps, d)
+		self.bits_per_symbol = bps
+
+	def slice(self, iq):
+		i_s = np.ascontiguousarray(iq[0], dtype=np.float64)
+		q_s = np.ascontiguousarray(iq[1], dtype=np.float64)
+		n = min(len(i_s), len(q_s))
+		cap = int(n / max(self.state.rollover_threshold, 1.0) * self.bits_per_symbol / 8) + 16
+		out_b = np.empty(cap, dtype=np.uint8)
+		out_a = np.empty(cap, dtype=np.int64)
+		cnt = lib().orc_quadrature_slice(ctypes.byref(self.state), _ptr(i_s), _ptr(q_s), n, _ptr(out_b), _ptr(out_a), cap)
+		assert cnt <= cap
+		return out_b[:cnt], out_a[:cnt]
 
 
 # ----------------------------------------------------------------------------
@@ -415,6 +655,12 @@ class Chain:
 			self.modem = AFSKModem(sample_rate, m['config'], m['options'])
 		elif m['type'] == 'fsk':
 			self.modem = FSKModem(sample_rate, m['config'], m['options'])
+		elif m['type'] == 'bpsk':
+			self.modem = BPSKModem(sample_rate, m['config'], m['options'])
+		elif m['type'] == 'mpsk':
+			self.modem = MPSKModem(sample_rate, m['config'], m['options'])
+		elif m['type'] == 'afsk_pll':
+			self.modem = AFSKPLLModem(sample_rate, m['config'], m['options'])
 		else:
 			raise NotImplementedError(f"oracle modem type {m['type']}")
 		# pymodem.py:86-90: slicer runs at modem.output_sample_rate if it has one
@@ -422,6 +668,8 @@ class Chain:
 		s = line['slicer']
 		if s['type'] == 'binary':
 			self.slicer = BinarySlicer(slicer_rate, s['config'], s['options'])
+		elif s['type'] == 'quadrature':
+			self.slicer = QuadratureSlicer(slicer_rate, s['config'], s['options'])
 		else:
 			raise NotImplementedError(f"oracle slicer type {s['type']}")
 		self.stream = LFSR(line['stream']['options'])

@@ -310,13 +310,39 @@ __device__ __forceinline__ uint32_t flag_word(const uint32_t *__restrict__ d, lo
 	return f;
 }
 
+// IL2P sync word (il2p.py:369-373) ending at each bit of word w, evaluated on the true stream bits
+// (the reference's partially filled shift register after a resume is handled by il2p_resolve_kernel).
+__device__ __forceinline__ uint32_t il2p_sync_word(const uint32_t *__restrict__ d, long long w, long long nb, int tol)
+{
+	const long long rem = nb - (w << 5);
+	if (rem <= 0) return 0;
+	const uint32_t cur = d[w];
+	const uint32_t prev = (w > 0) ? d[w - 1] : 0u;
+	const unsigned long long V = ((unsigned long long)cur << 32) | prev;
+	uint32_t f = 0;
+#pragma unroll
+	for (int i = 0; i < 32; i++) {
+		const uint32_t ww = __brev((uint32_t)(V >> (i + 1)));       // newest bit in bit 0
+		if (__popc((ww & 0xFFFFFFu) ^ 0xF15E48u) <= tol || __popc(ww ^ 0x5D57DF7Fu) <= tol) f |= 1u << i;
+	}
+	if (rem < 32) f &= (1u << (int)rem) - 1u;
+	return f;
+}
+
+__device__ __forceinline__ uint32_t event_word(const BitChain &C, const uint32_t *__restrict__ d, long long w, long long nb)
+{
+	return C.codec == 2 ? il2p_sync_word(d, w, nb, C.il2p_sync_tol) : flag_word(d, w, nb);
+}
+
 #define FL_WORDS 1024
 __global__ void __launch_bounds__(256)
-flag_count_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restrict__ d, long long bits_stride,
+flag_count_kernel(const BitChain *__restrict__ chains, const ChainCounters *__restrict__ cc,
+                  const uint32_t *__restrict__ d, long long bits_stride,
                   unsigned int *__restrict__ block_count, int n_blocks)
 {
 	__shared__ unsigned int s_warp[33];
 	const int ch = blockIdx.y;
+	const BitChain C = chains[ch];
 	const long long nb = cc[ch].nbytes * 8;
 	const uint32_t *src = d + (long long)ch * bits_stride;
 	const long long w0 = (long long)blockIdx.x * FL_WORDS + threadIdx.x * 4;
@@ -324,7 +350,7 @@ flag_count_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restri
 #pragma unroll
 	for (int q = 0; q < 4; q++) {
 		const long long w = w0 + q;
-		if ((w << 5) < nb) cnt += __popc(flag_word(src, w, nb));
+		if ((w << 5) < nb) cnt += __popc(event_word(C, src, w, nb));
 	}
 	unsigned int total;
 	block_excl_scan(cnt, s_warp, total);
@@ -332,12 +358,14 @@ flag_count_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restri
 }
 
 __global__ void __launch_bounds__(256)
-flag_write_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restrict__ d, long long bits_stride,
+flag_write_kernel(const BitChain *__restrict__ chains, const ChainCounters *__restrict__ cc,
+                  const uint32_t *__restrict__ d, long long bits_stride,
                   const unsigned int *__restrict__ block_base, int n_blocks,
                   unsigned int *__restrict__ flag_pos, long long flag_stride)
 {
 	__shared__ unsigned int s_warp[33];
 	const int ch = blockIdx.y;
+	const BitChain C = chains[ch];
 	const long long nb = cc[ch].nbytes * 8;
 	const uint32_t *src = d + (long long)ch * bits_stride;
 	unsigned int *fp = flag_pos + (long long)ch * flag_stride;
@@ -347,7 +375,7 @@ flag_write_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restri
 #pragma unroll
 	for (int q = 0; q < 4; q++) {
 		const long long w = w0 + q;
-		f[q] = ((w << 5) < nb) ? flag_word(src, w, nb) : 0u;
+		f[q] = ((w << 5) < nb) ? event_word(C, src, w, nb) : 0u;
 		cnt += __popc(f[q]);
 	}
 	unsigned int total;
@@ -357,7 +385,8 @@ flag_write_kernel(const ChainCounters *__restrict__ cc, const uint32_t *__restri
 		while (ff) {
 			const int i = __ffs(ff) - 1;
 			ff &= ff - 1;
-			fp[idx++] = (unsigned int)(((w0 + q) << 5) + i);
+			if ((long long)idx < flag_stride) fp[idx] = (unsigned int)(((w0 + q) << 5) + i);
+			idx++;
 		}
 	}
 }
@@ -715,9 +744,9 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 {
 	const int n_blocks = (int)((bits_stride + FL_WORDS - 1) / FL_WORDS);
 	dim3 grid(n_blocks, n_chains);
-	flag_count_kernel<<<grid, 256, 0, st>>>(cc, d, bits_stride, blk_count, n_blocks);
+	flag_count_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_count, n_blocks);
 	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, flag_totals);
-	flag_write_kernel<<<grid, 256, 0, st>>>(cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
+	flag_write_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
 	// gaps: at most flag_stride per chain
 	dim3 ggrid((unsigned int)((flag_stride + 127) / 128), n_chains);
 	ax25_gap_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals,

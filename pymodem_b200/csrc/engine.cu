@@ -39,6 +39,10 @@ cudaError_t pm_launch_lfsr(const BitChain *, int, const ChainCounters *, const u
 cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_t *, long long, unsigned int *,
 	unsigned int *, unsigned int *, unsigned int *, long long, const uint32_t *, long long, uint8_t *, long long,
 	GapRec *, long long, const ShardBits *, int, cudaStream_t);
+cudaError_t pm_il2p_init_tables(void);
+cudaError_t pm_launch_il2p(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const unsigned int *,
+	long long, const unsigned int *, int, unsigned char *, long long, Il2pRes *, const uint32_t *, long long,
+	uint8_t *, long long, GapRec *, long long, cudaStream_t);
 cudaError_t pm_launch_packets(int, ChainCounters *, const GapRec *, long long,
 	pm_packet_rec *, unsigned int *, unsigned long long, PacketTotals *, const uint8_t *, long long, uint8_t *,
 	unsigned long long, long long, cudaStream_t);
@@ -129,6 +133,10 @@ struct pm_engine {
 	DevBuf<GapRec> d_gaps;
 	DevBuf<pm_packet_rec> d_recs;
 	DevBuf<PacketTotals> d_totals;
+	DevBuf<unsigned char> d_il2p_slots;   // speculative IL2P decodes: (cand_cap + 1) slots per chain
+	DevBuf<Il2pRes> d_il2p_res;
+	int il2p_cand_cap = 0;
+	bool has_il2p = false, il2p_tables = false;
 	unsigned int *h_counters = nullptr;   // pinned
 	PacketTotals *h_totals = nullptr;     // pinned
 	// geometry of the last run
@@ -396,6 +404,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
 	e->d_arena.release(); e->d_gaps.release(); e->d_recs.release(); e->d_totals.release();
+	e->d_il2p_slots.release(); e->d_il2p_res.release();
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
 	if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -443,8 +452,10 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 		}
 		if (d.slicer_kind != PM_SLICER_BINARY)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: slicer kind %d not supported by this build", c, d.slicer_kind);
-		if (d.codec_kind != PM_CODEC_AX25)
+		if (d.codec_kind != PM_CODEC_AX25 && d.codec_kind != PM_CODEC_IL2P)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: codec kind %d not supported by this build", c, d.codec_kind);
+		if (d.codec_kind == PM_CODEC_IL2P && (d.il2p_sync_tol < 0 || d.il2p_sync_tol > 8))
+			return fail(e, PM_ERR_ARG, "chain %d: il2p sync_tol must be 0..8", c);
 		if (!(d.symbol_rate > 0) || !(d.slicer_sample_rate / d.symbol_rate >= 3.0))
 			return fail(e, PM_ERR_ARG, "chain %d: needs >= 3 samples per symbol", c);
 		// pointers in the copy are not valid after this call
@@ -452,6 +463,12 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 		hc.d.space_unit_i = hc.d.space_unit_q = hc.d.lpf = nullptr;
 		hc.d.loop = nullptr;
 		e->chains.push_back(std::move(hc));
+	}
+	e->has_il2p = false;
+	for (auto &hc : e->chains) if (hc.d.codec_kind == PM_CODEC_IL2P) e->has_il2p = true;
+	if (e->has_il2p && !e->il2p_tables) {
+		CK(pm_il2p_init_tables());
+		e->il2p_tables = true;
 	}
 	int rc = build_groups(e);
 	if (rc != PM_OK) return rc;
@@ -568,6 +585,10 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		memset(&b, 0, sizeof(b));
 		b.nout = nout; b.sign_row = c; b.bps = 1; b.lfsr_poly = hc.d.lfsr_poly; b.lfsr_invert = hc.d.lfsr_invert;
 		b.codec = hc.d.codec_kind;
+		b.il2p_crc = hc.d.il2p_crc; b.il2p_disable_rs = hc.d.il2p_disable_rs;
+		b.il2p_min_dist = hc.d.il2p_min_dist; b.il2p_sync_tol = hc.d.il2p_sync_tol;
+		if (sharded && hc.d.codec_kind == PM_CODEC_IL2P)
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: IL2P chains cannot be sharded on the sample axis yet", c);
 		e->h_init[c].clock = 0.0; e->h_init[c].last = 1; e->h_init[c].last_q = 1;    // slicer.py:50,55
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
 		const long long mb = nout / min_gap + 64 + plan.tail_bits;
@@ -619,6 +640,11 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	CK(e->d_rec_src.ensure((size_t)rec_cap));
 	CK(e->d_arena.ensure((size_t)arena_cap));
 	CK(e->d_guard_entries.ensure(e->guard_cap));
+	if (e->has_il2p) {
+		e->il2p_cand_cap = (int)std::min<long long>(e->flag_stride, max_bits / 256 + 64);
+		CK(e->d_il2p_slots.ensure((size_t)nc * (e->il2p_cand_cap + 1) * IL2P_SLOT));
+		CK(e->d_il2p_res.ensure((size_t)nc * e->il2p_cand_cap));
+	}
 	if (e->opt_keep_soft) {
 		e->soft_stride = n;
 		CK(e->d_soft.ensure((size_t)nc * n));
@@ -915,6 +941,14 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->sharded ? 0 : 1, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "ax25 launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches += e->sharded ? 4 : 5;
+	if (e->has_il2p) {
+		ce = pm_launch_il2p(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_flag_pos.p,
+			e->flag_stride, e->d_flag_totals.p, e->il2p_cand_cap, e->d_il2p_slots.p,
+			(long long)(e->il2p_cand_cap + 1) * IL2P_SLOT, e->d_il2p_res.p, e->d_byte_addr.p, e->addr_stride,
+			e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "il2p launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches += 2;
+	}
 	ce = pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p,
 		e->d_recs.n, e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base,
 		e->st);
@@ -931,6 +965,8 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 		if (e->h_cc[c].tail_short)
 			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
 				c, plan.tail_bits);
+		if (e->h_cc[c].seq_needed == 2)
+			return fail(e, PM_ERR_CAPACITY, "chain %d: IL2P sync candidates overflowed the candidate list", c);
 		if (e->sharded && e->h_cc[c].seq_needed)
 			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (run unsharded)", c);
 	}

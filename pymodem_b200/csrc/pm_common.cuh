@@ -123,6 +123,19 @@ struct BitChain {
 	unsigned long long lfsr_poly;
 	int lfsr_invert;
 	int codec;                 // PM_CODEC_*
+	int il2p_crc, il2p_disable_rs, il2p_min_dist, il2p_sync_tol;   // il2p.py:140-145
+};
+
+#define IL2P_SLOT 1056         // bytes per speculative IL2P decode (15-byte AX.25 header + PID, 1023 payload, FCS)
+#define IL2P_FAIL 0u
+#define IL2P_OK 1u
+#define IL2P_INCOMPLETE 2u
+struct Il2pRes {
+	long long end_bit;         // last stream bit the frame consumed (search resumes at end_bit + 1)
+	unsigned int status;
+	unsigned int len;          // bytes of the emitted packet (status OK)
+	unsigned int corrected;    // RS corrections of this frame (of the blocks decoded so far when it failed)
+	unsigned int pad;
 };
 
 struct ChainCounters {

@@ -1,7 +1,7 @@
 """String-typed factories for the four block kinds -- same names, arguments and
 behaviour as reference modems_codecs/chain_builder.py:17-69 (an unknown or
 missing 'type' yields [], as there)."""
-from . import afsk, ax25, fsk, lfsr, slicer
+from . import afsk, ax25, fsk, il2p, lfsr, slicer
 
 
 def ModemConfigurator(arg_sample_rate, input_args):
@@ -41,7 +41,8 @@ def CodecConfigurator(input_args, name):
 	new_object = []
 	kind = input_args['type'].lower()
 	if kind == 'il2p':
-		raise NotImplementedError("il2p codec has no GPU path in this build")
+		new_object = il2p.IL2PCodec(ident=name)
+		new_object.StringOptionsRetune(input_args['options'])
 	elif kind == 'ax25':
 		new_object = ax25.AX25Codec(ident=name)
 	return new_object

@@ -338,8 +338,8 @@ def afsk1200_il2p(duration_s, sample_rate=48000, frame_interval_s=1.0, amplitude
 
 
 def fsk9600_il2p(duration_s, sample_rate=48000, frame_interval_s=0.25, amplitude=0.5, noise_start=0.0,
-		noise_end=0.7, seed=0, noise_seed=1, baud=9600.0, first_frame_s=0.05, payload_len=None):
-	"""IL2P+CRC frames as a two-level baseband waveform (bit 1 = positive), idle = 0x55 pattern."""
+		noise_end=0.7, seed=0, noise_seed=1, baud=9600.0, first_frame_s=0.05, payload_len=None, trailing_crc=True):
+	"""IL2P(+CRC) frames as a two-level baseband waveform (bit 1 = positive), idle = 0x55 pattern."""
 	rng = np.random.default_rng(seed)
 	n = int(round(duration_s * sample_rate))
 	sps = sample_rate / baud
@@ -350,7 +350,7 @@ def fsk9600_il2p(duration_s, sample_rate=48000, frame_interval_s=0.25, amplitude
 	while True:
 		b0 = int(round(t * baud))
 		plen = payload_len[k % len(payload_len)] if isinstance(payload_len, (list, tuple)) else payload_len
-		air, ax = il2p_frame("MODEM", "NOISE", _il2p_payloads(k, rng, plen))
+		air, ax = il2p_frame("MODEM", "NOISE", _il2p_payloads(k, rng, plen), trailing_crc=trailing_crc)
 		fb = il2p_bits(air, preamble_bytes=4, postamble_bytes=1)
 		if b0 + len(fb) + 64 >= nbits:
 			break
@@ -362,6 +362,108 @@ def fsk9600_il2p(duration_s, sample_rate=48000, frame_interval_s=0.25, amplitude
 	idx = np.minimum((np.arange(n) / sps).astype(np.int64), nbits - 1)
 	sig = bits[idx].astype(np.float32) * 2.0 - 1.0
 	sig = np.convolve(sig, np.array([0.25, 0.5, 0.25], dtype=np.float32), 'same').astype(np.float32)
+	return _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed), frames, starts
+
+
+def _rrc_pulse(t, T, beta):
+	"""Root-raised-cosine pulse h(t) (unit symbol energy), evaluated at arbitrary times."""
+	t = np.asarray(t, dtype=np.float64)
+	out = np.empty_like(t)
+	x = t / T
+	sing0 = np.abs(x) < 1e-9
+	sing1 = np.abs(np.abs(4 * beta * x) - 1.0) < 1e-9
+	reg = ~(sing0 | sing1)
+	xr = x[reg]
+	out[reg] = (np.sin(np.pi * xr * (1 - beta)) + 4 * beta * xr * np.cos(np.pi * xr * (1 + beta))) \
+		/ (np.pi * xr * (1 - (4 * beta * xr) ** 2))
+	out[sing0] = 1 - beta + 4 * beta / np.pi
+	out[sing1] = beta / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * beta)) + (1 - 2 / np.pi) * np.cos(np.pi / (4 * beta)))
+	return out
+
+
+def _shape_symbols(symbols, n, sample_rate, baud, beta, span=6):
+	"""sum_k a_k h(t - kT) sampled at n/sample_rate (any samples-per-symbol ratio); symbols may be complex."""
+	T = 1.0 / baud
+	sps = sample_rate / baud
+	half = int(np.ceil(span * sps / 2)) + 1
+	sig = np.zeros(n + 2 * half + 2, dtype=np.complex128 if np.iscomplexobj(symbols) else np.float64)
+	offs = np.arange(-half, half + 1)
+	K = len(symbols)
+	for k0 in range(0, K, 4096):
+		ks = np.arange(k0, min(K, k0 + 4096))
+		centre = np.rint(ks * sps).astype(np.int64)
+		idx = centre[:, None] + offs[None, :]
+		tt = idx / sample_rate - (ks * T)[:, None]
+		contrib = symbols[ks][:, None] * _rrc_pulse(tt, T, beta)
+		ok = (idx >= 0) & (idx < n)
+		np.add.at(sig, idx[ok], contrib[ok])
+	return sig[:n]
+
+
+def _psk_il2p_bits(duration_s, baud_bits, frame_interval_s, first_frame_s, payload_len, rng):
+	"""The bit stream of a whole recording: 0x55 idle with IL2P+CRC frames dropped in."""
+	nbits = int(duration_s * baud_bits)
+	bits = np.tile(np.array([0, 1], dtype=np.uint8), nbits // 2 + 1)[:nbits]
+	frames, starts = [], []
+	t, k = first_frame_s, 0
+	while True:
+		b0 = int(round(t * baud_bits)) & ~7
+		plen = payload_len[k % len(payload_len)] if isinstance(payload_len, (list, tuple)) else payload_len
+		air, ax = il2p_frame("MODEM", "NOISE", _il2p_payloads(k, rng, plen))
+		fb = il2p_bits(air, preamble_bytes=8, postamble_bytes=2)
+		if b0 + len(fb) + 64 >= nbits:
+			break
+		bits[b0:b0 + len(fb)] = fb
+		frames.append(ax)
+		starts.append(b0)
+		k += 1
+		t += max(frame_interval_s, len(fb) / baud_bits + 0.05)
+	return bits, frames, starts
+
+
+def bpsk300_il2p(duration_s, sample_rate=8000, frame_interval_s=3.0, amplitude=0.5, noise_start=0.0,
+		noise_end=0.6, seed=0, noise_seed=1, carrier=1500.0, baud=300.0, rolloff=0.6, first_frame_s=1.5,
+		payload_len=None, carrier_phase=0.7):
+	"""Differentially encoded BPSK (a 1 keeps the phase, a 0 flips it: the receive side is
+	configs/bpsk_300.json's LFSR poly 0x3 + invert), RRC shaped, on a carrier that may be offset from
+	the nominal 1500 Hz.  Returns (audio, [reconstructed AX.25 frames], [frame start bit])."""
+	rng = np.random.default_rng(seed)
+	n = int(round(duration_s * sample_rate))
+	bits, frames, starts = _psk_il2p_bits(duration_s, baud, frame_interval_s, first_frame_s, payload_len, rng)
+	level = np.cumsum(1 - bits.astype(np.int64)) & 1          # in[n] = in[n-1] ^ (1 - d)
+	base = _shape_symbols(level * 2.0 - 1.0, n, sample_rate, baud, rolloff)
+	base /= max(np.max(np.abs(base)), 1e-12)
+	tt = np.arange(n) / sample_rate
+	sig = (base * np.cos(2.0 * np.pi * carrier * tt + carrier_phase)).astype(np.float32)
+	return _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed), frames, starts
+
+
+_QPSK_DEMAP = [3, 1, 2, 0, 2, 3, 0, 1, 1, 0, 3, 2, 0, 2, 1, 3]      # reference slicer.py:142-147
+
+
+def qpsk2400_il2p(duration_s, sample_rate=8000, frame_interval_s=1.0, amplitude=0.5, noise_start=0.0,
+		noise_end=0.5, seed=0, noise_seed=1, carrier=1500.0, baud=1200.0, rolloff=0.9, first_frame_s=1.5,
+		payload_len=None, carrier_phase=0.4):
+	"""Differential QPSK, 2 bits per symbol: each dibit picks the next quadrant so that the reference's
+	QuadratureSlicer demap table (indexed by previous and current I/Q signs) returns it."""
+	rng = np.random.default_rng(seed)
+	n = int(round(duration_s * sample_rate))
+	bits, frames, starts = _psk_il2p_bits(duration_s, 2 * baud, frame_interval_s, first_frame_s, payload_len, rng)
+	dibits = (bits[0::2][:len(bits) // 2] << 1) | bits[1::2][:len(bits) // 2]
+	nxt = np.zeros((4, 4), dtype=np.int64)
+	for prev in range(4):
+		for cur in range(4):
+			nxt[prev, _QPSK_DEMAP[prev * 4 + cur]] = cur
+	quad = np.empty(len(dibits), dtype=np.int64)
+	q = 0
+	for i, d in enumerate(dibits):
+		q = nxt[q, d]
+		quad[i] = q
+	sym = (np.where(quad & 2, 1.0, -1.0) + 1j * np.where(quad & 1, 1.0, -1.0))
+	base = _shape_symbols(sym, n, sample_rate, baud, rolloff)
+	base /= max(np.max(np.abs(base)), 1e-12)
+	tt = np.arange(n) / sample_rate
+	sig = np.real(base * np.exp(1j * (2.0 * np.pi * carrier * tt + carrier_phase))).astype(np.float32)
 	return _add_noise_and_quantise(sig, amplitude, noise_start, noise_end, noise_seed), frames, starts
 
 

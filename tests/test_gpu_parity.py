@@ -10,7 +10,8 @@ from util import Golden, as_tuples
 pytestmark = pytest.mark.gpu
 
 SOFT_RTOL = 1e-5          # BASELINE.json north_star: "within a stated relative tolerance (e.g. 1e-5)"
-CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k"]
+CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
+	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k"]
 
 
 def build_stack(sample_rate, lines):
@@ -248,3 +249,28 @@ def test_modem_demod_api(cuda_lib, oracle):
 	want = oracle.Chain(g.sample_rate, line).modem.demod(audio)
 	assert got.dtype == np.float64 and got.shape == want.shape
 	assert np.max(np.abs(got - want)) <= SOFT_RTOL * np.sqrt(np.mean(want ** 2))
+
+
+@pytest.mark.parametrize("sync_tol,disable_rs,crc", [(2, "no", "yes"), (0, "no", "no"), (4, "yes", "yes"), (1, "no", "yes")])
+def test_il2p_options_and_noise_match_oracle(cuda_lib, oracle, sync_tol, disable_rs, crc):
+	"""IL2P over heavy noise: false syncs (tolerance up to 4 bits), failed headers and blocks, corrected-byte
+	counts leaking from failed frames into the next emitted one (il2p.py:200-211), header-only and
+	multi-block frames, with and without the trailing CRC / RS."""
+	import json
+	from pymodem_b200 import synth
+	audio = synth.fsk9600_il2p(duration_s=6.0, sample_rate=48000, frame_interval_s=0.12, noise_start=0.35,
+		noise_end=1.1, seed=41 + sync_tol, noise_seed=43, first_frame_s=0.02, payload_len=[None, 500, 3, 0, 239, 240, 1023],
+		trailing_crc=(crc == "yes"))[0]
+	lines = [json.loads(json.dumps(l)) for l in Golden("fsk9600_il2p_48k").chain_lines()[:2]]
+	for l in lines:
+		l["codec"]["options"] = {"crc": crc, "disable_rs": disable_rs, "min_dist": "0", "sync_tol": str(sync_tol)}
+	want, _ = _oracle_vs_gpu(oracle, 48000, lines, audio)
+	assert sum(len(w) for w in want) > 0
+
+
+def test_il2p_min_distance(cuda_lib, oracle):
+	import json
+	g = Golden("fsk9600_il2p_48k")
+	lines = [json.loads(json.dumps(l)) for l in g.chain_lines()[:1]]
+	lines[0]["codec"]["options"]["min_dist"] = "2"
+	_oracle_vs_gpu(oracle, 48000, lines, g.audio())

@@ -10,9 +10,12 @@ from util import GOLD, Golden
 
 CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
 	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k"]
+# recursive modems (AGC + Costas / decision-directed / PLL loops): no chunked form, AGC.apply takes
+# max(buffer) of the whole recording (agc.py:67)
+PSK_CASES = ["bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k"]
 
 
-@pytest.mark.parametrize("tag", CASES)
+@pytest.mark.parametrize("tag", CASES + PSK_CASES)
 def test_oracle_packets_match_reference(oracle, tag):
 	g = Golden(tag)
 	got = oracle.run_config(g.sample_rate, g.lines, g.audio())
@@ -26,7 +29,7 @@ def test_oracle_chunked_equals_monolithic(oracle, tag):
 	assert got == g.all_packets()
 
 
-@pytest.mark.parametrize("tag", CASES)
+@pytest.mark.parametrize("tag", CASES + PSK_CASES)
 def test_oracle_stages_match_reference(oracle, tag):
 	g = Golden(tag)
 	audio = g.audio()
@@ -35,9 +38,14 @@ def test_oracle_stages_match_reference(oracle, tag):
 			continue
 		chain = oracle.Chain(g.sample_rate, line)
 		soft = chain.modem.demod(audio)
-		assert len(soft) == int(g.z[f"c{ci}_soft_len"])
+		atol = 1e-9 * float(g.z[f"c{ci}_soft_rms"])
+		soft_i = soft
+		if isinstance(soft, tuple):                  # IQData (psk.py:748-751)
+			soft_i = soft[0]
+			np.testing.assert_allclose(soft[1][::97], g.z[f"c{ci}_softq_dec"], rtol=0, atol=atol)
+		assert len(soft_i) == int(g.z[f"c{ci}_soft_len"])
 		# same numpy.convolve calls as the reference: bit-identical on this host
-		np.testing.assert_allclose(soft[::97], g.z[f"c{ci}_soft_dec"], rtol=0, atol=1e-9 * float(g.z[f"c{ci}_soft_rms"]))
+		np.testing.assert_allclose(soft_i[::97], g.z[f"c{ci}_soft_dec"], rtol=0, atol=atol)
 		b, a = chain.slicer.slice(soft)
 		np.testing.assert_array_equal(b, g.z[f"c{ci}_sl_bytes"])
 		np.testing.assert_array_equal(a, g.z[f"c{ci}_sl_addr"])
@@ -45,7 +53,7 @@ def test_oracle_stages_match_reference(oracle, tag):
 		np.testing.assert_array_equal(d, g.z[f"c{ci}_ds_bytes"])
 
 
-@pytest.mark.parametrize("tag", CASES)
+@pytest.mark.parametrize("tag", CASES + PSK_CASES)
 def test_oracle_correlate_matches_reference(oracle, tag):
 	g = Golden(tag)
 	names = [l["object_name"] for l in g.chain_lines()]

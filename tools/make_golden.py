@@ -77,6 +77,7 @@ def run_case(tag, config_name, lines, sr, audio, meta, stage_chains=(0,)):
 			if hasattr(soft, 'i_data'):
 				soft_i, soft_q = np.asarray(soft.i_data, dtype=np.float64), np.asarray(soft.q_data, dtype=np.float64)
 				out[f"c{ci}_softq_dec"] = soft_q[::97]
+				out[f"c{ci}_softq_win"] = soft_q[10000:10000 + 8192]
 			else:
 				soft_i = np.asarray(soft, dtype=np.float64)
 			out[f"c{ci}_soft_len"] = np.array(len(soft_i))
@@ -145,6 +146,7 @@ def main():
 		or l.get('object_type') == 'report']
 	run_case("fsk9600_ax25_48k", "fsk_9600.json", lines, 48000, audio, meta, stage_chains=(0,))
 	more_cases()
+	psk_cases()
 
 
 def more_cases():
@@ -170,6 +172,36 @@ def more_cases():
 	run_case("afsk300_real_8k", "afsk_300.json", lines, int(sr), wav, meta, stage_chains=(0, 1))
 
 
+def psk_cases():
+	# (7) bpsk_300.json as shipped (Costas loop, binary slicer, differential decode, IL2P+CRC) on synthetic
+	#     BPSK 300 at 8 kHz, carrier 3 Hz off nominal, noise ramp
+	meta = dict(gen="bpsk300_il2p", duration_s=60.0, sample_rate=8000, frame_interval_s=3.0, noise_start=0.0,
+		noise_end=0.9, seed=10, noise_seed=11, carrier=1503.0, first_frame_s=1.5, payload_len=[None, 120, 0, 30])
+	audio, _, _ = synth.bpsk300_il2p(**meta_args(meta))
+	run_case("bpsk300_il2p_8k", "bpsk_300.json", load_config("bpsk_300.json"), 8000, audio, meta, stage_chains=(0,))
+	# (8) qpsk_2400.json as shipped (3 MPSK chains at 1475/1500/1525 Hz, quadrature slicer, IL2P+CRC) at 8 kHz
+	meta = dict(gen="qpsk2400_il2p", duration_s=30.0, sample_rate=8000, frame_interval_s=1.0, noise_start=0.0,
+		noise_end=0.7, seed=12, noise_seed=13, carrier=1499.0, first_frame_s=1.5, payload_len=[None, 300, 0, 30])
+	audio, _, _ = synth.qpsk2400_il2p(**meta_args(meta))
+	run_case("qpsk2400_il2p_8k", "qpsk_2400.json", load_config("qpsk_2400.json"), 8000, audio, meta, stage_chains=(0, 1, 2))
+	# (9) the same modem at 22.05 kHz (18.375 samples per symbol; other tap counts everywhere)
+	meta = dict(gen="qpsk2400_il2p", duration_s=12.0, sample_rate=22050, frame_interval_s=1.0, noise_start=0.0,
+		noise_end=0.6, seed=14, noise_seed=15, carrier=1508.0, first_frame_s=1.2, payload_len=[None, 64])
+	audio, _, _ = synth.qpsk2400_il2p(**meta_args(meta))
+	run_case("qpsk2400_il2p_22k", "qpsk_2400.json", load_config("qpsk_2400.json")[1:], 22050, audio, meta, stage_chains=(0,))
+	# (10) afsk_300.json exactly as shipped (AFSK correlator + AFSK PLL chains) on the shipped WAV excerpt
+	z = np.load(os.path.join(GOLD, "afsk300_wav_excerpt.npz"))
+	wav, sr = np.ascontiguousarray(z["audio"]), int(z["sample_rate"])
+	meta = dict(gen="wav_excerpt", name="afsk300_wav_excerpt")
+	run_case("afsk300_full_8k", "afsk_300.json", load_config("afsk_300.json"), sr, wav, meta, stage_chains=(1, 2))
+	# (11) bpsk_1200.json if it is an mpsk/bpsk config: exercised through the 'bpsk' preset '1200' at 12 kHz
+	meta = dict(gen="bpsk300_il2p", duration_s=12.0, sample_rate=12000, frame_interval_s=0.8, noise_start=0.0,
+		noise_end=0.5, seed=16, noise_seed=17, carrier=1497.0, baud=1200.0, rolloff=0.9, first_frame_s=0.6,
+		payload_len=[None, 50])
+	audio, _, _ = synth.bpsk300_il2p(**meta_args(meta))
+	run_case("bpsk1200_il2p_12k", "bpsk_1200.json", load_config("bpsk_1200.json"), 12000, audio, meta, stage_chains=(0,))
+
+
 def meta_args(meta):
 	return {k: v for k, v in meta.items() if k != "gen"}
 
@@ -177,5 +209,7 @@ def meta_args(meta):
 if __name__ == "__main__":
 	if "--more" in sys.argv:
 		more_cases()
+	elif "--psk" in sys.argv:
+		psk_cases()
 	else:
 		main()
