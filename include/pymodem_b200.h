@@ -50,6 +50,35 @@ extern "C" {
  * reference's own tune() arithmetic on the host (afsk.py:102-146, fsk.py:115-147,
  * psk.py:111-160/640-703); the engine never re-derives them.
  */
+/*
+ * Constants of the recursive part of a PSK / PLL modem, computed on the host by the reference's own
+ * expressions (math.sin, math.tan, atan2 of the host libm), so that the device works from bit-identical
+ * numbers: AGC agc.py:8-24, NCO nco.py:14-32, IIR_1 iir.py:15-29, PI_control pi_control.py:8-13,
+ * PhaseDetector.qpsk_error_table phase_detector.py:34-45, Hilbert hilbert.py:9-34.
+ */
+typedef struct pm_loop_desc {
+	double agc_scaled_attack;       /* attack_rate / sample_rate            agc.py:15 */
+	double agc_scaled_decay;        /* decay_rate / sample_rate             agc.py:16 */
+	double agc_sustain_time;
+	double agc_sustain_increment;   /* 1 / sample_rate                      agc.py:17 */
+	double agc_target;              /* target_amplitude */
+	double nco_phase_scale;         /* 2.0 * pi / sample_rate               nco.py:30 */
+	double nco_index_scale;         /* wavetable_size / (2.0 * pi)          nco.py:28 */
+	double nco_set_frequency;       /* carrier_freq */
+	double nco_two_pi;              /* 2.0 * pi */
+	double nco_quarter;             /* wavetable_size / 4.0                 nco.py:46 */
+	const double *nco_wavetable;    /* amplitude * sin(i * 2.0 * pi / size) nco.py:24-26 */
+	int64_t nco_size;               /* <= 1024 */
+	double iir_b0, iir_b1, iir_a1;  /* gain*b0, gain*b1, a1                 iir.py:24-29 */
+	double pi_gain, pi_p, pi_i, pi_limit;
+	double pi_integral0;            /* PI integral at the first sample (psk.py:703 presets -max_freq_offset) */
+	const int32_t *pd_table;        /* [granularity][granularity], MPSK only */
+	int64_t pd_granularity;         /* <= 64 */
+	const double *hilbert;          /* Hilbert taps, MPSK only (numpy.convolve order) */
+	int32_t n_hilbert;
+	int32_t hilbert_delay;          /* hilbert.py:14 tap_count // 2 */
+} pm_loop_desc;
+
 typedef struct pm_chain_desc {
 	int32_t modem_kind;
 	int32_t slicer_kind;
@@ -91,7 +120,7 @@ typedef struct pm_chain_desc {
 	int32_t reserved1;
 
 	/* --- PSK / PLL loop constants (psk.py, afsk_pll.py); see pm_loop_desc --- */
-	const void *loop;               /* NULL unless modem_kind is BPSK/MPSK/AFSK_PLL */
+	const pm_loop_desc *loop;       /* NULL unless modem_kind is BPSK/MPSK/AFSK_PLL */
 } pm_chain_desc;
 
 /* One decoded packet == one reference PacketMeta (packet_meta.py:178-208). */
@@ -140,7 +169,9 @@ const char *pm_last_error(const pm_engine *e);
 int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_chains);
 
 /* Tunables: "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32),
- * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap". */
+ * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap",
+ * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
+ * close that |mark| - |space| cancels below FP32 resolution). */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
 
 /*

@@ -17,6 +17,19 @@ PM_CODEC_AX25, PM_CODEC_IL2P = 1, 2
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
+class LoopDesc(ctypes.Structure):
+	"""pm_loop_desc"""
+	_fields_ = [(n, ctypes.c_double) for n in (
+		"agc_scaled_attack", "agc_scaled_decay", "agc_sustain_time", "agc_sustain_increment", "agc_target",
+		"nco_phase_scale", "nco_index_scale", "nco_set_frequency", "nco_two_pi", "nco_quarter")] + [
+		("nco_wavetable", _dp), ("nco_size", ctypes.c_int64),
+		("iir_b0", ctypes.c_double), ("iir_b1", ctypes.c_double), ("iir_a1", ctypes.c_double),
+		("pi_gain", ctypes.c_double), ("pi_p", ctypes.c_double), ("pi_i", ctypes.c_double),
+		("pi_limit", ctypes.c_double), ("pi_integral0", ctypes.c_double),
+		("pd_table", ctypes.POINTER(ctypes.c_int32)), ("pd_granularity", ctypes.c_int64),
+		("hilbert", _dp), ("n_hilbert", ctypes.c_int32), ("hilbert_delay", ctypes.c_int32)]
+
+
 class ChainDesc(ctypes.Structure):
 	"""pm_chain_desc"""
 	_fields_ = [
@@ -32,7 +45,7 @@ class ChainDesc(ctypes.Structure):
 		("lfsr_poly", ctypes.c_uint64), ("lfsr_invert", ctypes.c_int32),
 		("il2p_crc", ctypes.c_int32), ("il2p_disable_rs", ctypes.c_int32),
 		("il2p_min_dist", ctypes.c_int32), ("il2p_sync_tol", ctypes.c_int32),
-		("reserved1", ctypes.c_int32), ("loop", ctypes.c_void_p),
+		("reserved1", ctypes.c_int32), ("loop", ctypes.POINTER(LoopDesc)),
 	]
 
 

@@ -39,6 +39,8 @@ cudaError_t pm_launch_lfsr(const BitChain *, int, const ChainCounters *, const u
 cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_t *, long long, unsigned int *,
 	unsigned int *, unsigned int *, unsigned int *, long long, const uint32_t *, long long, uint8_t *, long long,
 	GapRec *, long long, const ShardBits *, int, cudaStream_t);
+cudaError_t pm_launch_p64(const P64Chain *, const P64Chain *, int, const int16_t *, uint32_t *, long long, float *,
+	long long, unsigned long long *, cudaStream_t);
 cudaError_t pm_il2p_init_tables(void);
 cudaError_t pm_launch_il2p(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const unsigned int *,
 	long long, const unsigned int *, int, unsigned char *, long long, Il2pRes *, const uint32_t *, long long,
@@ -71,7 +73,12 @@ struct HostChain {
 	pm_chain_desc d;
 	std::vector<double> bpf, mark_i, mark_q, space_i, space_q, space_ui, space_uq, lpf;
 	int trim = 0;             // samples lost to 'valid' convolutions
-	int group = -1;           // front-end launch group
+	int group = -1;           // front-end launch group (-1: float64 pipeline)
+	bool p64 = false;         // runs through csrc/loops.cu
+	pm_loop_desc loop;
+	std::vector<double> wavetable, hilbert;
+	std::vector<int32_t> pd_table;
+	int sign_q_row = 0;
 };
 
 struct FrontGroup {
@@ -99,6 +106,8 @@ struct pm_engine {
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
+	int opt_precise = 0;          // all AFSK chains through the float64 pipeline
+	double opt_precise_ratio = 0.2;
 	long long opt_h2d_chunk = 8 << 20;
 	unsigned int guard_cap = 1u << 20;
 	// device tables
@@ -135,6 +144,12 @@ struct pm_engine {
 	DevBuf<PacketTotals> d_totals;
 	DevBuf<unsigned char> d_il2p_slots;   // speculative IL2P decodes: (cand_cap + 1) slots per chain
 	DevBuf<Il2pRes> d_il2p_res;
+	DevBuf<double> d_p64_work, d_p64_tabs;
+	DevBuf<int> d_p64_pd;
+	DevBuf<P64Chain> d_p64;
+	DevBuf<unsigned long long> d_p64_max;
+	std::vector<P64Chain> h_p64;
+	std::vector<size_t> p64_tab_off;      // per p64 chain: offsets into d_p64_tabs (wavetable, hilbert) and d_p64_pd
 	int il2p_cand_cap = 0;
 	bool has_il2p = false, il2p_tables = false;
 	unsigned int *h_counters = nullptr;   // pinned
@@ -225,21 +240,39 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 	return g;
 }
 
+// AFSK chains whose mark and space tones nearly coincide over the correlator window lose the soft value
+// to cancellation in FP32 (|mark| - |space| is a small difference of large magnitudes): float64 pipeline.
+static bool afsk_needs_fp64(const pm_engine *e, const HostChain &hc)
+{
+	if (e->opt_precise) return true;
+	double diff = 0, ref = 0;
+	for (size_t k = 0; k < hc.mark_i.size(); k++) {
+		const double di = hc.mark_i[k] - hc.space_i[k], dq = hc.mark_q[k] - hc.space_q[k];
+		diff += di * di + dq * dq;
+		ref += hc.mark_i[k] * hc.mark_i[k] + hc.mark_q[k] * hc.mark_q[k];
+	}
+	return ref > 0 && std::sqrt(diff / ref) < e->opt_precise_ratio;
+}
+
 static int build_groups(pm_engine *e)
 {
 	e->groups.clear();
 	const int nc = (int)e->chains.size();
-	for (int c = 0; c < nc; c++) e->chains[c].group = -1;
 	for (int c = 0; c < nc; c++) {
 		HostChain &hc = e->chains[c];
-		if (hc.group >= 0) continue;
+		hc.group = -1;
+		if (hc.d.modem_kind == PM_MODEM_AFSK) hc.p64 = afsk_needs_fp64(e, hc);
+	}
+	for (int c = 0; c < nc; c++) {
+		HostChain &hc = e->chains[c];
+		if (hc.group >= 0 || hc.p64) continue;
 		FrontGroup g;
 		g.kind = hc.d.modem_kind;
 		if (g.kind != PM_MODEM_AFSK && g.kind != PM_MODEM_FSK)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, g.kind);
 		for (int k = c; k < nc; k++) {
 			HostChain &o = e->chains[k];
-			if (o.group >= 0 || o.d.modem_kind != g.kind) continue;
+			if (o.group >= 0 || o.p64 || o.d.modem_kind != g.kind) continue;
 			if (!same_taps(o.bpf, hc.bpf)) continue;
 			if (g.kind == PM_MODEM_AFSK && !same_taps(o.lpf, hc.lpf)) continue;
 			if ((int)g.chains.size() >= PM_MAX_GCH) break;
@@ -405,6 +438,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
 	e->d_arena.release(); e->d_gaps.release(); e->d_recs.release(); e->d_totals.release();
 	e->d_il2p_slots.release(); e->d_il2p_res.release();
+	e->d_p64_work.release(); e->d_p64_tabs.release(); e->d_p64_pd.release(); e->d_p64.release(); e->d_p64_max.release();
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
 	if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -447,11 +481,40 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 			if (!d.bpf || d.n_bpf <= 0) return fail(e, PM_ERR_ARG, "chain %d: FSK needs input filter taps", c);
 			copy_vec(hc.bpf, d.bpf, d.n_bpf);
 			hc.trim = d.n_bpf - 1;
+		} else if (d.modem_kind == PM_MODEM_BPSK || d.modem_kind == PM_MODEM_MPSK || d.modem_kind == PM_MODEM_AFSK_PLL) {
+			const pm_loop_desc *lp = d.loop;
+			if (!d.bpf || d.n_bpf <= 0 || !d.lpf || d.n_lpf <= 0 || !lp || !lp->nco_wavetable || lp->nco_size <= 0)
+				return fail(e, PM_ERR_ARG, "chain %d: PSK/PLL modem needs input/output taps and loop constants", c);
+			if (lp->nco_size > 1024) return fail(e, PM_ERR_CAPACITY, "chain %d: NCO wavetable larger than 1024", c);
+			if (d.n_bpf > P64_MAX_TAPS || d.n_lpf > P64_MAX_TAPS)
+				return fail(e, PM_ERR_CAPACITY, "chain %d: more than %d taps in a float64 FIR", c, P64_MAX_TAPS);
+			copy_vec(hc.bpf, d.bpf, d.n_bpf);
+			copy_vec(hc.lpf, d.lpf, d.n_lpf);
+			hc.loop = *lp;
+			hc.wavetable.assign(lp->nco_wavetable, lp->nco_wavetable + lp->nco_size);
+			hc.trim = (d.n_bpf - 1) + (d.n_lpf - 1);
+			if (d.modem_kind == PM_MODEM_MPSK) {
+				if (!lp->hilbert || lp->n_hilbert <= 0 || lp->n_hilbert > P64_MAX_TAPS || !lp->pd_table ||
+				    lp->pd_granularity <= 0 || lp->pd_granularity > 64 || lp->hilbert_delay != lp->n_hilbert / 2)
+					return fail(e, PM_ERR_ARG, "chain %d: MPSK needs Hilbert taps and the phase-error table", c);
+				hc.hilbert.assign(lp->hilbert, lp->hilbert + lp->n_hilbert);
+				hc.pd_table.assign(lp->pd_table, lp->pd_table + lp->pd_granularity * lp->pd_granularity);
+				hc.trim += lp->n_hilbert - 1;
+			}
+			hc.loop.nco_wavetable = nullptr; hc.loop.pd_table = nullptr; hc.loop.hilbert = nullptr;
+			hc.p64 = true;
 		} else {
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, d.modem_kind);
 		}
-		if (d.slicer_kind != PM_SLICER_BINARY)
+		if (d.slicer_kind != PM_SLICER_BINARY && d.slicer_kind != PM_SLICER_QUADRATURE)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: slicer kind %d not supported by this build", c, d.slicer_kind);
+		// the reference's duck typing: MPSKModem.demod returns IQData (psk.py:748), which only
+		// QuadratureSlicer.slice can iterate (slicer.py:198); every other modem returns an ndarray
+		if ((d.slicer_kind == PM_SLICER_QUADRATURE) != (d.modem_kind == PM_MODEM_MPSK))
+			return fail(e, PM_ERR_ARG, "chain %d: the quadrature slicer goes with the mpsk modem (and only with it)", c);
+		if (d.slicer_kind == PM_SLICER_QUADRATURE &&
+		    (d.bits_per_symbol < 1 || d.bits_per_symbol > 2 || d.state_mask > 15 || 8 % d.bits_per_symbol))
+			return fail(e, PM_ERR_ARG, "chain %d: quadrature slicer needs 1 or 2 bits per symbol and a 4-bit state", c);
 		if (d.codec_kind != PM_CODEC_AX25 && d.codec_kind != PM_CODEC_IL2P)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: codec kind %d not supported by this build", c, d.codec_kind);
 		if (d.codec_kind == PM_CODEC_IL2P && (d.il2p_sync_tol < 0 || d.il2p_sync_tol > 8))
@@ -473,24 +536,31 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 	int rc = build_groups(e);
 	if (rc != PM_OK) return rc;
 
-	// FP64 taps (reversed = correlation order) for the guard-band fix-up
+	// FP64 taps (reversed = correlation order) for the guard-band fix-up and the float64 pipeline
 	std::vector<double> flat;
 	std::vector<Fp64Chain> f64(n);
-	std::vector<size_t> offs;
-	auto push = [&](const std::vector<double> &h) {
+	auto push = [&](const std::vector<double> &h, bool reverse = true) {
 		size_t off = flat.size();
-		for (size_t j = 0; j < h.size(); j++) flat.push_back(h[h.size() - 1 - j]);
+		for (size_t j = 0; j < h.size(); j++) flat.push_back(reverse ? h[h.size() - 1 - j] : h[j]);
 		return off;
 	};
-	struct Offs { size_t bpf, mi, mq, si, sq, lpf; };
+	struct Offs { size_t bpf, mi, mq, si, sq, lpf, hil, wt; };
 	std::vector<Offs> o(n);
+	std::vector<int> pd_flat;
+	std::vector<size_t> pd_off(n, 0);
 	for (int c = 0; c < n; c++) {
 		HostChain &hc = e->chains[c];
 		o[c].bpf = push(hc.bpf); o[c].mi = push(hc.mark_i); o[c].mq = push(hc.mark_q);
 		o[c].si = push(hc.space_i); o[c].sq = push(hc.space_q); o[c].lpf = push(hc.lpf);
+		o[c].hil = push(hc.hilbert); o[c].wt = push(hc.wavetable, false);
+		pd_off[c] = pd_flat.size();
+		pd_flat.insert(pd_flat.end(), hc.pd_table.begin(), hc.pd_table.end());
 	}
 	CK(e->d_taps64.ensure(flat.size() + 1));
 	CK(cudaMemcpy(e->d_taps64.p, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+	CK(e->d_p64_pd.ensure(pd_flat.size() + 1));
+	if (!pd_flat.empty())
+		CK(cudaMemcpy(e->d_p64_pd.p, pd_flat.data(), pd_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
 	for (int c = 0; c < n; c++) {
 		HostChain &hc = e->chains[c];
 		Fp64Chain &f = f64[c];
@@ -504,6 +574,50 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 	}
 	CK(e->d_fp64.ensure(n));
 	CK(cudaMemcpy(e->d_fp64.p, f64.data(), n * sizeof(Fp64Chain), cudaMemcpyHostToDevice));
+	// float64 pipeline table (buffers and lengths are filled in per run)
+	e->h_p64.clear();
+	for (int c = 0; c < n; c++) {
+		HostChain &hc = e->chains[c];
+		if (!hc.p64) continue;
+		if (hc.bpf.size() > P64_MAX_TAPS || hc.lpf.size() > P64_MAX_TAPS || hc.mark_i.size() > P64_MAX_TAPS)
+			return fail(e, PM_ERR_CAPACITY, "chain %d: more than %d taps in a float64 FIR", c, P64_MAX_TAPS);
+		P64Chain P;
+		memset(&P, 0, sizeof(P));
+		P.kind = hc.d.modem_kind;
+		P.gid = c;
+		P.n_bpf = (int)hc.bpf.size();
+		P.n_out = (int)hc.lpf.size();
+		P.bpf = e->d_taps64.p + o[c].bpf;
+		P.out_taps = e->d_taps64.p + o[c].lpf;
+		if (P.kind == PM_MODEM_AFSK) {
+			P.n_mid = (int)hc.mark_i.size();
+			P.mid0 = e->d_taps64.p + o[c].mi; P.mid1 = e->d_taps64.p + o[c].mq;
+			P.mid2 = e->d_taps64.p + o[c].si; P.mid3 = e->d_taps64.p + o[c].sq;
+		} else {
+			const pm_loop_desc &l = hc.loop;
+			LoopConst &L = P.lc;
+			L.agc_scaled_attack = l.agc_scaled_attack; L.agc_scaled_decay = l.agc_scaled_decay;
+			L.agc_sustain_time = l.agc_sustain_time; L.agc_sustain_increment = l.agc_sustain_increment;
+			L.agc_target = l.agc_target;
+			L.nco_phase_scale = l.nco_phase_scale; L.nco_index_scale = l.nco_index_scale;
+			L.nco_set_frequency = l.nco_set_frequency; L.nco_two_pi = l.nco_two_pi; L.nco_quarter = l.nco_quarter;
+			L.iir_b0 = l.iir_b0; L.iir_b1 = l.iir_b1; L.iir_a1 = l.iir_a1;
+			L.pi_gain = l.pi_gain; L.pi_p = l.pi_p; L.pi_i = l.pi_i; L.pi_limit = l.pi_limit;
+			L.pi_integral0 = l.pi_integral0;
+			P.wavetable = e->d_taps64.p + o[c].wt;
+			P.wt_size = (int)hc.wavetable.size();
+			if (P.kind == PM_MODEM_MPSK) {
+				P.n_mid = (int)hc.hilbert.size();
+				P.mid_delay = l.hilbert_delay;
+				P.mid0 = e->d_taps64.p + o[c].hil;
+				P.pd_table = e->d_p64_pd.p + pd_off[c];
+				P.pd_g = (int)l.pd_granularity;
+			}
+		}
+		e->h_p64.push_back(P);
+	}
+	CK(e->d_p64.ensure(e->h_p64.size() + 1));
+	CK(e->d_p64_max.ensure(e->h_p64.size() + 1));
 	CK(e->d_slicer.ensure(n));
 	CK(e->d_bitchain.ensure(n));
 	CK(e->d_cc.ensure(n));
@@ -527,6 +641,10 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
+	else if (k == "precise") {
+		if (!e->chains.empty()) return fail(e, PM_ERR_STATE, "set 'precise' before loading chains");
+		e->opt_precise = value != 0;
+	}
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
 	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);
@@ -560,7 +678,10 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	e->plan = plan;
 	e->sharded = sharded;
 	e->sample_base = plan.sample_base;
-	e->sign_rows = nc;
+	int n_quad = 0;
+	for (int c = 0; c < nc; c++)
+		if (e->chains[c].d.slicer_kind == PM_SLICER_QUADRATURE) e->chains[c].sign_q_row = nc + n_quad++;
+	e->sign_rows = nc + n_quad;
 	long long max_words = 0, max_bits = 0, max_nout = 0;
 	std::vector<SlicerChain> sl(nc);
 	std::vector<BitChain> bc(nc);
@@ -568,22 +689,29 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	long long rec_cap = 16, arena_cap = 64;
 	for (int c = 0; c < nc; c++) {
 		HostChain &hc = e->chains[c];
-		if (sharded && hc.d.slicer_kind != PM_SLICER_BINARY)
-			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: only binary-slicer chains can be sharded", c);
+		if (sharded && (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK)))
+			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: chains with a carrier loop (AGC takes max() of the whole "
+				"recording, agc.py:67) cannot be sharded on the sample axis", c);
 		const long long nout = std::max<long long>(0, n - hc.trim);
 		max_nout = std::max(max_nout, nout);
-		const FrontGroup &g = e->groups[hc.group];
-		const long long tiles = (nout + g.tile - 1) / g.tile;
-		max_words = std::max(max_words, tiles * g.tile / 32);
+		const int tile = hc.p64 ? P64_TILE : e->groups[hc.group].tile;
+		const long long tiles = (nout + tile - 1) / tile;
+		max_words = std::max(max_words, tiles * tile / 32);
 		SlicerChain &s = sl[c];
 		s.sps = hc.d.slicer_sample_rate / hc.d.symbol_rate;       // slicer.py:51
 		s.thr = (s.sps / 2.0) - 0.5;                              // slicer.py:52
 		s.lock = hc.d.lock_rate;
 		s.nout = nout;
-		s.quadrature = 0; s.sign_q_row = 0; s.sign_row = c; s.pad = 0;
+		const bool quad = hc.d.slicer_kind == PM_SLICER_QUADRATURE;
+		s.quadrature = quad ? 1 : 0; s.sign_q_row = quad ? hc.sign_q_row : 0; s.sign_row = c; s.pad = 0;
 		BitChain &b = bc[c];
 		memset(&b, 0, sizeof(b));
 		b.nout = nout; b.sign_row = c; b.bps = 1; b.lfsr_poly = hc.d.lfsr_poly; b.lfsr_invert = hc.d.lfsr_invert;
+		if (quad) {
+			b.quadrature = 1; b.sign_q_row = hc.sign_q_row; b.bps = (int)hc.d.bits_per_symbol;
+			b.state_mask = hc.d.state_mask;
+			for (int i = 0; i < 16; i++) b.demap[i] = hc.d.demap[i];
+		}
 		b.codec = hc.d.codec_kind;
 		b.il2p_crc = hc.d.il2p_crc; b.il2p_disable_rs = hc.d.il2p_disable_rs;
 		b.il2p_min_dist = hc.d.il2p_min_dist; b.il2p_sync_tol = hc.d.il2p_sync_tol;
@@ -591,7 +719,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: IL2P chains cannot be sharded on the sample axis yet", c);
 		e->h_init[c].clock = 0.0; e->h_init[c].last = 1; e->h_init[c].last_q = 1;    // slicer.py:50,55
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
-		const long long mb = nout / min_gap + 64 + plan.tail_bits;
+		const long long mb = (nout / min_gap + 8) * b.bps + 64 + plan.tail_bits;
 		max_bits = std::max(max_bits, mb);
 		rec_cap += mb / 152 + 4;
 		arena_cap += mb / 8 + 64;
@@ -647,7 +775,31 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	}
 	if (e->opt_keep_soft) {
 		e->soft_stride = n;
-		CK(e->d_soft.ensure((size_t)nc * n));
+		CK(e->d_soft.ensure((size_t)e->sign_rows * n));
+	}
+	if (!e->h_p64.empty()) {
+		// work buffers of the float64 pipeline: A (+B, +C, +D), n doubles each
+		size_t need = 0;
+		for (auto &P : e->h_p64) need += (size_t)(P.kind == PM_MODEM_MPSK ? 4 : 2) * (size_t)n;
+		CK(e->d_p64_work.ensure(need + 8));
+		double *w = e->d_p64_work.p;
+		for (size_t i = 0; i < e->h_p64.size(); i++) {
+			P64Chain &P = e->h_p64[i];
+			const HostChain &hc = e->chains[P.gid];
+			P.sign_row = P.gid;
+			P.sign_q_row = hc.sign_q_row;
+			P.n_audio = n;
+			P.L1 = std::max<long long>(0, n - (P.n_bpf - 1));
+			if (P.kind == PM_MODEM_AFSK || P.kind == PM_MODEM_MPSK) P.L2 = std::max<long long>(0, P.L1 - (P.n_mid - 1));
+			else P.L2 = P.L1;
+			P.L3 = std::max<long long>(0, P.L2 - (P.n_out - 1));
+			if (P.L3 == 0) P.L1 = P.L2 = 0;     // numpy.convolve 'valid' on a signal shorter than the taps: nothing usable
+			P.A = w; w += n;
+			P.B = w; w += n;
+			if (P.kind == PM_MODEM_MPSK) { P.C = w; w += n; P.D = w; w += n; }
+			P.max_slot = e->d_p64_max.p + i;
+		}
+		CK(cudaMemcpyAsync(e->d_p64.p, e->h_p64.data(), e->h_p64.size() * sizeof(P64Chain), cudaMemcpyHostToDevice, e->st));
 	}
 	CK(cudaMemcpyAsync(e->d_slicer.p, sl.data(), nc * sizeof(SlicerChain), cudaMemcpyHostToDevice, e->st));
 	CK(cudaMemcpyAsync(e->d_bitchain.p, bc.data(), nc * sizeof(BitChain), cudaMemcpyHostToDevice, e->st));
@@ -801,6 +953,13 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 	} else {
 		rc = launch_front(e, d_audio, n, 0, n, true);
 		if (rc != PM_OK) return rc;
+	}
+	if (!e->h_p64.empty()) {
+		// float64 pipeline (needs the whole recording: AGC.normal = max over the band-passed buffer)
+		cudaError_t pe = pm_launch_p64(e->d_p64.p, e->h_p64.data(), (int)e->h_p64.size(), d_audio, e->d_sign.p,
+			e->sign_stride, e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, e->d_p64_max.p, e->st);
+		if (pe != cudaSuccess) return fail(e, PM_ERR_CUDA, "float64 pipeline launch failed: %s", cudaGetErrorString(pe));
+		e->stats.kernel_launches += 6;
 	}
 	e->run_audio = d_audio;
 	CK(cudaEventRecord(e->ev[1], e->st));
@@ -1102,11 +1261,13 @@ extern "C" int pm_engine_get_soft(const pm_engine *ce, int32_t chain, int32_t co
 	pm_engine *e = const_cast<pm_engine *>(ce);
 	if (!e || !e->have_run) return PM_ERR_STATE;
 	if (!e->opt_keep_soft || !e->d_soft.p) return fail(e, PM_ERR_STATE, "soft values were not kept (option keep_soft)");
-	if (component != 0) return fail(e, PM_ERR_ARG, "component %d not available", component);
 	const int64_t len = pm_engine_soft_len(e, chain);
 	if (len < 0 || cap < len) return PM_ERR_CAPACITY;
+	int row = chain;
+	if (component == 1 && e->chains[chain].d.slicer_kind == PM_SLICER_QUADRATURE) row = e->chains[chain].sign_q_row;
+	else if (component != 0) return fail(e, PM_ERR_ARG, "component %d not available", component);
 	cudaSetDevice(e->device);
-	CK(cudaMemcpy(out, e->d_soft.p + (size_t)chain * e->soft_stride, (size_t)len * sizeof(float), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(out, e->d_soft.p + (size_t)row * e->soft_stride, (size_t)len * sizeof(float), cudaMemcpyDeviceToHost));
 	return PM_OK;
 }
 

@@ -138,6 +138,37 @@ struct Il2pRes {
 	unsigned int pad;
 };
 
+// ---- float64 pipeline (csrc/loops.cu): the modems with a recursive stage (BPSK Costas loop, MPSK
+// decision-directed loop, AFSK PLL) and AFSK chains whose tone pair is too close for FP32 ----------
+#define P64_TILE 1024          // outputs per CTA of a float64 FIR stage
+#define P64_THREADS 256
+#define P64_MAX_TAPS 4096
+
+struct LoopConst {             // mirrors pm_loop_desc (include/pymodem_b200.h) without the pointers
+	double agc_scaled_attack, agc_scaled_decay, agc_sustain_time, agc_sustain_increment, agc_target;
+	double nco_phase_scale, nco_index_scale, nco_set_frequency, nco_two_pi, nco_quarter;
+	double iir_b0, iir_b1, iir_a1;
+	double pi_gain, pi_p, pi_i, pi_limit, pi_integral0;
+};
+
+struct P64Chain {
+	int kind;                  // PM_MODEM_AFSK (1), PM_MODEM_BPSK (3), PM_MODEM_MPSK (4), PM_MODEM_AFSK_PLL (5)
+	int gid;                   // engine chain index (row of the soft-value export)
+	int sign_row, sign_q_row;
+	int n_bpf, n_mid, n_out, mid_delay;
+	long long n_audio;
+	long long L1, L2, L3;      // samples after the input FIR, after the middle stage, final soft samples
+	const double *bpf;         // all taps reversed (correlation order)
+	const double *mid0, *mid1, *mid2, *mid3;   // AFSK: mark_i, mark_q, space_i, space_q; MPSK: mid0 = Hilbert
+	const double *out_taps;
+	double *A, *B, *C, *D;
+	LoopConst lc;
+	const double *wavetable;
+	const int *pd_table;
+	int wt_size, pd_g;
+	unsigned long long *max_slot;   // ordered-integer image of max(A) for AGC.normal (agc.py:67)
+};
+
 struct ChainCounters {
 	long long nbits;           // local stream bits of the chain (incl. hand-off tail and padding when sharded)
 	long long nbytes;          // nbits / 8 (trailing partial byte dropped, slicer.py:95)

@@ -206,14 +206,26 @@ def engine_for(demod_stack, device=0, **options):
 
 
 def demod_only(modem, audio):
-	"""modem.demod(audio) on the GPU: float64 ndarray of soft values."""
-	from .modems_codecs import ax25, lfsr, slicer
-	s = slicer.BinarySlicer(sample_rate=getattr(modem, 'output_sample_rate', modem.sample_rate),
-		config=str(int(getattr(modem, 'symbol_rate', 1200))))
+	"""modem.demod(audio) on the GPU: float64 ndarray of soft values (IQData for MPSKModem, psk.py:748)."""
+	from . import _lib as L
+	from .modems_codecs import ax25, data_classes, lfsr, slicer
+	rate = getattr(modem, 'output_sample_rate', modem.sample_rate)
+	iq = modem.modem_kind == L.PM_MODEM_MPSK
+	if iq:
+		s = slicer.QuadratureSlicer(sample_rate=rate, config='qpsk_2400')
+		s.retune(symbol_rate=modem.symbol_rate)
+	else:
+		s = slicer.BinarySlicer(sample_rate=rate, config='1200')
+		s.retune(symbol_rate=getattr(modem, 'symbol_rate', 1200))
 	eng = Engine([["demod", modem, s, lfsr.LFSR(), ax25.AX25Codec()]], keep_soft=1)
 	try:
 		eng.run_raw(audio)
-		return eng.soft(0).astype(np.float64)
+		if not iq:
+			return eng.soft(0).astype(np.float64)
+		out = data_classes.IQData()
+		out.i_data = eng.soft(0, 0).astype(np.float64)
+		out.q_data = eng.soft(0, 1).astype(np.float64)
+		return out
 	finally:
 		eng.close()
 

@@ -1,15 +1,17 @@
 """String-typed factories for the four block kinds -- same names, arguments and
 behaviour as reference modems_codecs/chain_builder.py:17-69 (an unknown or
 missing 'type' yields [], as there)."""
-from . import afsk, ax25, fsk, il2p, lfsr, slicer
+from . import afsk, afsk_pll, ax25, fsk, il2p, lfsr, psk, slicer
 
 
 def ModemConfigurator(arg_sample_rate, input_args):
 	new_object = []
 	kind = input_args.get('type')
-	cls = {'afsk': afsk.AFSKModem, 'fsk': fsk.FSKModem}.get(kind)
-	if kind in ('qpsk', 'mpsk', 'bpsk', 'afsk_pll'):
-		raise NotImplementedError(f"modem type '{kind}' has no GPU path in this build")
+	cls = {'afsk': afsk.AFSKModem, 'fsk': fsk.FSKModem, 'bpsk': psk.BPSKModem, 'mpsk': psk.MPSKModem,
+		'afsk_pll': afsk_pll.AFSKPLLModem}.get(kind)
+	if kind == 'qpsk':
+		# psk.py:197 QPSKModem: the legacy branch-filter Costas loop, used by no shipped config
+		raise NotImplementedError("modem type 'qpsk' (legacy QPSKModem) has no GPU path; use 'mpsk'")
 	if cls:
 		new_object = cls(sample_rate=arg_sample_rate, config=input_args['config'])
 		new_object.StringOptionsRetune(input_args['options'])

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 
 SOFT_RTOL = 1e-5          # BASELINE.json north_star: "within a stated relative tolerance (e.g. 1e-5)"
 CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
-	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k"]
+	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k",
+	# recursive modems (float64 pipeline: AGC + Costas / decision-directed / PLL loops)
+	"bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k"]
 
 
 def build_stack(sample_rate, lines):
@@ -52,6 +54,10 @@ def test_stages_match_reference_fixture(cuda_lib, tag):
 			assert len(soft) == int(g.z[f"c{ci}_soft_len"])
 			assert np.max(np.abs(soft[::97] - g.z[f"c{ci}_soft_dec"])) <= SOFT_RTOL * rms
 			assert np.max(np.abs(soft[10000:10000 + 8192] - g.z[f"c{ci}_soft_win"])) <= SOFT_RTOL * rms
+			if f"c{ci}_softq_dec" in g.z:            # IQData.q_data of an MPSK chain (psk.py:751)
+				softq = eng.soft(ci, 1).astype(np.float64)
+				assert np.max(np.abs(softq[::97] - g.z[f"c{ci}_softq_dec"])) <= SOFT_RTOL * rms
+				assert np.max(np.abs(softq[10000:10000 + 8192] - g.z[f"c{ci}_softq_win"])) <= SOFT_RTOL * rms
 			b, a = eng.stream(ci, 0)
 			np.testing.assert_array_equal(b, g.z[f"c{ci}_sl_bytes"])
 			np.testing.assert_array_equal(a, g.z[f"c{ci}_sl_addr"])
