@@ -44,51 +44,73 @@ def make_audio(seconds, rank):
 
 
 class ClockSampler:
-	"""nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-	Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+	"""SM clock, power and clock-event (throttle) reasons DURING the timed region (B200_PROFILING.md's clocks line).
+	Read in-process through NVML (the library nvidia-smi itself queries) every 25 ms: a looping `nvidia-smi -lms`
+	child was measured to stall the driver for milliseconds per poll and inflated a 14 ms step to 16-27 ms.
+	Falls back to one-shot nvidia-smi calls when pynvml is missing."""
+	SMI_Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
 		"clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-	def __init__(self, gpu_index):
-		self.gpu = gpu_index
-		self.rows = []
-		self.proc = None
+	def __init__(self, gpu_index, period_s=0.025):
+		self.gpu, self.period = gpu_index, period_s
+		self.sm, self.power, self.reasons = [], [], set()
+		self.sm_max = None
+		self.stop_flag = threading.Event()
+		self.thread = None
+		self.source = None
+
+	def _nvml_loop(self):
+		import pynvml as nv
+		h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+		self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+		names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+			nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+		while not self.stop_flag.is_set():
+			self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+			self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+			bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+			for bit, name in names.items():
+				if bits & bit:
+					self.reasons.add(name)
+			self.stop_flag.wait(self.period)
+
+	def _smi_loop(self):
+		while not self.stop_flag.is_set():
+			try:
+				out = subprocess.run(["nvidia-smi", f"--query-gpu={self.SMI_Q}", "--format=csv,noheader,nounits", "-i",
+					str(self.gpu)], capture_output=True, text=True, timeout=10).stdout
+				f = [x.strip() for x in out.strip().split(",")]
+				self.sm.append(float(f[1])); self.sm_max = float(f[2]); self.power.append(float(f[3]))
+				for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+					if val.lower().startswith("active"):
+						self.reasons.add(name)
+			except Exception:
+				pass
+			self.stop_flag.wait(0.5)
 
 	def start(self):
 		try:
-			self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-				"-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-		except OSError:
-			self.proc = None
-			return
-		self.thread = threading.Thread(target=self._read, daemon=True)
+			import pynvml as nv
+			nv.nvmlInit()
+			# CUDA_VISIBLE_DEVICES may renumber devices: NVML wants the physical index
+			vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+			if vis:
+				ids = [v for v in vis.split(",") if v.strip() != ""]
+				if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+					self.gpu = int(ids[self.gpu])
+			target, self.source = self._nvml_loop, "nvml"
+		except Exception:
+			target, self.source = self._smi_loop, "nvidia-smi"
+		self.thread = threading.Thread(target=target, daemon=True)
 		self.thread.start()
 
-	def _read(self):
-		for line in self.proc.stdout:
-			self.rows.append(line.strip())
-
 	def stop(self):
-		if not self.proc:
-			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-		self.proc.terminate()
-		try:
-			self.proc.wait(timeout=5)
-		except subprocess.TimeoutExpired:
-			self.proc.kill()
-		sm, mx, reasons, power = [], [], set(), []
-		for row in self.rows:
-			f = [x.strip() for x in row.split(",")]
-			if len(f) < 9:
-				continue
-			try:
-				sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-			except ValueError:
-				continue
-			for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-				if val.lower().startswith("active"):
-					reasons.add(name)
-		return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-			"power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+		self.stop_flag.set()
+		if self.thread:
+			self.thread.join(timeout=15)
+		return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+			"power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+			"reasons": sorted(self.reasons), "source": self.source}
 
 
 def measured_peaks():
@@ -225,12 +247,12 @@ def run_b200_arm(args):
 
 		def step_device():
 			merged['r'] = run_protocol([ShardWorker(eng, plan, dev_audio.data_ptr(), n, on_device=True)], ex, ex.var,
-				timing=phase_ms)
+				timing=phase_ms, merge=False)
 			return eng.stats()
 
 		def step_host():
 			merged['r'] = run_protocol([ShardWorker(eng, plan, pinned.data_ptr(), n, on_device=False)], ex, ex.var,
-				timing=phase_ms)
+				timing=phase_ms, merge=False)
 			return eng.stats()
 
 	def timed(step, k):
@@ -266,6 +288,11 @@ def run_b200_arm(args):
 	clocks = sampler.stop() if rank == 0 else None
 
 	n_packets = stats[-1]["n_packets"]
+	if world > 1:
+		# every rank holds the records of all ranks (all-gathered inside the step); merging them into one
+		# (chain, position)-ordered table is the consumer's bookkeeping, like fetch()/packets() after a 1-GPU run
+		recs_all, _arena_all = merged['r'].merge()
+		n_packets = int(len(recs_all))
 	launches = sum(s["kernel_launches"] for s in stats)
 	front_ms = statistics.mean(s["front_ms"] for s in stats)
 	front_launches = stats[-1]["front_launches"]

@@ -59,6 +59,23 @@ def _states_from_bytes(blob, n_chains):
 	return arr
 
 
+_STATE_DTYPE = np.dtype([('start_clock', '<u8'), ('end_clock', '<u8'), ('start_last', '<u4'), ('start_last_q', '<u4'),
+	('end_last', '<u4'), ('end_last_q', '<u4'), ('n_symbols', '<i8')])      # pm_shard_state, clocks as bit patterns
+assert _STATE_DTYPE.itemsize == ctypes.sizeof(_lib.ShardState)
+
+
+def handoffs_verified(all_blobs):
+	"""True when every rank's speculated start state is bit for bit the previous rank's end state, i.e. when no
+	rank has anything to repair.  Every rank evaluates this on the same gathered data, so all of them take the
+	same branch without another collective."""
+	st = [np.frombuffer(b, dtype=_STATE_DTYPE) for b in all_blobs]
+	for prev, cur in zip(st, st[1:]):
+		if (not np.array_equal(prev['end_clock'], cur['start_clock']) or not np.array_equal(prev['end_last'], cur['start_last'])
+				or not np.array_equal(prev['end_last_q'], cur['start_last_q'])):
+			return False
+	return True
+
+
 class ShardWorker:
 	"""The per-rank side of the protocol; `engine` is a pymodem_b200.engine.Engine (or, in the
 	CPU tests, an object with the same shard_* / fetch methods)."""
@@ -98,34 +115,83 @@ class ShardWorker:
 
 
 def _unpack_result(blob):
+	"""-> (records as uint64[n, 5] rows -- 40-byte pm_packet_rec, column 0 = chain | len << 32, column 1 = arena
+	offset -- and the arena bytes); views into the blob, nothing is copied."""
 	n, nb = struct.unpack_from("<qq", blob, 0)
 	off = 16
-	recs = np.frombuffer(blob, dtype=REC_DTYPE, count=n, offset=off).copy()
-	arena = np.frombuffer(blob, dtype=np.uint8, count=nb, offset=off + n * REC_DTYPE.itemsize).copy()
-	return recs, arena
+	rows = np.frombuffer(blob, dtype=np.uint64, count=n * 5, offset=off).reshape(n, 5)
+	arena = np.frombuffer(blob, dtype=np.uint8, count=nb, offset=off + n * REC_DTYPE.itemsize)
+	return rows, arena
 
 
-def merge_results(blobs):
-	"""Per-rank (records, arena) blobs in rank order -> one (records, arena) ordered by
-	(chain, stream position), offsets rebased into the merged arena."""
+_merge_buf = {}
+
+
+def _scratch(name, n, dtype):
+	"""Reused output buffers: a fresh multi-megabyte numpy array costs more in page faults than the copy into it."""
+	buf = _merge_buf.get(name)
+	if buf is None or len(buf) < n:
+		buf = _merge_buf[name] = np.empty(max(n, 1) * 5 // 4 + 64, dtype=dtype)
+	return buf[:n]
+
+
+def merge_results(blobs, n_chains=None):
+	"""Per-rank (records, arena) blobs in rank order -> one (records, arena) ordered by (chain, stream position),
+	offsets rebased into the merged arena.  Every rank's records are already sorted by (chain, position) and ranks
+	are in stream order, so the merge is a block interleave: chain c of rank 0, chain c of rank 1, ...  The records
+	are handled as plain uint64 rows (fancy indexing a structured dtype with a sub-array field costs ~100 ns each).
+	The returned arrays are views of module-level scratch buffers: valid until the next merge."""
 	parts = [_unpack_result(b) for b in blobs]
-	base, recs_all = 0, []
-	for recs, arena in parts:
-		recs = recs.copy()
-		recs['offset'] += base
+	total = sum(len(p[0]) for p in parts)
+	rows = _scratch('rows', total * 5, np.uint64).reshape(total, 5)
+	chains = [r.view(np.uint32)[:, 0] for r, _ in parts]        # low half of column 0, strided view
+	if n_chains is None:
+		n_chains = 1 + max([int(c[-1]) for c in chains if len(c)], default=0)
+	keys = np.arange(n_chains + 1, dtype=np.uint32)
+	bounds = [np.searchsorted(c, keys) for c in chains]
+	bases, base = [], 0
+	for _, arena in parts:
+		bases.append(base)
 		base += len(arena)
-		recs_all.append(recs)
-	recs = np.concatenate(recs_all) if recs_all else np.zeros(0, dtype=REC_DTYPE)
-	arena = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, dtype=np.uint8)
-	order = np.argsort(recs['chain'], kind='stable')       # ranks are already in stream order within a chain
-	return recs[order], arena
+	pos = 0
+	counts, shifts = [], []
+	for c in range(n_chains):
+		for (r, _), b, ab in zip(parts, bounds, bases):
+			lo, hi = int(b[c]), int(b[c + 1])
+			if hi > lo:
+				rows[pos:pos + hi - lo] = r[lo:hi]
+				pos += hi - lo
+				counts.append(hi - lo)
+				shifts.append(ab)
+	if counts:
+		rows[:, 1] += np.repeat(np.array(shifts, dtype=np.uint64), counts)
+	arena = _scratch('arena', base, np.uint8)
+	if parts:
+		np.concatenate([p[1] for p in parts], out=arena)
+	return rows.view(REC_DTYPE).reshape(-1), arena
 
 
-def run_protocol(workers, exchange, exchange_var=None, timing=None):
+class Gathered:
+	"""The packet records of all ranks as they arrived (one blob per rank, rank order = stream order), on the host
+	of every rank.  merge() turns them into one (records, arena) pair ordered like a single engine's output; it is
+	host bookkeeping on the consumer's side, like Engine.fetch()/packets() after an unsharded run."""
+
+	def __init__(self, blobs):
+		self.blobs = blobs
+
+	def n_packets(self):
+		return sum(struct.unpack_from("<q", b, 0)[0] for b in self.blobs)
+
+	def merge(self):
+		return merge_results(self.blobs)
+
+
+def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True):
 	"""Drive the shard protocol.  `workers` are the ShardWorkers living in this process (one per
 	rank under torch.distributed; all of them when several shards are emulated in one process).
 	exchange(list of equally long local blobs) -> the blobs of ALL ranks in rank order.
-	Four collectives per run when every speculated hand-off verifies (the normal case)."""
+	Three collectives per run when every speculated hand-off verifies (the normal case): slicer states + symbol
+	counts, bit tails, packet records."""
 	import time
 	exchange_var = exchange_var or exchange
 	t = [time.perf_counter()]
@@ -136,17 +202,15 @@ def run_protocol(workers, exchange, exchange_var=None, timing=None):
 			timing[name] = timing.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
 	blobs = [w.begin() for w in workers]
 	lap("begin")
-	blobs = exchange([b + b"\x01" for b in blobs])
+	blobs = exchange(blobs)
 	lap("exchange")
 	while True:
-		blobs = [b[:-1] for b in blobs]
 		outs = [w.handoff(blobs) for w in workers]
 		lap("handoff")
-		blobs = exchange([o[0] + (b"\x01" if o[1] else b"\x00") for o in outs])      # states + "changed" flag
-		lap("exchange")
-		if not any(b[-1] for b in blobs):
+		if handoffs_verified(blobs):          # nobody had to repair: the states every rank holds are final
 			break
-	blobs = [b[:-1] for b in blobs]
+		blobs = exchange([o[0] for o in outs])
+		lap("exchange")
 	tails = [w.gather(blobs) for w in workers]
 	lap("gather")
 	tails = exchange(tails)
@@ -155,7 +219,11 @@ def run_protocol(workers, exchange, exchange_var=None, timing=None):
 	lap("finish")
 	results = exchange_var(results)
 	lap("exchange")
-	return merge_results(results)
+	if not merge:
+		return Gathered(results)
+	merged = merge_results(results)
+	lap("merge")
+	return merged
 
 
 def local_exchange(blobs):
@@ -174,7 +242,7 @@ class TorchExchange:
 		self.world = dist.get_world_size()
 		self.cuda = self.device.type == "cuda"
 		self._bufs = {}
-		self._cap = 1 << 16
+		self._cap = 1 << 16          # common blob capacity of var(), a multiple of 64 KiB
 
 	def _staging(self, n):
 		torch = self.torch
@@ -192,7 +260,7 @@ class TorchExchange:
 		n = len(blob)
 		h_in, h_out, d_in, d_out = self._staging(n)
 		if n:
-			h_in[:n].copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+			h_in.numpy()[:n] = np.frombuffer(blob, dtype=np.uint8)
 		if self.cuda:
 			d_in.copy_(h_in, non_blocking=True)
 			dist.all_gather_into_tensor(d_out, d_in)
@@ -200,9 +268,9 @@ class TorchExchange:
 			torch.cuda.current_stream().synchronize()
 		else:
 			dist.all_gather_into_tensor(d_out, d_in)
-		raw = h_out.numpy().tobytes()
+		raw = h_out.numpy()
 		m = max(n, 1)
-		return [raw[r * m:r * m + n] for r in range(self.world)]
+		return [raw[r * m:r * m + n].tobytes() for r in range(self.world)]
 
 	def var(self, blobs):
 		"""Blobs of different lengths in ONE collective: every rank sends a length header + its blob
@@ -215,8 +283,7 @@ class TorchExchange:
 			lens = [struct.unpack_from("<q", o, 0)[0] for o in out]
 			if max(lens) <= cap:
 				return [o[8:8 + k] for o, k in zip(out, lens)]
-			while self._cap < max(lens):
-				self._cap *= 2
+			self._cap = (max(lens) * 9 // 8 + 0xFFFF) & ~0xFFFF
 
 
 def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **options):
