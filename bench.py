@@ -231,10 +231,12 @@ def run_b200_arm(args):
 	else:
 		# ONE recording of world x seconds (the synthetic hour repeated), sharded on the sample axis:
 		# rank r gets its slice + FIR/warm-up history + a few forward symbols (pymodem_b200/sharded.py)
-		from pymodem_b200.sharded import ShardWorker, TorchExchange, plan_shards, run_protocol
+		from pymodem_b200.sharded import LinkedRun, TorchExchange, plan_shards
 		n_total = n_hour * world
-		plan = plan_shards(n_total, world, segment_len=32768, warm_len=32768, trim_max=305,
-			samples_per_symbol=40.0, tail_bits=16384)[rank]
+		plans = plan_shards(n_total, world, segment_len=32768, warm_len=32768, trim_max=305,
+			samples_per_symbol=40.0, tail_bits=16384)
+		plan = plans[rank]
+		max_local = max(p['audio_end'] - p['audio_begin'] for p in plans)      # the link layout must be the same on every rank
 		idx = np.arange(plan['audio_begin'], plan['audio_end'], dtype=np.int64) % n_hour
 		audio = hour[idx]
 		del idx
@@ -242,17 +244,19 @@ def run_b200_arm(args):
 		pinned = torch.from_numpy(audio).pin_memory()
 		dev_audio = pinned.cuda(non_blocking=False)
 		torch.cuda.synchronize()
+		# the ranks trade CUDA IPC handles once (NCCL all-gather); after that the hand-off, the bit tails and the
+		# packet records travel over NVLink peer memory inside each rank's own kernel stream (csrc/link.cu).
+		# NCCL is used again only if a speculated slicer start state does not verify (repair protocol).
 		ex = TorchExchange(torch.device("cuda", local))
+		linked = LinkedRun(eng, rank, world, max_local, ex, ex.var, tail_bits=16384)
 		merged = {}
 
 		def step_device():
-			merged['r'] = run_protocol([ShardWorker(eng, plan, dev_audio.data_ptr(), n, on_device=True)], ex, ex.var,
-				timing=phase_ms, merge=False)
+			merged['r'] = linked.run(plan, dev_audio.data_ptr(), n, on_device=True, timing=phase_ms, fetch=False)
 			return eng.stats()
 
 		def step_host():
-			merged['r'] = run_protocol([ShardWorker(eng, plan, pinned.data_ptr(), n, on_device=False)], ex, ex.var,
-				timing=phase_ms, merge=False)
+			merged['r'] = linked.run(plan, pinned.data_ptr(), n, on_device=False, timing=phase_ms, fetch=False)
 			return eng.stats()
 
 	def timed(step, k):
@@ -288,11 +292,7 @@ def run_b200_arm(args):
 	clocks = sampler.stop() if rank == 0 else None
 
 	n_packets = stats[-1]["n_packets"]
-	if world > 1:
-		# every rank holds the records of all ranks (all-gathered inside the step); merging them into one
-		# (chain, position)-ordered table is the consumer's bookkeeping, like fetch()/packets() after a 1-GPU run
-		recs_all, _arena_all = merged['r'].merge()
-		n_packets = int(len(recs_all))
+	link_fallbacks = linked.fallbacks if world > 1 else 0
 	launches = sum(s["kernel_launches"] for s in stats)
 	front_ms = statistics.mean(s["front_ms"] for s in stats)
 	front_launches = stats[-1]["front_launches"]
@@ -344,12 +344,14 @@ def run_b200_arm(args):
 			"AWGN AX.25 audio per GPU", "chains": n_chains, "sample_rate": SAMPLE_RATE, "samples_per_gpu": n_hour,
 			"l2": "inputs larger than L2 (345.6 MB int16 audio per GPU per step)" if n * 2 > 126e6 else "input fits L2",
 			"recording": "one recording of n_gpus x seconds (the synthetic hour repeated), sharded on the sample axis",
-			"parallelism": f"chains x audio segments on {world} GPU(s); one shard of the recording per rank, "
-				"slicer hand-off + bit tails + packet records exchanged with NCCL all-gathers"},
+			"parallelism": f"chains x audio segments on {world} GPU(s); one shard of the recording per rank; slicer "
+				"hand-off, bit tails and packet records exchanged by the GPUs over NVLink peer memory (csrc/link.cu), "
+				"every rank ends the step with the merged records of all ranks on its host"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
 			"h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"]},
 		"gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-		"stage_ms": stage_ms, "shard_phase_ms_rank0": shard_phase, "packets_per_step": n_packets,
+		"stage_ms": stage_ms, "shard_phase_ms_rank0": shard_phase, "link_fallbacks": link_fallbacks,
+		"packets_per_step": n_packets,
 		"slicer": {"segments": stats[-1]["slicer_segments"], "repairs": stats[-1]["slicer_repairs"],
 			"guard_flagged": stats[-1]["guard_flagged"]},
 		"timing": {"cuda_event_ms": ev_ms, "wall_ms": wall_ms, "e2e_cuda_event_ms": e2e_ev_ms, "e2e_wall_ms": e2e_wall_ms},

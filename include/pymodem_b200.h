@@ -191,8 +191,8 @@ int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_sampl
  * soft samples (the demod output the slicer addresses, slicer.py:75): global soft
  * sample = local + sample_base, and audio[i] is the recording's sample
  * sample_base + i.  A rank owns soft samples [own_begin, own_begin + own_len) of
- * its local buffer; the samples before own_begin are slicer warm-up (and FIR
- * history), the ones after the own range let the last stream byte complete.
+ * its local buffer; the samples before own_begin are slicer history/warm-up (and
+ * FIR history), the ones after the own range let the last stream byte complete.
  * own_begin and own_len must be multiples of the segment length (option
  * "segment_len"), except own_len on the last shard.
  *
@@ -217,7 +217,10 @@ typedef struct pm_shard_plan {
 	int32_t first;                  /* shard holds the start of the recording */
 	int32_t last;                   /* shard holds the end of the recording */
 	int32_t tail_bits;              /* hand-off tail per chain, multiple of 32 */
-	int32_t reserved;
+	int32_t pre_segments;           /* whole segments of slicer history processed (and verified) before own_begin, on
+	                                   top of the warm-up of the first of them: the speculated state at own_begin then
+	                                   rests on (pre_segments + 1) x warm-up of samples; needs own_begin >=
+	                                   pre_segments * segment_len.  0 on the first shard. */
 } pm_shard_plan;
 
 typedef struct pm_shard_state {     /* one per chain */
@@ -233,6 +236,28 @@ int pm_engine_shard_begin(pm_engine *e, const int16_t *audio, int64_t n_samples,
 int pm_engine_shard_handoff(pm_engine *e, const pm_shard_state *prev, pm_shard_state *out, int32_t *changed);
 int pm_engine_shard_gather(pm_engine *e, const int64_t *symbols_before, uint32_t *tail_out);
 int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in);
+
+/*
+ * Shard link: the same hand-off carried out by the GPUs themselves over NVLink peer memory (csrc/link.cu).
+ * Every rank creates a link buffer, the ranks exchange the 64-byte CUDA IPC handles once (any transport) and
+ * map each other's buffers.  run_linked_begin then enqueues the whole sharded run -- front end, slicer, state
+ * push, bit placement, tail push/wait, decode, record push, merge -- on the engine's stream with no host round
+ * trip after the slicer; run_linked_end waits for it and leaves the MERGED records of all ranks (ordered like an
+ * unsharded run: chain, then stream position) in the engine for pm_engine_get_packets.
+ *   *verified == 0: some rank's speculated slicer start state was wrong.  All ranks see the same states, so all
+ *   of them get 0 and continue with the host-driven protocol: pm_engine_shard_states (what shard_begin would
+ *   have returned) -> shard_handoff ... -> shard_gather -> shard_finish.
+ * use_ipc = 1: `handles` is world x 64 bytes of cudaIpcMemHandle_t (one process per GPU);
+ * use_ipc = 0: `handles` is world device pointers (several engines in one process, e.g. tests on one GPU).
+ * A rank that waits more than a few seconds for a peer gives up with PM_ERR_STATE instead of hanging.
+ */
+int pm_engine_link_create(pm_engine *e, int32_t rank, int32_t world, int32_t tail_bits, int64_t max_samples,
+                          void *ipc_handle_out /* 64 bytes */, void **base_out);
+int pm_engine_link_connect(pm_engine *e, const void *handles, int32_t use_ipc);
+int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, int64_t n_samples, int32_t audio_on_device,
+                               const pm_shard_plan *plan);
+int pm_engine_run_linked_end(pm_engine *e, int32_t *verified);
+int pm_engine_shard_states(pm_engine *e, pm_shard_state *out);
 
 int64_t pm_engine_num_packets(const pm_engine *e);
 int64_t pm_engine_arena_bytes(const pm_engine *e);

@@ -75,7 +75,7 @@ class ShardPlan(ctypes.Structure):
 	"""pm_shard_plan"""
 	_fields_ = [
 		("sample_base", ctypes.c_int64), ("own_begin", ctypes.c_int64), ("own_len", ctypes.c_int64),
-		("first", ctypes.c_int32), ("last", ctypes.c_int32), ("tail_bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
+		("first", ctypes.c_int32), ("last", ctypes.c_int32), ("tail_bits", ctypes.c_int32), ("pre_segments", ctypes.c_int32),
 	]
 
 
@@ -102,6 +102,11 @@ PROTOTYPES = {
 	"pm_engine_shard_handoff": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState), ctypes.POINTER(ShardState), ctypes.POINTER(_i32)]),
 	"pm_engine_shard_gather": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _vp]),
 	"pm_engine_shard_finish": (ctypes.c_int, [_vp, _vp]),
+	"pm_engine_link_create": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i64, _vp, ctypes.POINTER(_vp)]),
+	"pm_engine_link_connect": (ctypes.c_int, [_vp, _vp, _i32]),
+	"pm_engine_run_linked_begin": (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.POINTER(ShardPlan)]),
+	"pm_engine_run_linked_end": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
+	"pm_engine_shard_states": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState)]),
 	"pm_engine_num_packets": (_i64, [_vp]),
 	"pm_engine_arena_bytes": (_i64, [_vp]),
 	"pm_engine_get_packets": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),

@@ -41,6 +41,18 @@ cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_
 	GapRec *, long long, const ShardBits *, int, cudaStream_t);
 cudaError_t pm_launch_p64(const P64Chain *, const P64Chain *, int, const int16_t *, uint32_t *, long long, float *,
 	long long, unsigned long long *, cudaStream_t);
+cudaError_t pm_link_preload(void);
+cudaError_t pm_link_push_states(LinkGeom, LinkPeers, int, unsigned int, const SegState *, const SegState *, int, int,
+	const unsigned long long *, cudaStream_t);
+cudaError_t pm_link_wait_states(LinkGeom, unsigned char *, int, unsigned int, const BitChain *, int, int, int, ShardBits *,
+	int *, cudaStream_t);
+cudaError_t pm_link_set_flag(unsigned int *, unsigned int, cudaStream_t);
+cudaError_t pm_link_wait_flag(const unsigned int *, unsigned int, int *, cudaStream_t);
+cudaError_t pm_link_push_records(LinkGeom, LinkPeers, int, unsigned int, const PacketRecDev *, const uint8_t *,
+	const PacketTotals *, int *, cudaStream_t);
+cudaError_t pm_link_merge(LinkGeom, unsigned char *, int, unsigned int, unsigned int *, unsigned long long *,
+	unsigned long long *, PacketTotals *, PacketRecDev *, unsigned long long, uint8_t *, unsigned long long, int *,
+	cudaStream_t);
 cudaError_t pm_il2p_init_tables(void);
 cudaError_t pm_launch_il2p(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const unsigned int *,
 	long long, const unsigned int *, int, unsigned char *, long long, Il2pRes *, const uint32_t *, long long,
@@ -134,7 +146,8 @@ struct pm_engine {
 	int phase = 0;                        // 0 idle, 1 begun (slicer converged locally), 2 gathered
 	const int16_t *run_audio = nullptr;   // device pointer of the current run's audio
 	long long own_w0 = 0, own_w1 = 0, end_w = 0;   // own range / processed range in words
-	int k_end = 0;                        // segment whose end state is the shard's end state
+	int k0 = 0;                           // first own segment (= plan.pre_segments)
+	int k_end = 0;                        // segment after the one whose end state is the shard's end state
 	std::vector<pm_shard_state> shard_out;
 	std::vector<SegState> h_init;
 	DevBuf<unsigned int> d_blk_count, d_blk_base, d_sym_totals, d_flag_totals, d_flag_pos, d_rec_src;
@@ -150,6 +163,22 @@ struct pm_engine {
 	DevBuf<unsigned long long> d_p64_max;
 	std::vector<P64Chain> h_p64;
 	std::vector<size_t> p64_tab_off;      // per p64 chain: offsets into d_p64_tabs (wavetable, hilbert) and d_p64_pd
+	// shard link (csrc/link.cu)
+	bool link_on = false;
+	LinkGeom lg;
+	LinkPeers lp;
+	DevBuf<unsigned char> d_link;
+	std::vector<void *> link_opened;      // peer mappings opened with cudaIpcOpenMemHandle
+	unsigned int link_epoch = 0;
+	int link_tail_bits = 0;
+	DevBuf<int> d_link_status;
+	DevBuf<unsigned int> d_link_lb;
+	DevBuf<unsigned long long> d_link_obase;
+	DevBuf<pm_packet_rec> d_mrecs;
+	DevBuf<uint8_t> d_marena;
+	DevBuf<PacketTotals> d_mtotals;
+	int *h_link_status = nullptr;         // pinned
+	PacketTotals *h_mtotals = nullptr;    // pinned
 	int il2p_cand_cap = 0;
 	bool has_il2p = false, il2p_tables = false;
 	unsigned int *h_counters = nullptr;   // pinned
@@ -441,6 +470,11 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_p64_work.release(); e->d_p64_tabs.release(); e->d_p64_pd.release(); e->d_p64.release(); e->d_p64_max.release();
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
+	for (void *p : e->link_opened) cudaIpcCloseMemHandle(p);
+	e->d_link.release(); e->d_link_status.release(); e->d_link_lb.release(); e->d_link_obase.release();
+	e->d_mrecs.release(); e->d_marena.release(); e->d_mtotals.release();
+	if (e->h_link_status) cudaFreeHost(e->h_link_status);
+	if (e->h_mtotals) cudaFreeHost(e->h_mtotals);
 	if (e->h_counters) cudaFreeHost(e->h_counters);
 	if (e->h_totals) cudaFreeHost(e->h_totals);
 	cudaStreamDestroy(e->st);
@@ -672,6 +706,8 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	if (plan.first && (plan.own_begin != 0 || plan.sample_base != 0))
 		return fail(e, PM_ERR_ARG, "the first shard starts at sample 0");
 	if (plan.tail_bits < 0 || plan.tail_bits % 32) return fail(e, PM_ERR_ARG, "tail_bits must be a multiple of 32");
+	if (plan.pre_segments < 0 || (plan.first && plan.pre_segments) || plan.own_begin < (long long)plan.pre_segments * seg_len)
+		return fail(e, PM_ERR_ARG, "pre_segments needs own_begin >= pre_segments * segment_len (and 0 on the first shard)");
 	if (sharded && !(plan.first && plan.last) && plan.tail_bits < 128)
 		return fail(e, PM_ERR_ARG, "tail_bits must be at least 128");
 	e->n_samples = n;
@@ -733,14 +769,17 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	else e->own_w1 = (plan.own_begin + plan.own_len) / 32;
 	if (e->own_w0 > e->end_w) e->own_w0 = e->end_w;
 	SlicerGeom &G = e->geom;
-	G.origin_w = e->own_w0;
+	e->k0 = plan.pre_segments;
+	G.origin_w = e->own_w0 - (long long)e->k0 * seg_words;
+	G.k_init = 0;
 	G.seg_words = seg_words;
 	G.warm_words = e->opt_warm_words;
 	G.chk_words = chk_words;
 	G.n_chk = seg_words / chk_words;
-	G.n_seg = (int)std::max<long long>(1, (e->end_w - e->own_w0 + seg_words - 1) / seg_words);
+	G.n_seg = e->k0 + (int)std::max<long long>(1, (e->end_w - e->own_w0 + seg_words - 1) / seg_words);
 	G.true_start = plan.first ? 1 : 0;
-	e->k_end = (int)std::min<long long>(G.n_seg, std::max<long long>(1, (e->own_w1 - e->own_w0 + seg_words - 1) / seg_words));
+	e->k_end = e->k0 + (int)std::min<long long>(G.n_seg - e->k0,
+		std::max<long long>(1, (e->own_w1 - e->own_w0 + seg_words - 1) / seg_words));
 	e->n_seg = G.n_seg;
 	e->bits_stride = round_up((int)((max_bits + 31) / 32) + 8, 4);
 	e->addr_stride = max_bits / 8 + 16;
@@ -889,7 +928,7 @@ static int slicer_converge(pm_engine *e)
 	return PM_OK;
 }
 
-// start state (S of segment 0), end state (E of segment k_end-1) and own symbol count of every chain
+// start state (S of the first own segment k0), end state (E of segment k_end-1) and own symbol count of every chain
 static int read_shard_states(pm_engine *e)
 {
 	const int nc = (int)e->chains.size();
@@ -900,7 +939,7 @@ static int read_shard_states(pm_engine *e)
 		e->d_symcount.p, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "symbol count launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches++;
-	CK(cudaMemcpy2DAsync(s0.data(), sizeof(SegState), e->d_S.p, (size_t)n_seg * sizeof(SegState), sizeof(SegState), nc,
+	CK(cudaMemcpy2DAsync(s0.data(), sizeof(SegState), e->d_S.p + e->k0, (size_t)n_seg * sizeof(SegState), sizeof(SegState), nc,
 		cudaMemcpyDeviceToHost, e->st));
 	CK(cudaMemcpy2DAsync(e1.data(), sizeof(SegState), e->E_cur + (e->k_end - 1), (size_t)n_seg * sizeof(SegState),
 		sizeof(SegState), nc, cudaMemcpyDeviceToHost, e->st));
@@ -913,6 +952,20 @@ static int read_shard_states(pm_engine *e)
 		o.end_clock = e1[c].clock; o.end_last = e1[c].last; o.end_last_q = e1[c].last_q;
 		o.n_symbols = (int64_t)cnt[c];
 	}
+	return PM_OK;
+}
+
+// shard states to the host; on a later shard the device-side init[] holds the speculated start states
+static int fetch_shard_states(pm_engine *e)
+{
+	int rc = read_shard_states(e);
+	if (rc != PM_OK) return rc;
+	if (!e->plan.first)
+		for (size_t c = 0; c < e->chains.size(); c++) {
+			e->h_init[c].clock = e->shard_out[c].start_clock;
+			e->h_init[c].last = e->shard_out[c].start_last;
+			e->h_init[c].last_q = e->shard_out[c].start_last_q;
+		}
 	return PM_OK;
 }
 
@@ -994,7 +1047,7 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 }
 
 static int shard_begin_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
-                            bool sharded)
+                            bool sharded, bool read_states = true)
 {
 	if (!e) return PM_ERR_ARG;
 	if (!audio) return fail(e, PM_ERR_ARG, "audio is NULL");
@@ -1010,15 +1063,9 @@ static int shard_begin_impl(pm_engine *e, const int16_t *audio, long long n, boo
 			continue;
 		}
 		if (rc != PM_OK) return rc;
-		if (sharded) {
-			rc = read_shard_states(e);
+		if (sharded && read_states) {
+			rc = fetch_shard_states(e);
 			if (rc != PM_OK) return rc;
-			if (!plan.first)       // what the device-side init[] holds now: the speculated start states
-				for (size_t c = 0; c < e->chains.size(); c++) {
-					e->h_init[c].clock = e->shard_out[c].start_clock;
-					e->h_init[c].last = e->shard_out[c].start_last;
-					e->h_init[c].last_q = e->shard_out[c].start_last_q;
-				}
 		}
 		e->phase = 1;
 		return PM_OK;
@@ -1207,6 +1254,7 @@ extern "C" int pm_engine_shard_handoff(pm_engine *e, const pm_shard_state *prev,
 		}
 		if (mismatch) {
 			const std::vector<pm_shard_state> before = e->shard_out;
+			e->geom.k_init = e->k0;      // the true state enters at the first own segment; the history before it is final
 			CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
 			int rc = slicer_converge(e);
 			if (rc != PM_OK) return rc;
@@ -1235,6 +1283,227 @@ extern "C" int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in)
 	if (!e) return PM_ERR_ARG;
 	cudaSetDevice(e->device);
 	return shard_finish_impl(e, tail_in);
+}
+
+
+// ---------------------------------------------------------------------------
+// Shard link: the hand-off done on the devices over peer memory (csrc/link.cu)
+// ---------------------------------------------------------------------------
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+extern "C" int pm_engine_link_create(pm_engine *e, int32_t rank, int32_t world, int32_t tail_bits, int64_t max_samples,
+                                     void *ipc_handle_out, void **base_out)
+{
+	if (!e || rank < 0 || world < 1 || rank >= world || world > LINK_MAX_WORLD || tail_bits < 0 || tail_bits % 32 || max_samples <= 0)
+		return fail(e, PM_ERR_ARG, "link_create: bad arguments");
+	if (world > 1 && tail_bits < 128) return fail(e, PM_ERR_ARG, "tail_bits must be at least 128");
+	const int nc = (int)e->chains.size();
+	if (nc == 0) return fail(e, PM_ERR_STATE, "load chains before creating the link");
+	if ((long long)nc * world > 8192) return fail(e, PM_ERR_CAPACITY, "too many chains x ranks for the link");
+	cudaSetDevice(e->device);
+	// worst-case records + packet bytes of one rank (the bounds prepare_run uses)
+	long long rec_cap = 16, arena_cap = 64;
+	for (auto &hc : e->chains) {
+		if (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK) || hc.d.codec_kind != PM_CODEC_AX25)
+			return fail(e, PM_ERR_UNSUPPORTED, "only binary-slicer AX.25 chains without a carrier loop can be sharded");
+		const double thr = hc.d.slicer_sample_rate / hc.d.symbol_rate / 2.0 - 0.5;
+		const long long min_gap = std::max<long long>(1, (long long)std::ceil(thr));
+		const long long mb = (max_samples / min_gap + 8) + 64 + tail_bits;
+		rec_cap += mb / 152 + 4;
+		arena_cap += mb / 8 + 64;
+	}
+	LinkGeom &G = e->lg;
+	memset(&G, 0, sizeof(G));
+	G.rank = rank; G.world = world; G.nc = nc; G.tail_words = tail_bits / 32;
+	G.rec_region = align_up(rec_cap * (long long)sizeof(pm_packet_rec) + arena_cap, 256);
+	long long off = 0;
+	G.off_states = off; off = align_up(off + (long long)world * nc * sizeof(pm_shard_state), 256);
+	G.off_sflag = off; off = align_up(off + 4ll * world, 256);
+	G.off_tail = off; off = align_up(off + 4ll * nc * std::max(1, G.tail_words), 256);
+	G.off_tflag = off; off += 256;
+	G.off_rflag = off; off = align_up(off + 4ll * world, 256);
+	G.off_rhdr = off; off = align_up(off + 16ll * world, 256);
+	G.off_rdata = off; off += (long long)world * G.rec_region;
+	G.slot_bytes = align_up(off, 4096);
+	CK(e->d_link.ensure((size_t)(2 * G.slot_bytes)));
+	CK(cudaMemset(e->d_link.p, 0, (size_t)(2 * G.slot_bytes)));
+	CK(e->d_link_status.ensure(8));
+	CK(e->d_link_lb.ensure((size_t)world * (nc + 1)));
+	CK(e->d_link_obase.ensure((size_t)world * (nc + 1) + world));
+	CK(e->d_mrecs.ensure((size_t)(rec_cap * world)));
+	CK(e->d_marena.ensure((size_t)(arena_cap * world)));
+	CK(e->d_mtotals.ensure(1));
+	if (!e->h_link_status) CK(cudaHostAlloc((void **)&e->h_link_status, 64, cudaHostAllocDefault));
+	if (!e->h_mtotals) CK(cudaHostAlloc((void **)&e->h_mtotals, sizeof(PacketTotals), cudaHostAllocDefault));
+	e->link_tail_bits = tail_bits;
+	e->link_epoch = 0;
+	e->link_on = false;
+	if (ipc_handle_out) {
+		cudaIpcMemHandle_t h;
+		CK(cudaIpcGetMemHandle(&h, e->d_link.p));
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+		memcpy(ipc_handle_out, &h, sizeof(h));
+	}
+	if (base_out) *base_out = e->d_link.p;
+	return PM_OK;
+}
+
+extern "C" int pm_engine_link_connect(pm_engine *e, const void *handles, int32_t use_ipc)
+{
+	if (!e || !handles || !e->d_link.p) return fail(e, PM_ERR_STATE, "link_connect: create the link first");
+	cudaSetDevice(e->device);
+	for (void *p : e->link_opened) cudaIpcCloseMemHandle(p);
+	e->link_opened.clear();
+	memset(&e->lp, 0, sizeof(e->lp));
+	for (int q = 0; q < e->lg.world; q++) {
+		if (q == e->lg.rank) { e->lp.base[q] = e->d_link.p; continue; }
+		if (use_ipc) {
+			cudaIpcMemHandle_t h;
+			memcpy(&h, (const char *)handles + 64 * q, 64);
+			void *p = nullptr;
+			CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+			e->link_opened.push_back(p);
+			e->lp.base[q] = (unsigned char *)p;
+		} else {
+			e->lp.base[q] = (unsigned char *)((void *const *)handles)[q];
+		}
+	}
+	CK(pm_link_preload());
+	e->link_on = true;
+	return PM_OK;
+}
+
+#define CKL(call)                                                                                      \
+	do {                                                                                               \
+		cudaError_t _e = (call);                                                                       \
+		if (_e != cudaSuccess) return fail(e, PM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+	} while (0)
+
+extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, int64_t n_samples, int32_t audio_on_device,
+                                          const pm_shard_plan *plan)
+{
+	if (!e || !plan) return fail(e, PM_ERR_ARG, "run_linked_begin: bad arguments");
+	if (!e->link_on) return fail(e, PM_ERR_STATE, "run_linked_begin: connect the link first");
+	const LinkGeom &G = e->lg;
+	if (plan->tail_bits != e->link_tail_bits || (plan->first != 0) != (G.rank == 0) || (plan->last != 0) != (G.rank == G.world - 1))
+		return fail(e, PM_ERR_ARG, "run_linked_begin: plan does not match the link (rank %d of %d, tail %d)", G.rank, G.world,
+			e->link_tail_bits);
+	int rc = shard_begin_impl(e, audio, n_samples, !audio_on_device, *plan, true, false);
+	if (rc != PM_OK) return rc;
+	const int nc = (int)e->chains.size();
+	const unsigned int epoch = ++e->link_epoch;
+	const int parity = (int)(epoch & 1u);
+	cudaStream_t st = e->st;
+	unsigned char *own = e->d_link.p;
+	int *status = e->d_link_status.p;
+	CK(cudaMemsetAsync(status, 0, 8 * sizeof(int), st));
+	CKL(pm_launch_slicer_count(e->d_slicer.p, nc, e->d_mask.p, e->sign_stride, e->own_w0, e->own_w1, e->d_symcount.p, st));
+	CKL(pm_link_push_states(G, e->lp, parity, epoch, e->d_S.p + e->k0, e->E_cur, e->geom.n_seg, e->k_end, e->d_symcount.p, st));
+	CKL(pm_link_wait_states(G, own, parity, epoch, e->d_bitchain.p, plan->first, plan->last, plan->tail_bits,
+		e->d_shardbits.p, status, st));
+	CKL(pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride, e->own_w0,
+		std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p, e->d_sym_totals.p, e->d_bits_raw.p,
+		e->bits_stride, e->d_byte_addr.p, e->addr_stride, nullptr, e->d_shardbits.p, st));
+	e->stats.kernel_launches += 7;
+	if (!plan->last && G.tail_words > 0) {
+		unsigned char *next = e->lp.base[G.rank + 1] + (long long)parity * G.slot_bytes;
+		CKL(pm_launch_tail_extract(e->d_bits_raw.p, e->bits_stride, e->d_shardbits.p, nc, G.tail_words,
+			(uint32_t *)(next + G.off_tail), st));
+		CKL(pm_link_set_flag((unsigned int *)(next + G.off_tflag), epoch, st));
+		e->stats.kernel_launches += 2;
+	}
+	if (!plan->first && G.tail_words > 0) {
+		unsigned char *slot = own + (long long)parity * G.slot_bytes;
+		CKL(pm_link_wait_flag((const unsigned int *)(slot + G.off_tflag), epoch, status, st));
+		CKL(pm_launch_tail_inject(e->d_bits_raw.p, e->bits_stride, e->d_shardbits.p, nc, G.tail_words,
+			(const uint32_t *)(slot + G.off_tail), st));
+		e->stats.kernel_launches += 2;
+	}
+	CKL(pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, st));
+	CKL(pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p, e->d_blk_base.p,
+		e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride, e->d_scratch.p,
+		e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, 0, st));
+	CKL(pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p, e->d_recs.n,
+		e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base, st));
+	CK(cudaEventRecord(e->ev[4], st));
+	CKL(pm_link_push_records(G, e->lp, parity, epoch, (const PacketRecDev *)e->d_recs.p, e->d_arena.p, e->d_totals.p, status, st));
+	CKL(pm_link_merge(G, own, parity, epoch, e->d_link_lb.p, e->d_link_obase.p, e->d_link_obase.p + (size_t)G.world * (nc + 1),
+		e->d_mtotals.p, (PacketRecDev *)e->d_mrecs.p, e->d_mrecs.n, e->d_marena.p, e->d_marena.n, status, st));
+	e->stats.kernel_launches += 12;
+	CK(cudaMemcpyAsync(e->h_link_status, status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(e->h_mtotals, e->d_mtotals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, st));
+	// (nothing here may block the host: a copy into pageable memory would wait for the stream, i.e. for the peers)
+	e->phase = 3;
+	return PM_OK;
+}
+
+extern "C" int pm_engine_run_linked_end(pm_engine *e, int32_t *verified)
+{
+	if (!e || !verified) return fail(e, PM_ERR_ARG, "run_linked_end: bad arguments");
+	if (e->phase != 3) return fail(e, PM_ERR_STATE, "run_linked_end: call run_linked_begin first");
+	cudaSetDevice(e->device);
+	const int nc = (int)e->chains.size();
+	CK(cudaStreamSynchronize(e->st));
+	*verified = e->h_link_status[0];
+	if (e->h_link_status[1] != 0) {
+		e->phase = 0;
+		static const char *where[] = {"", "waiting for the slicer states of the other ranks", "waiting for the previous rank's bit tail",
+			"pushing packet records (link region too small)", "waiting for the packet records of the other ranks",
+			"another rank reported a failure"};
+		const int w = e->h_link_status[2];
+		return fail(e, e->h_link_status[1], "shard link failed while %s", (w >= 1 && w <= 5) ? where[w] : "running");
+	}
+	if (!*verified) {
+		// some rank's speculated start state was wrong: every rank saw the same states and falls back to the
+		// host-driven repair protocol (pm_engine_shard_states -> handoff -> gather -> finish)
+		e->phase = 1;
+		return PM_OK;
+	}
+	const unsigned long long np = e->h_mtotals->n_packets, nb = e->h_mtotals->n_bytes;
+	if (np > e->d_mrecs.n || nb > e->d_marena.n)
+		return fail(e, PM_ERR_CAPACITY, "merged packet buffers too small (%llu records, %llu bytes)", np, nb);
+	e->h_recs.resize(np);
+	e->h_arena.resize(nb);
+	e->h_cc.resize(nc);
+	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
+	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_mrecs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
+	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_marena.p, nb, cudaMemcpyDeviceToHost, e->st));
+	CK(cudaEventRecord(e->ev[5], e->st));
+	CK(cudaStreamSynchronize(e->st));
+	for (int c = 0; c < nc; c++) {
+		if (e->h_cc[c].tail_short)
+			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
+				c, e->plan.tail_bits);
+		if (e->h_cc[c].seq_needed)
+			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (run unsharded)", c);
+	}
+	e->stats.d2h_bytes = (int64_t)(np * sizeof(pm_packet_rec) + nb + sizeof(PacketTotals) + nc * sizeof(ChainCounters) + 16);
+	e->stats.n_packets = (int64_t)np;
+	e->stats.n_stream_bits = 0;
+	for (auto &c : e->h_cc) e->stats.n_stream_bits += c.nbits;
+	float ms = 0;
+	auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, e->ev[a], e->ev[b]); return (double)ms; };
+	e->stats.total_ms = el(0, 5);
+	e->stats.front_ms = el(0, 1);
+	e->stats.fixup_ms = el(1, 2);
+	e->stats.slicer_ms = el(2, 3);
+	e->stats.bits_ms = el(3, 4);
+	e->stats.d2h_ms = el(4, 5);
+	e->phase = 0;
+	e->have_run = true;
+	return PM_OK;
+}
+
+// the states shard_begin reports, for a rank that began through run_linked_begin and has to fall back
+extern "C" int pm_engine_shard_states(pm_engine *e, pm_shard_state *out)
+{
+	if (!e || !out) return fail(e, PM_ERR_ARG, "shard_states: bad arguments");
+	if (e->phase != 1 || !e->sharded) return fail(e, PM_ERR_STATE, "shard_states: no sharded run in progress");
+	cudaSetDevice(e->device);
+	int rc = fetch_shard_states(e);
+	if (rc != PM_OK) return rc;
+	memcpy(out, e->shard_out.data(), e->shard_out.size() * sizeof(pm_shard_state));
+	return PM_OK;
 }
 
 extern "C" int64_t pm_engine_num_packets(const pm_engine *e) { return (e && e->have_run) ? (int64_t)e->h_recs.size() : -1; }

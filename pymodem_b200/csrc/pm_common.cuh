@@ -99,6 +99,8 @@ struct SlicerGeom {
 	int chk_words;           // checkpoint spacing (divides seg_words)
 	int n_chk;               // seg_words / chk_words
 	int true_start;          // local sample 0 is the true start of the recording
+	int k_init;              // segment whose predecessor state is init[] (0 during the local pass; the first own
+	                         // segment when a hand-off repair starts there -- the segments before it are frozen)
 };
 
 // Per-chain placement of the local bitstream when the recording is sharded on
@@ -167,6 +169,24 @@ struct P64Chain {
 	const int *pd_table;
 	int wt_size, pd_g;
 	unsigned long long *max_slot;   // ordered-integer image of max(A) for AGC.normal (agc.py:67)
+};
+
+// ---- shard link over NVLink peer memory (csrc/link.cu) -------------------------------------------------
+#define LINK_MAX_WORLD 16
+struct LinkGeom {
+	int rank, world, nc, tail_words;
+	long long slot_bytes;      // one parity slot
+	long long off_states;      // pm_shard_state[world][nc]
+	long long off_sflag;       // unsigned[world]
+	long long off_tail;        // uint32[nc][tail_words]   (written by rank - 1)
+	long long off_tflag;       // unsigned
+	long long off_rflag;       // unsigned[world]
+	long long off_rhdr;        // u64[world][2]: records, arena bytes
+	long long off_rdata;       // world regions of rec_region bytes: records then arena
+	long long rec_region;
+};
+struct LinkPeers {
+	unsigned char *base[LINK_MAX_WORLD];
 };
 
 struct ChainCounters {

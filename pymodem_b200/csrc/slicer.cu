@@ -129,7 +129,11 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
 	const int ch = blockIdx.y;
 	if (k >= G.n_seg) return;
 	const long long idx = (long long)ch * G.n_seg + k;
-	const SegState prev = (k == 0) ? init[ch] : E_in[idx - 1];
+	if (k < G.k_init) {                 // history segments before a repaired hand-off: already final
+		E_out[idx] = E_in[idx];
+		return;
+	}
+	const SegState prev = (k == G.k_init) ? init[ch] : E_in[idx - 1];
 	const SegState mine = S[idx];
 	if (seg_state_equal(prev, mine)) {
 		E_out[idx] = E_in[idx];
@@ -177,7 +181,7 @@ __global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, cons
 	uint32_t *mk = mask + (long long)ch * mask_stride;
 	SegState prev = init[ch];
 	unsigned int fixed = 0;
-	for (int k = 0; k < G.n_seg; k++) {
+	for (int k = G.k_init; k < G.n_seg; k++) {
 		const long long idx = (long long)ch * G.n_seg + k;
 		const long long w_begin = G.origin_w + (long long)k * G.seg_words;
 		if (!seg_state_equal(S[idx], prev)) {

@@ -99,7 +99,7 @@ class Engine:
 	def shard_begin(self, audio_ptr, n, plan, on_device=False):
 		"""plan: dict(sample_base, own_begin, own_len, first, last, tail_bits) -> ShardState array"""
 		p = _lib.ShardPlan(int(plan['sample_base']), int(plan['own_begin']), int(plan['own_len']),
-			int(bool(plan['first'])), int(bool(plan['last'])), int(plan['tail_bits']), 0)
+			int(bool(plan['first'])), int(bool(plan['last'])), int(plan['tail_bits']), int(plan.get('pre_segments', 0)))
 		self._tail_words = int(plan['tail_bits']) // 32
 		out = (_lib.ShardState * self.n_chains)()
 		self._check(self._lib.pm_engine_shard_begin(self._h, audio_ptr, int(n), int(bool(on_device)), ctypes.byref(p), out))
@@ -126,6 +126,43 @@ class Engine:
 		else:
 			t = np.ascontiguousarray(tail_in, dtype=np.uint32)
 			self._check(self._lib.pm_engine_shard_finish(self._h, t.ctypes.data))
+
+	# -- shard link: the hand-off done by the GPUs over peer memory (csrc/link.cu) ---------------
+	def link_create(self, rank, world, tail_bits, max_samples):
+		"""-> (64-byte CUDA IPC handle of this rank's link buffer, its device address)"""
+		handle = ctypes.create_string_buffer(64)
+		base = ctypes.c_void_p()
+		self._check(self._lib.pm_engine_link_create(self._h, int(rank), int(world), int(tail_bits), int(max_samples),
+			handle, ctypes.byref(base)))
+		return handle.raw, int(base.value)
+
+	def link_connect(self, handles=None, pointers=None):
+		"""handles: the IPC handles of all ranks in rank order (one process per GPU); pointers: the link buffer
+		addresses of all ranks (several engines inside one process)."""
+		if handles is not None:
+			blob = b"".join(handles)
+			self._check(self._lib.pm_engine_link_connect(self._h, ctypes.c_char_p(blob), 1))
+		else:
+			arr = (ctypes.c_void_p * len(pointers))(*pointers)
+			self._check(self._lib.pm_engine_link_connect(self._h, arr, 0))
+
+	def run_linked_begin(self, audio_ptr, n, plan, on_device=False):
+		p = _lib.ShardPlan(int(plan['sample_base']), int(plan['own_begin']), int(plan['own_len']),
+			int(bool(plan['first'])), int(bool(plan['last'])), int(plan['tail_bits']), int(plan.get('pre_segments', 0)))
+		self._tail_words = int(plan['tail_bits']) // 32
+		self._check(self._lib.pm_engine_run_linked_begin(self._h, audio_ptr, int(n), int(bool(on_device)), ctypes.byref(p)))
+
+	def run_linked_end(self):
+		"""-> True when every hand-off verified (merged records of all ranks are ready for fetch());
+		False when the ranks have to fall back to the host-driven repair protocol."""
+		v = ctypes.c_int32(0)
+		self._check(self._lib.pm_engine_run_linked_end(self._h, ctypes.byref(v)))
+		return bool(v.value)
+
+	def shard_states(self):
+		out = (_lib.ShardState * self.n_chains)()
+		self._check(self._lib.pm_engine_shard_states(self._h, out))
+		return out
 
 	def fetch(self):
 		n = self._lib.pm_engine_num_packets(self._h)

@@ -28,9 +28,15 @@ from .engine import REC_DTYPE
 
 
 def plan_shards(n_samples, world, segment_len=32768, warm_len=32768, trim_max=305, samples_per_symbol=40.0,
-		tail_bits=16384):
+		tail_bits=16384, pre_segments=4):
 	"""Split n_samples over `world` ranks.  Returns one dict per rank:
-	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields."""
+	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields.
+
+	pre_segments: whole segments of slicer history every later rank runs (and verifies) before its own range, so that
+	its speculated state at own_begin rests on (pre_segments + 1) warm-ups instead of one.  A single 32768-sample
+	warm-up fails to become bit-identical in ~1 % of the cases (profiles/r01_slicer_sweep.txt); inside one GPU that
+	costs a cheap re-run of the segment, at a shard boundary it would cost the hand-off's fast path.  The history is
+	0.1 % more front-end work per rank."""
 	if world < 1:
 		raise ValueError("world must be >= 1")
 	per = int(math.ceil(n_samples / world / segment_len)) * segment_len
@@ -41,11 +47,12 @@ def plan_shards(n_samples, world, segment_len=32768, warm_len=32768, trim_max=30
 	plans = []
 	for r in range(world):
 		b0 = r * per
-		base = max(0, b0 - back)
+		pre = 0 if r == 0 else max(0, min(pre_segments, (b0 - back) // segment_len))
+		base = max(0, b0 - back - pre * segment_len)
 		last = r == world - 1
 		a1 = n_samples if last else min(n_samples, b0 + per + fwd + trim_max)
 		plans.append(dict(rank=r, audio_begin=base, audio_end=a1, sample_base=base, own_begin=b0 - base,
-			own_len=per, first=(r == 0), last=last, tail_bits=tail_bits if world > 1 else 0))
+			own_len=per, first=(r == 0), last=last, tail_bits=tail_bits if world > 1 else 0, pre_segments=pre))
 	return plans
 
 
@@ -88,6 +95,11 @@ class ShardWorker:
 
 	def begin(self):
 		self.states = self.engine.shard_begin(self.audio_ptr, self.n_local, self.plan, self.on_device)
+		return _states_to_bytes(self.states)
+
+	def resume(self):
+		"""The states of a run that was begun through the shard link (Engine.run_linked_begin) and did not verify."""
+		self.states = self.engine.shard_states()
 		return _states_to_bytes(self.states)
 
 	def handoff(self, all_blobs):
@@ -186,7 +198,7 @@ class Gathered:
 		return merge_results(self.blobs)
 
 
-def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True):
+def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True, resume=False):
 	"""Drive the shard protocol.  `workers` are the ShardWorkers living in this process (one per
 	rank under torch.distributed; all of them when several shards are emulated in one process).
 	exchange(list of equally long local blobs) -> the blobs of ALL ranks in rank order.
@@ -200,7 +212,7 @@ def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True):
 		t.append(time.perf_counter())
 		if timing is not None:
 			timing[name] = timing.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
-	blobs = [w.begin() for w in workers]
+	blobs = [w.resume() if resume else w.begin() for w in workers]
 	lap("begin")
 	blobs = exchange(blobs)
 	lap("exchange")
@@ -284,6 +296,84 @@ class TorchExchange:
 			if max(lens) <= cap:
 				return [o[8:8 + k] for o, k in zip(out, lens)]
 			self._cap = (max(lens) * 9 // 8 + 0xFFFF) & ~0xFFFF
+
+
+class LinkedRun:
+	"""One rank of a linked multi-GPU run: the hand-off, the bit tails and the packet records travel between the
+	GPUs over NVLink peer memory inside one stream of kernels (csrc/link.cu); the host only launches and collects.
+	`exchange(list of one blob) -> blobs of all ranks` is used once, to trade the IPC handles, and again only when a
+	speculated slicer start state did not verify (then the repair protocol above takes over)."""
+
+	def __init__(self, engine, rank, world, max_samples, exchange, exchange_var=None, tail_bits=16384):
+		self.engine, self.rank, self.world = engine, rank, world
+		self.exchange, self.exchange_var = exchange, exchange_var or exchange
+		self.tail_bits = tail_bits if world > 1 else 0
+		handle, _ = engine.link_create(rank, world, self.tail_bits, max_samples)
+		# the link layout follows from (chains, world, tail_bits, max_samples): it has to be the same everywhere
+		blobs = exchange([handle + struct.pack("<qqq", int(max_samples), int(self.tail_bits), engine.n_chains)])
+		if len({b[64:] for b in blobs}) != 1:
+			raise ValueError("LinkedRun: ranks disagree on max_samples / tail_bits / chain count")
+		engine.link_connect(handles=[b[:64] for b in blobs])
+		self.fallbacks = 0
+
+	def run(self, plan, audio_ptr, n_local, on_device=False, timing=None, fetch=True):
+		"""-> (records, arena) of ALL ranks, ordered like an unsharded run.  fetch=False leaves them in the engine
+		(host memory, like an unsharded pm_engine_run) and returns None when the fast path held."""
+		import time
+		t0 = time.perf_counter()
+		self.engine.run_linked_begin(audio_ptr, n_local, plan, on_device)
+		t1 = time.perf_counter()
+		ok = self.engine.run_linked_end()
+		t2 = time.perf_counter()
+		if timing is not None:
+			timing['linked_begin'] = timing.get('linked_begin', 0.0) + (t1 - t0) * 1e3
+			timing['linked_end'] = timing.get('linked_end', 0.0) + (t2 - t1) * 1e3
+		if ok:
+			return self.engine.fetch() if fetch else None
+		self.fallbacks += 1
+		worker = ShardWorker(self.engine, plan, audio_ptr, n_local, on_device)
+		return run_protocol([worker], self.exchange, self.exchange_var, timing=timing, resume=True)
+
+
+def run_linked_local(demod_stack, audio, world, device=0, tail_bits=16384, **options):
+	"""`world` ranks emulated on ONE GPU with the shard link (link buffers connected by plain device pointers):
+	all ranks are enqueued first, then collected -- a waiting rank spins in a one-block kernel while the others
+	run.  Returns (per-chain PacketMeta lists as rank 0 sees them, info)."""
+	from .engine import Engine
+	audio = np.ascontiguousarray(audio, dtype=np.int16)
+	seg = int(options.get('segment_len', 32768))
+	warm = int(options.get('warmup_len', 32768))
+	trim = max(_chain_trim(c) for c in demod_stack)
+	sps = max(float(c[2].sample_rate) / float(c[2].symbol_rate) for c in demod_stack)
+	plans = plan_shards(len(audio), world, segment_len=seg, warm_len=max(warm, seg), trim_max=trim,
+		samples_per_symbol=sps, tail_bits=tail_bits)
+	engines = [Engine(demod_stack, device=device, **options) for _ in plans]
+	try:
+		locals_ = [audio[p['audio_begin']:p['audio_end']] for p in plans]
+		bases = [e.link_create(p['rank'], world, p['tail_bits'], max(len(l) for l in locals_))[1] for e, p in zip(engines, plans)]
+		for e in engines:
+			e.link_connect(pointers=bases)
+		# One process, one GPU: cudaMalloc and first-use kernel loading synchronise the whole device, which would
+		# block behind another rank's spinning wait kernel.  Size every buffer with a host-driven pass over the same
+		# shards first.  (With one process per GPU nothing of the sort can happen: a rank only ever waits for *other*
+		# devices.)
+		run_protocol([ShardWorker(e, p, l.ctypes.data, len(l)) for e, p, l in zip(engines, plans, locals_)], local_exchange)
+		for e, p, l in zip(engines, plans, locals_):
+			e.run_linked_begin(l.ctypes.data, len(l), p)
+		verified = [e.run_linked_end() for e in engines]
+		info = dict(verified=verified, plans=plans, repairs=[e.stats()['slicer_repairs'] for e in engines])
+		if all(verified):
+			results = [e.fetch() for e in engines]
+			info['all_ranks_equal'] = all(np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1])
+				for r in results[1:])
+			return engines[0].packets(*results[0]), info
+		assert not any(verified), "ranks disagree on the hand-off verdict"
+		workers = [ShardWorker(e, p, l.ctypes.data, len(l)) for e, p, l in zip(engines, plans, locals_)]
+		recs, arena = run_protocol(workers, local_exchange, resume=True)
+		return engines[0].packets(recs, arena), info
+	finally:
+		for e in engines:
+			e.close()
 
 
 def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **options):

@@ -34,15 +34,17 @@ def test_struct_layouts_match_header(tmp_path):
 	from pymodem_b200 import _lib
 	prog = tmp_path / "layout.c"
 	prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pymodem_b200.h"\n'
-		'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pm_chain_desc), offsetof(pm_chain_desc, lpf),'
+		'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pm_chain_desc), offsetof(pm_chain_desc, lpf),'
 		' offsetof(pm_chain_desc, demap), offsetof(pm_chain_desc, loop), sizeof(pm_packet_rec),'
-		' offsetof(pm_packet_rec, streamaddress), sizeof(pm_stats), sizeof(pm_shard_state));return 0;}\n')
+		' offsetof(pm_packet_rec, streamaddress), sizeof(pm_stats), sizeof(pm_shard_state), sizeof(pm_loop_desc),'
+		' offsetof(pm_loop_desc, nco_wavetable), offsetof(pm_loop_desc, pd_table), offsetof(pm_loop_desc, hilbert_delay));return 0;}\n')
 	exe = tmp_path / "layout"
 	subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
 	got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
 	C, P = _lib.ChainDesc, _lib.PacketRec
 	want = [ctypes.sizeof(C), C.lpf.offset, C.demap.offset, C.loop.offset, ctypes.sizeof(P), P.streamaddress.offset,
-		ctypes.sizeof(_lib.Stats), ctypes.sizeof(_lib.ShardState)]
+		ctypes.sizeof(_lib.Stats), ctypes.sizeof(_lib.ShardState), ctypes.sizeof(_lib.LoopDesc),
+		_lib.LoopDesc.nco_wavetable.offset, _lib.LoopDesc.pd_table.offset, _lib.LoopDesc.hilbert_delay.offset]
 	assert got == want
 
 

@@ -85,3 +85,82 @@ def test_frame_straddling_a_boundary(cuda_lib, oracle):
 	assert any(3.7 * 48000 < a < 4.6 * 48000 for a, _d, _c in want[0])      # the straddling frame is in the result
 	with pytest.raises(EngineError):
 		run_sharded_local(stack, audio, 2, tail_bits=64, segment_len=4096, warmup_len=8192)
+
+
+# ---- shard link: the same hand-off carried out by the GPU(s) over peer memory (csrc/link.cu) --------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("tag", ["afsk1200_superopt_48k", "fsk9600_ax25_48k"])
+def test_linked_equals_reference(cuda_lib, tag, world):
+	"""Every rank ends up with the merged records of all ranks, identical to the unsharded reference result."""
+	from pymodem_b200.sharded import run_linked_local
+	g = Golden(tag)
+	got, info = run_linked_local(build_stack(g.sample_rate, g.lines), g.audio(), world, tail_bits=2048,
+		segment_len=4096, warmup_len=16384)
+	assert as_tuples(got) == g.all_packets()
+	if all(info['verified']):
+		assert info['all_ranks_equal']
+
+
+def test_linked_falls_back_when_a_handoff_does_not_verify(cuda_lib):
+	"""No warm-up: the speculated start states are wrong, all ranks agree on that and the repair protocol finishes."""
+	from pymodem_b200.sharded import run_linked_local
+	g = Golden("afsk1200_superopt_48k")
+	got, info = run_linked_local(build_stack(g.sample_rate, g.lines), g.audio(), 4, tail_bits=2048,
+		segment_len=4096, warmup_len=0)
+	assert not any(info['verified'])
+	assert as_tuples(got) == g.all_packets()
+
+
+def test_linked_frame_straddling_a_boundary(cuda_lib, oracle):
+	from pymodem_b200 import configs, synth
+	from pymodem_b200.engine import EngineError
+	from pymodem_b200.sharded import run_linked_local
+	lines = configs.afsk_1200_ax25_super_opt()
+	audio = synth.afsk1200_ax25(duration_s=8.0, sample_rate=48000, frame_interval_s=0.7, noise_start=0.02,
+		noise_end=0.05, seed=51, noise_seed=52, first_frame_s=0.2)[0]
+	want = oracle.run_config(48000, lines, audio)
+	stack = build_stack(48000, lines)
+	got, info = run_linked_local(stack, audio, 2, tail_bits=2048, segment_len=4096, warmup_len=16384)
+	assert as_tuples(got) == want
+	with pytest.raises(EngineError):
+		run_linked_local(stack, audio, 2, tail_bits=128, segment_len=4096, warmup_len=16384)
+
+
+def test_linked_engine_is_reusable(cuda_lib):
+	"""Epoch flags and the two parity slots: several runs through the same link, alternating inputs."""
+	from pymodem_b200.engine import Engine
+	from pymodem_b200.sharded import ShardWorker, local_exchange, plan_shards, run_protocol
+	g = Golden("afsk1200_superopt_48k")
+	stack = build_stack(g.sample_rate, g.lines)
+	audio = g.audio()
+	half = np.ascontiguousarray(audio[: len(audio) // 2 + 7777])
+	world = 2
+	engines = [Engine(stack, segment_len=4096, warmup_len=32768) for _ in range(world)]
+	try:
+		bases = [e.link_create(r, world, 2048, len(audio))[1] for r, e in enumerate(engines)]
+		for e in engines:
+			e.link_connect(pointers=bases)
+		outs, verdicts = [], []
+		for rec in (audio, half, audio, audio):
+			plans = plan_shards(len(rec), world, segment_len=4096, warm_len=32768, trim_max=305, samples_per_symbol=40.0, tail_bits=2048)
+			loc = [np.ascontiguousarray(rec[p['audio_begin']:p['audio_end']]) for p in plans]
+			if not outs:                     # size every device buffer up front (see run_linked_local)
+				run_protocol([ShardWorker(e, p, l.ctypes.data, len(l)) for e, p, l in zip(engines, plans, loc)], local_exchange)
+			for e, p, l in zip(engines, plans, loc):
+				e.run_linked_begin(l.ctypes.data, len(l), p)
+			verdict = [e.run_linked_end() for e in engines]
+			assert all(verdict) or not any(verdict)          # every rank sees the same states
+			if all(verdict):
+				outs.append([as_tuples(e.packets(*e.fetch())) for e in engines])
+			else:                                             # a start state did not verify: repair protocol
+				recs, arena = run_protocol([ShardWorker(e, p, l.ctypes.data, len(l)) for e, p, l in zip(engines, plans, loc)],
+					local_exchange, resume=True)
+				outs.append([as_tuples(engines[0].packets(recs, arena))] * world)
+			verdicts.append(all(verdict))
+	finally:
+		for e in engines:
+			e.close()
+	assert outs[0][0] == outs[0][1] == g.all_packets()
+	assert outs[2] == outs[0] and outs[3] == outs[0]
+	assert verdicts[0] == verdicts[2] == verdicts[3]
+	assert outs[1][0] == outs[1][1] and outs[1][0] != outs[0][0]
