@@ -198,6 +198,9 @@ def run_b200_arm(args):
 	if not torch.cuda.is_available():
 		raise SystemExit("bench.py: no CUDA device -- the demod_chain engine has no CPU fallback")
 	torch.cuda.set_device(local)
+	from pymodem_b200.sharded import bind_to_gpu_numa_node
+	numa = bind_to_gpu_numa_node(local)          # before any pinned allocation
+	print(f"[bench rank {rank}] {numa}", file=sys.stderr, flush=True)
 	if world > 1:
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -355,7 +358,7 @@ def run_b200_arm(args):
 		"slicer": {"segments": stats[-1]["slicer_segments"], "repairs": stats[-1]["slicer_repairs"],
 			"guard_flagged": stats[-1]["guard_flagged"]},
 		"timing": {"cuda_event_ms": ev_ms, "wall_ms": wall_ms, "e2e_cuda_event_ms": e2e_ev_ms, "e2e_wall_ms": e2e_wall_ms},
-		"host_cpus": os.cpu_count()}
+		"host_cpus": os.cpu_count(), "numa": numa}
 	print(json.dumps(line), flush=True)
 	eng.close()
 	if world > 1:

@@ -81,6 +81,31 @@ struct DevBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// pinned host buffer that only grows (results come back with plain async copies, no staging through pageable memory)
+template <typename T>
+struct HostBuf {
+	T *p = nullptr;
+	size_t cap = 0, n = 0;
+	cudaError_t resize(size_t want)
+	{
+		if (want > cap) {
+			if (p) cudaFreeHost(p);
+			p = nullptr; cap = 0; n = 0;
+			const size_t c = want + want / 4 + 1024;
+			cudaError_t e = cudaHostAlloc((void **)&p, c * sizeof(T), cudaHostAllocDefault);
+			if (e != cudaSuccess) return e;
+			cap = c;
+		}
+		n = want;
+		return cudaSuccess;
+	}
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	T *data() { return p; }
+	const T *data() const { return p; }
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+};
+
 struct HostChain {
 	pm_chain_desc d;
 	std::vector<double> bpf, mark_i, mark_q, space_i, space_q, space_ui, space_uq, lpf;
@@ -190,8 +215,8 @@ struct pm_engine {
 	int sign_rows = 0;
 	long long sample_base = 0;
 	std::vector<ChainCounters> h_cc;
-	std::vector<pm_packet_rec> h_recs;
-	std::vector<uint8_t> h_arena;
+	HostBuf<pm_packet_rec> h_recs;
+	HostBuf<uint8_t> h_arena;
 	pm_stats stats;
 	cudaEvent_t ev[8] = {};
 	std::vector<cudaEvent_t> ev_chunks;
@@ -475,6 +500,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_mrecs.release(); e->d_marena.release(); e->d_mtotals.release();
 	if (e->h_link_status) cudaFreeHost(e->h_link_status);
 	if (e->h_mtotals) cudaFreeHost(e->h_mtotals);
+	e->h_recs.release(); e->h_arena.release();
 	if (e->h_counters) cudaFreeHost(e->h_counters);
 	if (e->h_totals) cudaFreeHost(e->h_totals);
 	cudaStreamDestroy(e->st);
@@ -1179,8 +1205,8 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 	const unsigned long long np = e->h_totals->n_packets, nb = e->h_totals->n_bytes;
 	if (np > e->d_recs.n || nb > e->d_arena.n)
 		return fail(e, PM_ERR_CAPACITY, "packet buffers too small (%llu records, %llu bytes)", np, nb);
-	e->h_recs.resize(np);
-	e->h_arena.resize(nb);
+	CK(e->h_recs.resize(np));
+	CK(e->h_arena.resize(nb));
 	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
 	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, nb, cudaMemcpyDeviceToHost, e->st));
 	CK(cudaEventRecord(e->ev[5], e->st));
@@ -1462,8 +1488,8 @@ extern "C" int pm_engine_run_linked_end(pm_engine *e, int32_t *verified)
 	const unsigned long long np = e->h_mtotals->n_packets, nb = e->h_mtotals->n_bytes;
 	if (np > e->d_mrecs.n || nb > e->d_marena.n)
 		return fail(e, PM_ERR_CAPACITY, "merged packet buffers too small (%llu records, %llu bytes)", np, nb);
-	e->h_recs.resize(np);
-	e->h_arena.resize(nb);
+	CK(e->h_recs.resize(np));
+	CK(e->h_arena.resize(nb));
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
 	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_mrecs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
