@@ -318,8 +318,15 @@ def run_b200_arm(args):
 	achieved = executed_flop / max(front_launches, 1) / t_front / 1e12
 	peaks, peaks_src = measured_peaks()
 	algo_bytes = 2.0 * n + n_chains * n / 8.0        # int16 audio in, 1 sign bit per chain-sample out
+	traffic = None
+	try:      # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this launch's samples
+		with open(os.path.join(REPO, "profiles", "front_traffic.json")) as f:
+			tr = json.load(f)
+		traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n / tr["samples_per_launch"]) / max(front_launches, 1)
+	except (OSError, ValueError, KeyError):
+		pass
 	roofline = {"kernel": "afsk_front_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
-		"unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+		"unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
 		"peak_source": "pm_measure_fp32_peak: register-resident FFMA loop timed in this run "
 			f"(nominal {FP32_NOMINAL_TFLOPS:.1f} at max clocks; MEASURED_PEAKS.json has no FP32 entry)",
 		"executed_mac_per_sample": macs,

@@ -9,6 +9,7 @@
 //
 // Stream bit g lives in word g>>5 at bit g&31 (LSB-first), so "earlier" bits
 // are at lower positions; the reference's bytes are MSB-first groups of 8.
+#include <algorithm>
 #include "pm_common.cuh"
 
 #define GB_WORDS 1024          // mask words per gather block (32768 samples)
@@ -472,42 +473,43 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 	const int ch = blockIdx.y;
 	if (chains[ch].codec != 1) return;
 	const unsigned int nfl = flag_totals[ch];
-	const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j == 0 && threadIdx.x == 0) cc[ch].nflags = (int)nfl;
-	if (j >= nfl) return;
+	if (blockIdx.x == 0 && threadIdx.x == 0) cc[ch].nflags = (int)nfl;
 	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
-	const long long end = fp[j];
-	long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
 	const ShardBits B = sb[ch];
-	GapRec r;
-	r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
-	// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is
-	// emitted by the shard that holds its closing bit
-	const bool mine = end >= B.own_lo && end < B.own_hi;
-	// On a later shard the stream starts in the middle of the recording: a gap whose opening flag is
-	// not a reliably detected one (all 8 bits of its pattern at valid positions) reaches back past the
-	// hand-off tail.  It is replayed from the first valid bit with unknown history.
-	const bool open_start = !B.first && (j == 0 || (long long)fp[j - 1] < B.valid_from + 8);
-	if (open_start && start < B.valid_from) start = B.valid_from;
-	if (mine && (end - start + 1 >= 18 * 8 + 8 || open_start)) {
-		int overflow = 0;
-		unsigned int len = 0;
-		bool aborted = false;
-		const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
-			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
-		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
-		if (open_start && (emit || !aborted)) {
-			// either junk bytes from before the tail would be part of the frame, or the
-			// emission decision itself depends on bits we do not have (an abort -- seven ones, all
-			// of them valid bits -- resets the machine whatever came before)
-			atomicExch(&cc[ch].tail_short, 1);
-		} else {
-			r.emit = emit ? 1u : 0u;
-			r.len = len;
-			r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
+	// the number of gaps is only known on the device: a moderate grid strides over them
+	for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < nfl; j += gridDim.x * blockDim.x) {
+		const long long end = fp[j];
+		long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
+		GapRec r;
+		r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
+		// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is
+		// emitted by the shard that holds its closing bit
+		const bool mine = end >= B.own_lo && end < B.own_hi;
+		// On a later shard the stream starts in the middle of the recording: a gap whose opening flag is
+		// not a reliably detected one (all 8 bits of its pattern at valid positions) reaches back past the
+		// hand-off tail.  It is replayed from the first valid bit with unknown history.
+		const bool open_start = !B.first && (j == 0 || (long long)fp[j - 1] < B.valid_from + 8);
+		if (open_start && start < B.valid_from) start = B.valid_from;
+		if (mine && (end - start + 1 >= 18 * 8 + 8 || open_start)) {
+			int overflow = 0;
+			unsigned int len = 0;
+			bool aborted = false;
+			const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
+				scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
+			if (overflow) atomicExch(&cc[ch].seq_needed, 1);
+			if (open_start && (emit || !aborted)) {
+				// either junk bytes from before the tail would be part of the frame, or the
+				// emission decision itself depends on bits we do not have (an abort -- seven ones, all
+				// of them valid bits -- resets the machine whatever came before)
+				atomicExch(&cc[ch].tail_short, 1);
+			} else {
+				r.emit = emit ? 1u : 0u;
+				r.len = len;
+				r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
+			}
 		}
+		gaps[(long long)ch * gap_stride + j] = r;
 	}
-	gaps[(long long)ch * gap_stride + j] = r;
 }
 
 // Sequential replay of one whole chain (only when a gap overflowed
@@ -748,7 +750,7 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, flag_totals);
 	flag_write_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
 	// gaps: at most flag_stride per chain
-	dim3 ggrid((unsigned int)((flag_stride + 127) / 128), n_chains);
+	dim3 ggrid((unsigned int)std::min<long long>((flag_stride + 127) / 128, 148 * 16), n_chains);
 	ax25_gap_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals,
 		byte_addr, addr_stride, scratch, scratch_stride, gaps, gap_stride, sb);
 	if (allow_sequential)

@@ -1045,7 +1045,11 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 
 	// FP64 guard-band fix-up
 	int max_sum = 8;
-	for (auto &hc : e->chains) max_sum = std::max(max_sum, (int)(hc.mark_i.size() + hc.lpf.size() + 2));
+	for (auto &hc : e->chains) {     // guard_fixup_kernel: audio window, band-passed window, 2 magnitude rows, partial sums
+		const int nx = (int)(hc.mark_i.size() + hc.lpf.size()), na = nx + (int)hc.bpf.size();
+		const int parts = 4 * std::max(nx + 8, 4 * ((int)hc.lpf.size() + 8));
+		max_sum = std::max(max_sum, na + nx + 16 + 2 * (int)hc.lpf.size() + parts);
+	}
 	cudaError_t ce = pm_launch_guard_fixup(e->d_fp64.p, max_sum, d_audio, n, e->d_sign.p, e->sign_stride,
 		e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 8, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));

@@ -86,6 +86,15 @@ struct FirUnit {
 	}
 };
 
+// sqrt.approx.f32: one MUFU instead of the IEEE sequence with its slow path; maximum relative error 2^-23, far
+// inside the FP32 front end's error budget (the sign guard is 2^-16)
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
 // Stage a_len int16 samples starting at n0 into shared memory as floats
 // (zero beyond the end of the recording).
 __device__ __forceinline__ void stage_audio(float *s_a, const int16_t *__restrict__ audio,
@@ -150,7 +159,7 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 #pragma unroll
 			for (int t = 0; t < 4; t++) {
 				const float ci = f.a[4 * q + t], cq = f.b[4 * q + t];
-				m[t] = sqrtf(fmaf(ci, ci, cq * cq));
+				m[t] = fast_sqrt(fmaf(ci, ci, cq * cq));
 			}
 			sts4(dst, 16 * ui + 4 * q, m[0], m[1], m[2], m[3]);
 		}
@@ -272,14 +281,31 @@ fir_front_kernel(const __grid_constant__ FirPlan P, const int16_t *__restrict__ 
 // output and overwrite the sign bit (and the soft value when kept).
 // ---------------------------------------------------------------------------
 
-#define PM_FIX_THREADS 128
+#define PM_FIX_THREADS 224
+#define FIX_TG 4               // tap groups a FIR is split into (partial sums combined through shared memory)
 
+// block-wide sum of one double per thread (any order: the reference's numpy dot products have none to copy)
+__device__ __forceinline__ double fix_block_sum(double v, double *s_red)
+{
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double t = 0.0;
+	for (int w = 0; w < PM_FIX_THREADS / 32; w++) t += s_red[w];
+	__syncthreads();
+	return t;
+}
+
+// One CTA per queued (chain, sample).  AFSK: the audio window is staged once as doubles; thread i computes
+// band-passed sample i; threads then split into (output, mark|space) items that run the I and Q correlators over
+// the same window; the low-pass is a block-wide reduction.
 __global__ void __launch_bounds__(PM_FIX_THREADS)
 guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restrict__ audio, long long n_audio,
                    uint32_t *__restrict__ sign, long long sign_stride, float *__restrict__ soft,
                    long long soft_stride, GuardList guard)
 {
 	extern __shared__ __align__(16) double sm64[];
+	__shared__ double s_red[PM_FIX_THREADS / 32];
 	const unsigned int n_entries = min(*guard.count, guard.cap);
 	for (unsigned int e = blockIdx.x; e < n_entries; e += gridDim.x) {
 		const unsigned long long ent = guard.entries[e];
@@ -291,44 +317,85 @@ guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restri
 			// y[n] = sum_j hr[j] a[n+j]
 			double acc = 0.0;
 			for (int j = threadIdx.x; j < C.n_bpf; j += PM_FIX_THREADS)
-				acc += C.bpf[j] * (double)audio[n + j];
-			sm64[threadIdx.x] = acc;
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				double t = 0.0;
-				for (int i = 0; i < PM_FIX_THREADS; i++) t += sm64[i];
-				sm64[PM_FIX_THREADS] = t;
-			}
-			__syncthreads();
-			y = sm64[PM_FIX_THREADS];
+				acc = fma(C.bpf[j], (double)audio[n + j], acc);
+			y = fix_block_sum(acc, s_red);
 			if (C.neg) y = -y;
 		} else {
-			double *x1 = sm64;                               // n_corr + n_lpf - 1 values
-			double *d = sm64 + (C.n_corr + C.n_lpf);          // n_lpf values
-			const int nx = C.n_corr + C.n_lpf - 1;
-			for (int i = threadIdx.x; i < nx; i += PM_FIX_THREADS) {
-				double acc = 0.0;
-				for (int j = 0; j < C.n_bpf; j++) acc += C.bpf[j] * (double)audio[n + i + j];
-				x1[i] = acc;
-			}
+			const int nx = C.n_corr + C.n_lpf - 1;               // band-passed samples needed
+			const int na = nx + C.n_bpf - 1;                     // audio samples needed
+			const int nx4 = (nx + 3) >> 2, nl4 = (C.n_lpf + 3) >> 2;
+			double *a = sm64;                                    // na + 4 (zero padded)
+			double *x1 = a + na + 4;                             // nx + 4
+			double *mag = x1 + nx + 4;                           // 2 x n_lpf: |mark|, |space|
+			double *part = mag + 2 * C.n_lpf;                    // FIX_TG partial sums per output and filter
+			for (int i = threadIdx.x; i < na + 4; i += PM_FIX_THREADS)
+				a[i] = (i < na && n + i < n_audio) ? (double)audio[n + i] : 0.0;
 			__syncthreads();
-			for (int i = threadIdx.x; i < C.n_lpf; i += PM_FIX_THREADS) {
-				double mi = 0.0, mq = 0.0, si = 0.0, sq = 0.0;
-				for (int j = 0; j < C.n_corr; j++) {
-					const double x = x1[i + j];
-					mi += C.mark_i[j] * x; mq += C.mark_q[j] * x;
-					si += C.space_i[j] * x; sq += C.space_q[j] * x;
+			// band-pass: item = (block of 4 outputs, tap group); a 4-output sliding window turns two loads per
+			// multiply-add into half a load (the kernel is load/store-unit bound, not FP64 bound)
+			{
+				const int tg_len = (C.n_bpf + FIX_TG - 1) / FIX_TG;
+				for (int it = threadIdx.x; it < nx4 * FIX_TG; it += PM_FIX_THREADS) {
+					const int ob = it % nx4, tg = it / nx4;
+					const int j0 = tg * tg_len, j1 = min(C.n_bpf, j0 + tg_len);
+					const double *w = a + 4 * ob + j0;
+					double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+					double w0 = w[0], w1 = w[1], w2 = w[2];
+					for (int j = j0; j < j1; j++) {
+						const double h = C.bpf[j], w3 = w[j - j0 + 3];
+						s0 = fma(h, w0, s0); s1 = fma(h, w1, s1); s2 = fma(h, w2, s2); s3 = fma(h, w3, s3);
+						w0 = w1; w1 = w2; w2 = w3;
+					}
+					double *p = part + (long long)tg * (4 * nx4) + 4 * ob;
+					p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
 				}
-				d[i] = sqrt(mi * mi + mq * mq) - sqrt(si * si + sq * sq);
 			}
 			__syncthreads();
-			if (threadIdx.x == 0) {
-				double acc = 0.0;
-				for (int i = 0; i < C.n_lpf; i++) acc += C.lpf[i] * d[i];
-				d[C.n_lpf] = acc;
+			for (int i = threadIdx.x; i < nx + 4; i += PM_FIX_THREADS) {
+				double t = 0.0;
+				if (i < nx)
+					for (int tg = 0; tg < FIX_TG; tg++) t += part[(long long)tg * (4 * nx4) + i];
+				x1[i] = t;
 			}
 			__syncthreads();
-			y = d[C.n_lpf];
+			// correlators: item = (block of 4 outputs, mark|space, tap group), I and Q over the same window
+			{
+				const int tg_len = (C.n_corr + FIX_TG - 1) / FIX_TG;
+				const int row = 4 * nl4;                         // partial sums per (tap group, mark|space, I|Q)
+				for (int it = threadIdx.x; it < nl4 * 2 * FIX_TG; it += PM_FIX_THREADS) {
+					const int ob = it % nl4, which = (it / nl4) & 1, tg = it / (2 * nl4);
+					const int j0 = tg * tg_len, j1 = min(C.n_corr, j0 + tg_len);
+					const double *ti = which ? C.space_i : C.mark_i, *tq = which ? C.space_q : C.mark_q;
+					const double *w = x1 + 4 * ob + j0;
+					double i0 = 0.0, i1 = 0.0, i2 = 0.0, i3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+					double w0 = w[0], w1 = w[1], w2 = w[2];
+					for (int j = j0; j < j1; j++) {
+						const double hi = ti[j], hq = tq[j], w3 = w[j - j0 + 3];
+						i0 = fma(hi, w0, i0); i1 = fma(hi, w1, i1); i2 = fma(hi, w2, i2); i3 = fma(hi, w3, i3);
+						q0 = fma(hq, w0, q0); q1 = fma(hq, w1, q1); q2 = fma(hq, w2, q2); q3 = fma(hq, w3, q3);
+						w0 = w1; w1 = w2; w2 = w3;
+					}
+					double *pi = part + (long long)((tg * 2 + which) * 2) * row + 4 * ob, *pq = pi + row;
+					pi[0] = i0; pi[1] = i1; pi[2] = i2; pi[3] = i3;
+					pq[0] = q0; pq[1] = q1; pq[2] = q2; pq[3] = q3;
+				}
+				__syncthreads();
+				for (int it = threadIdx.x; it < 2 * C.n_lpf; it += PM_FIX_THREADS) {
+					const int which = it >= C.n_lpf, i = it - which * C.n_lpf;
+					double ci = 0.0, cq = 0.0;
+					for (int tg = 0; tg < FIX_TG; tg++) {
+						const double *pi = part + (long long)((tg * 2 + which) * 2) * row + i;
+						ci += pi[0];
+						cq += pi[row];
+					}
+					mag[it] = sqrt(ci * ci + cq * cq);
+				}
+			}
+			__syncthreads();
+			double part_y = 0.0;
+			for (int i = threadIdx.x; i < C.n_lpf; i += PM_FIX_THREADS)
+				part_y = fma(C.lpf[i], mag[i] - mag[C.n_lpf + i], part_y);
+			y = fix_block_sum(part_y, s_red);
 		}
 		if (threadIdx.x == 0) {
 			uint32_t *w = sign + gid * sign_stride + (n >> 5);
@@ -407,7 +474,7 @@ extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int max_ta
 	long long n_audio, uint32_t *sign, long long sign_stride, float *soft, long long soft_stride,
 	GuardList guard, int grid, cudaStream_t st)
 {
-	size_t smem = sizeof(double) * (size_t)(2 * max_taps_sum + PM_FIX_THREADS + 8);
+	size_t smem = sizeof(double) * (size_t)(max_taps_sum + 16);
 	guard_fixup_kernel<<<grid, PM_FIX_THREADS, smem, st>>>(chains, audio, n_audio, sign, sign_stride, soft,
 		soft_stride, guard);
 	return cudaGetLastError();

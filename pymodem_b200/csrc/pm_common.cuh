@@ -38,7 +38,7 @@ struct AfskPlan {
 	long long chain_nout[PM_MAX_GCH];  // valid demod outputs of the chain (N - trim)
 	int s_x1_off, s_m_off, s_m_stride; // shared-memory carve-up, in floats
 	float guard_eps;
-	float taps[PM_MAX_TAPS];
+	alignas(16) float taps[PM_MAX_TAPS];   // every tap set starts at a multiple of 4 floats: read as float4
 };
 
 // Plan of a single-FIR front end (FSK: fsk.py:149-159).
@@ -52,7 +52,7 @@ struct FirPlan {
 	int chain_neg[PM_MAX_GCH];         // fsk.py:153 invert
 	long long chain_nout[PM_MAX_GCH];
 	float guard_eps;
-	float taps[PM_MAX_TAPS];
+	alignas(16) float taps[PM_MAX_TAPS];
 };
 
 // Samples whose FP32 soft value is too close to zero to trust its sign are

@@ -280,3 +280,16 @@ def test_il2p_min_distance(cuda_lib, oracle):
 	lines = [json.loads(json.dumps(l)) for l in g.chain_lines()[:1]]
 	lines[0]["codec"]["options"]["min_dist"] = "2"
 	_oracle_vs_gpu(oracle, 48000, lines, g.audio())
+
+
+@pytest.mark.parametrize("dc,hum", [(12000, 0.0), (0, 0.45), (-9000, 0.3)])
+def test_strong_out_of_band_energy(cuda_lib, oracle, dc, hum):
+	"""A weak in-band signal under a large DC offset / 100 Hz hum: the FP32 front end's rounding error then scales
+	with the out-of-band amplitude, not with the band-passed magnitudes the sign guard is relative to."""
+	from pymodem_b200 import configs, synth
+	sig = synth.afsk1200_ax25(duration_s=10.0, sample_rate=48000, frame_interval_s=0.9, amplitude=0.03, noise_start=0.02,
+		noise_end=0.5, seed=61, noise_seed=62, first_frame_s=0.1)[0].astype(np.float64)
+	t = np.arange(len(sig)) / 48000.0
+	audio = np.clip(np.rint(sig + dc + hum * 32767.0 * np.sin(2 * np.pi * 100.0 * t)), -32768, 32767).astype(np.int16)
+	want, _ = _oracle_vs_gpu(oracle, 48000, configs.afsk_1200_ax25_super_opt(), audio)
+	assert sum(len(w) for w in want) > 0
