@@ -349,8 +349,29 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 		r.status = IL2P_INCOMPLETE; r.len = 0; r.corrected = 0; r.end_bit = nb - 1;
 		if (lane == 0 && pos < nb) {
 			const long long lim = min(pos + 32, nb);
-			for (long long g = pos; g < lim; g++)
-				if (il2p_sync_match(il2p_window(d, g, pos, at_start), C.il2p_sync_tol)) { found = g; break; }
+			if (at_start) {
+				for (long long g = pos; g < lim; g++)
+					if (il2p_sync_match(il2p_window(d, g, pos, at_start), C.il2p_sync_tol)) { found = g; break; }
+			} else {
+				// the 32 windows ending at pos .. pos+31 all lie inside stream bits [pos-31, pos+31]: fetch them once
+				// (bit j of span = stream bit pos-31+j), blank what the reference's register no longer holds (everything
+				// before the last collected byte, i.e. before pos-8) and slide
+				unsigned long long span = 0;
+				const long long b0 = pos - 31;
+				for (int q = 0; q < 3; q++) {
+					const long long w = (b0 >> 5) + q;               // floor division: b0 may be negative
+					if (w < 0 || (w << 5) >= nb) continue;
+					const unsigned long long word = d[w];
+					const long long sh = (w << 5) - b0;              // position of the word's bit 0 inside span
+					if (sh >= 64) continue;
+					span |= sh >= 0 ? (word << sh) : (word >> (-sh));
+				}
+				span &= ~((1ull << 23) - 1ull);                      // indices below pos-8 read as 0
+				for (long long g = pos; g < lim; g++) {
+					const unsigned int ww = __brev((unsigned int)(span >> (int)(g - pos)));
+					if (il2p_sync_match(ww, C.il2p_sync_tol)) { found = g; break; }
+				}
+			}
 			if (found < 0) {
 				while (ci < ncand && (long long)cp[ci] < pos + 32) ci++;
 				if (ci < ncand) found = cp[ci];

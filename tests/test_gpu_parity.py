@@ -293,3 +293,84 @@ def test_strong_out_of_band_energy(cuda_lib, oracle, dc, hum):
 	audio = np.clip(np.rint(sig + dc + hum * 32767.0 * np.sin(2 * np.pi * 100.0 * t)), -32768, 32767).astype(np.int16)
 	want, _ = _oracle_vs_gpu(oracle, 48000, configs.afsk_1200_ax25_super_opt(), audio)
 	assert sum(len(w) for w in want) > 0
+
+
+# ---- recursive modems: edge cases against the oracle ----------------------------------------------------------------
+def _psk_lines(which):
+	tag = {"bpsk": "bpsk300_il2p_8k", "qpsk": "qpsk2400_il2p_8k", "pll": "afsk300_full_8k"}[which]
+	lines = Golden(tag).chain_lines()
+	return [l for l in lines if l["modem"]["type"] in ("bpsk", "mpsk", "afsk_pll")]
+
+
+@pytest.mark.parametrize("which", ["bpsk", "qpsk", "pll"])
+@pytest.mark.parametrize("kind", ["noise", "silence", "tone", "short"])
+def test_recursive_modems_edge_inputs(cuda_lib, oracle, which, kind):
+	"""AGC on silence (normal = 0: the envelope never rises, samples pass unscaled), loops on pure noise and on an
+	unmodulated carrier, inputs shorter than / barely longer than the FIR chain, lengths around the float64 tile."""
+	lines = _psk_lines(which)
+	rng = np.random.default_rng(7)
+	sr = 8000
+	if kind == "noise":
+		audios = [np.clip(rng.standard_normal(sr * 6) * 5000, -32768, 32767).astype(np.int16)]
+	elif kind == "silence":
+		audios = [np.zeros(sr * 3, dtype=np.int16)]
+	elif kind == "tone":
+		t = np.arange(sr * 5) / sr
+		audios = [np.rint(12000 * np.sin(2 * np.pi * 1502.5 * t) + rng.standard_normal(len(t)) * 300).astype(np.int16)]
+	else:
+		base = np.clip(rng.standard_normal(5000) * 4000, -32768, 32767).astype(np.int16)
+		audios = [base[:n] for n in (260, 400, 1023 + 240, 1024 + 240, 1025 + 240, 2311, 4097)]
+	for audio in audios:
+		eng = engine(build_stack(sr, lines))
+		try:
+			got = as_tuples(eng.run(audio))
+			streams = [eng.stream(ci, 1) for ci in range(len(lines))]
+		finally:
+			eng.close()
+		if len(audio) <= 300:       # shorter than the FIR chain: numpy.convolve 'valid' swaps its operands; no soft samples here
+			assert all(len(g) == 0 for g in got)
+			continue
+		for ci, line in enumerate(lines):          # descrambled AddressedData stream and packets of every chain
+			chain = oracle.Chain(sr, line)
+			b, a = chain.slicer.slice(chain.modem.demod(audio))
+			d, _ = chain.stream.stream_unscramble_8bit(b, a)
+			np.testing.assert_array_equal(streams[ci][0], d)
+			np.testing.assert_array_equal(streams[ci][1], a)
+			assert got[ci] == chain.codec.decode(d, a)
+
+
+def test_recursive_modem_stages_against_oracle(cuda_lib, oracle):
+	"""Slicer bytes + addresses and descrambled bytes of a noisy BPSK and a noisy QPSK run, bit for bit."""
+	from pymodem_b200 import synth
+	for which, audio in (("bpsk", synth.bpsk300_il2p(20.0, carrier=1496.0, noise_start=0.3, noise_end=1.2, seed=71, noise_seed=72)[0]),
+			("qpsk", synth.qpsk2400_il2p(10.0, carrier=1504.0, noise_start=0.2, noise_end=0.9, seed=73, noise_seed=74)[0])):
+		lines = _psk_lines(which)[:1]
+		chain = oracle.Chain(8000, lines[0])
+		soft = chain.modem.demod(audio)
+		b, a = chain.slicer.slice(soft)
+		d, _ = chain.stream.stream_unscramble_8bit(b, a)
+		eng = engine(build_stack(8000, lines), keep_soft=1)
+		try:
+			eng.run_raw(audio)
+			gb, ga = eng.stream(0, 0)
+			gd, _ = eng.stream(0, 1)
+			gsoft = eng.soft(0).astype(np.float64)
+		finally:
+			eng.close()
+		np.testing.assert_array_equal(gb, b)
+		np.testing.assert_array_equal(ga, a)
+		np.testing.assert_array_equal(gd, d)
+		ref_i = soft[0] if isinstance(soft, tuple) else soft
+		assert np.max(np.abs(gsoft - ref_i)) <= SOFT_RTOL * np.sqrt(np.mean(ref_i ** 2))
+
+
+def test_unsupported_combinations_are_rejected(cuda_lib):
+	"""The reference's duck typing only works for (mpsk, quadrature) and (everything else, binary)."""
+	from pymodem_b200.engine import EngineError
+	from pymodem_b200.modems_codecs import chain_builder
+	good = Golden("qpsk2400_il2p_8k").chain_lines()[0]
+	bad = dict(good, slicer={"type": "binary", "config": "1200", "options": {}})
+	with pytest.raises(EngineError):
+		engine([chain_builder.build_chain(8000, bad)])
+	with pytest.raises(NotImplementedError):
+		chain_builder.ModemConfigurator(8000, {"type": "qpsk", "config": "600", "options": {}})
