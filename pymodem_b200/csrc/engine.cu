@@ -279,17 +279,19 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 	g.U_x = (16 * g.U_m + cmax + 15) / 16;
 	g.a_len = round_up(16 * g.U_x + p.n_bpf, 8);
 	const int a_phys = round_up(pm_phys(g.a_len) + 4, 4);
-	const int x_phys = round_up(pm_phys(16 * g.U_x) + 4, 4);
-	g.s_m_stride = round_up(pm_phys(16 * g.U_m) + 4, 4);
-	g.s_x1_off = a_phys;
-	g.s_m_off = a_phys + x_phys;
-	g.smem = sizeof(float) * (size_t)(g.s_m_off + p.n_mag * g.s_m_stride);
+	const int x_phys = round_up(2 * pm_phys2(16 * g.U_x) + 8, 4);   // band-passed samples stored as (x, x) pairs
+	g.s_m_stride = round_up(2 * pm_phys2(16 * g.U_m) + 8, 4);      // one (mark, space) pair stream of float2
+	// the staged audio is dead once the band-pass is done and the magnitudes are born after it: they share a region
+	g.s_m_off = 0;
+	g.s_x1_off = std::max(a_phys, p.n_pair * g.s_m_stride);
+	g.smem = sizeof(float) * (size_t)(g.s_x1_off + x_phys);
 	// issue-slot cost per output sample (warp granular)
 	auto warps = [](int units) { return (units + 31) / 32 * 32; };
 	double c = (double)warps(g.U_x) * p.n_bpf;
 	// magnitude units are laid out stream after stream
-	c += (double)warps(p.n_mag * g.U_m) * 2.0 * (corr_sum / std::max(1, p.n_mag));
-	c += (double)warps(p.n_pair * g.U_l) * 2.0 * p.n_lpf;
+	// the correlator (I, Q) and the low-pass (mark, space) stages run packed FFMA2: one issue slot per tap and pair
+	c += (double)warps(p.n_mag * g.U_m) * 1.15 * (corr_sum / std::max(1, p.n_mag));
+	c += (double)warps(p.n_pair * g.U_l) * 1.15 * p.n_lpf;
 	g.cost = c / tile;
 	return g;
 }
@@ -367,6 +369,13 @@ static int build_groups(pm_engine *e)
 				p.mag_q_off[t] = push_taps(p.taps, used, *tones[t].q, npad2);
 				if (p.mag_i_off[t] < 0 || p.mag_q_off[t] < 0) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
 				p.mag_n[t] = npad;
+				if (used + 2 * npad > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+				p.mag_iq_off[t] = used;
+				for (int j = 0; j < npad; j++) {
+					p.taps[used + 2 * j] = p.taps[p.mag_i_off[t] + j];
+					p.taps[used + 2 * j + 1] = p.taps[p.mag_q_off[t] + j];
+				}
+				used += 2 * npad;
 			}
 			// pairs, chains sorted by pair
 			std::vector<std::pair<int, int>> pairs;
@@ -394,6 +403,23 @@ static int build_groups(pm_engine *e)
 			p.pair_first[p.n_pair] = ci;
 			p.n_chain = ci;
 			p.guard_eps = (float)e->opt_guard_eps;
+			// where each tone's magnitude goes: the (mark, space) slots of the pair streams the low-pass reads
+			{
+				int k = 0;
+				for (int t = 0; t < p.n_mag; t++) {
+					p.mag_dst_first[t] = k;
+					for (int pi = 0; pi < p.n_pair; pi++) {
+						if (p.pair_mark[pi] == t) p.mag_dst[k++] = pi * 2;
+						if (p.pair_space[pi] == t) p.mag_dst[k++] = pi * 2 + 1;
+					}
+				}
+				p.mag_dst_first[p.n_mag] = k;
+			}
+			// low-pass taps once more, each twice in a row: the (h, h) operand of the packed FFMA2
+			if (used + 2 * p.n_lpf > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+			p.lpf2_off = used;
+			for (int j = 0; j < p.n_lpf; j++) p.taps[used + 2 * j] = p.taps[used + 2 * j + 1] = p.taps[p.lpf_off + j];
+			used += 2 * p.n_lpf;
 			// tile: cheapest issue-slot cost that still fits two CTAs per SM
 			int best = 0;
 			double best_cost = 1e300;

@@ -86,6 +86,63 @@ struct FirUnit {
 	}
 };
 
+// The same register-blocked FIR on PAIRS: the window holds float2 samples (the mark and the space magnitude of one
+// tone pair), the tap is the same for both halves, so one packed FFMA2 (fma.rn.f32x2, sm_100) does both low-pass
+// filters.  FFMA2 alone is no faster than two FFMAs, but it halves the issue slots the multiply-adds take and
+// leaves room for the loads, tap fetches and register moves around them (tools/ubench/ffma2.cu: 57.9 vs 49.2 TFLOP/s
+// in a FIR-shaped loop).
+__device__ __forceinline__ void fma2(unsigned long long &c, unsigned long long a, unsigned long long b)
+{
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+
+struct FirUnitPair {
+	unsigned long long a[16];
+
+	__device__ __forceinline__ static void load2(const float *__restrict__ s, int i, unsigned long long &x, unsigned long long &y)
+	{
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s + 2 * pm_phys2(i));
+		x = v.x; y = v.y;
+	}
+
+	// s: one pair stream; base: first output (multiple of 16); tdup: taps stored twice each; ntaps multiple of 4
+	__device__ __forceinline__ void run(const float *__restrict__ s, int base, const float *__restrict__ tdup, int ntaps)
+	{
+		unsigned long long w[32];
+#pragma unroll
+		for (int q = 0; q < 8; q++) load2(s, base + 2 * q, w[2 * q], w[2 * q + 1]);
+#pragma unroll
+		for (int r = 0; r < 16; r++) a[r] = 0ull;
+		int j0 = 0;
+		for (; j0 + 16 <= ntaps; j0 += 16) {
+#pragma unroll
+			for (int q = 0; q < 8; q++) load2(s, base + j0 + 16 + 2 * q, w[16 + 2 * q], w[17 + 2 * q]);
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				const unsigned long long hh = *reinterpret_cast<const unsigned long long *>(tdup + 2 * (j0 + k));
+#pragma unroll
+				for (int r = 0; r < 16; r++) fma2(a[r], hh, w[r + k]);
+			}
+#pragma unroll
+			for (int r = 0; r < 16; r++) w[r] = w[r + 16];
+		}
+		for (; j0 < ntaps; j0 += 4) {
+			load2(s, base + j0 + 16, w[16], w[17]);
+			load2(s, base + j0 + 18, w[18], w[19]);
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const unsigned long long hh = *reinterpret_cast<const unsigned long long *>(tdup + 2 * (j0 + k));
+#pragma unroll
+				for (int r = 0; r < 16; r++) fma2(a[r], hh, w[r + k]);
+			}
+#pragma unroll
+			for (int r = 0; r < 16; r++) w[r] = w[r + 4];
+		}
+	}
+	__device__ __forceinline__ float lo(int r) const { return __uint_as_float((unsigned int)a[r]); }
+	__device__ __forceinline__ float hi(int r) const { return __uint_as_float((unsigned int)(a[r] >> 32)); }
+};
+
 // sqrt.approx.f32: one MUFU instead of the IEEE sequence with its slow path; maximum relative error 2^-23, far
 // inside the FP32 front end's error budget (the sign guard is 2^-16)
 __device__ __forceinline__ float fast_sqrt(float x)
@@ -136,32 +193,35 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	stage_audio(s_a, audio, n0, n_audio, P.a_len);
 	__syncthreads();
 
-	// input band-pass (afsk.py:151)
+	// input band-pass (afsk.py:151); the result is stored as (x, x) pairs: the window operand of the packed correlators
 	for (int u = tid; u < P.U_x; u += PM_FRONT_THREADS) {
 		FirUnit<1> f;
 		f.run(s_a, 16 * u, P.taps + P.bpf_off, nullptr, P.n_bpf);
+		float *dst = s_x1 + 2 * pm_phys2(16 * u);
 #pragma unroll
-		for (int q = 0; q < 4; q++)
-			sts4(s_x1, 16 * u + 4 * q, f.a[4 * q], f.a[4 * q + 1], f.a[4 * q + 2], f.a[4 * q + 3]);
+		for (int q = 0; q < 8; q++)
+			*reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(f.a[2 * q], f.a[2 * q], f.a[2 * q + 1], f.a[2 * q + 1]);
 	}
 	__syncthreads();
 
-	// tone correlators and magnitudes (afsk.py:153-160)
+	// tone correlators and magnitudes (afsk.py:153-160): I and Q of one tone in the two halves of an FFMA2
 	for (int u = tid; u < P.n_mag * P.U_m; u += PM_FRONT_THREADS) {
 		const int j = u / P.U_m;
 		const int ui = u - j * P.U_m;
-		FirUnit<2> f;
-		f.run(s_x1, 16 * ui, P.taps + P.mag_i_off[j], P.taps + P.mag_q_off[j], P.mag_n[j]);
-		float *dst = s_m + j * P.s_m_stride;
+		FirUnitPair f;
+		f.run(s_x1, 16 * ui, P.taps + P.mag_iq_off[j], P.mag_n[j]);
+		// the magnitude goes into the mark or space half of every pair stream this tone belongs to
+		float m[16];
 #pragma unroll
-		for (int q = 0; q < 4; q++) {
-			float m[4];
+		for (int r = 0; r < 16; r++) {
+			const float ci = f.lo(r), cq = f.hi(r);
+			m[r] = fast_sqrt(fmaf(ci, ci, cq * cq));
+		}
+		for (int di = P.mag_dst_first[j]; di < P.mag_dst_first[j + 1]; di++) {
+			const int dd = P.mag_dst[di];
+			float *dst = s_m + (dd >> 1) * P.s_m_stride + (dd & 1) + 2 * pm_phys2(16 * ui);
 #pragma unroll
-			for (int t = 0; t < 4; t++) {
-				const float ci = f.a[4 * q + t], cq = f.b[4 * q + t];
-				m[t] = fast_sqrt(fmaf(ci, ci, cq * cq));
-			}
-			sts4(dst, 16 * ui + 4 * q, m[0], m[1], m[2], m[3]);
+			for (int r = 0; r < 16; r++) dst[2 * r] = m[r];
 		}
 	}
 	__syncthreads();
@@ -174,12 +234,11 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 		const int u = ub + lane;
 		const bool active = u < total;
 		int p = 0, ui = 0;
-		FirUnit<1> fm, fs;
+		FirUnitPair fp;
 		if (active) {
 			p = u / P.U_l;
 			ui = u - p * P.U_l;
-			fm.run(s_m + P.pair_mark[p] * P.s_m_stride, 16 * ui, P.taps + P.lpf_off, nullptr, P.n_lpf);
-			fs.run(s_m + P.pair_space[p] * P.s_m_stride, 16 * ui, P.taps + P.lpf_off, nullptr, P.n_lpf);
+			fp.run(s_m + p * P.s_m_stride, 16 * ui, P.taps + P.lpf2_off, P.n_lpf);
 		}
 		// chains are visited in lock-step by the whole warp (a warp may
 		// straddle two pairs; lanes of the shorter pair idle)
@@ -197,7 +256,7 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 				const long long nout = P.chain_nout[c];
 #pragma unroll
 				for (int r = 0; r < 16; r++) {
-					const float lm = fm.a[r], ls = fs.a[r];
+					const float lm = fp.lo(r), ls = fp.hi(r);
 					const float y = fmaf(-g, ls, lm);
 					if (y >= 0.f) half |= (1u << r);
 					const float scale = fabsf(lm) + g * fabsf(ls);

@@ -6,7 +6,7 @@
 #define PM_MAX_MAG     8      // tone-magnitude streams per AFSK front-end group
 #define PM_MAX_PAIR    8      // (mark stream, space stream) pairs per group
 #define PM_MAX_GCH     16     // chains per front-end group
-#define PM_MAX_TAPS    1536   // floats of FIR taps carried in the kernel parameter block
+#define PM_MAX_TAPS    3072   // floats of FIR taps carried in the kernel parameter block
 #define PM_FRONT_THREADS 256
 
 // Shared-memory sample arrays use a padded layout: 4 floats of padding after
@@ -14,6 +14,10 @@
 // 80 B apart instead of 64 B and the 128-bit window loads of the 8 lanes of a
 // quarter-warp fall into 8 different 16-byte bank groups (conflict-free).
 __host__ __device__ __forceinline__ int pm_phys(int i) { return i + ((i >> 4) << 2); }
+// The same idea for arrays of float2 (a mark/space magnitude pair per sample): 2 float2 (16 B) of padding after every
+// 16, so unit bases are 144 B apart and a quarter-warp's 128-bit loads hit 8 different 16-byte bank groups.
+// Returns the index in float2 units.
+__host__ __device__ __forceinline__ int pm_phys2(int i) { return i + ((i >> 4) << 1); }
 
 // Plan of one fused AFSK front-end launch (all chains that share the input
 // band-pass and output low-pass taps).  Passed as a __grid_constant__ kernel
@@ -27,7 +31,9 @@ struct AfskPlan {
 	int mag_n[PM_MAX_MAG];    // correlator taps (multiple of 4)
 	int mag_i_off[PM_MAX_MAG];
 	int mag_q_off[PM_MAX_MAG];
+	int mag_iq_off[PM_MAX_MAG];   // the same taps interleaved (i[0], q[0], i[1], q[1], ...): operands of the packed FFMA2
 	int n_lpf, lpf_off;
+	int lpf2_off;             // the low-pass taps, each stored twice in a row: (h, h) operands of the packed FFMA2
 	int n_pair;
 	int pair_mark[PM_MAX_PAIR];
 	int pair_space[PM_MAX_PAIR];
@@ -36,7 +42,9 @@ struct AfskPlan {
 	int chain_gid[PM_MAX_GCH];         // engine-wide chain index
 	float chain_gain[PM_MAX_GCH];      // space_gain (afsk.py:143)
 	long long chain_nout[PM_MAX_GCH];  // valid demod outputs of the chain (N - trim)
-	int s_x1_off, s_m_off, s_m_stride; // shared-memory carve-up, in floats
+	int s_x1_off, s_m_off, s_m_stride; // shared-memory carve-up, in floats; s_m_stride = one PAIR stream (float2 per sample)
+	int mag_dst_first[PM_MAX_MAG + 1]; // tone j feeds mag_dst[mag_dst_first[j] .. mag_dst_first[j+1])
+	int mag_dst[2 * PM_MAX_PAIR];      // pair * 2 + slot (0: mark, 1: space)
 	float guard_eps;
 	alignas(16) float taps[PM_MAX_TAPS];   // every tap set starts at a multiple of 4 floats: read as float4
 };
