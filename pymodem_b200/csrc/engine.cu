@@ -581,7 +581,8 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 			hc.trim = (d.n_bpf - 1) + (d.n_lpf - 1);
 			if (d.modem_kind == PM_MODEM_MPSK) {
 				if (!lp->hilbert || lp->n_hilbert <= 0 || lp->n_hilbert > P64_MAX_TAPS || !lp->pd_table ||
-				    lp->pd_granularity <= 0 || lp->pd_granularity > 64 || lp->hilbert_delay != lp->n_hilbert / 2)
+				    lp->pd_granularity <= 0 || lp->pd_granularity > 64 || (lp->pd_granularity & (lp->pd_granularity - 1)) ||
+				    lp->hilbert_delay != lp->n_hilbert / 2)
 					return fail(e, PM_ERR_ARG, "chain %d: MPSK needs Hilbert taps and the phase-error table", c);
 				hc.hilbert.assign(lp->hilbert, lp->hilbert + lp->n_hilbert);
 				hc.pd_table.assign(lp->pd_table, lp->pd_table + lp->pd_granularity * lp->pd_granularity);

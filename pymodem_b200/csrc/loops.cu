@@ -197,7 +197,30 @@ struct LoopState {
 	double integral, proportional;                  // pi_control.py:12-13
 };
 
-// AGC.peak_detect + the scaling line of AGC.apply -- agc.py:26-37, 72-76
+// AGC.peak_detect -- agc.py:26-37: the envelope after this sample.  Only this part is a recurrence; the scaling
+// line of AGC.apply (agc.py:72-76, a division) is applied afterwards by all 32 lanes at once (agc_scale).
+__device__ __forceinline__ double agc_envelope(const LoopConst &L, LoopState &s, double sample)
+{
+	const double compare_value = fabs(sample);
+	if (compare_value > s.envelope) {
+		s.envelope = __dadd_rn(s.envelope, s.attack_step);
+		if (s.envelope > compare_value) s.envelope = compare_value;
+		s.sustain_count = 0.0;
+	}
+	if (s.sustain_count >= L.agc_sustain_time) {
+		s.envelope = __dsub_rn(s.envelope, s.decay_step);
+		if (s.envelope < 0.0) s.envelope = 0.0;
+	}
+	s.sustain_count = __dadd_rn(s.sustain_count, L.agc_sustain_increment);
+	return s.envelope;
+}
+
+__device__ __forceinline__ double agc_scale(const LoopConst &L, double sample, double envelope)
+{
+	return envelope != 0.0 ? __ddiv_rn(__dmul_rn(L.agc_target, sample), envelope) : sample;
+}
+
+// (fused form, kept for reference: envelope + scaling of one sample)
 __device__ __forceinline__ double agc_step(const LoopConst &L, LoopState &s, double sample)
 {
 	const double compare_value = fabs(sample);
@@ -250,41 +273,44 @@ __device__ __forceinline__ double pi_step(const LoopConst &L, LoopState &s, doub
 	return __dadd_rn(s.proportional, s.integral);
 }
 
-// PhaseDetector.get_qpsk_angle_error -- phase_detector.py:124-149
-__device__ __forceinline__ int pd_qpsk_error(const int *__restrict__ tab, int g, double re, double im)
+// PhaseDetector.get_qpsk_angle_error -- phase_detector.py:124-149.  floor(x * granularity * 0.5): both factors are
+// powers of two, so one multiplication by granularity/2 gives the identical double; the floor and the conversion are
+// one saturating F2I (the clips at +-granularity follow anyway).  The table is kept as doubles: its value goes
+// straight into the loop filter.
+__device__ __forceinline__ double pd_qpsk_error(const double *__restrict__ tab, int g, double half_g, double re, double im)
 {
-	double fr = floor(__dmul_rn(__dmul_rn(re, (double)g), 0.5)), fi = floor(__dmul_rn(__dmul_rn(im, (double)g), 0.5));
-	fr = fmin(fmax(fr, -1e9), 1e9);
-	fi = fmin(fmax(fi, -1e9), 1e9);
-	int real = (int)fr, imag = (int)fi;
-	if (real >= g) real = g - 1;
-	if (imag >= g) imag = g - 1;
+	int real = __double2int_rd(__dmul_rn(re, half_g)), imag = __double2int_rd(__dmul_rn(im, half_g));
+	real = min(real, g - 1);
+	imag = min(imag, g - 1);
 	if (real <= -g) real = -(g - 1);
 	if (imag <= -g) imag = -(g - 1);
 	if (real >= 0) return imag >= 0 ? tab[real * g + imag] : tab[(-imag) * g + real];
 	return imag >= 0 ? tab[imag * g + (-real)] : tab[(-real) * g + (-imag)];
 }
 
-#define SEQ_CHUNK 256
+#define SEQ_CHUNK 128
 #define SEQ_MAX_WT 1024
 #define SEQ_MAX_PD (64 * 64)
 
 // pass 0: BPSK: AGC + Costas loop, A -> B.  PLL: AGC + PLL, A -> B.  MPSK: AGC in place on A.
 // pass 1: MPSK decision-directed loop, (A[d + k], B[k]) -> (C[k], D[k]).
-__global__ void __launch_bounds__(32)
+// Two warps per chain.  Warp 1 feeds: it loads the next chunk and, in pass 0, runs the AGC on it (envelope recurrence
+// on its lane 0, divisions on all lanes).  Warp 0 consumes the previous chunk: its lane 0 runs the carrier loop, its
+// lanes store the results.  The chunks are double buffered, so the AGC costs nothing on top of the loop.
+__global__ void __launch_bounds__(64)
 p64_seq_kernel(const P64Chain *__restrict__ chains, int pass)
 {
 	__shared__ double s_wt[SEQ_MAX_WT];
-	__shared__ int s_pd[SEQ_MAX_PD];
-	__shared__ double s_in0[SEQ_CHUNK], s_in1[SEQ_CHUNK], s_out0[SEQ_CHUNK], s_out1[SEQ_CHUNK];
+	__shared__ double s_pd[SEQ_MAX_PD];
+	__shared__ double s_feed0[2][SEQ_CHUNK], s_feed1[2][SEQ_CHUNK], s_env[SEQ_CHUNK], s_res0[SEQ_CHUNK], s_res1[SEQ_CHUNK];
 	const P64Chain C = chains[blockIdx.x];
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	if (C.kind == KIND_AFSK) return;
 	if (pass == 1 && C.kind != KIND_MPSK) return;
 	const LoopConst L = C.lc;
-	for (int i = lane; i < C.wt_size; i += 32) s_wt[i] = C.wavetable[i];
+	for (int i = threadIdx.x; i < C.wt_size; i += 64) s_wt[i] = C.wavetable[i];
 	if (C.kind == KIND_MPSK && pass == 1)
-		for (int i = lane; i < C.pd_g * C.pd_g; i += 32) s_pd[i] = C.pd_table[i];
+		for (int i = threadIdx.x; i < C.pd_g * C.pd_g; i += 64) s_pd[i] = (double)C.pd_table[i];
 	LoopState s;
 	s.envelope = 0.0; s.sustain_count = 0.0;
 	const double normal = p64_order_value(*C.max_slot);
@@ -294,61 +320,87 @@ p64_seq_kernel(const P64Chain *__restrict__ chains, int pass)
 	s.x1 = 0.0; s.y1 = 0.0;
 	s.integral = L.pi_integral0; s.proportional = 0.0;
 	const double gain_p = __dmul_rn(L.pi_gain, L.pi_p);
+	const double half_g = 0.5 * (double)C.pd_g;
 	const long long n = (pass == 0) ? C.L1 : C.L2;
 	const double *src0 = (pass == 0) ? C.A : C.A + C.mid_delay;
 	const double *src1 = C.B;
 	double *dst0 = (pass == 0) ? (C.kind == KIND_MPSK ? C.A : C.B) : C.C;
 	double *dst1 = C.D;
 	const bool two = (pass == 1);
-	__syncwarp();
-	for (long long c0 = 0; c0 < n; c0 += SEQ_CHUNK) {
+	const long long n_chunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+
+	auto feed = [&](long long k) {            // warp 1: chunk k -> buffer k & 1
+		const int bsel = (int)(k & 1);
+		const long long c0 = k * SEQ_CHUNK;
 		const int cnt = (int)min((long long)SEQ_CHUNK, n - c0);
 		for (int i = lane; i < cnt; i += 32) {
-			s_in0[i] = src0[c0 + i];
-			if (two) s_in1[i] = src1[c0 + i];
+			s_feed0[bsel][i] = src0[c0 + i];
+			if (two) s_feed1[bsel][i] = src1[c0 + i];
 		}
-		__syncwarp();
-		if (lane == 0) {
+		if (pass == 0) {
+			__syncwarp();
+			if (lane == 0)
+				for (int i = 0; i < cnt; i++) s_env[i] = agc_envelope(L, s, s_feed0[bsel][i]);
+			__syncwarp();
+			for (int i = lane; i < cnt; i += 32) s_feed0[bsel][i] = agc_scale(L, s_feed0[bsel][i], s_env[i]);
+		}
+	};
+
+	__syncthreads();
+	if (wid == 1 && n_chunks > 0) feed(0);
+	__syncthreads();
+	for (long long k = 0; k < n_chunks; k++) {
+		if (wid == 1) {
+			if (k + 1 < n_chunks) feed(k + 1);
+		} else {
+			const int bsel = (int)(k & 1);
+			const long long c0 = k * SEQ_CHUNK;
+			const int cnt = (int)min((long long)SEQ_CHUNK, n - c0);
+			const double *in0 = s_feed0[bsel], *in1 = s_feed1[bsel];
 			if (pass == 0 && C.kind == KIND_MPSK) {
-				for (int i = 0; i < cnt; i++) s_out0[i] = agc_step(L, s, s_in0[i]);
-			} else if (pass == 0 && C.kind == KIND_BPSK) {                 // psk.py:173-189
-				for (int i = 0; i < cnt; i++) {
-					const double sample = agc_step(L, s, s_in0[i]);
-					nco_step(L, s, s_wt, C.wt_size);
-					const double i_mixer = __dmul_rn(sample, s.cosine);
-					const double q_mixer = __dmul_rn(sample, -s.sine);
-					const double f = iir_step(L, s, __dmul_rn(i_mixer, q_mixer));
-					s.control = pi_step(L, s, gain_p, f);
-					s_out0[i] = i_mixer;
+				for (int i = lane; i < cnt; i += 32) dst0[c0 + i] = in0[i];          // AGC only (psk.py:713)
+			} else {
+				if (lane == 0) {
+					if (pass == 0 && C.kind == KIND_BPSK) {                         // psk.py:173-189
+						for (int i = 0; i < cnt; i++) {
+							const double sample = in0[i];
+							nco_step(L, s, s_wt, C.wt_size);
+							const double i_mixer = __dmul_rn(sample, s.cosine);
+							const double q_mixer = __dmul_rn(sample, -s.sine);
+							const double f = iir_step(L, s, __dmul_rn(i_mixer, q_mixer));
+							s.control = pi_step(L, s, gain_p, f);
+							s_res0[i] = i_mixer;
+						}
+					} else if (pass == 0) {                                         // afsk_pll.py:152-165
+						for (int i = 0; i < cnt; i++) {
+							const double sample = in0[i];
+							nco_step(L, s, s_wt, C.wt_size);
+							const double f = iir_step(L, s, __dmul_rn(sample, s.sine));
+							s.control = pi_step(L, s, gain_p, f);
+							s_res0[i] = s.proportional;
+						}
+					} else {                                                        // psk.py:733-746
+						for (int i = 0; i < cnt; i++) {
+							nco_step(L, s, s_wt, C.wt_size);
+							const double c_re = s.cosine, c_im = -s.sine;
+							const double re = in0[i], im = in1[i];
+							const double real = __dsub_rn(__dmul_rn(re, c_re), __dmul_rn(im, c_im));     // complexmath.py:15-19
+							const double imag = __dadd_rn(__dmul_rn(c_re, im), __dmul_rn(re, c_im));
+							const double f = iir_step(L, s, pd_qpsk_error(s_pd, C.pd_g, half_g, real, imag));
+							s.control = rint(pi_step(L, s, gain_p, f));             // python round(): half to even
+							s_res0[i] = real;
+							s_res1[i] = imag;
+						}
+					}
 				}
-			} else if (pass == 0) {                                         // afsk_pll.py:152-165
-				for (int i = 0; i < cnt; i++) {
-					const double sample = agc_step(L, s, s_in0[i]);
-					nco_step(L, s, s_wt, C.wt_size);
-					const double f = iir_step(L, s, __dmul_rn(sample, s.sine));
-					s.control = pi_step(L, s, gain_p, f);
-					s_out0[i] = s.proportional;
-				}
-			} else {                                                        // psk.py:733-746
-				for (int i = 0; i < cnt; i++) {
-					nco_step(L, s, s_wt, C.wt_size);
-					const double c_re = s.cosine, c_im = -s.sine;
-					const double re = s_in0[i], im = s_in1[i];
-					const double real = __dsub_rn(__dmul_rn(re, c_re), __dmul_rn(im, c_im));     // complexmath.py:15-19
-					const double imag = __dadd_rn(__dmul_rn(c_re, im), __dmul_rn(re, c_im));
-					const double f = iir_step(L, s, (double)pd_qpsk_error(s_pd, C.pd_g, real, imag));
-					s.control = rint(pi_step(L, s, gain_p, f));             // python round(): half to even
-					s_out0[i] = real;
-					s_out1[i] = imag;
+				__syncwarp();
+				for (int i = lane; i < cnt; i += 32) {
+					dst0[c0 + i] = s_res0[i];
+					if (two) dst1[c0 + i] = s_res1[i];
 				}
 			}
 		}
-		__syncwarp();
-		for (int i = lane; i < cnt; i += 32) {
-			dst0[c0 + i] = s_out0[i];
-			if (two) dst1[c0 + i] = s_out1[i];
-		}
-		__syncwarp();
+		__syncthreads();
 	}
 }
 
@@ -383,11 +435,11 @@ extern "C" cudaError_t pm_launch_p64(const P64Chain *d_chains, const P64Chain *h
 	p64_bpf_kernel<<<dim3(tiles(L1), n_chains), P64_THREADS, sizeof(double) * (P64_TILE + 2 * m_bpf), st>>>(d_chains, audio);
 	if (any_loop) {
 		p64_max_kernel<<<dim3(min(tiles(L1) * 4u, 1184u), n_chains), P64_THREADS, 0, st>>>(d_chains);
-		p64_seq_kernel<<<n_chains, 32, 0, st>>>(d_chains, 0);
+		p64_seq_kernel<<<n_chains, 64, 0, st>>>(d_chains, 0);
 	}
 	if (any_mid && L2 > 0)
 		p64_mid_kernel<<<dim3(tiles(L2), n_chains), P64_THREADS, sizeof(double) * (P64_TILE + m_mid), st>>>(d_chains);
-	if (any_mpsk) p64_seq_kernel<<<n_chains, 32, 0, st>>>(d_chains, 1);
+	if (any_mpsk) p64_seq_kernel<<<n_chains, 64, 0, st>>>(d_chains, 1);
 	p64_out_kernel<<<dim3(max(tiles(L3), 1u), n_chains, any_mpsk ? 2 : 1), P64_THREADS,
 		sizeof(double) * (P64_TILE + 2 * m_out), st>>>(d_chains, sign, sign_stride, soft, soft_stride);
 	return cudaGetLastError();
