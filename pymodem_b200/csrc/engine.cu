@@ -143,6 +143,7 @@ struct pm_engine {
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
+	int opt_slicer_fast = 1;      // shortened slicer clock update where it is exact (0: always the plain form)
 	int opt_precise = 0;          // all AFSK chains through the float64 pipeline
 	double opt_precise_ratio = 0.2;
 	long long opt_h2d_chunk = 8 << 20;
@@ -728,6 +729,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
+	else if (k == "slicer_fast") e->opt_slicer_fast = value != 0;
 	else if (k == "precise") {
 		if (!e->chains.empty()) return fail(e, PM_ERR_STATE, "set 'precise' before loading chains");
 		e->opt_precise = value != 0;
@@ -792,7 +794,31 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		s.lock = hc.d.lock_rate;
 		s.nout = nout;
 		const bool quad = hc.d.slicer_kind == PM_SLICER_QUADRATURE;
-		s.quadrature = quad ? 1 : 0; s.sign_q_row = quad ? hc.sign_q_row : 0; s.sign_row = c; s.pad = 0;
+		s.quadrature = quad ? 1 : 0; s.sign_q_row = quad ? hc.sign_q_row : 0; s.sign_row = c;
+		{
+			// shortened clock update (SlicerChain): c_star = smallest double with fl(c_star + 1.0) >= thr; usable when
+			// [c_star, thr + 1) lies inside one binade
+			volatile double probe;
+			double cs = s.thr - 1.0;
+			bool fast = cs >= 1.0 && e->opt_slicer_fast;
+			if (fast) {
+				for (int k = 0; k < 4; k++) cs = std::nextafter(cs, -INFINITY);
+				for (int guard = 0; guard < 16; guard++) {
+					probe = cs + 1.0;
+					if (probe >= s.thr) break;
+					cs = std::nextafter(cs, INFINITY);
+				}
+				probe = cs + 1.0;
+				int ex = 0;
+				std::frexp(cs, &ex);                       // cs in [2^(ex-1), 2^ex)
+				fast = probe >= s.thr && cs >= 1.0 && s.thr + 1.0 <= std::ldexp(1.0, ex);
+				probe = std::nextafter(cs, -INFINITY) + 1.0;
+				fast = fast && !(probe >= s.thr);          // cs really is the smallest
+			}
+			s.fast = fast ? 1 : 0;
+			memcpy(&s.c_star_bits, &cs, sizeof(double));
+			s.sps_m1 = s.sps - 1.0;
+		}
 		BitChain &b = bc[c];
 		memset(&b, 0, sizeof(b));
 		b.nout = nout; b.sign_row = c; b.bps = 1; b.lfsr_poly = hc.d.lfsr_poly; b.lfsr_invert = hc.d.lfsr_invert;

@@ -89,7 +89,14 @@ struct SlicerChain {
 	int quadrature;          // zero crossings on I or Q (slicer.py:226-233)
 	int sign_q_row;          // row of the Q sign stream (quadrature)
 	int sign_row;            // row of the (I) sign stream
-	int pad;
+	int fast;                // the shortened update below is exact for this chain
+	// Shortened clock update.  A roll-over happens when fl(clock + 1.0) >= thr, i.e. (rounding is monotonic) when
+	// clock >= c_star, the smallest double whose successor step reaches thr; clock < thr always, so for positive
+	// c_star this is an integer comparison of the bit patterns.  When [c_star, thr + 1) lies inside one binade,
+	// clock + 1.0 is exact in that range and fl(fl(clock + 1.0) - sps) == fl(clock - (sps - 1.0)): both candidates
+	// of the next clock come straight from the old one, one double operation deep instead of two plus a compare.
+	long long c_star_bits;
+	double sps_m1;           // sps - 1.0 (exact for sps >= 1)
 };
 
 struct SegState {

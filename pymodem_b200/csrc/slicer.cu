@@ -31,14 +31,15 @@ __device__ __forceinline__ bool seg_state_equal(const SegState &a, const SegStat
 }
 
 // Advance the slicer over samples [w0*32, min(w1*32, nout)) of one chain.
-template <bool WRITE>
-__device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *__restrict__ sg,
-                                          const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
-                                          long long w0, long long w1, SegState &st)
+template <bool WRITE, bool FAST>
+__device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                            const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
+                                            long long w0, long long w1, SegState &st)
 {
 	double c = st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
-	const double thr = C.thr, sps = C.sps, lam = C.lock;
+	const double thr = C.thr, sps = C.sps, lam = C.lock, spm1 = C.sps_m1;
+	const long long c_star = C.c_star_bits;
 	for (long long w = w0; w < w1; w++) {
 		const long long first = w << 5;
 		if (first >= C.nout) break;
@@ -52,15 +53,23 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
 		}
 		uint32_t m = 0;
 		const long long remain = C.nout - first;
-		if (remain >= 32) {
+		const int cnt = remain >= 32 ? 32 : (int)remain;
+		if (cnt == 32) {
 #pragma unroll
 			for (int i = 0; i < 32; i++) {
-				c += 1.0;                                // slicer.py:77
-				if (c >= thr) { c -= sps; m |= (1u << i); }   // slicer.py:79-81
-				if ((z >> i) & 1u) c *= lam;             // slicer.py:104
+				if (FAST) {
+					// both candidates straight from the old clock (see SlicerChain): same bits as the plain form below
+					const bool roll = __double_as_longlong(c) >= c_star;
+					const double up = __dadd_rn(c, 1.0), over = __dsub_rn(c, spm1);
+					c = roll ? over : up;
+					m |= (roll ? 1u : 0u) << i;
+				} else {
+					c += 1.0;                                // slicer.py:77
+					if (c >= thr) { c -= sps; m |= (1u << i); }   // slicer.py:79-81
+				}
+				if ((z >> i) & 1u) c *= lam;                 // slicer.py:104
 			}
 		} else {
-			const int cnt = (int)remain;
 			for (int i = 0; i < cnt; i++) {
 				c += 1.0;
 				if (c >= thr) { c -= sps; m |= (1u << i); }
@@ -75,6 +84,15 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
 	st.clock = c;
 	st.last = last;
 	st.last_q = last_q;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                          const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
+                                          long long w0, long long w1, SegState &st)
+{
+	if (C.fast) run_words_t<WRITE, true>(C, sg, sgq, mk, w0, w1, st);      // uniform per chain (blockIdx.y)
+	else run_words_t<WRITE, false>(C, sg, sgq, mk, w0, w1, st);
 }
 
 // grid: (ceil(n_seg / 128), n_chains); block 128

@@ -374,3 +374,20 @@ def test_unsupported_combinations_are_rejected(cuda_lib):
 		engine([chain_builder.build_chain(8000, bad)])
 	with pytest.raises(NotImplementedError):
 		chain_builder.ModemConfigurator(8000, {"type": "qpsk", "config": "600", "options": {}})
+
+
+@pytest.mark.parametrize("tag", ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k", "qpsk2400_il2p_8k", "bpsk300_il2p_8k"])
+def test_shortened_slicer_update_is_exact(cuda_lib, tag):
+	"""The one-operation-deep clock update (SlicerChain.fast: 40, 36.75 and 26.67 samples per symbol here; 5, 6.67 and
+	others fall back to the plain form) gives the same AddressedData streams as the plain form, which the fixtures pin."""
+	g = Golden(tag)
+	out = []
+	for fast in (1, 0):
+		eng = engine(build_stack(g.sample_rate, g.lines), slicer_fast=fast)
+		try:
+			pk = as_tuples(eng.run(g.audio()))
+			out.append((pk, [tuple(map(bytes, map(np.ndarray.tobytes, eng.stream(ci, 0)))) for ci in range(g.n_chains)]))
+		finally:
+			eng.close()
+	assert out[0] == out[1]
+	assert out[0][0] == g.all_packets()
