@@ -461,52 +461,150 @@ __device__ bool ax25_replay(const uint32_t *__restrict__ d, long long start, lon
 	return emit;
 }
 
-__global__ void __launch_bounds__(128)
-ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
-                const uint32_t *__restrict__ d, long long bits_stride,
-                const unsigned int *__restrict__ flag_pos, long long flag_stride,
-                const unsigned int *__restrict__ flag_totals,
-                const uint32_t *__restrict__ byte_addr, long long addr_stride,
-                uint8_t *__restrict__ scratch, long long scratch_stride,
-                GapRec *__restrict__ gaps, long long gap_stride, const ShardBits *__restrict__ sb)
+// ---- which gaps can emit at all? ------------------------------------------------------------------------------
+// Only about one gap in fourteen ends in a packet (>= 18 bytes and a whole number of bytes + 7 bits at the closing
+// flag, ax25.py:76), and that follows from the bit COUNT alone: data bits since the gap start or since the zero that
+// ended the last abort run (seven or more ones zero bit_index and byte_index, ax25.py:35-38), minus the stuffed
+// zeros.  The count is taken four stream bits at a time from a table indexed by (run of ones so far, nibble);
+// only the gaps that pass (and the rare ones that need care: open at a shard start, or long enough to overflow
+// max_packet_length) are replayed bit by bit, densely, by a second kernel.
+//   table entry: bits 0-2 = ones run after the nibble (capped at 7), bit 3 = an abort happened inside the nibble,
+//   bits 4-6 = data bits counted (after the last abort inside the nibble, if any)
+__device__ __forceinline__ unsigned int hdlc_nibble_entry(unsigned int oc, unsigned int nib)
 {
+	unsigned int cnt = 0, reset = 0;
+	for (int b = 0; b < 4; b++) {
+		if ((nib >> b) & 1u) {
+			oc = min(oc + 1u, 7u);
+			cnt++;
+			if (oc >= 7u) { cnt = 0; reset = 1; }              // one_count > 6: abort
+		} else {
+			if (oc < 5u) cnt++;                                // oc == 5: stuffed zero; oc >= 7: the zero ending an abort run
+			oc = 0;
+		}
+	}
+	return oc | (reset << 3) | (cnt << 4);
+}
+
+__device__ __forceinline__ void hdlc_count_step(const unsigned char *__restrict__ tab, unsigned int &oc, unsigned int &cnt,
+                                                unsigned int nib)
+{
+	const unsigned int e = tab[oc * 16u + nib];
+	cnt = (e & 8u) ? (e >> 4) : cnt + (e >> 4);
+	oc = e & 7u;
+}
+
+// data-bit count at the closing flag of the gap [start, end] (end = the flag's final zero, not counted)
+__device__ unsigned int hdlc_gap_count(const uint32_t *__restrict__ d, const unsigned char *__restrict__ tab,
+                                       long long start, long long end)
+{
+	unsigned int oc = 0, cnt = 0;
+	long long p = start;
+	while (p + 32 <= end) {
+		const long long w = p >> 5;
+		const int r = (int)(p & 31);
+		uint32_t v = r ? __funnelshift_r(d[w], d[w + 1], r) : d[w];
+#pragma unroll
+		for (int q = 0; q < 8; q++) { hdlc_count_step(tab, oc, cnt, v & 15u); v >>= 4; }
+		p += 32;
+	}
+	if (p < end) {
+		const long long w = p >> 5;
+		const int r = (int)(p & 31);
+		const int left = (int)(end - p);                           // 1..31 bits
+		uint32_t v = d[w] >> r;
+		if (r && r + left > 32) v |= d[w + 1] << (32 - r);
+		int done = 0;
+		for (; done + 4 <= left; done += 4) { hdlc_count_step(tab, oc, cnt, v & 15u); v >>= 4; }
+		for (; done < left; done++) {                              // last 1..3 bits one at a time
+			if (v & 1u) { oc = min(oc + 1u, 7u); cnt++; if (oc >= 7u) cnt = 0; }
+			else { if (oc < 5u) cnt++; oc = 0; }
+			v >>= 1;
+		}
+	}
+	return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+ax25_gap_filter_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
+                       const uint32_t *__restrict__ d, long long bits_stride,
+                       const unsigned int *__restrict__ flag_pos, long long flag_stride,
+                       const unsigned int *__restrict__ flag_totals,
+                       GapRec *__restrict__ gaps, long long gap_stride, const ShardBits *__restrict__ sb,
+                       unsigned int *__restrict__ cand, unsigned int *__restrict__ ncand)
+{
+	__shared__ unsigned char s_tab[128];
+	if (threadIdx.x < 128) s_tab[threadIdx.x] = (unsigned char)hdlc_nibble_entry(threadIdx.x >> 4, threadIdx.x & 15u);
+	__syncthreads();
 	const int ch = blockIdx.y;
 	if (chains[ch].codec != 1) return;
 	const unsigned int nfl = flag_totals[ch];
 	if (blockIdx.x == 0 && threadIdx.x == 0) cc[ch].nflags = (int)nfl;
 	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
+	const uint32_t *bits = d + (long long)ch * bits_stride;
 	const ShardBits B = sb[ch];
-	// the number of gaps is only known on the device: a moderate grid strides over them
 	for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < nfl; j += gridDim.x * blockDim.x) {
+		const long long end = fp[j];
+		const long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
+		GapRec r;
+		r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
+		gaps[(long long)ch * gap_stride + j] = r;
+		// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is emitted by the shard
+		// that holds its closing bit
+		const bool mine = end >= B.own_lo && end < B.own_hi;
+		const bool open_start = !B.first && (j == 0 || (long long)fp[j - 1] < B.valid_from + 8);
+		const long long len = end - start + 1;
+		if (!mine || !(len >= 18 * 8 + 8 || open_start)) continue;
+		bool replay = open_start || len >= 8192;                    // unknown history / max_packet_length overflow possible
+		if (!replay) {
+			const unsigned int cnt = hdlc_gap_count(bits, s_tab, start, end);
+			replay = (cnt & 7u) == 7u && (cnt >> 3) >= 18u;
+		}
+		if (replay) cand[(long long)ch * flag_stride + atomicAdd(&ncand[ch], 1u)] = j;
+	}
+}
+
+// the gaps that passed the filter, replayed bit by bit (ax25.py:25-93)
+__global__ void __launch_bounds__(128)
+ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
+                const uint32_t *__restrict__ d, long long bits_stride,
+                const unsigned int *__restrict__ flag_pos, long long flag_stride,
+                const uint32_t *__restrict__ byte_addr, long long addr_stride,
+                uint8_t *__restrict__ scratch, long long scratch_stride,
+                GapRec *__restrict__ gaps, long long gap_stride, const ShardBits *__restrict__ sb,
+                const unsigned int *__restrict__ cand, const unsigned int *__restrict__ ncand)
+{
+	const int ch = blockIdx.y;
+	if (chains[ch].codec != 1) return;
+	const unsigned int n = ncand[ch];
+	const unsigned int *fp = flag_pos + (long long)ch * flag_stride;
+	const ShardBits B = sb[ch];
+	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const unsigned int j = cand[(long long)ch * flag_stride + k];
 		const long long end = fp[j];
 		long long start = (j == 0) ? 0 : (long long)fp[j - 1] + 1;
 		GapRec r;
 		r.emit = 0; r.len = 0; r.scratch_off = (unsigned int)(start >> 3); r.addr = 0; r.corrected = 0;
-		// a frame needs >= 18 bytes + the 7 leading flag bits before the closing 0, and is
-		// emitted by the shard that holds its closing bit
-		const bool mine = end >= B.own_lo && end < B.own_hi;
 		// On a later shard the stream starts in the middle of the recording: a gap whose opening flag is
 		// not a reliably detected one (all 8 bits of its pattern at valid positions) reaches back past the
 		// hand-off tail.  It is replayed from the first valid bit with unknown history.
 		const bool open_start = !B.first && (j == 0 || (long long)fp[j - 1] < B.valid_from + 8);
 		if (open_start && start < B.valid_from) start = B.valid_from;
-		if (mine && (end - start + 1 >= 18 * 8 + 8 || open_start)) {
-			int overflow = 0;
-			unsigned int len = 0;
-			bool aborted = false;
-			const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
-				scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
-			if (overflow) atomicExch(&cc[ch].seq_needed, 1);
-			if (open_start && (emit || !aborted)) {
-				// either junk bytes from before the tail would be part of the frame, or the
-				// emission decision itself depends on bits we do not have (an abort -- seven ones, all
-				// of them valid bits -- resets the machine whatever came before)
-				atomicExch(&cc[ch].tail_short, 1);
-			} else {
-				r.emit = emit ? 1u : 0u;
-				r.len = len;
-				r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
-			}
+		int overflow = 0;
+		unsigned int len = 0;
+		bool aborted = false;
+		const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
+			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
+		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
+		if (open_start && (emit || !aborted)) {
+			// either junk bytes from before the tail would be part of the frame, or the
+			// emission decision itself depends on bits we do not have (an abort -- seven ones, all
+			// of them valid bits -- resets the machine whatever came before)
+			atomicExch(&cc[ch].tail_short, 1);
+		} else {
+			r.emit = emit ? 1u : 0u;
+			r.len = len;
+			r.addr = byte_addr[(long long)ch * addr_stride + (end >> 3)];
 		}
 		gaps[(long long)ch * gap_stride + j] = r;
 	}
@@ -742,7 +840,7 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 	long long bits_stride, unsigned int *blk_count, unsigned int *blk_base, unsigned int *flag_totals,
 	unsigned int *flag_pos, long long flag_stride, const uint32_t *byte_addr, long long addr_stride,
 	uint8_t *scratch, long long scratch_stride, GapRec *gaps, long long gap_stride, const ShardBits *sb,
-	int allow_sequential, cudaStream_t st)
+	int allow_sequential, unsigned int *gap_cand, unsigned int *gap_ncand, cudaStream_t st)
 {
 	const int n_blocks = (int)((bits_stride + FL_WORDS - 1) / FL_WORDS);
 	dim3 grid(n_blocks, n_chains);
@@ -751,8 +849,11 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 	flag_write_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
 	// gaps: at most flag_stride per chain
 	dim3 ggrid((unsigned int)std::min<long long>((flag_stride + 127) / 128, 148 * 16), n_chains);
-	ax25_gap_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals,
-		byte_addr, addr_stride, scratch, scratch_stride, gaps, gap_stride, sb);
+	cudaMemsetAsync(gap_ncand, 0, sizeof(unsigned int) * n_chains, st);
+	ax25_gap_filter_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals, gaps,
+		gap_stride, sb, gap_cand, gap_ncand);
+	ax25_gap_kernel<<<dim3(148 * 2, n_chains), 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, byte_addr,
+		addr_stride, scratch, scratch_stride, gaps, gap_stride, sb, gap_cand, gap_ncand);
 	if (allow_sequential)
 		ax25_sequential_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, byte_addr, addr_stride, scratch,
 			scratch_stride, gaps, gap_stride);

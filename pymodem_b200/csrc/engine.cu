@@ -38,7 +38,7 @@ cudaError_t pm_launch_lfsr(const BitChain *, int, const ChainCounters *, const u
 	cudaStream_t);
 cudaError_t pm_launch_ax25(const BitChain *, int, ChainCounters *, const uint32_t *, long long, unsigned int *,
 	unsigned int *, unsigned int *, unsigned int *, long long, const uint32_t *, long long, uint8_t *, long long,
-	GapRec *, long long, const ShardBits *, int, cudaStream_t);
+	GapRec *, long long, const ShardBits *, int, unsigned int *, unsigned int *, cudaStream_t);
 cudaError_t pm_launch_p64(const P64Chain *, const P64Chain *, int, const int16_t *, uint32_t *, long long, float *,
 	long long, unsigned long long *, cudaStream_t);
 cudaError_t pm_link_preload(void);
@@ -179,6 +179,7 @@ struct pm_engine {
 	DevBuf<unsigned int> d_blk_count, d_blk_base, d_sym_totals, d_flag_totals, d_flag_pos, d_rec_src;
 	DevBuf<uint8_t> d_scratch, d_arena;
 	DevBuf<GapRec> d_gaps;
+	DevBuf<unsigned int> d_gap_cand, d_gap_ncand;   // gaps that can emit (filtered by bit count), per chain
 	DevBuf<pm_packet_rec> d_recs;
 	DevBuf<PacketTotals> d_totals;
 	DevBuf<unsigned char> d_il2p_slots;   // speculative IL2P decodes: (cand_cap + 1) slots per chain
@@ -517,6 +518,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_guard_entries.release(); e->d_counters.release(); e->d_S.release(); e->d_E0.release();
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
+	e->d_gap_cand.release(); e->d_gap_ncand.release();
 	e->d_arena.release(); e->d_gaps.release(); e->d_recs.release(); e->d_totals.release();
 	e->d_il2p_slots.release(); e->d_il2p_res.release();
 	e->d_p64_work.release(); e->d_p64_tabs.release(); e->d_p64_pd.release(); e->d_p64.release(); e->d_p64_max.release();
@@ -881,6 +883,8 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	CK(e->d_byte_addr.ensure((size_t)nc * e->addr_stride));
 	CK(e->d_flag_pos.ensure((size_t)nc * e->flag_stride));
 	CK(e->d_gaps.ensure((size_t)nc * e->flag_stride));
+	CK(e->d_gap_cand.ensure((size_t)nc * e->flag_stride));
+	CK(e->d_gap_ncand.ensure(nc));
 	CK(e->d_scratch.ensure((size_t)nc * e->scratch_stride));
 	CK(e->d_recs.ensure((size_t)rec_cap));
 	CK(e->d_rec_src.ensure((size_t)rec_cap));
@@ -1227,7 +1231,8 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 	e->stats.kernel_launches++;
 	ce = pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p,
 		e->d_blk_base.p, e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride,
-		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->sharded ? 0 : 1, e->st);
+		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->sharded ? 0 : 1,
+		e->d_gap_cand.p, e->d_gap_ncand.p, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "ax25 launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches += e->sharded ? 4 : 5;
 	if (e->has_il2p) {
@@ -1505,7 +1510,7 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, st));
 	CKL(pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p, e->d_blk_base.p,
 		e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride, e->d_scratch.p,
-		e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, 0, st));
+		e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, 0, e->d_gap_cand.p, e->d_gap_ncand.p, st));
 	CKL(pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p, e->d_recs.n,
 		e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base, st));
 	CK(cudaEventRecord(e->ev[4], st));

@@ -391,3 +391,21 @@ def test_shortened_slicer_update_is_exact(cuda_lib, tag):
 			eng.close()
 	assert out[0] == out[1]
 	assert out[0][0] == g.all_packets()
+
+
+def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
+	"""150 s of band-limited noise: ~45 000 inter-flag gaps per chain with aborts, stuffed zeros and every residue of
+	the bit count; the count-based filter (bits.cu ax25_gap_filter_kernel) must let through exactly the gaps the
+	reference's state machine emits (a few hundred bad-CRC frames)."""
+	from pymodem_b200 import configs
+	rng = np.random.default_rng(2024)
+	audio = np.clip(rng.standard_normal(48000 * 150) * 9000, -32768, 32767).astype(np.int16)
+	lines = configs.afsk_1200_ax25_super_opt()
+	want = oracle.run_config(48000, lines, audio, chunk=1 << 20)
+	eng = engine(build_stack(48000, lines))
+	try:
+		got = as_tuples(eng.run(audio))
+	finally:
+		eng.close()
+	assert got == want
+	assert sum(len(w) for w in want) > 100
