@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -74,3 +75,15 @@ def test_product_path_does_not_import_oracle():
 				text = open(os.path.join(root, f)).read()
 				assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
 				assert "liboracle" not in text, f
+
+
+def test_command_line_exit_codes(tmp_path):
+	"""python -m pymodem_b200 keeps the reference's usage and exit codes (pymodem.py:27-49) up to the point where
+	a GPU is needed."""
+	def run(*args):
+		return subprocess.run([sys.executable, "-m", "pymodem_b200", *args], cwd=REPO, capture_output=True, text=True)
+	assert run().returncode == 2
+	assert run(str(tmp_path / "missing.json"), str(tmp_path / "missing.wav")).returncode == 3
+	cfg = tmp_path / "c.json"
+	cfg.write_text('{"object_type": "report", "object_name": "r", "options": {}}\n')
+	assert run(str(cfg), str(tmp_path / "missing.wav")).returncode == 4

@@ -409,3 +409,20 @@ def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
 		eng.close()
 	assert got == want
 	assert sum(len(w) for w in want) > 100
+
+
+def test_command_line_end_to_end(cuda_lib, tmp_path, capsys):
+	"""python -m pymodem_b200 <config> <wav>: the reference's CLI flow (pymodem.py:25-183) on the shipped-WAV excerpt
+	with afsk_300.json as shipped; unique/bad counts as the reference reports them."""
+	import json
+	from scipy.io.wavfile import write as writewav
+	from pymodem_b200.__main__ import main
+	g = Golden("afsk300_full_8k")
+	cfg = tmp_path / "afsk_300.json"
+	cfg.write_text("".join(json.dumps(l) + "\n" for l in g.lines))
+	wav = tmp_path / "excerpt.wav"
+	writewav(str(wav), g.sample_rate, g.audio())
+	assert main(["pymodem_b200", str(cfg), str(wav)]) == 0
+	out = capsys.readouterr().out
+	assert f"Unique, valid packets: {len(g.z['uniq_addr'])}" in out
+	assert f"Packets rejected from all decoders for CRC failure: {int(g.z['bad_count'])}" in out
