@@ -201,8 +201,14 @@ def run_b200_arm(args):
 	from pymodem_b200.sharded import bind_to_gpu_numa_node
 	numa = bind_to_gpu_numa_node(local)          # before any pinned allocation
 	print(f"[bench rank {rank}] {numa}", file=sys.stderr, flush=True)
+	# stdout carries exactly one JSON line: whatever libraries print while the process group and the first communicator
+	# come up (NCCL's version banner) goes to stderr
+	sys.stdout.flush()
+	saved_stdout = os.dup(1)
+	os.dup2(2, 1)
 	if world > 1:
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+		dist.barrier()
 
 	def barrier():
 		if world > 1:
@@ -283,6 +289,9 @@ def run_b200_arm(args):
 
 	for _ in range(args.warmup):
 		step_device()
+	sys.stdout.flush()
+	os.dup2(saved_stdout, 1)
+	os.close(saved_stdout)
 	sampler = ClockSampler(local)
 	if rank == 0:
 		sampler.start()
