@@ -238,6 +238,21 @@ int pm_engine_shard_gather(pm_engine *e, const int64_t *symbols_before, uint32_t
 int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in);
 
 /*
+ * IL2P chains keep decoder state across a shard boundary (is the decoder searching or inside a frame, il2p.py:360-519;
+ * corrected-byte counts of failed frames, il2p.py:200-211), so their shards finish ONE AFTER THE OTHER: rank r calls
+ * shard_finish_il2p with the state rank r-1 returned (NULL on the first shard) and passes its own on.  Positions are
+ * global stream bits.  A frame is decoded by the shard that holds its last bit; the previous shard's tail_bits must
+ * cover the longest frame (a 1023-byte payload is 10 552 bits on the air).  Engines without IL2P chains may use
+ * either call.
+ */
+typedef struct pm_il2p_state {      /* one per chain (ignored for AX.25 chains) */
+	int64_t  pos;                   /* the sync search (re)starts at this stream bit */
+	uint32_t mode;                  /* 0 start of recording, 1 right after a frame, 2 plain search */
+	uint32_t leak;                  /* corrected bytes of failed frames since the last emitted packet */
+} pm_il2p_state;
+int pm_engine_shard_finish_il2p(pm_engine *e, const uint32_t *tail_in, const pm_il2p_state *prev, pm_il2p_state *out);
+
+/*
  * Shard link: the same hand-off carried out by the GPUs themselves over NVLink peer memory (csrc/link.cu).
  * Every rank creates a link buffer, the ranks exchange the 64-byte CUDA IPC handles once (any transport) and
  * map each other's buffers.  run_linked_begin then enqueues the whole sharded run -- front end, slicer, state

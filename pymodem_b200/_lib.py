@@ -79,6 +79,11 @@ class ShardPlan(ctypes.Structure):
 	]
 
 
+class Il2pState(ctypes.Structure):
+	"""pm_il2p_state"""
+	_fields_ = [("pos", ctypes.c_int64), ("mode", ctypes.c_uint32), ("leak", ctypes.c_uint32)]
+
+
 class ShardState(ctypes.Structure):
 	"""pm_shard_state"""
 	_fields_ = [
@@ -102,6 +107,7 @@ PROTOTYPES = {
 	"pm_engine_shard_handoff": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState), ctypes.POINTER(ShardState), ctypes.POINTER(_i32)]),
 	"pm_engine_shard_gather": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _vp]),
 	"pm_engine_shard_finish": (ctypes.c_int, [_vp, _vp]),
+	"pm_engine_shard_finish_il2p": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(Il2pState), ctypes.POINTER(Il2pState)]),
 	"pm_engine_link_create": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i64, _vp, ctypes.POINTER(_vp)]),
 	"pm_engine_link_connect": (ctypes.c_int, [_vp, _vp, _i32]),
 	"pm_engine_run_linked_begin": (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.POINTER(ShardPlan)]),

@@ -56,7 +56,7 @@ cudaError_t pm_link_merge(LinkGeom, unsigned char *, int, unsigned int, unsigned
 cudaError_t pm_il2p_init_tables(void);
 cudaError_t pm_launch_il2p(const BitChain *, int, ChainCounters *, const uint32_t *, long long, const unsigned int *,
 	long long, const unsigned int *, int, unsigned char *, long long, Il2pRes *, const uint32_t *, long long,
-	uint8_t *, long long, GapRec *, long long, cudaStream_t);
+	uint8_t *, long long, GapRec *, long long, const ShardBits *, const Il2pHand *, Il2pHand *, cudaStream_t);
 cudaError_t pm_launch_packets(int, ChainCounters *, const GapRec *, long long,
 	pm_packet_rec *, unsigned int *, unsigned long long, PacketTotals *, const uint8_t *, long long, uint8_t *,
 	unsigned long long, long long, cudaStream_t);
@@ -184,6 +184,9 @@ struct pm_engine {
 	DevBuf<PacketTotals> d_totals;
 	DevBuf<unsigned char> d_il2p_slots;   // speculative IL2P decodes: (cand_cap + 1) slots per chain
 	DevBuf<Il2pRes> d_il2p_res;
+	DevBuf<Il2pHand> d_il2p_hand;         // [0, nc): where each chain's IL2P walk starts; [nc, 2 nc): where it stands at the end
+	std::vector<long long> h_A0;          // global index of local stream bit 0, per chain (sharded runs)
+	std::vector<long long> h_valid_from;  // first local stream bit whose descrambled value is right, per chain
 	DevBuf<double> d_p64_work, d_p64_tabs;
 	DevBuf<int> d_p64_pd;
 	DevBuf<P64Chain> d_p64;
@@ -520,7 +523,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
 	e->d_gap_cand.release(); e->d_gap_ncand.release();
 	e->d_arena.release(); e->d_gaps.release(); e->d_recs.release(); e->d_totals.release();
-	e->d_il2p_slots.release(); e->d_il2p_res.release();
+	e->d_il2p_slots.release(); e->d_il2p_res.release(); e->d_il2p_hand.release();
 	e->d_p64_work.release(); e->d_p64_tabs.release(); e->d_p64_pd.release(); e->d_p64.release(); e->d_p64_max.release();
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
@@ -832,8 +835,6 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		b.codec = hc.d.codec_kind;
 		b.il2p_crc = hc.d.il2p_crc; b.il2p_disable_rs = hc.d.il2p_disable_rs;
 		b.il2p_min_dist = hc.d.il2p_min_dist; b.il2p_sync_tol = hc.d.il2p_sync_tol;
-		if (sharded && hc.d.codec_kind == PM_CODEC_IL2P)
-			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: IL2P chains cannot be sharded on the sample axis yet", c);
 		e->h_init[c].clock = 0.0; e->h_init[c].last = 1; e->h_init[c].last_q = 1;    // slicer.py:50,55
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
 		const long long mb = (nout / min_gap + 8) * b.bps + 64 + plan.tail_bits;
@@ -894,6 +895,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		e->il2p_cand_cap = (int)std::min<long long>(e->flag_stride, max_bits / 256 + 64);
 		CK(e->d_il2p_slots.ensure((size_t)nc * (e->il2p_cand_cap + 1) * IL2P_SLOT));
 		CK(e->d_il2p_res.ensure((size_t)nc * e->il2p_cand_cap));
+		CK(e->d_il2p_hand.ensure((size_t)2 * nc));
 	}
 	if (e->opt_keep_soft) {
 		e->soft_stride = n;
@@ -1166,6 +1168,8 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 	const int nc = (int)e->chains.size();
 	const pm_shard_plan &plan = e->plan;
 	std::vector<ShardBits> sb(nc);
+	e->h_A0.assign(nc, 0);
+	e->h_valid_from.assign(nc, 0);
 	for (int c = 0; c < nc; c++) {
 		ShardBits &b = sb[c];
 		b.first = plan.first ? 1 : 0; b.pad = 0;
@@ -1177,11 +1181,13 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 			if (P < plan.tail_bits)
 				return fail(e, PM_ERR_CAPACITY, "chain %d: earlier shards hold fewer bits (%lld) than the hand-off tail", c, P);
 			const long long A0 = ((P - plan.tail_bits) >> 3) << 3;              // global bit index of local bit 0
+			e->h_A0[c] = A0;
 			b.bit_off = P - A0;
 			b.own_lo = b.bit_off;
 			int deg = 0;                                                        // LFSR history (lfsr.py:38-44)
 			for (unsigned long long q = e->chains[c].d.lfsr_poly; q > 1; q >>= 1) deg++;
 			b.valid_from = b.bit_off - plan.tail_bits + deg;
+			e->h_valid_from[c] = b.valid_from;
 		}
 		if (plan.last) b.own_hi = 0x7fffffffffffffffll;
 		else {
@@ -1211,12 +1217,34 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 	return PM_OK;
 }
 
-static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
+static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2p_state *il2p_prev = nullptr,
+                             pm_il2p_state *il2p_out = nullptr)
 {
 	if (!e || e->phase != 2) return fail(e, PM_ERR_STATE, "shard_finish: call shard_gather first");
 	const int nc = (int)e->chains.size();
 	const pm_shard_plan &plan = e->plan;
 	cudaError_t ce;
+	std::vector<Il2pHand> hand(nc);
+	if (e->has_il2p) {
+		if (e->sharded && !(plan.first && plan.last) && (!il2p_out || (!plan.first && !il2p_prev)))
+			return fail(e, PM_ERR_ARG, "a sharded run with IL2P chains finishes through pm_engine_shard_finish_il2p, rank after rank");
+		if (e->h_A0.size() != (size_t)nc) e->h_A0.assign(nc, 0);
+		for (int c = 0; c < nc; c++) {
+			Il2pHand &h = hand[c];
+			h.pos = 0; h.mode = 0; h.leak = 0;
+			if (e->sharded && !plan.first && e->chains[c].d.codec_kind == PM_CODEC_IL2P) {
+				h.pos = il2p_prev[c].pos - e->h_A0[c];
+				h.mode = il2p_prev[c].mode;
+				h.leak = il2p_prev[c].leak;
+				// the walk restarts inside the previous shard's bits: everything it looks at has to lie in the hand-off tail
+				const long long vf = e->h_valid_from.size() == (size_t)nc ? e->h_valid_from[c] : 0;
+				const long long need = h.mode == 1 ? h.pos - 8 : h.pos - 63;
+				if (h.mode > 2 || h.mode == 0 || need < vf)
+					return fail(e, PM_ERR_STATE, "chain %d: an IL2P frame reaches back past the %d-bit hand-off tail", c, plan.tail_bits);
+			}
+		}
+		CK(cudaMemcpyAsync(e->d_il2p_hand.p, hand.data(), nc * sizeof(Il2pHand), cudaMemcpyHostToDevice, e->st));
+	}
 	if (e->sharded && !plan.first && plan.tail_bits > 0) {
 		if (!tail_in) return fail(e, PM_ERR_ARG, "shard_finish: the previous shard's tail is required");
 		CK(cudaMemcpyAsync(e->d_tail.p, tail_in, (size_t)nc * (plan.tail_bits / 32) * sizeof(uint32_t),
@@ -1239,9 +1267,11 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 		ce = pm_launch_il2p(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_flag_pos.p,
 			e->flag_stride, e->d_flag_totals.p, e->il2p_cand_cap, e->d_il2p_slots.p,
 			(long long)(e->il2p_cand_cap + 1) * IL2P_SLOT, e->d_il2p_res.p, e->d_byte_addr.p, e->addr_stride,
-			e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->st);
+			e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->d_il2p_hand.p,
+			e->d_il2p_hand.p + nc, e->st);
 		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "il2p launch failed: %s", cudaGetErrorString(ce));
 		e->stats.kernel_launches += 2;
+		CK(cudaMemcpyAsync(hand.data(), e->d_il2p_hand.p + nc, nc * sizeof(Il2pHand), cudaMemcpyDeviceToHost, e->st));
 	}
 	ce = pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p,
 		e->d_recs.n, e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base,
@@ -1255,6 +1285,12 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in)
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
 	CK(cudaStreamSynchronize(e->st));
+	if (e->has_il2p && il2p_out)
+		for (int c = 0; c < nc; c++) {
+			il2p_out[c].pos = hand[c].pos + e->h_A0[c];
+			il2p_out[c].mode = hand[c].mode;
+			il2p_out[c].leak = hand[c].leak;
+		}
 	for (int c = 0; c < nc; c++) {
 		if (e->h_cc[c].tail_short)
 			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
@@ -1592,6 +1628,13 @@ extern "C" int pm_engine_shard_states(pm_engine *e, pm_shard_state *out)
 	if (rc != PM_OK) return rc;
 	memcpy(out, e->shard_out.data(), e->shard_out.size() * sizeof(pm_shard_state));
 	return PM_OK;
+}
+
+extern "C" int pm_engine_shard_finish_il2p(pm_engine *e, const uint32_t *tail_in, const pm_il2p_state *prev, pm_il2p_state *out)
+{
+	if (!e || !out) return fail(e, PM_ERR_ARG, "shard_finish_il2p: bad arguments");
+	cudaSetDevice(e->device);
+	return shard_finish_impl(e, tail_in, prev, out);
 }
 
 extern "C" int64_t pm_engine_num_packets(const pm_engine *e) { return (e && e->have_run) ? (int64_t)e->h_recs.size() : -1; }

@@ -311,6 +311,10 @@ __device__ __forceinline__ bool il2p_sync_match(unsigned int ww, int tol)     //
 }
 
 // --- 3. sequential resolution, one warp per chain -------------------------------------
+// hand_in / hand_out: where the walk starts and where it stands when it reaches the end of the shard's own range
+// (sb[ch].own_hi; the whole stream on an unsharded run).  A frame is processed by the shard that holds its last bit:
+// a sync whose frame runs past own_hi (or past the local stream) is left, with the state in front of it, to the next
+// shard, which sees the same bits through its hand-off tail.
 __global__ void __launch_bounds__(32)
 il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__ cc,
                     const uint32_t *__restrict__ dall, long long bits_stride,
@@ -320,7 +324,8 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
                     const Il2pRes *__restrict__ results,
                     const uint32_t *__restrict__ byte_addr, long long addr_stride,
                     uint8_t *__restrict__ scratch, long long scratch_stride,
-                    GapRec *__restrict__ gaps, long long gap_stride)
+                    GapRec *__restrict__ gaps, long long gap_stride,
+                    const ShardBits *__restrict__ sb, const Il2pHand *__restrict__ hand_in, Il2pHand *__restrict__ hand_out)
 {
 	const int ch = blockIdx.x;
 	const BitChain C = chains[ch];
@@ -328,6 +333,7 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 	const int lane = threadIdx.x;
 	const uint32_t *d = dall + (long long)ch * bits_stride;
 	const long long nb = cc[ch].nbytes * 8;
+	const long long own_hi = sb[ch].own_hi;
 	const unsigned int *cp = cand_pos + (long long)ch * cand_stride;
 	const unsigned int ncand = cand_totals[ch];
 	if ((long long)ncand > cand_stride) {                           // sync tolerance so loose the list overflowed
@@ -338,9 +344,9 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 	unsigned char *tmp = slots + (long long)cand_cap * IL2P_SLOT;        // slot for inline decodes
 	uint8_t *dst = scratch + (long long)ch * scratch_stride;
 	GapRec *out = gaps + (long long)ch * gap_stride;
-	long long pos = 0;
-	bool at_start = true;
-	unsigned int ci = 0, nrec = 0, leak = 0, out_off = 0;
+	long long pos = hand_in[ch].pos;
+	unsigned int mode = hand_in[ch].mode;
+	unsigned int ci = 0, nrec = 0, leak = hand_in[ch].leak, out_off = 0;
 	while (true) {
 		// lane 0 finds the next accepted sync and its decode result
 		long long found = -1;
@@ -349,10 +355,10 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 		r.status = IL2P_INCOMPLETE; r.len = 0; r.corrected = 0; r.end_bit = nb - 1;
 		if (lane == 0 && pos < nb) {
 			const long long lim = min(pos + 32, nb);
-			if (at_start) {
+			if (mode == 0) {
 				for (long long g = pos; g < lim; g++)
-					if (il2p_sync_match(il2p_window(d, g, pos, at_start), C.il2p_sync_tol)) { found = g; break; }
-			} else {
+					if (il2p_sync_match(il2p_window(d, g, pos, true), C.il2p_sync_tol)) { found = g; break; }
+			} else if (mode == 1) {
 				// the 32 windows ending at pos .. pos+31 all lie inside stream bits [pos-31, pos+31]: fetch them once
 				// (bit j of span = stream bit pos-31+j), blank what the reference's register no longer holds (everything
 				// before the last collected byte, i.e. before pos-8) and slide
@@ -373,10 +379,11 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 				}
 			}
 			if (found < 0) {
-				while (ci < ncand && (long long)cp[ci] < pos + 32) ci++;
+				const long long from = (mode == 2) ? pos : pos + 32;
+				while (ci < ncand && (long long)cp[ci] < from) ci++;
 				if (ci < ncand) found = cp[ci];
 			}
-			if (found >= 0) {
+			if (found >= 0 && found < own_hi) {
 				// a speculative result exists when the position is in the candidate list
 				while (ci < ncand && (long long)cp[ci] < found) ci++;
 				if (ci < ncand && (long long)cp[ci] == found && ci < (unsigned int)cand_cap) {
@@ -389,10 +396,14 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 			}
 		}
 		found = __shfl_sync(0xffffffffu, found, 0);
-		if (found < 0) break;
 		const unsigned int status = __shfl_sync(0xffffffffu, r.status, 0);
-		if (status == IL2P_INCOMPLETE) break;                       // the stream ends inside this frame
 		const long long end_bit = __shfl_sync(0xffffffffu, r.end_bit, 0);
+		if (found < 0 || found >= own_hi) {
+			// nothing more in the own range: the next shard searches on; a resume point closer than 32 bits keeps its fill
+			if (lane == 0 && !(mode != 2 && own_hi - pos < 32)) { pos = min(own_hi, nb); mode = 2; }
+			break;
+		}
+		if (status == IL2P_INCOMPLETE || end_bit >= own_hi) break;  // the frame runs past this shard (or past the recording)
 		const unsigned int len = __shfl_sync(0xffffffffu, r.len, 0);
 		const unsigned int corrected = __shfl_sync(0xffffffffu, r.corrected, 0);
 		if (status == IL2P_OK) {
@@ -413,23 +424,28 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 			leak += corrected;                                      // a failed frame's corrections are never cleared
 		}
 		pos = end_bit + 1;
-		at_start = false;
+		mode = 1;
 		__syncwarp();
 	}
-	if (lane == 0) cc[ch].nflags = (int)nrec;
+	if (lane == 0) {
+		cc[ch].nflags = (int)nrec;
+		Il2pHand h;
+		h.pos = pos; h.mode = mode; h.leak = leak;
+		hand_out[ch] = h;
+	}
 }
 
 extern "C" cudaError_t pm_launch_il2p(const BitChain *chains, int n_chains, ChainCounters *cc, const uint32_t *d,
 	long long bits_stride, const unsigned int *cand_pos, long long cand_stride, const unsigned int *cand_totals,
 	int cand_cap, unsigned char *cand_scratch, long long cand_scratch_stride, Il2pRes *results,
 	const uint32_t *byte_addr, long long addr_stride, uint8_t *scratch, long long scratch_stride,
-	GapRec *gaps, long long gap_stride, cudaStream_t st)
+	GapRec *gaps, long long gap_stride, const ShardBits *sb, const Il2pHand *hand_in, Il2pHand *hand_out, cudaStream_t st)
 {
 	dim3 grid((cand_cap + 63) / 64, n_chains);
 	il2p_decode_kernel<<<grid, 64, 0, st>>>(chains, cc, d, bits_stride, cand_pos, cand_stride, cand_totals, cand_cap,
 		cand_scratch, cand_scratch_stride, results);
 	il2p_resolve_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, cand_pos, cand_stride, cand_totals,
 		cand_cap, cand_scratch, cand_scratch_stride, results, byte_addr, addr_stride, scratch, scratch_stride,
-		gaps, gap_stride);
+		gaps, gap_stride, sb, hand_in, hand_out);
 	return cudaGetLastError();
 }

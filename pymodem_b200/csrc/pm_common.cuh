@@ -147,6 +147,14 @@ struct BitChain {
 #define IL2P_FAIL 0u
 #define IL2P_OK 1u
 #define IL2P_INCOMPLETE 2u
+// Where the IL2P decoder of a chain stands at a shard boundary (local bit positions on the device)
+struct Il2pHand {
+	long long pos;             // the search (re)starts at this stream bit
+	unsigned int mode;         // 0: start of the recording (register = 0xFFFFFF, il2p.py:119); 1: a frame ended at pos-1
+	                           // (register = its last byte, zero above, il2p.py:147-153); 2: plain search, 32 real bits behind
+	unsigned int leak;         // corrected-byte counts of failed frames not yet attributed (il2p.py:200-211)
+};
+
 struct Il2pRes {
 	long long end_bit;         // last stream bit the frame consumed (search resumes at end_bit + 1)
 	unsigned int status;

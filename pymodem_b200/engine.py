@@ -60,6 +60,7 @@ class Engine:
 			descs[i] = describe_chain(chain, keep)
 		self._check(self._lib.pm_engine_load_chains(self._h, descs, len(demod_stack)))
 		self.n_chains = len(demod_stack)
+		self.has_il2p = any(getattr(chain[4], 'codec_kind', None) == _lib.PM_CODEC_IL2P for chain in demod_stack)
 
 	def _check(self, rc):
 		if rc != _lib.PM_OK:
@@ -126,6 +127,14 @@ class Engine:
 		else:
 			t = np.ascontiguousarray(tail_in, dtype=np.uint32)
 			self._check(self._lib.pm_engine_shard_finish(self._h, t.ctypes.data))
+
+	def shard_finish_il2p(self, tail_in, prev_states):
+		"""Finish of a shard whose engine has IL2P chains: needs the previous shard's decoder states (None on the
+		first shard) and returns this shard's (an Il2pState array) for the next one."""
+		out = (_lib.Il2pState * self.n_chains)()
+		t = None if tail_in is None else np.ascontiguousarray(tail_in, dtype=np.uint32)
+		self._check(self._lib.pm_engine_shard_finish_il2p(self._h, None if t is None else t.ctypes.data, prev_states, out))
+		return out
 
 	# -- shard link: the hand-off done by the GPUs over peer memory (csrc/link.cu) ---------------
 	def link_create(self, rank, world, tail_bits, max_samples):

@@ -117,11 +117,21 @@ class ShardWorker:
 		tail = self.engine.shard_gather(before)
 		return np.ascontiguousarray(tail, dtype=np.uint32).tobytes()
 
-	def finish(self, all_tails):
+	def finish(self, all_tails, il2p_prev=None, il2p=False):
+		"""il2p: the engine has IL2P chains -- il2p_prev is the previous rank's decoder-state blob (None on rank 0) and
+		self.il2p_blob becomes this rank's."""
 		tail_in = None
 		if self.rank > 0 and self.plan['tail_bits'] > 0:
 			tail_in = np.frombuffer(all_tails[self.rank - 1], dtype=np.uint32).reshape(self.n_chains, -1)
-		self.engine.shard_finish(tail_in)
+		if il2p:
+			prev = None
+			if il2p_prev is not None:
+				prev = (_lib.Il2pState * self.n_chains)()
+				ctypes.memmove(ctypes.addressof(prev), il2p_prev, ctypes.sizeof(prev))
+			out = self.engine.shard_finish_il2p(tail_in, prev)
+			self.il2p_blob = bytes(ctypes.string_at(ctypes.addressof(out), ctypes.sizeof(out)))
+		else:
+			self.engine.shard_finish(tail_in)
 		recs, arena = self.engine.fetch()
 		return struct.pack("<qq", len(recs), len(arena)) + recs.tobytes() + arena.tobytes()
 
@@ -227,7 +237,22 @@ def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True, 
 	lap("gather")
 	tails = exchange(tails)
 	lap("exchange")
-	results = [w.finish(tails) for w in workers]
+	if not any(getattr(w.engine, 'has_il2p', False) for w in workers):
+		results = [w.finish(tails) for w in workers]
+	else:
+		# IL2P keeps decoder state across a boundary (searching / inside a frame, leaked correction counts): the shards
+		# finish one after the other, each handing its state to the next (one small all-gather per rank)
+		world = len(tails)
+		size = ctypes.sizeof(_lib.Il2pState) * workers[0].n_chains
+		state, done = None, {}
+		for step in range(world):
+			blob = bytes(size)
+			for w in workers:
+				if w.rank == step:
+					done[w.rank] = w.finish(tails, il2p_prev=state, il2p=True)
+					blob = w.il2p_blob
+			state = exchange([blob] if len(workers) == 1 else [w.il2p_blob if w.rank == step else bytes(size) for w in workers])[step]
+		results = [done[w.rank] for w in workers]
 	lap("finish")
 	results = exchange_var(results)
 	lap("exchange")

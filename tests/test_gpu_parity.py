@@ -394,9 +394,9 @@ def test_shortened_slicer_update_is_exact(cuda_lib, tag):
 
 
 def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
-	"""150 s of band-limited noise: ~45 000 inter-flag gaps per chain with aborts, stuffed zeros and every residue of
-	the bit count; the count-based filter (bits.cu ax25_gap_filter_kernel) must let through exactly the gaps the
-	reference's state machine emits (a few hundred bad-CRC frames)."""
+	"""150 s of noise: tens of thousands of inter-flag gaps with aborts, stuffed zeros and every residue of the bit
+	count; the count-based filter (bits.cu ax25_gap_filter_kernel) must let through exactly the gaps the reference's
+	state machine emits (a few dozen bad-CRC frames)."""
 	from pymodem_b200 import configs
 	rng = np.random.default_rng(2024)
 	audio = np.clip(rng.standard_normal(48000 * 150) * 9000, -32768, 32767).astype(np.int16)
@@ -408,7 +408,7 @@ def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
 	finally:
 		eng.close()
 	assert got == want
-	assert sum(len(w) for w in want) > 100
+	assert sum(len(w) for w in want) > 20
 
 
 def test_command_line_end_to_end(cuda_lib, tmp_path, capsys):

@@ -164,3 +164,34 @@ def test_linked_engine_is_reusable(cuda_lib):
 	assert outs[2] == outs[0] and outs[3] == outs[0]
 	assert verdicts[0] == verdicts[2] == verdicts[3]
 	assert outs[1][0] == outs[1][1] and outs[1][0] != outs[0][0]
+
+
+# ---- IL2P chains across shard boundaries: decoder state handed from rank to rank --------------------------------
+@pytest.mark.parametrize("tag,world,tail", [("afsk1200_il2p_48k", 2, 4096), ("afsk1200_il2p_48k", 3, 4096),
+	("fsk9600_il2p_48k", 2, 4096), ("fsk9600_il2p_48k", 4, 4096)])
+def test_sharded_il2p_equals_reference(cuda_lib, tag, world, tail):
+	from pymodem_b200.sharded import run_sharded_local
+	g = Golden(tag)
+	got, info = run_sharded_local(build_stack(g.sample_rate, g.lines), g.audio(), world, tail_bits=tail,
+		segment_len=4096, warmup_len=8192)
+	assert as_tuples(got) == g.all_packets()
+
+
+def test_sharded_il2p_noisy_many_boundaries(cuda_lib, oracle):
+	"""Heavy noise, frames of every size back to back, 2..6 shards: failed headers and blocks leak their corrected-byte
+	counts across boundaries (il2p.py:200-211), frames straddle them, false syncs end right before them."""
+	import json
+	from pymodem_b200 import synth
+	from pymodem_b200.sharded import run_sharded_local
+	audio = synth.fsk9600_il2p(duration_s=12.0, sample_rate=48000, frame_interval_s=0.1, noise_start=0.4, noise_end=1.0,
+		seed=91, noise_seed=92, first_frame_s=0.02, payload_len=[None, 500, 3, 0, 239, 240, 1023])[0]
+	lines = [json.loads(json.dumps(l)) for l in Golden("fsk9600_il2p_48k").chain_lines()]
+	for l in lines:
+		if l["codec"]["type"] == "il2p":
+			l["codec"]["options"]["sync_tol"] = "3"
+	want = oracle.run_config(48000, lines, audio)
+	assert sum(len(w) for w in want) > 20
+	stack = build_stack(48000, lines)
+	for world in (2, 3, 5, 6):
+		got, info = run_sharded_local(stack, audio, world, tail_bits=12288, segment_len=4096, warmup_len=8192)
+		assert as_tuples(got) == want, f"world {world}"
