@@ -150,3 +150,65 @@ def test_merge_results_orders_by_chain_then_rank():
 	recs, arena = merge_results([b0, b1])
 	assert [int(r['streamaddress']) for r in recs] == [10, 30, 20]
 	assert [bytes(arena[int(r['offset']):int(r['offset']) + int(r['len'])]) for r in recs] == [b"\x01\x02", b"\x04", b"\x03"]
+
+
+def test_il2p_finish_phase_runs_rank_after_rank():
+	"""IL2P decoder state is handed from shard to shard: with one worker per 'process' (threads + a barrier exchange
+	standing in for the all-gather) every rank must finish only after its predecessor, with the predecessor's state."""
+	import struct
+	import threading
+	from pymodem_b200 import _lib
+	from pymodem_b200.sharded import run_protocol
+	world, nc = 3, 2
+	order, lock = [], threading.Lock()
+	barrier = threading.Barrier(world)
+	slots = [None] * world
+
+	def make_exchange(rank):
+		def exchange(blobs):
+			(blob,) = blobs
+			slots[rank] = blob
+			barrier.wait()
+			out = list(slots)
+			barrier.wait()
+			return out
+		return exchange
+
+	class FakeEngine:
+		n_chains = nc
+		has_il2p = True
+
+	class FakeWorker:
+		def __init__(self, rank):
+			self.rank, self.n_chains, self.engine, self.rounds = rank, nc, FakeEngine(), 0
+			self.plan = dict(tail_bits=0)
+		def begin(self):
+			return struct.pack("<QQIIIIq", 0, 0, 1, 1, 1, 1, 10) * nc
+		def handoff(self, blobs):
+			return self.begin(), False
+		def gather(self, blobs):
+			return b"tail%d" % self.rank
+		def finish(self, tails, il2p_prev=None, il2p=False):
+			assert il2p
+			with lock:
+				order.append(self.rank)
+			prev = 0 if il2p_prev is None else struct.unpack_from("<q", il2p_prev, 0)[0]
+			assert prev == self.rank * 100          # rank r sees exactly what rank r-1 produced
+			st = (_lib.Il2pState * nc)()
+			for c in range(nc):
+				st[c].pos = (self.rank + 1) * 100
+			self.il2p_blob = bytes(st)
+			return struct.pack("<qq", 0, 0)
+
+	results = [None] * world
+
+	def run(rank):
+		ex = make_exchange(rank)
+		results[rank] = run_protocol([FakeWorker(rank)], ex)
+	threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+	for t in threads:
+		t.start()
+	for t in threads:
+		t.join(timeout=60)
+	assert order == [0, 1, 2]
+	assert all(r is not None and len(r[0]) == 0 for r in results)
