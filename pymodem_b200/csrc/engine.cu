@@ -132,6 +132,9 @@ struct FrontGroup {
 struct pm_engine {
 	int device = 0;
 	cudaStream_t st = nullptr, st_copy = nullptr;
+	cudaStream_t st_front[2] = {nullptr, nullptr};   // chunk launches of the host-buffer path alternate between these, so
+	                                                 // that the last partial wave of one launch overlaps the next launch
+	cudaEvent_t ev_front[2] = {nullptr, nullptr};
 	std::string err;
 	std::vector<HostChain> chains;
 	std::vector<FrontGroup> groups;
@@ -498,6 +501,10 @@ extern "C" int pm_engine_create(int device, pm_engine **out)
 	if (cudaSetDevice(device) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->st_front[0], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->st_front[1], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e->ev_front[0], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e->ev_front[1], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaHostAlloc((void **)&e->h_counters, 64, cudaHostAllocDefault) != cudaSuccess ||
 	    cudaHostAlloc((void **)&e->h_totals, sizeof(PacketTotals), cudaHostAllocDefault) != cudaSuccess) {
 		delete e;
@@ -537,6 +544,10 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	if (e->h_totals) cudaFreeHost(e->h_totals);
 	cudaStreamDestroy(e->st);
 	cudaStreamDestroy(e->st_copy);
+	for (int i = 0; i < 2; i++) {
+		if (e->st_front[i]) cudaStreamDestroy(e->st_front[i]);
+		if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
+	}
 	delete e;
 }
 
@@ -954,8 +965,9 @@ static GuardList guard_of(pm_engine *e)
 // launch the front-end tiles of every group that became complete with the
 // samples in [0, avail_to) and were not launched for [0, avail_from)
 static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long long avail_from, long long avail_to,
-                        bool last)
+                        bool last, cudaStream_t stream = nullptr)
 {
+	if (!stream) stream = e->st;
 	for (auto &g : e->groups) {
 		const int a_len = (g.kind == PM_MODEM_AFSK) ? g.afsk.a_len : g.fir.a_len;
 		long long nout_max = 0;
@@ -974,10 +986,10 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 			cudaError_t ce;
 			if (g.kind == PM_MODEM_AFSK)
 				ce = pm_launch_afsk_front(&g.afsk, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
-					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), e->st);
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), stream);
 			else
 				ce = pm_launch_fir_front(&g.fir, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
-					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), e->st);
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), stream);
 			if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "front-end launch failed: %s", cudaGetErrorString(ce));
 			e->stats.kernel_launches++;
 			e->stats.front_launches++;
@@ -1066,8 +1078,19 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 	if (on_host) {
 		CK(e->d_audio.ensure((size_t)n + 64));
 		d_audio = e->d_audio.p;
-		const long long chunk = e->opt_h2d_chunk;
-		const int n_chunks = (int)((n + chunk - 1) / chunk);
+		// chunk sizes ramp up (512 Ki samples, doubling to "h2d_chunk"): the front end cannot start before the first
+		// chunk has landed, so that one is small; afterwards the copy runs ahead of the (slower) front-end kernels
+		std::vector<long long> cuts;
+		{
+			long long done = 0, len = std::min<long long>(e->opt_h2d_chunk, 512 << 10);
+			while (done < n) {
+				const long long take = std::min(len, n - done);
+				done += take;
+				cuts.push_back(done);
+				len = std::min(e->opt_h2d_chunk, len * 2);
+			}
+		}
+		const int n_chunks = (int)cuts.size();
 		while ((int)e->ev_chunks.size() < n_chunks) {
 			cudaEvent_t ev;
 			CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1076,16 +1099,22 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 		// the copy stream must not start before the engine stream reached this point
 		CK(cudaEventRecord(e->ev[6], e->st));
 		CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
+		for (int q = 0; q < 2; q++) CK(cudaStreamWaitEvent(e->st_front[q], e->ev[6], 0));
 		long long done = 0;
 		for (int i = 0; i < n_chunks; i++) {
-			const long long len = std::min(chunk, n - done);
+			const long long len = cuts[i] - done;
+			cudaStream_t fs = e->st_front[i & 1];
 			CK(cudaMemcpyAsync(e->d_audio.p + done, audio + done, (size_t)len * sizeof(int16_t),
 				cudaMemcpyHostToDevice, e->st_copy));
 			CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
-			CK(cudaStreamWaitEvent(e->st, e->ev_chunks[i], 0));
-			rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1);
+			CK(cudaStreamWaitEvent(fs, e->ev_chunks[i], 0));
+			rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1, fs);
 			if (rc != PM_OK) return rc;
 			done += len;
+		}
+		for (int q = 0; q < 2; q++) {          // the engine stream continues when both launch streams are done
+			CK(cudaEventRecord(e->ev_front[q], e->st_front[q]));
+			CK(cudaStreamWaitEvent(e->st, e->ev_front[q], 0));
 		}
 		e->stats.h2d_bytes = (int64_t)n * 2;
 	} else {
