@@ -1133,13 +1133,13 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 
 	// FP64 guard-band fix-up
 	int max_sum = 8;
-	for (auto &hc : e->chains) {     // guard_fixup_kernel: audio window, band-passed window, 2 magnitude rows, partial sums
-		const int nx = (int)(hc.mark_i.size() + hc.lpf.size()), na = nx + (int)hc.bpf.size();
-		const int parts = 4 * std::max(nx + 8, 4 * ((int)hc.lpf.size() + 8));
-		max_sum = std::max(max_sum, na + nx + 16 + 2 * (int)hc.lpf.size() + parts);
+	for (auto &hc : e->chains) {     // guard_fixup_kernel, doubles per warp: audio window, band-passed window, 2 magnitude rows
+		const int nx = (int)(hc.mark_i.size() + hc.lpf.size());
+		const int nx_pad = (nx + 159) / 160 * 160, mrow = ((int)hc.lpf.size() + 223) / 224 * 224;
+		max_sum = std::max(max_sum, nx_pad + (int)hc.bpf.size() + nx_pad + (int)hc.mark_i.size() + 7 * 32 + 2 * mrow + 8);
 	}
 	cudaError_t ce = pm_launch_guard_fixup(e->d_fp64.p, max_sum, d_audio, n, e->d_sign.p, e->sign_stride,
-		e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 8, e->st);
+		e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 5, e->st);
 	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));
 	e->stats.kernel_launches++;
 	CK(cudaEventRecord(e->ev[2], e->st));

@@ -340,129 +340,92 @@ fir_front_kernel(const __grid_constant__ FirPlan P, const int16_t *__restrict__ 
 // output and overwrite the sign bit (and the soft value when kept).
 // ---------------------------------------------------------------------------
 
-#define PM_FIX_THREADS 224
-#define FIX_TG 4               // tap groups a FIR is split into (partial sums combined through shared memory)
+#define PM_FIX_THREADS 128       // four warps; every warp re-evaluates its own (chain, sample) entries
+#define FIX_OB1 5                // band-pass outputs per lane and round (159 needed at 48 kHz: one round of 32 x 5)
+#define FIX_OB2 7                // correlator outputs per lane and round (100 x {mark, space} -> 30 items: one round)
 
-// block-wide sum of one double per thread (any order: the reference's numpy dot products have none to copy)
-__device__ __forceinline__ double fix_block_sum(double v, double *s_red)
-{
-	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-	__syncthreads();
-	double t = 0.0;
-	for (int w = 0; w < PM_FIX_THREADS / 32; w++) t += s_red[w];
-	__syncthreads();
-	return t;
-}
-
-// One CTA per queued (chain, sample).  AFSK: the audio window is staged once as doubles; thread i computes
-// band-passed sample i; threads then split into (output, mark|space) items that run the I and Q correlators over
-// the same window; the low-pass is a block-wide reduction.
+// One WARP per queued (chain, sample): no block-wide barriers, a handful of warps per SM keep the FP64 pipe busy.
+// The audio window is staged once as doubles; each lane slides a small register window over the taps (one tap load
+// and one sample load per FIX_OB multiply-adds), the low-pass is a warp reduction.
 __global__ void __launch_bounds__(PM_FIX_THREADS)
 guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restrict__ audio, long long n_audio,
                    uint32_t *__restrict__ sign, long long sign_stride, float *__restrict__ soft,
-                   long long soft_stride, GuardList guard)
+                   long long soft_stride, GuardList guard, int warp_doubles)
 {
 	extern __shared__ __align__(16) double sm64[];
-	__shared__ double s_red[PM_FIX_THREADS / 32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	double *base = sm64 + (long long)wid * warp_doubles;
 	const unsigned int n_entries = min(*guard.count, guard.cap);
-	for (unsigned int e = blockIdx.x; e < n_entries; e += gridDim.x) {
+	const unsigned int n_warps = gridDim.x * (PM_FIX_THREADS / 32);
+	for (unsigned int e = blockIdx.x * (PM_FIX_THREADS / 32) + wid; e < n_entries; e += n_warps) {
 		const unsigned long long ent = guard.entries[e];
 		const int gid = (int)(ent >> 48);
 		const long long n = (long long)(ent & 0xFFFFFFFFFFFFull);
 		const Fp64Chain C = chains[gid];
-		double y;
+		double part = 0.0;
 		if (C.kind == 2) {
 			// y[n] = sum_j hr[j] a[n+j]
-			double acc = 0.0;
-			for (int j = threadIdx.x; j < C.n_bpf; j += PM_FIX_THREADS)
-				acc = fma(C.bpf[j], (double)audio[n + j], acc);
-			y = fix_block_sum(acc, s_red);
-			if (C.neg) y = -y;
+			for (int j = lane; j < C.n_bpf; j += 32) part = fma(C.bpf[j], (double)audio[n + j], part);
 		} else {
 			const int nx = C.n_corr + C.n_lpf - 1;               // band-passed samples needed
-			const int na = nx + C.n_bpf - 1;                     // audio samples needed
-			const int nx4 = (nx + 3) >> 2, nl4 = (C.n_lpf + 3) >> 2;
-			double *a = sm64;                                    // na + 4 (zero padded)
-			double *x1 = a + na + 4;                             // nx + 4
-			double *mag = x1 + nx + 4;                           // 2 x n_lpf: |mark|, |space|
-			double *part = mag + 2 * C.n_lpf;                    // FIX_TG partial sums per output and filter
-			for (int i = threadIdx.x; i < na + 4; i += PM_FIX_THREADS)
-				a[i] = (i < na && n + i < n_audio) ? (double)audio[n + i] : 0.0;
-			__syncthreads();
-			// band-pass: item = (block of 4 outputs, tap group); a 4-output sliding window turns two loads per
-			// multiply-add into half a load (the kernel is load/store-unit bound, not FP64 bound)
-			{
-				const int tg_len = (C.n_bpf + FIX_TG - 1) / FIX_TG;
-				for (int it = threadIdx.x; it < nx4 * FIX_TG; it += PM_FIX_THREADS) {
-					const int ob = it % nx4, tg = it / nx4;
-					const int j0 = tg * tg_len, j1 = min(C.n_bpf, j0 + tg_len);
-					const double *w = a + 4 * ob + j0;
-					double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-					double w0 = w[0], w1 = w[1], w2 = w[2];
-					for (int j = j0; j < j1; j++) {
-						const double h = C.bpf[j], w3 = w[j - j0 + 3];
-						s0 = fma(h, w0, s0); s1 = fma(h, w1, s1); s2 = fma(h, w2, s2); s3 = fma(h, w3, s3);
-						w0 = w1; w1 = w2; w2 = w3;
-					}
-					double *p = part + (long long)tg * (4 * nx4) + 4 * ob;
-					p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
+			const int nx_pad = (nx + 32 * FIX_OB1 - 1) / (32 * FIX_OB1) * (32 * FIX_OB1);
+			const int na = nx_pad + C.n_bpf;                     // audio samples staged (zero beyond the window)
+			double *a = base;                                    // na
+			double *x1 = a + na;                                 // nx_pad + n_corr + FIX_OB2 (zero padded)
+			double *mag = x1 + nx_pad + C.n_corr + FIX_OB2 * 32; // 2 rows of n_lpf (+ padding)
+			const int mrow = (C.n_lpf + 32 * FIX_OB2 - 1) / (32 * FIX_OB2) * (32 * FIX_OB2);
+			for (int i = lane; i < na; i += 32)
+				a[i] = (i < nx + C.n_bpf - 1 && n + i < n_audio) ? (double)audio[n + i] : 0.0;
+			for (int i = nx + lane; i < nx_pad + C.n_corr + FIX_OB2 * 32; i += 32) x1[i] = 0.0;
+			__syncwarp();
+			for (int o0 = lane * FIX_OB1; o0 < nx_pad; o0 += 32 * FIX_OB1) {      // band-pass, FIX_OB1 outputs per lane
+				double acc[FIX_OB1], w[FIX_OB1];
+#pragma unroll
+				for (int r = 0; r < FIX_OB1; r++) { acc[r] = 0.0; w[r] = a[o0 + r]; }
+				for (int j = 0; j < C.n_bpf; j++) {
+					const double h = C.bpf[j];
+#pragma unroll
+					for (int r = 0; r < FIX_OB1; r++) acc[r] = fma(h, w[r], acc[r]);
+#pragma unroll
+					for (int r = 0; r < FIX_OB1 - 1; r++) w[r] = w[r + 1];
+					w[FIX_OB1 - 1] = a[o0 + j + FIX_OB1];
 				}
+#pragma unroll
+				for (int r = 0; r < FIX_OB1; r++)
+					if (o0 + r < nx) x1[o0 + r] = acc[r];
 			}
-			__syncthreads();
-			for (int i = threadIdx.x; i < nx + 4; i += PM_FIX_THREADS) {
-				double t = 0.0;
-				if (i < nx)
-					for (int tg = 0; tg < FIX_TG; tg++) t += part[(long long)tg * (4 * nx4) + i];
-				x1[i] = t;
-			}
-			__syncthreads();
-			// correlators: item = (block of 4 outputs, mark|space, tap group), I and Q over the same window
-			{
-				const int tg_len = (C.n_corr + FIX_TG - 1) / FIX_TG;
-				const int row = 4 * nl4;                         // partial sums per (tap group, mark|space, I|Q)
-				for (int it = threadIdx.x; it < nl4 * 2 * FIX_TG; it += PM_FIX_THREADS) {
-					const int ob = it % nl4, which = (it / nl4) & 1, tg = it / (2 * nl4);
-					const int j0 = tg * tg_len, j1 = min(C.n_corr, j0 + tg_len);
-					const double *ti = which ? C.space_i : C.mark_i, *tq = which ? C.space_q : C.mark_q;
-					const double *w = x1 + 4 * ob + j0;
-					double i0 = 0.0, i1 = 0.0, i2 = 0.0, i3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-					double w0 = w[0], w1 = w[1], w2 = w[2];
-					for (int j = j0; j < j1; j++) {
-						const double hi = ti[j], hq = tq[j], w3 = w[j - j0 + 3];
-						i0 = fma(hi, w0, i0); i1 = fma(hi, w1, i1); i2 = fma(hi, w2, i2); i3 = fma(hi, w3, i3);
-						q0 = fma(hq, w0, q0); q1 = fma(hq, w1, q1); q2 = fma(hq, w2, q2); q3 = fma(hq, w3, q3);
-						w0 = w1; w1 = w2; w2 = w3;
-					}
-					double *pi = part + (long long)((tg * 2 + which) * 2) * row + 4 * ob, *pq = pi + row;
-					pi[0] = i0; pi[1] = i1; pi[2] = i2; pi[3] = i3;
-					pq[0] = q0; pq[1] = q1; pq[2] = q2; pq[3] = q3;
+			__syncwarp();
+			const int n_ob = mrow / FIX_OB2;                     // output blocks per magnitude row
+			for (int it = lane; it < 2 * n_ob; it += 32) {        // correlators: (block of outputs, mark | space)
+				const int which = it >= n_ob, o0 = (it - which * n_ob) * FIX_OB2;
+				const double *ti = which ? C.space_i : C.mark_i, *tq = which ? C.space_q : C.mark_q;
+				double ai[FIX_OB2], aq[FIX_OB2], w[FIX_OB2];
+#pragma unroll
+				for (int r = 0; r < FIX_OB2; r++) { ai[r] = 0.0; aq[r] = 0.0; w[r] = x1[o0 + r]; }
+				for (int j = 0; j < C.n_corr; j++) {
+					const double hi = ti[j], hq = tq[j];
+#pragma unroll
+					for (int r = 0; r < FIX_OB2; r++) { ai[r] = fma(hi, w[r], ai[r]); aq[r] = fma(hq, w[r], aq[r]); }
+#pragma unroll
+					for (int r = 0; r < FIX_OB2 - 1; r++) w[r] = w[r + 1];
+					w[FIX_OB2 - 1] = x1[o0 + j + FIX_OB2];
 				}
-				__syncthreads();
-				for (int it = threadIdx.x; it < 2 * C.n_lpf; it += PM_FIX_THREADS) {
-					const int which = it >= C.n_lpf, i = it - which * C.n_lpf;
-					double ci = 0.0, cq = 0.0;
-					for (int tg = 0; tg < FIX_TG; tg++) {
-						const double *pi = part + (long long)((tg * 2 + which) * 2) * row + i;
-						ci += pi[0];
-						cq += pi[row];
-					}
-					mag[it] = sqrt(ci * ci + cq * cq);
-				}
+#pragma unroll
+				for (int r = 0; r < FIX_OB2; r++) mag[which * mrow + o0 + r] = sqrt(ai[r] * ai[r] + aq[r] * aq[r]);
 			}
-			__syncthreads();
-			double part_y = 0.0;
-			for (int i = threadIdx.x; i < C.n_lpf; i += PM_FIX_THREADS)
-				part_y = fma(C.lpf[i], mag[i] - mag[C.n_lpf + i], part_y);
-			y = fix_block_sum(part_y, s_red);
+			__syncwarp();
+			for (int i = lane; i < C.n_lpf; i += 32) part = fma(C.lpf[i], mag[i] - mag[mrow + i], part);
 		}
-		if (threadIdx.x == 0) {
+		for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+		double y = part;
+		if (C.kind == 2 && C.neg) y = -y;
+		if (lane == 0) {
 			uint32_t *w = sign + gid * sign_stride + (n >> 5);
 			const uint32_t bit = 1u << (n & 31);
 			if (y >= 0.0) atomicOr(w, bit); else atomicAnd(w, ~bit);
 			if (soft) soft[gid * soft_stride + n] = (float)y;
 		}
-		__syncthreads();
+		__syncwarp();
 	}
 }
 
@@ -529,13 +492,18 @@ extern "C" cudaError_t pm_launch_fir_front(const FirPlan *plan, size_t smem_byte
 	return cudaGetLastError();
 }
 
-extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int max_taps_sum, const int16_t *audio,
+extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int warp_doubles, const int16_t *audio,
 	long long n_audio, uint32_t *sign, long long sign_stride, float *soft, long long soft_stride,
 	GuardList guard, int grid, cudaStream_t st)
 {
-	size_t smem = sizeof(double) * (size_t)(max_taps_sum + 16);
+	const size_t smem = sizeof(double) * (size_t)warp_doubles * (PM_FIX_THREADS / 32);
+	static size_t attr = 0;
+	if (smem > 48 * 1024 && smem > attr) {
+		cudaFuncSetAttribute(guard_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr = smem;
+	}
 	guard_fixup_kernel<<<grid, PM_FIX_THREADS, smem, st>>>(chains, audio, n_audio, sign, sign_stride, soft,
-		soft_stride, guard);
+		soft_stride, guard, warp_doubles);
 	return cudaGetLastError();
 }
 
