@@ -298,7 +298,7 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 	double c = (double)warps(g.U_x) * p.n_bpf;
 	// magnitude units are laid out stream after stream
 	// the correlator (I, Q) and the low-pass (mark, space) stages run packed FFMA2: one issue slot per tap and pair
-	c += (double)warps(p.n_mag * g.U_m) * 1.15 * (corr_sum / std::max(1, p.n_mag));
+	c += (double)warps(g.U_m) * 1.15 * corr_sum;          // tone after tone (uniform taps)
 	c += (double)warps(p.n_pair * g.U_l) * 1.15 * p.n_lpf;
 	g.cost = c / tile;
 	return g;

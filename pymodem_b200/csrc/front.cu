@@ -194,7 +194,9 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	__syncthreads();
 
 	// input band-pass (afsk.py:151); the result is stored as (x, x) pairs: the window operand of the packed correlators
-	for (int u = tid; u < P.U_x; u += PM_FRONT_THREADS) {
+	for (int ub = tid - (tid & 31); ub < P.U_x; ub += PM_FRONT_THREADS) {        // warp-uniform control flow: uniform taps
+		const int u = ub + (tid & 31);
+		if (u >= P.U_x) continue;
 		FirUnit<1> f;
 		f.run(s_a, 16 * u, P.taps + P.bpf_off, nullptr, P.n_bpf);
 		float *dst = s_x1 + 2 * pm_phys2(16 * u);
@@ -205,9 +207,12 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	__syncthreads();
 
 	// tone correlators and magnitudes (afsk.py:153-160): I and Q of one tone in the two halves of an FFMA2
-	for (int u = tid; u < P.n_mag * P.U_m; u += PM_FRONT_THREADS) {
-		const int j = u / P.U_m;
-		const int ui = u - j * P.U_m;
+	// (tone by tone, so that the tap operands are warp-uniform: an FFMA2 whose tap comes from a uniform register runs
+	// at the full FP32 rate, one with three vector-register operands only at ~78 % -- tools/ubench/ffma2.cu)
+	for (int j = 0; j < P.n_mag; j++)
+	for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {      // warp-uniform control flow
+		const int ui = ub + (tid & 31);
+		if (ui >= P.U_m) continue;
 		FirUnitPair f;
 		f.run(s_x1, 16 * ui, P.taps + P.mag_iq_off[j], P.mag_n[j]);
 		// the magnitude goes into the mark or space half of every pair stream this tone belongs to

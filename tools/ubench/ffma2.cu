@@ -47,6 +47,29 @@ __global__ void __launch_bounds__(256, 2) ffma2_only(float *out, const float *in
 	out[blockIdx.x * 256 + threadIdx.x] = t;
 }
 
+// FFMA2 with the tap operand in a uniform register (kernel parameters): fewer vector register reads per instruction
+struct TapParams { float2 h[16]; };
+__global__ void __launch_bounds__(256, 2) ffma2_uniform(float *out, const float *in, int iters, const __grid_constant__ TapParams P)
+{
+	unsigned long long a[16], w[16];
+	for (int r = 0; r < 16; r++) {
+		a[r] = 0ull;
+		float2 v = make_float2(in[(threadIdx.x + r) & 255], in[(threadIdx.x + r + 7) & 255]);
+		w[r] = *reinterpret_cast<unsigned long long *>(&v);
+	}
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const unsigned long long h = *reinterpret_cast<const unsigned long long *>(&P.h[k]);
+#pragma unroll
+			for (int r = 0; r < 16; r++) fma2(a[r], h, w[(r + k) & 15]);
+		}
+	}
+	float t = 0;
+	for (int r = 0; r < 16; r++) { float2 v = *reinterpret_cast<float2 *>(&a[r]); t += v.x + v.y; }
+	out[blockIdx.x * 256 + threadIdx.x] = t;
+}
+
 // FIR-like: 16 outputs x 16 taps per chunk, window refilled from shared memory (4 LDS.128 per 256 FMA)
 __global__ void __launch_bounds__(256, 2) ffma_fir(float *out, const float *in, int iters)
 {
@@ -136,6 +159,9 @@ int main()
 	const double f1 = 2.0 * blocks * 256.0 * iters * 256;
 	printf("ffma_only   %.1f TFLOP/s\n", timeit([&] { ffma_only<<<blocks, 256>>>(out, in, iters); }, f1));
 	printf("ffma2_only  %.1f TFLOP/s\n", timeit([&] { ffma2_only<<<blocks, 256>>>(out, in, iters); }, 2 * f1));
+	TapParams tp;
+	for (int i = 0; i < 16; i++) tp.h[i] = make_float2(0.f, 0.f);
+	printf("ffma2_unif  %.1f TFLOP/s\n", timeit([&] { ffma2_uniform<<<blocks, 256>>>(out, in, iters, tp); }, 2 * f1));
 	printf("ffma_fir    %.1f TFLOP/s\n", timeit([&] { ffma_fir<<<blocks, 256>>>(out, in, iters); }, f1));
 	printf("ffma2_fir   %.1f TFLOP/s\n", timeit([&] { ffma2_fir<<<blocks, 256>>>(out, in, iters); }, 2 * f1));
 	cudaError_t e = cudaDeviceSynchronize();
