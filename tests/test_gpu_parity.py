@@ -426,3 +426,20 @@ def test_command_line_end_to_end(cuda_lib, tmp_path, capsys):
 	out = capsys.readouterr().out
 	assert f"Unique, valid packets: {len(g.z['uniq_addr'])}" in out
 	assert f"Packets rejected from all decoders for CRC failure: {int(g.z['bad_count'])}" in out
+
+
+def test_bench_workload_excerpt_matches_oracle(cuda_lib, oracle):
+	"""Five minutes of the bench recording (same generator and seeds as bench.py / tools/verify_hour.py, which checks the
+	whole hour: profiles/r01e_verify_hour.txt) through the 8-chain super-opt config, packet for packet."""
+	from pymodem_b200 import configs, synth
+	audio = synth.afsk1200_ax25(duration_s=300.0, sample_rate=48000, frame_interval_s=3.1, noise_start=0.0, noise_end=1.6,
+		seed=1000, noise_seed=1001)[0]
+	lines = configs.afsk_1200_ax25_super_opt()
+	want = oracle.run_config(48000, lines, audio, chunk=1 << 20)
+	eng = engine(build_stack(48000, lines))
+	try:
+		got = as_tuples(eng.run(audio))
+	finally:
+		eng.close()
+	assert got == want
+	assert sum(len(w) for w in want) > 300
