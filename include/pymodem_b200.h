@@ -258,7 +258,8 @@ int pm_engine_shard_finish_il2p(pm_engine *e, const uint32_t *tail_in, const pm_
  * map each other's buffers.  run_linked_begin then enqueues the whole sharded run -- front end, slicer, state
  * push, bit placement, tail push/wait, decode, record push, merge -- on the engine's stream with no host round
  * trip after the slicer; run_linked_end waits for it and leaves the MERGED records of all ranks (ordered like an
- * unsharded run: chain, then stream position) in the engine for pm_engine_get_packets.
+ * unsharded run: chain, then stream position; their `offset` fields point into an arena that holds rank 0's packet
+ * bytes first, then rank 1's, ...) in the engine for pm_engine_get_packets.
  *   *verified == 0: some rank's speculated slicer start state was wrong.  All ranks see the same states, so all
  *   of them get 0 and continue with the host-driven protocol: pm_engine_shard_states (what shard_begin would
  *   have returned) -> shard_handoff ... -> shard_gather -> shard_finish.
