@@ -443,3 +443,14 @@ def test_bench_workload_excerpt_matches_oracle(cuda_lib, oracle):
 		eng.close()
 	assert got == want
 	assert sum(len(w) for w in want) > 300
+
+
+@pytest.mark.parametrize("rate", [22050, 32000, 96000])
+def test_other_sample_rates_match_oracle(cuda_lib, oracle, rate):
+	"""Tap counts follow the WAV rate (pymodem.py:46, 79-82): 68/28/46 taps at 22.05 kHz up to 296/120/200 at 96 kHz;
+	18.375 and 26.67 samples per symbol exercise the plain and the shortened slicer update."""
+	from pymodem_b200 import configs, synth
+	audio = synth.afsk1200_ax25(duration_s=8.0, sample_rate=rate, frame_interval_s=0.8, noise_start=0.05, noise_end=0.9,
+		seed=81, noise_seed=82, first_frame_s=0.1)[0]
+	want, _ = _oracle_vs_gpu(oracle, rate, configs.afsk_1200_ax25_super_opt(), audio)
+	assert sum(len(w) for w in want) >= 8
