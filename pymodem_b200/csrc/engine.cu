@@ -143,6 +143,7 @@ struct pm_engine {
 	int opt_warm_words = 1024;    // 32768 samples
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
+	int opt_warm_exact_words = 512; // float64 tail of a warm-up (16384 samples); the part before it runs in FP32 (0: all float64)
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
@@ -742,6 +743,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "warmup_len") e->opt_warm_words = std::max(0, (int)((value + 31) / 32));
 	else if (k == "checkpoint_len") e->opt_chk_words = std::max(1, (int)(value / 32));
 	else if (k == "verify_passes") e->opt_verify_passes = std::max(0, (int)value);
+	else if (k == "warmup_exact_len") e->opt_warm_exact_words = std::max(0, (int)((value + 31) / 32));
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
@@ -865,6 +867,8 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	e->k0 = plan.pre_segments;
 	G.origin_w = e->own_w0 - (long long)e->k0 * seg_words;
 	G.k_init = 0;
+	G.warm_f32_words = (e->opt_warm_exact_words > 0 && e->opt_warm_exact_words < G.warm_words) ?
+		G.warm_words - e->opt_warm_exact_words : 0;
 	G.seg_words = seg_words;
 	G.warm_words = e->opt_warm_words;
 	G.chk_words = chk_words;

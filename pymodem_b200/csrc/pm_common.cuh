@@ -114,6 +114,9 @@ struct SlicerGeom {
 	int chk_words;           // checkpoint spacing (divides seg_words)
 	int n_chk;               // seg_words / chk_words
 	int true_start;          // local sample 0 is the true start of the recording
+	int warm_f32_words;      // the first warm_f32_words of every warm-up run in FP32 (3x shorter dependency chain per sample):
+	                         // a warm-up only has to get NEAR the true state, the exact float64 tail after it contracts what
+	                         // is left (every zero crossing multiplies the error by lock_rate) and the verify pass decides
 	int k_init;              // segment whose predecessor state is init[] (0 during the local pass; the first own
 	                         // segment when a hand-off repair starts there -- the segments before it are frozen)
 };

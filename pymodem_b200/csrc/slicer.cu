@@ -86,6 +86,36 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 	st.last_q = last_q;
 }
 
+// The same loop in FP32, for the far end of a warm-up only (no outputs, no claim of exactness: a roll-over taken one
+// sample early or late leaves the same clock behind, and whatever error remains is contracted by the float64 tail).
+__device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                              const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
+{
+	float c = (float)st.clock;
+	unsigned int last = st.last, last_q = st.last_q;
+	const float thr = (float)C.thr, sps = (float)C.sps, lam = (float)C.lock;
+	for (long long w = w0; w < w1; w++) {
+		if (((w + 1) << 5) > C.nout) break;            // whole words only; the float64 tail handles the rest
+		const uint32_t s = sg[w];
+		uint32_t z = s ^ ((s << 1) | last);
+		last = s >> 31;
+		if (sgq) {
+			const uint32_t q = sgq[w];
+			z |= q ^ ((q << 1) | last_q);
+			last_q = q >> 31;
+		}
+#pragma unroll
+		for (int i = 0; i < 32; i++) {
+			const float up = c + 1.0f;
+			c = up >= thr ? up - sps : up;
+			if ((z >> i) & 1u) c *= lam;
+		}
+	}
+	st.clock = (double)c;
+	st.last = last;
+	st.last_q = last_q;
+}
+
 template <bool WRITE>
 __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                           const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
@@ -121,6 +151,13 @@ slicer_segments_kernel(const SlicerChain *__restrict__ chains, const uint32_t *_
 	} else {
 		if (w_warm < 0) w_warm = 0;
 		st.clock = 0.0; st.last = 1u; st.last_q = 1u;   // cold start (slicer.py:50,55)
+	}
+	if (G.warm_f32_words > 0 && w_begin - w_warm > G.warm_f32_words / 4) {
+		const long long w_mid = min(w_begin, w_warm + G.warm_f32_words);
+		if (((w_mid) << 5) <= C.nout) {
+			run_words_f32(C, sg, sgq, w_warm, w_mid, st);
+			w_warm = w_mid;
+		}
 	}
 	run_words<false>(C, sg, sgq, mk, w_warm, w_begin, st);
 	const long long idx = (long long)ch * G.n_seg + k;

@@ -11,8 +11,9 @@ audio = synth.afsk1200_ax25(duration_s=3600.0, sample_rate=48000, frame_interval
 	seed=1000, noise_seed=1001)[0]
 dev = torch.from_numpy(audio).cuda(); torch.cuda.synchronize()
 n = len(audio)
-for seg, warm in [(32768, 32768), (16384, 32768), (8192, 32768), (16384, 24576), (24576, 32768), (32768, 24576), (65536, 32768), (12288, 32768)]:
-	eng = Engine(stack, segment_len=seg, warmup_len=warm)
+for seg, warm, exact in [(32768, 32768, 0), (32768, 32768, 16384), (32768, 32768, 8192), (32768, 32768, 4096), (32768, 49152, 8192),
+		(32768, 65536, 8192), (24576, 32768, 8192), (16384, 32768, 8192), (16384, 49152, 8192), (32768, 32768, 12288)]:
+	eng = Engine(stack, segment_len=seg, warmup_len=warm, warmup_exact_len=exact)
 	for _ in range(3):
 		eng.run_device_ptr(dev.data_ptr(), n)
 	best = None
@@ -21,5 +22,5 @@ for seg, warm in [(32768, 32768), (16384, 32768), (8192, 32768), (16384, 24576),
 		st = eng.stats()
 		if best is None or st['slicer_ms'] < best['slicer_ms']:
 			best = st
-	print(f"seg {seg:6d} warm {warm:6d}: slicer_ms {best['slicer_ms']:.3f} total {best['total_ms']:.3f} repairs {best['slicer_repairs']} segments {best['slicer_segments']}", flush=True)
+	print(f"seg {seg:6d} warm {warm:6d} exact {exact:6d}: slicer_ms {best['slicer_ms']:.3f} total {best['total_ms']:.3f} repairs {best['slicer_repairs']} segments {best['slicer_segments']}", flush=True)
 	eng.close()
