@@ -242,8 +242,7 @@ def run_b200_arm(args):
 		# rank r gets its slice + FIR/warm-up history + a few forward symbols (pymodem_b200/sharded.py)
 		from pymodem_b200.sharded import LinkedRun, TorchExchange, plan_shards
 		n_total = n_hour * world
-		plans = plan_shards(n_total, world, segment_len=32768, warm_len=32768, trim_max=305,
-			samples_per_symbol=40.0, tail_bits=16384)
+		plans = plan_shards(n_total, world, trim_max=305, samples_per_symbol=40.0, tail_bits=16384)
 		plan = plans[rank]
 		max_local = max(p['audio_end'] - p['audio_begin'] for p in plans)      # the link layout must be the same on every rank
 		idx = np.arange(plan['audio_begin'], plan['audio_end'], dtype=np.int64) % n_hour

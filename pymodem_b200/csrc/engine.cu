@@ -139,8 +139,8 @@ struct pm_engine {
 	std::vector<HostChain> chains;
 	std::vector<FrontGroup> groups;
 	// options
-	int opt_seg_words = 1024;     // 32768 samples  (profiles/r01_slicer_sweep.txt)
-	int opt_warm_words = 1024;    // 32768 samples
+	int opt_seg_words = 768;      // 24576 samples  (sweeps: profiles/r01_slicer_sweep.txt, tools/slicer_sweep2.py)
+	int opt_warm_words = 1536;    // 49152 samples, of which the last 16384 in float64
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	int opt_warm_exact_words = 512; // float64 tail of a warm-up (16384 samples); the part before it runs in FP32 (0: all float64)

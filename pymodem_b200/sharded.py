@@ -27,13 +27,18 @@ from . import _lib
 from .engine import REC_DTYPE
 
 
-def plan_shards(n_samples, world, segment_len=32768, warm_len=32768, trim_max=305, samples_per_symbol=40.0,
+# the engine's slicer geometry defaults (csrc/engine.cu opt_seg_words / opt_warm_words): shard boundaries are segment aligned
+DEFAULT_SEGMENT_LEN = 24576
+DEFAULT_WARMUP_LEN = 49152
+
+
+def plan_shards(n_samples, world, segment_len=DEFAULT_SEGMENT_LEN, warm_len=DEFAULT_WARMUP_LEN, trim_max=305, samples_per_symbol=40.0,
 		tail_bits=16384, pre_segments=4):
 	"""Split n_samples over `world` ranks.  Returns one dict per rank:
 	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields.
 
 	pre_segments: whole segments of slicer history every later rank runs (and verifies) before its own range, so that
-	its speculated state at own_begin rests on (pre_segments + 1) warm-ups instead of one.  A single 32768-sample
+	its speculated state at own_begin rests on (pre_segments + 1) warm-ups instead of one.  A single
 	warm-up fails to become bit-identical in ~1 % of the cases (profiles/r01_slicer_sweep.txt); inside one GPU that
 	costs a cheap re-run of the segment, at a shard boundary it would cost the hand-off's fast path.  The history is
 	0.1 % more front-end work per rank."""
@@ -405,8 +410,8 @@ def run_linked_local(demod_stack, audio, world, device=0, tail_bits=16384, **opt
 	run.  Returns (per-chain PacketMeta lists as rank 0 sees them, info)."""
 	from .engine import Engine
 	audio = np.ascontiguousarray(audio, dtype=np.int16)
-	seg = int(options.get('segment_len', 32768))
-	warm = int(options.get('warmup_len', 32768))
+	seg = int(options.get('segment_len', DEFAULT_SEGMENT_LEN))
+	warm = int(options.get('warmup_len', DEFAULT_WARMUP_LEN))
 	trim = max(_chain_trim(c) for c in demod_stack)
 	sps = max(float(c[2].sample_rate) / float(c[2].symbol_rate) for c in demod_stack)
 	plans = plan_shards(len(audio), world, segment_len=seg, warm_len=max(warm, seg), trim_max=trim,
@@ -446,8 +451,8 @@ def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **op
 	ShardWorker protocol with one process per GPU."""
 	from .engine import Engine
 	audio = np.ascontiguousarray(audio, dtype=np.int16)
-	seg = int(options.get('segment_len', 32768))
-	warm = int(options.get('warmup_len', 32768))
+	seg = int(options.get('segment_len', DEFAULT_SEGMENT_LEN))
+	warm = int(options.get('warmup_len', DEFAULT_WARMUP_LEN))
 	trim = max(_chain_trim(c) for c in demod_stack)
 	sps = max(float(c[2].sample_rate) / float(c[2].symbol_rate) for c in demod_stack)
 	plans = plan_shards(len(audio), world, segment_len=seg, warm_len=max(warm, seg), trim_max=trim,

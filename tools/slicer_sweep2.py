@@ -11,8 +11,8 @@ audio = synth.afsk1200_ax25(duration_s=3600.0, sample_rate=48000, frame_interval
 	seed=1000, noise_seed=1001)[0]
 dev = torch.from_numpy(audio).cuda(); torch.cuda.synchronize()
 n = len(audio)
-for seg, warm, exact in [(32768, 32768, 0), (32768, 32768, 16384), (32768, 32768, 8192), (32768, 32768, 4096), (32768, 49152, 8192),
-		(32768, 65536, 8192), (24576, 32768, 8192), (16384, 32768, 8192), (16384, 49152, 8192), (32768, 32768, 12288)]:
+for seg, warm, exact in [(24576, 49152, 16384), (24576, 40960, 16384), (24576, 57344, 16384), (24576, 49152, 12288), (20480, 49152, 16384),
+		(16384, 49152, 16384), (20480, 40960, 16384), (28672, 49152, 16384), (24576, 49152, 24576), (16384, 40960, 12288)]:
 	eng = Engine(stack, segment_len=seg, warmup_len=warm, warmup_exact_len=exact)
 	for _ in range(3):
 		eng.run_device_ptr(dev.data_ptr(), n)
