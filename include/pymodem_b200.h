@@ -169,7 +169,7 @@ const char *pm_last_error(const pm_engine *e);
 int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_chains);
 
 /* Tunables: "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32),
- * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap", "slicer_fast", "warmup_exact_len" (samples of float64 tail of
+ * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap", "slicer_fast", "slide_correlator", "warmup_exact_len" (samples of float64 tail of
  * every slicer warm-up; the part before it runs in FP32 -- a warm-up only has to get near the true state; 0 = all float64),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
  * close that |mark| - |space| cancels below FP32 resolution). */

@@ -147,6 +147,7 @@ struct pm_engine {
 	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
+	int opt_slide = 1;            // rotation-tap correlators as sliding window sums (0: always the direct FIR)
 	int opt_slicer_fast = 1;      // shortened slicer clock update where it is exact (0: always the plain form)
 	int opt_precise = 0;          // all AFSK chains through the float64 pipeline
 	double opt_precise_ratio = 0.2;
@@ -269,6 +270,23 @@ static int push_taps(float *dst, int &used, const std::vector<double> &h, int &n
 	return off;
 }
 
+// True when (ti[k], tq[k]) = a e^{i(phi + w k)}: a rectangular-window tone correlator (afsk.py:134-144).
+static bool rotation_taps(const std::vector<double> &ti, const std::vector<double> &tq, double &w)
+{
+	const int N = (int)ti.size();
+	if (N < 16 || (int)tq.size() != N) return false;
+	const double a = std::hypot(ti[0], tq[0]);
+	if (!(a > 0)) return false;
+	const double phi = std::atan2(tq[0], ti[0]);
+	// step angle from the first pair, refined over the whole window (the phase advance stays below pi per tap)
+	w = std::atan2(tq[1] * ti[0] - ti[1] * tq[0], ti[1] * ti[0] + tq[1] * tq[0]);
+	const double turns = std::round((w * (N - 1) + phi - std::atan2(tq[N - 1], ti[N - 1])) / (2 * M_PI));
+	w = (std::atan2(tq[N - 1], ti[N - 1]) - phi + 2 * M_PI * turns) / (N - 1);
+	for (int k = 0; k < N; k++)
+		if (std::hypot(ti[k] - a * std::cos(phi + w * k), tq[k] - a * std::sin(phi + w * k)) > 1e-10 * a) return false;
+	return true;
+}
+
 // ---- AFSK group geometry for a candidate tile ---------------------------------
 struct AfskGeom {
 	int U_x, U_m, U_l, a_len;
@@ -373,18 +391,39 @@ static int build_groups(pm_engine *e)
 			g.chains = kept;
 			p.n_mag = (int)tones.size();
 			for (int t = 0; t < p.n_mag; t++) {
-				int npad = 0, npad2 = 0;
-				p.mag_i_off[t] = push_taps(p.taps, used, *tones[t].i, npad);
-				p.mag_q_off[t] = push_taps(p.taps, used, *tones[t].q, npad2);
-				if (p.mag_i_off[t] < 0 || p.mag_q_off[t] < 0) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+				const std::vector<double> &ti = *tones[t].i, &tq = *tones[t].q;
+				const int N = (int)ti.size(), npad = round_up(N, 4);
 				p.mag_n[t] = npad;
-				if (used + 2 * npad > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
-				p.mag_iq_off[t] = used;
-				for (int j = 0; j < npad; j++) {
-					p.taps[used + 2 * j] = p.taps[p.mag_i_off[t] + j];
-					p.taps[used + 2 * j + 1] = p.taps[p.mag_q_off[t] + j];
+				p.mag_slide[t] = 0;
+				p.mag_iq_off[t] = p.mag_e_off[t] = 0;
+				double w = 0;
+				used = round_up(used, 4);
+				if (e->opt_slide && rotation_taps(ti, tq, w)) {
+					// rotation taps (afsk.py:134-144: cos/sin of w k, rectangular window): sliding-window path
+					if (used + 2 * (N + 32) > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+					p.mag_slide[t] = N;
+					p.mag_e_off[t] = used;
+					const double a = std::hypot(ti[0], tq[0]);
+					for (int k = 0; k < N + 16; k++) {
+						p.taps[used + 2 * k] = (float)(a * std::cos(w * k));
+						p.taps[used + 2 * k + 1] = (float)(a * std::sin(w * k));
+					}
+					used += 2 * (N + 16);
+					for (int k = 0; k < 16; k++) {
+						p.taps[used + 2 * k] = -p.taps[p.mag_e_off[t] + 2 * k];
+						p.taps[used + 2 * k + 1] = -p.taps[p.mag_e_off[t] + 2 * k + 1];
+					}
+					used += 32;
+				} else {
+					// arbitrary taps: reversed, interleaved (i[0], q[0], i[1], q[1], ...), zero padded to a multiple of 4
+					if (used + 2 * npad > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+					p.mag_iq_off[t] = used;
+					for (int j = 0; j < npad; j++) {
+						p.taps[used + 2 * j] = j < N ? (float)ti[N - 1 - j] : 0.f;
+						p.taps[used + 2 * j + 1] = j < N ? (float)tq[N - 1 - j] : 0.f;
+					}
+					used += 2 * npad;
 				}
-				used += 2 * npad;
 			}
 			// pairs, chains sorted by pair
 			std::vector<std::pair<int, int>> pairs;
@@ -448,7 +487,8 @@ static int build_groups(pm_engine *e)
 			g.smem = gg.smem;
 			g.tile = best;
 			double macs = hc.bpf.size() + 2.0 * p.n_pair * hc.lpf.size();
-			for (int t = 0; t < p.n_mag; t++) macs += 2.0 * tones[t].i->size();
+			for (int t = 0; t < p.n_mag; t++)
+				macs += p.mag_slide[t] ? 2.0 * (p.mag_slide[t] + 30) / 16.0 : 2.0 * tones[t].i->size();
 			g.macs_per_sample = macs;
 		} else {
 			FirPlan &p = g.fir;
@@ -748,6 +788,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
 	else if (k == "slicer_fast") e->opt_slicer_fast = value != 0;
+	else if (k == "slide_correlator") { e->opt_slide = value != 0; replan = true; }
 	else if (k == "precise") {
 		if (!e->chains.empty()) return fail(e, PM_ERR_STATE, "set 'precise' before loading chains");
 		e->opt_precise = value != 0;

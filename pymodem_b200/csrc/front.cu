@@ -143,6 +143,108 @@ struct FirUnitPair {
 	__device__ __forceinline__ float hi(int r) const { return __uint_as_float((unsigned int)(a[r] >> 32)); }
 };
 
+// Sliding tone correlator.  The reference's correlator taps are a rotation, cos/sin(w k) over a rectangular window
+// (afsk.py:134-144), and only the magnitude of the (I, Q) output is used (afsk.py:153-160).  That magnitude equals
+// |sum_{m in window} x[m] e^{i w (m - m0)}| for ANY phase origin m0, so a thread that owns 16 consecutive outputs
+// takes its own first sample as the origin, sums the first window directly (N FFMA2: (x, x) * (cos, sin)) and then
+// slides: one FFMA2 adds the sample that enters, one removes the sample that leaves.  (N + 30) instead of 16 N
+// packed multiply-adds per 16 outputs; the rounding error of the 30 extra updates stays ~1e-7 of the window sum.
+struct SlideUnit {
+	float m[16];
+
+	__device__ __forceinline__ static float mag(unsigned long long S)
+	{
+		const float ci = __uint_as_float((unsigned int)S), cq = __uint_as_float((unsigned int)(S >> 32));
+		float r;
+		asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ci, ci, cq * cq)));
+		return r;
+	}
+	__device__ __forceinline__ static unsigned long long add2(unsigned long long a, unsigned long long b)
+	{
+		unsigned long long r;
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+		return r;
+	}
+
+	// s: the (x, x) stream; base: first output (multiple of 16); E: rotation table (see AfskPlan::mag_e_off); N >= 16.
+	// The first window is summed in four interleaved partial sums (shorter dependency chains, and each partial sum
+	// rounds at a quarter of the magnitude); the slides accumulate in D, which stays small while the tone is steady,
+	// and every output is S0 + D: about one rounding at the magnitude of the result instead of N of them.
+	// pg points at sample `base` (a multiple of 16, so the padding of base + off is that of base plus that of off):
+	// the offset part depends on uniform values only and stays in the uniform datapath
+	__device__ __forceinline__ static void ldp(const float *__restrict__ pg, int off, unsigned long long &x, unsigned long long &y)
+	{
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(pg + 2 * pm_phys2(off));
+		x = v.x; y = v.y;
+	}
+
+	__device__ __forceinline__ void run(const float *__restrict__ s, int base, const float *__restrict__ E, int N)
+	{
+		const float *__restrict__ pg = s + 2 * pm_phys2(base);
+		const unsigned long long *__restrict__ E2 = reinterpret_cast<const unsigned long long *>(E);
+		const unsigned long long *__restrict__ nE2 = E2 + N + 16;
+		unsigned long long h[16];
+#pragma unroll
+		for (int q = 0; q < 8; q++) ldp(pg, 2 * q, h[2 * q], h[2 * q + 1]);
+		unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+		for (int j = 0; j < 16; j++) fma2(acc[j & 3], h[j], E2[j]);
+		int j = 16;
+		for (; j + 8 <= N; j += 8) {
+			unsigned long long v[8];
+#pragma unroll
+			for (int q = 0; q < 4; q++) ldp(pg, j + 2 * q, v[2 * q], v[2 * q + 1]);
+#pragma unroll
+			for (int k = 0; k < 8; k++) fma2(acc[k & 3], v[k], E2[j + k]);
+		}
+		for (; j + 2 <= N; j += 2) {
+			unsigned long long v0, v1;
+			ldp(pg, j, v0, v1);
+			fma2(acc[0], v0, E2[j]);
+			fma2(acc[1], v1, E2[j + 1]);
+		}
+		const unsigned long long *__restrict__ En = E2 + N;
+		unsigned long long D = 0ull;
+		if (N & 1) {                          // j == N - 1 (even): the pair's second half is the first sample to enter
+			unsigned long long v0, carry;
+			ldp(pg, j, v0, carry);
+			fma2(acc[3], v0, E2[j]);
+			const unsigned long long S0 = add2(add2(acc[0], acc[1]), add2(acc[2], acc[3]));
+			m[0] = mag(S0);
+			fma2(D, carry, En[0]);
+			fma2(D, h[0], nE2[0]);
+			m[1] = mag(add2(S0, D));
+#pragma unroll
+			for (int q = 0; q < 7; q++) {
+				unsigned long long a, b;
+				ldp(pg, N + 1 + 2 * q, a, b);
+				fma2(D, a, En[1 + 2 * q]);
+				fma2(D, h[1 + 2 * q], nE2[1 + 2 * q]);
+				m[2 + 2 * q] = mag(add2(S0, D));
+				fma2(D, b, En[2 + 2 * q]);
+				fma2(D, h[2 + 2 * q], nE2[2 + 2 * q]);
+				m[3 + 2 * q] = mag(add2(S0, D));
+			}
+		} else {
+			const unsigned long long S0 = add2(add2(acc[0], acc[1]), add2(acc[2], acc[3]));
+			m[0] = mag(S0);
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				unsigned long long a, b;
+				ldp(pg, N + 2 * q, a, b);
+				fma2(D, a, En[2 * q]);
+				fma2(D, h[2 * q], nE2[2 * q]);
+				m[1 + 2 * q] = mag(add2(S0, D));
+				if (q < 7) {
+					fma2(D, b, En[1 + 2 * q]);
+					fma2(D, h[1 + 2 * q], nE2[1 + 2 * q]);
+					m[2 + 2 * q] = mag(add2(S0, D));
+				}
+			}
+		}
+	}
+};
+
 // sqrt.approx.f32: one MUFU instead of the IEEE sequence with its slow path; maximum relative error 2^-23, far
 // inside the FP32 front end's error budget (the sign guard is 2^-16)
 __device__ __forceinline__ float fast_sqrt(float x)
@@ -213,15 +315,22 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {      // warp-uniform control flow
 		const int ui = ub + (tid & 31);
 		if (ui >= P.U_m) continue;
-		FirUnitPair f;
-		f.run(s_x1, 16 * ui, P.taps + P.mag_iq_off[j], P.mag_n[j]);
-		// the magnitude goes into the mark or space half of every pair stream this tone belongs to
 		float m[16];
+		if (P.mag_slide[j]) {
+			SlideUnit f;
+			f.run(s_x1, 16 * ui, P.taps + P.mag_e_off[j], P.mag_slide[j]);
 #pragma unroll
-		for (int r = 0; r < 16; r++) {
-			const float ci = f.lo(r), cq = f.hi(r);
-			m[r] = fast_sqrt(fmaf(ci, ci, cq * cq));
+			for (int r = 0; r < 16; r++) m[r] = f.m[r];
+		} else {
+			FirUnitPair f;
+			f.run(s_x1, 16 * ui, P.taps + P.mag_iq_off[j], P.mag_n[j]);
+#pragma unroll
+			for (int r = 0; r < 16; r++) {
+				const float ci = f.lo(r), cq = f.hi(r);
+				m[r] = fast_sqrt(fmaf(ci, ci, cq * cq));
+			}
 		}
+		// the magnitude goes into the mark or space half of every pair stream this tone belongs to
 		for (int di = P.mag_dst_first[j]; di < P.mag_dst_first[j + 1]; di++) {
 			const int dd = P.mag_dst[di];
 			float *dst = s_m + (dd >> 1) * P.s_m_stride + (dd & 1) + 2 * pm_phys2(16 * ui);
@@ -257,20 +366,37 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 			if (active && ci < P.pair_first[p + 1] - P.pair_first[p]) {
 				c = P.pair_first[p] + ci;
 				const float g = P.chain_gain[c];
-				const int gid = P.chain_gid[c];
-				const long long nout = P.chain_nout[c];
+				const float neg_eps = -P.guard_eps;
+				// five instructions per sample: y, the magnitude scale, |y| - eps * scale, and one funnel shift each to
+				// collect the sign bits of y and of the guard test (y is never -0: the accumulators start at +0)
+				unsigned int neg = 0, near = 0;
 #pragma unroll
-				for (int r = 0; r < 16; r++) {
+				for (int r = 15; r >= 0; r--) {
 					const float lm = fp.lo(r), ls = fp.hi(r);
 					const float y = fmaf(-g, ls, lm);
-					if (y >= 0.f) half |= (1u << r);
-					const float scale = fabsf(lm) + g * fabsf(ls);
-					if (fabsf(y) < P.guard_eps * scale && nbase + r < nout) {
-						unsigned int slot = atomicAdd(guard.count, 1u);
-						if (slot < guard.cap)
-							guard.entries[slot] = ((unsigned long long)gid << 48) | (unsigned long long)(nbase + r);
+					const float scale = fmaf(g, fabsf(ls), fabsf(lm));
+					const float d = fmaf(neg_eps, scale, fabsf(y));
+					neg = __funnelshift_l(__float_as_uint(y), neg, 1);
+					near = __funnelshift_l(__float_as_uint(d), near, 1);
+				}
+				half = ~neg & 0xFFFFu;
+				near &= 0xFFFFu;
+				if (near || WRITE_SOFT) {
+					const int gid = P.chain_gid[c];
+					const long long nout = P.chain_nout[c];
+					for (int r = 0; r < 16; r++) {
+						if (nbase + r >= nout) break;
+						if ((near >> r) & 1u) {
+							unsigned int slot = atomicAdd(guard.count, 1u);
+							if (slot < guard.cap)
+								guard.entries[slot] = ((unsigned long long)gid << 48) | (unsigned long long)(nbase + r);
+						}
 					}
-					if (WRITE_SOFT && nbase + r < nout) soft[gid * soft_stride + nbase + r] = y;
+					if (WRITE_SOFT) {
+#pragma unroll
+						for (int r = 0; r < 16; r++)
+							if (nbase + r < nout) soft[gid * soft_stride + nbase + r] = fmaf(-g, fp.hi(r), fp.lo(r));
+					}
 				}
 			}
 			// lanes 2k / 2k+1 hold the low / high half of one 32-sample word

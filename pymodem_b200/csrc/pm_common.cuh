@@ -29,9 +29,10 @@ struct AfskPlan {
 	int n_bpf, bpf_off;       // input BPF (taps reversed, count multiple of 4)
 	int n_mag;
 	int mag_n[PM_MAX_MAG];    // correlator taps (multiple of 4)
-	int mag_i_off[PM_MAX_MAG];
-	int mag_q_off[PM_MAX_MAG];
-	int mag_iq_off[PM_MAX_MAG];   // the same taps interleaved (i[0], q[0], i[1], q[1], ...): operands of the packed FFMA2
+	int mag_iq_off[PM_MAX_MAG];   // taps interleaved (i[0], q[0], i[1], q[1], ...): operands of the packed FFMA2
+	int mag_slide[PM_MAX_MAG];    // window length N when the taps are a rotation e^{i(phi + w k)} (afsk.py:134-144): sliding
+	                              // window sum instead of the FIR; 0 = arbitrary taps, direct FIR
+	int mag_e_off[PM_MAX_MAG];    // (cos wk, sin wk) for k in [0, N + 16), then (-cos wk, -sin wk) for k in [0, 16)
 	int n_lpf, lpf_off;
 	int lpf2_off;             // the low-pass taps, each stored twice in a row: (h, h) operands of the packed FFMA2
 	int n_pair;

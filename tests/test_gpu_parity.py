@@ -393,6 +393,27 @@ def test_shortened_slicer_update_is_exact(cuda_lib, tag):
 	assert out[0][0] == g.all_packets()
 
 
+@pytest.mark.parametrize("tag", ["afsk1200_superopt_48k", "afsk1200_ax25_44k1"])
+def test_sliding_correlator_matches_direct_fir(cuda_lib, tag):
+	"""The tone correlators run as sliding window sums when their taps are a rotation (front.cu SlideUnit); with
+	"slide_correlator" 0 they run as plain FIRs.  Both must give the fixture's packets and streams, and soft values
+	that agree with each other far inside the FP32 budget (40/60-tap windows at 48 kHz, 37 taps -- odd -- at 44.1)."""
+	g = Golden(tag)
+	out, softs = [], []
+	for slide in (1, 0):
+		eng = engine(build_stack(g.sample_rate, g.lines), slide_correlator=slide, keep_soft=1)
+		try:
+			pk = as_tuples(eng.run(g.audio()))
+			out.append((pk, [tuple(map(bytes, map(np.ndarray.tobytes, eng.stream(ci, 0)))) for ci in range(g.n_chains)]))
+			softs.append([eng.soft(ci).astype(np.float64) for ci in range(g.n_chains)])
+		finally:
+			eng.close()
+	assert out[0] == out[1]
+	assert out[0][0] == g.all_packets()
+	for a, b in zip(*softs):
+		assert np.max(np.abs(a - b)) <= 8e-6 * np.sqrt(np.mean(b ** 2))
+
+
 def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
 	"""150 s of noise: tens of thousands of inter-flag gaps with aborts, stuffed zeros and every residue of the bit
 	count; the count-based filter (bits.cu ax25_gap_filter_kernel) must let through exactly the gaps the reference's
