@@ -30,16 +30,51 @@ __device__ __forceinline__ bool seg_state_equal(const SegState &a, const SegStat
 	       a.last_q == b.last_q;
 }
 
+// One sample of the loop (slicer.py:77-81, 104), arranged so that the compiler cannot put selects of float64 VALUES
+// on the dependency chain: the roll-over selects the ADDEND (1.0 or -(sps - 1), resp. 0.0 or sps in the plain form)
+// and a zero crossing selects the FACTOR (1.0 or lock_rate) -- x + 1.0, x - 0.0 and x * 1.0 are exact, so the clock
+// is bit-identical to the reference's conditional statements -- and the chain per sample is compare, add,
+// multiply.  Six or seven instructions instead of eleven (compare x2, add x2, select x2, multiply, select x2, bit
+// tests); the kernel is bound by that stream (ncu r01e: ALU pipe 63 % busy at 9 warps per SM).
+// A0 / F0: the low word of the roll-over addend (-(sps - 1) in the FAST form, -sps in the plain form) resp. of
+// lock_rate is zero (40 or 36.75 samples per symbol, lock_rate 0.75 ...): one 32-bit select of the high word makes
+// the operand instead of two.  The roll-over mask is collected from the SIGN of the addend (negative <=> roll) with
+// one funnel shift per sample, most recent sample in bit 0: the caller bit-reverses the finished word.
+template <bool WRITE, bool FAST, bool A0, bool F0>
+__device__ __forceinline__ void slicer_step(double &c, uint32_t &m, uint32_t z, uint32_t bit, const SlicerChain &C,
+                                            double cs, double a_roll, double a_keep)
+{
+	bool roll;
+	double base;
+	if (FAST) {
+		// both candidates straight from the old clock (SlicerChain::c_star_bits): roll <=> bits(c) >= c_star <=> c >= cs
+		roll = c >= cs;
+		base = c;
+	} else {
+		base = __dadd_rn(c, 1.0);                        // slicer.py:77
+		roll = base >= C.thr;                            // slicer.py:79
+	}
+	// FAST: c + 1.0 or c - (sps - 1); plain: up + 0.0 (exact: up is never -0) or up - sps (slicer.py:81)
+	const double add = A0 ? __hiloint2double(roll ? __double2hiint(a_roll) : __double2hiint(a_keep), 0)
+	                      : (roll ? a_roll : a_keep);
+	const double t = __dadd_rn(base, add);
+	const bool cross = (z & bit) != 0;                   // slicer.py:99-104
+	const double f = F0 ? __hiloint2double(cross ? __double2hiint(C.lock) : 0x3FF00000, 0) : (cross ? C.lock : 1.0);
+	c = __dmul_rn(t, f);
+	if (WRITE) m = __funnelshift_l((uint32_t)__double2hiint(add), m, 1);
+}
+
 // Advance the slicer over samples [w0*32, min(w1*32, nout)) of one chain.
-template <bool WRITE, bool FAST>
+template <bool WRITE, bool FAST, bool A0, bool F0>
 __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                             const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
                                             long long w0, long long w1, SegState &st)
 {
 	double c = st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
-	const double thr = C.thr, sps = C.sps, lam = C.lock, spm1 = C.sps_m1;
-	const long long c_star = C.c_star_bits;
+	const double thr = C.thr, sps = C.sps, lam = C.lock;
+	const double cs = __longlong_as_double(C.c_star_bits);
+	const double a_roll = FAST ? -C.sps_m1 : -C.sps, a_keep = FAST ? 1.0 : 0.0;
 	for (long long w = w0; w < w1; w++) {
 		const long long first = w << 5;
 		if (first >= C.nout) break;
@@ -56,24 +91,13 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 		const int cnt = remain >= 32 ? 32 : (int)remain;
 		if (cnt == 32) {
 #pragma unroll
-			for (int i = 0; i < 32; i++) {
-				if (FAST) {
-					// both candidates straight from the old clock (see SlicerChain): same bits as the plain form below
-					const bool roll = __double_as_longlong(c) >= c_star;
-					const double up = __dadd_rn(c, 1.0), over = __dsub_rn(c, spm1);
-					c = roll ? over : up;
-					m |= (roll ? 1u : 0u) << i;
-				} else {
-					c += 1.0;                                // slicer.py:77
-					if (c >= thr) { c -= sps; m |= (1u << i); }   // slicer.py:79-81
-				}
-				if ((z >> i) & 1u) c *= lam;                 // slicer.py:104
-			}
+			for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+			if (WRITE) m = __brev(m);
 		} else {
 			for (int i = 0; i < cnt; i++) {
-				c += 1.0;
-				if (c >= thr) { c -= sps; m |= (1u << i); }
-				if ((z >> i) & 1u) c *= lam;
+				c += 1.0;                                // slicer.py:77
+				if (c >= thr) { c -= sps; m |= (1u << i); }   // slicer.py:79-81
+				if ((z >> i) & 1u) c *= lam;                 // slicer.py:104
 			}
 			// state after a partial word: last signs are those of sample cnt-1
 			last = (s >> (cnt - 1)) & 1u;
@@ -86,14 +110,20 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 	st.last_q = last_q;
 }
 
-// The same loop in FP32, for the far end of a warm-up only (no outputs, no claim of exactness: a roll-over taken one
-// sample early or late leaves the same clock behind, and whatever error remains is contracted by the float64 tail).
+// The far end of a warm-up in FP32, crossing by crossing (no outputs, no claim of exactness: whatever error remains
+// is contracted by the float64 tail).  Between two crossings the loop only counts -- d steps of +1 with a roll-over
+// whenever the clock reaches thr -- which has the closed form below, so a word costs one short iteration per zero
+// crossing (0-3 in a 32-sample word of 1200 Bd audio) instead of 32 unrolled steps.
 __device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                               const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
 {
 	float c = (float)st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
-	const float thr = (float)C.thr, sps = (float)C.sps, lam = (float)C.lock;
+	const float thr = (float)C.thr, sps = (float)C.sps, lam = (float)C.lock, inv_sps = 1.0f / sps;
+	auto advance = [&](int d) {                      // d samples without a crossing
+		const float u = c + (float)d;
+		c = u >= thr ? u - sps * (floorf((u - thr) * inv_sps) + 1.0f) : u;
+	};
 	for (long long w = w0; w < w1; w++) {
 		if (((w + 1) << 5) > C.nout) break;            // whole words only; the float64 tail handles the rest
 		const uint32_t s = sg[w];
@@ -104,12 +134,15 @@ __device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32
 			z |= q ^ ((q << 1) | last_q);
 			last_q = q >> 31;
 		}
-#pragma unroll
-		for (int i = 0; i < 32; i++) {
-			const float up = c + 1.0f;
-			c = up >= thr ? up - sps : up;
-			if ((z >> i) & 1u) c *= lam;
+		int pos = 0;
+		while (z) {
+			const int t = __ffs(z);                      // crossing at sample t - 1: count up to and including it, then lock
+			z &= z - 1;
+			advance(t - pos);
+			c *= lam;
+			pos = t;
 		}
+		advance(32 - pos);
 	}
 	st.clock = (double)c;
 	st.last = last;
@@ -121,8 +154,20 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
                                           const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
                                           long long w0, long long w1, SegState &st)
 {
-	if (C.fast) run_words_t<WRITE, true>(C, sg, sgq, mk, w0, w1, st);      // uniform per chain (blockIdx.y)
-	else run_words_t<WRITE, false>(C, sg, sgq, mk, w0, w1, st);
+	// uniform per chain (blockIdx.y)
+	const bool a0 = __double2loint(C.fast ? C.sps_m1 : C.sps) == 0, f0 = __double2loint(C.lock) == 0;
+	if (C.fast) {
+		if (a0) {
+			if (f0) run_words_t<WRITE, true, true, true>(C, sg, sgq, mk, w0, w1, st);
+			else run_words_t<WRITE, true, true, false>(C, sg, sgq, mk, w0, w1, st);
+		} else {
+			if (f0) run_words_t<WRITE, true, false, true>(C, sg, sgq, mk, w0, w1, st);
+			else run_words_t<WRITE, true, false, false>(C, sg, sgq, mk, w0, w1, st);
+		}
+	} else {
+		if (a0 && f0) run_words_t<WRITE, false, true, true>(C, sg, sgq, mk, w0, w1, st);
+		else run_words_t<WRITE, false, false, false>(C, sg, sgq, mk, w0, w1, st);
+	}
 }
 
 // grid: (ceil(n_seg / 128), n_chains); block 128
