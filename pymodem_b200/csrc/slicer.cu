@@ -114,15 +114,18 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 // is contracted by the float64 tail).  Between two crossings the loop only counts -- d steps of +1 with a roll-over
 // whenever the clock reaches thr -- which has the closed form below, so a word costs one short iteration per zero
 // crossing (0-3 in a 32-sample word of 1200 Bd audio) instead of 32 unrolled steps.
-__device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32_t *__restrict__ sg,
-                                              const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
+// ONE_WRAP: at least 32 samples per symbol, so the clock rolls over at most once between two crossings of a word.
+template <bool ONE_WRAP>
+__device__ __forceinline__ void run_words_f32_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                                const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
 {
 	float c = (float)st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
 	const float thr = (float)C.thr, sps = (float)C.sps, lam = (float)C.lock, inv_sps = 1.0f / sps;
 	auto advance = [&](int d) {                      // d samples without a crossing
 		const float u = c + (float)d;
-		c = u >= thr ? u - sps * (floorf((u - thr) * inv_sps) + 1.0f) : u;
+		if (ONE_WRAP) c = u >= thr ? u - sps : u;
+		else c = u >= thr ? u - sps * (floorf((u - thr) * inv_sps) + 1.0f) : u;
 	};
 	for (long long w = w0; w < w1; w++) {
 		if (((w + 1) << 5) > C.nout) break;            // whole words only; the float64 tail handles the rest
@@ -147,6 +150,13 @@ __device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32
 	st.clock = (double)c;
 	st.last = last;
 	st.last_q = last_q;
+}
+
+__device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                              const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
+{
+	if (C.sps >= 32.0) run_words_f32_t<true>(C, sg, sgq, w0, w1, st);      // uniform per chain
+	else run_words_f32_t<false>(C, sg, sgq, w0, w1, st);
 }
 
 template <bool WRITE>

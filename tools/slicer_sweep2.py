@@ -11,8 +11,8 @@ audio = synth.afsk1200_ax25(duration_s=3600.0, sample_rate=48000, frame_interval
 	seed=1000, noise_seed=1001)[0]
 dev = torch.from_numpy(audio).cuda(); torch.cuda.synchronize()
 n = len(audio)
-for seg, warm, exact in [(24576, 49152, 16384), (16384, 49152, 16384), (12288, 49152, 16384), (8192, 49152, 16384), (12288, 65536, 16384),
-		(12288, 49152, 12288), (8192, 65536, 12288), (16384, 65536, 12288), (12288, 57344, 8192), (6144, 49152, 16384), (8192, 40960, 16384)]:
+for seg, warm, exact in [(24576, 49152, 16384), (32768, 49152, 16384), (28672, 49152, 16384), (20480, 49152, 16384), (24576, 65536, 16384),
+		(32768, 65536, 14336), (24576, 49152, 14336), (28672, 57344, 14336), (36864, 49152, 16384)]:
 	eng = Engine(stack, segment_len=seg, warmup_len=warm, warmup_exact_len=exact)
 	for _ in range(3):
 		eng.run_device_ptr(dev.data_ptr(), n)
