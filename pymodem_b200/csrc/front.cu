@@ -185,7 +185,7 @@ struct SlideUnit {
 		const unsigned long long *__restrict__ nE2 = E2 + N + 16;
 		unsigned long long h[16];
 #pragma unroll
-		for (int q = 0; q < 8; q++) ldp(pg, 2 * q, h[2 * q], h[2 * q + 1]);
+		for (int q = 0; q < 8; q++) FirUnitPair::load2(s, base + 2 * q, h[2 * q], h[2 * q + 1]);
 		unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
 		for (int j = 0; j < 16; j++) fma2(acc[j & 3], h[j], E2[j]);
@@ -193,13 +193,13 @@ struct SlideUnit {
 		for (; j + 8 <= N; j += 8) {
 			unsigned long long v[8];
 #pragma unroll
-			for (int q = 0; q < 4; q++) ldp(pg, j + 2 * q, v[2 * q], v[2 * q + 1]);
+			for (int q = 0; q < 4; q++) FirUnitPair::load2(s, base + j + 2 * q, v[2 * q], v[2 * q + 1]);
 #pragma unroll
 			for (int k = 0; k < 8; k++) fma2(acc[k & 3], v[k], E2[j + k]);
 		}
 		for (; j + 2 <= N; j += 2) {
 			unsigned long long v0, v1;
-			ldp(pg, j, v0, v1);
+			FirUnitPair::load2(s, base + j, v0, v1);
 			fma2(acc[0], v0, E2[j]);
 			fma2(acc[1], v1, E2[j + 1]);
 		}
@@ -207,7 +207,7 @@ struct SlideUnit {
 		unsigned long long D = 0ull;
 		if (N & 1) {                          // j == N - 1 (even): the pair's second half is the first sample to enter
 			unsigned long long v0, carry;
-			ldp(pg, j, v0, carry);
+			FirUnitPair::load2(s, base + j, v0, carry);
 			fma2(acc[3], v0, E2[j]);
 			const unsigned long long S0 = add2(add2(acc[0], acc[1]), add2(acc[2], acc[3]));
 			m[0] = mag(S0);
@@ -217,7 +217,7 @@ struct SlideUnit {
 #pragma unroll
 			for (int q = 0; q < 7; q++) {
 				unsigned long long a, b;
-				ldp(pg, N + 1 + 2 * q, a, b);
+				FirUnitPair::load2(s, base + N + 1 + 2 * q, a, b);
 				fma2(D, a, En[1 + 2 * q]);
 				fma2(D, h[1 + 2 * q], nE2[1 + 2 * q]);
 				m[2 + 2 * q] = mag(add2(S0, D));
@@ -231,7 +231,7 @@ struct SlideUnit {
 #pragma unroll
 			for (int q = 0; q < 8; q++) {
 				unsigned long long a, b;
-				ldp(pg, N + 2 * q, a, b);
+				FirUnitPair::load2(s, base + N + 2 * q, a, b);
 				fma2(D, a, En[2 * q]);
 				fma2(D, h[2 * q], nE2[2 * q]);
 				m[1 + 2 * q] = mag(add2(S0, D));
