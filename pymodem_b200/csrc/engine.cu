@@ -144,7 +144,7 @@ struct pm_engine {
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	int opt_warm_exact_words = 512; // float64 tail of a warm-up (16384 samples); the part before it runs in FP32 (0: all float64)
-	double opt_guard_eps = 1.52587890625e-05;   // 2^-16
+	double opt_guard_eps = 3.814697265625e-06;  // 2^-18: 4x the largest guard that still changed a sign in 1.4e9 samples (tools/guard_sweep.py)
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
 	int opt_slide = 1;            // rotation-tap correlators as sliding window sums (0: always the direct FIR)
