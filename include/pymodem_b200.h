@@ -168,11 +168,17 @@ const char *pm_last_error(const pm_engine *e);
  * uploads taps.  Chains keep their index (= config order). */
 int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_chains);
 
-/* Tunables: "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32),
- * "verify_passes", "guard_eps", "tile", "keep_soft", "h2d_chunk", "guard_cap", "slicer_fast", "slide_correlator", "warmup_exact_len" (samples of float64 tail of
- * every slicer warm-up; the part before it runs in FP32 -- a warm-up only has to get near the true state; 0 = all float64),
+/* Tunables (results do not depend on any of them; they trade time against the amount of float64 re-evaluation):
+ * "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32; slicer geometry, defaults 24576 / 49152 / 1024),
+ * "warmup_exact_len" (samples of float64 tail of every slicer warm-up; the part before it runs in FP32 -- a warm-up
+ *   only has to get near the true state; 0 = all float64), "verify_passes", "slicer_fast" (0: always the plain clock update),
+ * "guard_eps" (relative width of the FP32 front end's sign guard band, default 2^-18; samples inside it are
+ *   re-evaluated in float64), "guard_cap" (initial capacity of the guard list; grows on demand),
+ * "slide_correlator" (0: tone correlators as plain FIRs even when their taps are a rotation), "tile" (front-end outputs
+ *   per CTA, 0 = cost model), "keep_soft" (1: keep the soft values for pm_engine_get_soft), "h2d_chunk" (samples per
+ *   host-to-device copy of pm_engine_run),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
- * close that |mark| - |space| cancels below FP32 resolution). */
+ *   close that |mark| - |space| cancels below FP32 resolution; set before pm_engine_load_chains). */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
 
 /*
