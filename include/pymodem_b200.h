@@ -174,9 +174,10 @@ int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_c
  *   only has to get near the true state; 0 = all float64), "verify_passes", "slicer_fast" (0: always the plain clock update),
  * "guard_eps" (relative width of the FP32 front end's sign guard band, default 2^-18; samples inside it are
  *   re-evaluated in float64), "guard_cap" (initial capacity of the guard list; grows on demand),
- * "slide_correlator" (0: tone correlators as plain FIRs even when their taps are a rotation), "tile" (front-end outputs
+ * "slide_correlator" (0: tone correlators as plain FIRs even when their taps are a rotation), "fuse_pairs" (0: sliding
+ *   windows tone by tone instead of mark and space of a pair together), "tile" (front-end outputs
  *   per CTA, 0 = cost model), "keep_soft" (1: keep the soft values for pm_engine_get_soft), "h2d_chunk" (samples per
- *   host-to-device copy of pm_engine_run),
+ *   host-to-device copy of pm_engine_run), "stage_clocks" (1: trace the front end's stages, pm_engine_stage_clocks),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
  *   close that |mark| - |space| cancels below FP32 resolution; set before pm_engine_load_chains). */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
@@ -309,6 +310,11 @@ int pm_measure_fp32_peak(int device, double *tflops);
  * launch group -- reported by bench.py next to the roofline. */
 double pm_engine_front_macs_per_sample(const pm_engine *e);
 int pm_engine_front_tile(const pm_engine *e, int group);
+
+/* Tracing (option "stage_clocks" = 1): SM cycles per stage of the AFSK front-end kernel, summed over the CTAs launched
+ * since the last call: out8[0..3] = staging, band-pass, tone correlators, low-pass + epilogue (each including the
+ * wait for the CTA's slowest warp), out8[4] = number of CTAs.  Resets the counters. */
+int pm_engine_stage_clocks(pm_engine *e, uint64_t *out8);
 
 /* Pinned host memory for callers that want the overlapped H2D path. */
 void *pm_host_alloc(size_t bytes);

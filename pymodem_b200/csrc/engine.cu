@@ -147,6 +147,7 @@ struct pm_engine {
 	double opt_guard_eps = 3.814697265625e-06;  // 2^-18: 4x the largest guard that still changed a sign in 1.4e9 samples (tools/guard_sweep.py)
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
+	int opt_fuse_pairs = 1;       // mark and space sliding windows of a pair in one pass (0: tone by tone)
 	int opt_slide = 1;            // rotation-tap correlators as sliding window sums (0: always the direct FIR)
 	int opt_slicer_fast = 1;      // shortened slicer clock update where it is exact (0: always the plain form)
 	int opt_precise = 0;          // all AFSK chains through the float64 pipeline
@@ -166,6 +167,8 @@ struct pm_engine {
 	DevBuf<float> d_soft;
 	DevBuf<unsigned long long> d_guard_entries;
 	DevBuf<unsigned int> d_counters;      // [0] guard count, [1] repairs
+	DevBuf<unsigned long long> d_stage_clk;   // option "stage_clocks": GuardList::stage_clk
+	int opt_stage_clocks = 0;
 	DevBuf<SegState> d_S, d_E0, d_E1, d_chk;
 	DevBuf<ShardBits> d_shardbits;
 	DevBuf<unsigned long long> d_symcount;
@@ -451,12 +454,28 @@ static int build_groups(pm_engine *e)
 			p.pair_first[p.n_pair] = ci;
 			p.n_chain = ci;
 			p.guard_eps = (float)e->opt_guard_eps;
-			// where each tone's magnitude goes: the (mark, space) slots of the pair streams the low-pass reads
+			// pairs whose two tones are sliding-window tones of one length, each used by this pair only, are computed
+			// together (front.cu SlidePair)
+			for (int pi = 0; pi < p.n_pair; pi++) {
+				const int m = p.pair_mark[pi], sp = p.pair_space[pi];
+				int uses_m = 0, uses_s = 0;
+				for (int q = 0; q < p.n_pair; q++) {
+					uses_m += (p.pair_mark[q] == m) + (p.pair_space[q] == m);
+					uses_s += (p.pair_mark[q] == sp) + (p.pair_space[q] == sp);
+				}
+				const bool fuse = e->opt_fuse_pairs && m != sp && p.mag_slide[m] > 0 && p.mag_slide[m] == p.mag_slide[sp] &&
+					uses_m == 1 && uses_s == 1;
+				p.pair_fused[pi] = fuse ? p.mag_slide[m] : 0;
+				p.pair_ea[pi] = p.mag_e_off[m];
+				p.pair_eb[pi] = p.mag_e_off[sp];
+			}
+			// where each remaining tone's magnitude goes: the (mark, space) slots of the pair streams the low-pass reads
 			{
 				int k = 0;
 				for (int t = 0; t < p.n_mag; t++) {
 					p.mag_dst_first[t] = k;
 					for (int pi = 0; pi < p.n_pair; pi++) {
+						if (p.pair_fused[pi]) continue;
 						if (p.pair_mark[pi] == t) p.mag_dst[k++] = pi * 2;
 						if (p.pair_space[pi] == t) p.mag_dst[k++] = pi * 2 + 1;
 					}
@@ -566,7 +585,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_cc.release(); e->d_init.release(); e->d_audio.release(); e->d_sign.release(); e->d_mask.release();
 	e->d_bits_raw.release(); e->d_bits_lfsr.release(); e->d_byte_addr.release(); e->d_soft.release();
 	e->d_chk.release(); e->d_shardbits.release(); e->d_symcount.release(); e->d_tail.release();
-	e->d_guard_entries.release(); e->d_counters.release(); e->d_S.release(); e->d_E0.release();
+	e->d_guard_entries.release(); e->d_counters.release(); e->d_stage_clk.release(); e->d_S.release(); e->d_E0.release();
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
 	e->d_gap_cand.release(); e->d_gap_ncand.release();
@@ -789,9 +808,18 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
 	else if (k == "slicer_fast") e->opt_slicer_fast = value != 0;
 	else if (k == "slide_correlator") { e->opt_slide = value != 0; replan = true; }
+	else if (k == "fuse_pairs") { e->opt_fuse_pairs = value != 0; replan = true; }
 	else if (k == "precise") {
 		if (!e->chains.empty()) return fail(e, PM_ERR_STATE, "set 'precise' before loading chains");
 		e->opt_precise = value != 0;
+	}
+	else if (k == "stage_clocks") {
+		e->opt_stage_clocks = value != 0;
+		if (e->opt_stage_clocks) {
+			cudaSetDevice(e->device);
+			CK(e->d_stage_clk.ensure(8));
+			CK(cudaMemset(e->d_stage_clk.p, 0, 8 * sizeof(unsigned long long)));
+		}
 	}
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
@@ -1004,6 +1032,7 @@ static GuardList guard_of(pm_engine *e)
 	g.entries = e->d_guard_entries.p;
 	g.count = e->d_counters.p;
 	g.cap = e->guard_cap;
+	g.stage_clk = e->opt_stage_clocks ? e->d_stage_clk.p : nullptr;
 	return g;
 }
 
@@ -1791,6 +1820,18 @@ extern "C" double pm_engine_front_macs_per_sample(const pm_engine *e)
 	double m = 0;
 	if (e) for (auto &g : e->groups) m += g.macs_per_sample;
 	return m;
+}
+
+// cycles per stage of the AFSK front end summed over the CTAs launched since the last call (option "stage_clocks")
+extern "C" int pm_engine_stage_clocks(pm_engine *e, uint64_t *out8)
+{
+	if (!e || !out8) return PM_ERR_ARG;
+	if (!e->opt_stage_clocks || !e->d_stage_clk.p) return fail(e, PM_ERR_STATE, "set option 'stage_clocks' first");
+	cudaSetDevice(e->device);
+	CK(cudaStreamSynchronize(e->st));
+	CK(cudaMemcpy(out8, e->d_stage_clk.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	CK(cudaMemset(e->d_stage_clk.p, 0, 8 * sizeof(unsigned long long)));
+	return PM_OK;
 }
 
 extern "C" int pm_engine_front_tile(const pm_engine *e, int group)

@@ -245,6 +245,89 @@ struct SlideUnit {
 	}
 };
 
+// The same for the mark and the space tone of one pair at once (equal window lengths): the two window sums are
+// independent dependency chains over the same samples, so one thread interleaves them -- twice the instruction-level
+// parallelism of a stage that is bound by the latency of its chains, not by their number of operations (stage
+// tracing: as many cycles per CTA as the band-pass with a tenth of its multiply-adds) -- and the magnitudes leave
+// as (mark, space) pairs, two samples per 128-bit store, instead of one 32-bit store per tone and sample.
+struct SlidePair {
+	// dst: the pair stream at sample `base` (16 (mark, space) float2 in a row, 16-byte aligned)
+	__device__ __forceinline__ static void run(const float *__restrict__ s, int base, const float *__restrict__ EA,
+	                                           const float *__restrict__ EB, int N, float *__restrict__ dst)
+	{
+		const unsigned long long *__restrict__ A2 = reinterpret_cast<const unsigned long long *>(EA);
+		const unsigned long long *__restrict__ B2 = reinterpret_cast<const unsigned long long *>(EB);
+		const unsigned long long *__restrict__ nA2 = A2 + N + 16, *__restrict__ nB2 = B2 + N + 16;
+		unsigned long long h[16];
+#pragma unroll
+		for (int q = 0; q < 8; q++) FirUnitPair::load2(s, base + 2 * q, h[2 * q], h[2 * q + 1]);
+		unsigned long long a[4] = {0ull, 0ull, 0ull, 0ull}, b[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+		for (int j = 0; j < 16; j++) { fma2(a[j & 3], h[j], A2[j]); fma2(b[j & 3], h[j], B2[j]); }
+		int j = 16;
+		for (; j + 8 <= N; j += 8) {
+			unsigned long long v[8];
+#pragma unroll
+			for (int q = 0; q < 4; q++) FirUnitPair::load2(s, base + j + 2 * q, v[2 * q], v[2 * q + 1]);
+#pragma unroll
+			for (int k = 0; k < 8; k++) { fma2(a[k & 3], v[k], A2[j + k]); fma2(b[k & 3], v[k], B2[j + k]); }
+		}
+		for (; j + 2 <= N; j += 2) {
+			unsigned long long v0, v1;
+			FirUnitPair::load2(s, base + j, v0, v1);
+			fma2(a[0], v0, A2[j]); fma2(b[0], v0, B2[j]);
+			fma2(a[1], v1, A2[j + 1]); fma2(b[1], v1, B2[j + 1]);
+		}
+		const unsigned long long *__restrict__ An = A2 + N, *__restrict__ Bn = B2 + N;
+		unsigned long long DA = 0ull, DB = 0ull, SA, SB;
+		float pa = 0.f, pb = 0.f;
+		// output r: even ones wait for their odd neighbour, then both leave in one 128-bit store
+		auto emit = [&](int r) {
+			const float ma = SlideUnit::mag(SlideUnit::add2(SA, DA)), mb = SlideUnit::mag(SlideUnit::add2(SB, DB));
+			if (r & 1) *reinterpret_cast<float4 *>(dst + 2 * (r - 1)) = make_float4(pa, pb, ma, mb);
+			else { pa = ma; pb = mb; }
+		};
+		auto slide = [&](int r, unsigned long long xin) {          // window r -> r + 1
+			fma2(DA, xin, An[r]); fma2(DB, xin, Bn[r]);
+			fma2(DA, h[r], nA2[r]); fma2(DB, h[r], nB2[r]);
+		};
+		if (N & 1) {                          // j == N - 1 (even): the pair's second half is the first sample to enter
+			unsigned long long v0, carry;
+			FirUnitPair::load2(s, base + j, v0, carry);
+			fma2(a[3], v0, A2[j]); fma2(b[3], v0, B2[j]);
+			SA = SlideUnit::add2(SlideUnit::add2(a[0], a[1]), SlideUnit::add2(a[2], a[3]));
+			SB = SlideUnit::add2(SlideUnit::add2(b[0], b[1]), SlideUnit::add2(b[2], b[3]));
+			emit(0);
+			slide(0, carry);
+			emit(1);
+#pragma unroll
+			for (int q = 0; q < 7; q++) {
+				unsigned long long x0, x1;
+				FirUnitPair::load2(s, base + N + 1 + 2 * q, x0, x1);
+				slide(1 + 2 * q, x0);
+				emit(2 + 2 * q);
+				slide(2 + 2 * q, x1);
+				emit(3 + 2 * q);
+			}
+		} else {
+			SA = SlideUnit::add2(SlideUnit::add2(a[0], a[1]), SlideUnit::add2(a[2], a[3]));
+			SB = SlideUnit::add2(SlideUnit::add2(b[0], b[1]), SlideUnit::add2(b[2], b[3]));
+			emit(0);
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				unsigned long long x0, x1;
+				FirUnitPair::load2(s, base + N + 2 * q, x0, x1);
+				slide(2 * q, x0);
+				emit(1 + 2 * q);
+				if (q < 7) {
+					slide(1 + 2 * q, x1);
+					emit(2 + 2 * q);
+				}
+			}
+		}
+	}
+};
+
 // sqrt.approx.f32: one MUFU instead of the IEEE sequence with its slow path; maximum relative error 2^-23, far
 // inside the FP32 front end's error budget (the sign guard is 2^-16)
 __device__ __forceinline__ float fast_sqrt(float x)
@@ -291,9 +374,20 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	float *s_m = smem + P.s_m_off;
 	const long long n0 = (tile_first + blockIdx.x) * (long long)P.tile;
 	const int tid = threadIdx.x;
+	// stage tracing: thread 0 adds the cycles between barriers (its own work plus the wait for the slowest warp)
+	const bool trace = guard.stage_clk != nullptr && tid == 0;
+	long long t_prev = trace ? clock64() : 0;
+	auto stage_done = [&](int i) {
+		if (trace) {
+			const long long t = clock64();
+			atomicAdd(&guard.stage_clk[i], (unsigned long long)(t - t_prev));
+			t_prev = t;
+		}
+	};
 
 	stage_audio(s_a, audio, n0, n_audio, P.a_len);
 	__syncthreads();
+	stage_done(0);
 
 	// input band-pass (afsk.py:151); the result is stored as (x, x) pairs: the window operand of the packed correlators
 	for (int ub = tid - (tid & 31); ub < P.U_x; ub += PM_FRONT_THREADS) {        // warp-uniform control flow: uniform taps
@@ -307,11 +401,22 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 			*reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(f.a[2 * q], f.a[2 * q], f.a[2 * q + 1], f.a[2 * q + 1]);
 	}
 	__syncthreads();
+	stage_done(1);
 
 	// tone correlators and magnitudes (afsk.py:153-160): I and Q of one tone in the two halves of an FFMA2
 	// (tone by tone, so that the tap operands are warp-uniform: an FFMA2 whose tap comes from a uniform register runs
 	// at the full FP32 rate, one with three vector-register operands only at ~78 % -- tools/ubench/ffma2.cu)
-	for (int j = 0; j < P.n_mag; j++)
+	for (int p = 0; p < P.n_pair; p++) {                                        // fused pairs: both tones in one pass
+		if (!P.pair_fused[p]) continue;
+		for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {   // warp-uniform control flow
+			const int ui = ub + (tid & 31);
+			if (ui >= P.U_m) continue;
+			SlidePair::run(s_x1, 16 * ui, P.taps + P.pair_ea[p], P.taps + P.pair_eb[p], P.pair_fused[p],
+				s_m + p * P.s_m_stride + 2 * pm_phys2(16 * ui));
+		}
+	}
+	for (int j = 0; j < P.n_mag; j++) {
+	if (P.mag_dst_first[j] == P.mag_dst_first[j + 1]) continue;                 // both uses of the tone are fused pairs
 	for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {      // warp-uniform control flow
 		const int ui = ub + (tid & 31);
 		if (ui >= P.U_m) continue;
@@ -338,7 +443,9 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 			for (int r = 0; r < 16; r++) dst[2 * r] = m[r];
 		}
 	}
+	}
 	__syncthreads();
+	stage_done(2);
 
 	// output low-pass of the mark and space magnitudes, per-chain combination,
 	// sign packing (afsk.py:162-166 -> slicer.py:85,99)
@@ -406,6 +513,11 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 				sign[P.chain_gid[c] * sign_stride + word] = half | (hi << 16);
 			}
 		}
+	}
+	if (trace) {
+		__syncwarp();
+		stage_done(3);
+		atomicAdd(&guard.stage_clk[4], 1ull);
 	}
 }
 

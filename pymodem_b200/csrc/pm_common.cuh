@@ -39,6 +39,10 @@ struct AfskPlan {
 	int pair_mark[PM_MAX_PAIR];
 	int pair_space[PM_MAX_PAIR];
 	int pair_first[PM_MAX_PAIR + 1];   // chains of pair p: chain_*[pair_first[p] .. pair_first[p+1])
+	int pair_fused[PM_MAX_PAIR];       // window length when both tones are sliding-window tones of one length used by this pair
+	                                   // only: one pass computes both (front.cu SlidePair; their mag_dst lists are empty); else 0
+	int pair_ea[PM_MAX_PAIR];          // mag_e_off of the mark and of the space tone of a fused pair (indexed by the pair,
+	int pair_eb[PM_MAX_PAIR];          // so that the table addresses stay warp-uniform for the compiler)
 	int n_chain;
 	int chain_gid[PM_MAX_GCH];         // engine-wide chain index
 	float chain_gain[PM_MAX_GCH];      // space_gain (afsk.py:143)
@@ -70,6 +74,8 @@ struct GuardList {
 	unsigned long long *entries;       // (chain gid << 48) | sample index
 	unsigned int *count;
 	unsigned int cap;
+	unsigned long long *stage_clk;     // optional tracing (option "stage_clocks"): per-CTA cycles of the AFSK front end's
+	                                   // stages summed over CTAs [stage, band-pass, correlators, low-pass+epilogue], [4] = CTAs
 };
 
 // ---- tables shared by the kernels and the host engine -------------------------

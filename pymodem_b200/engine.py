@@ -232,6 +232,12 @@ class Engine:
 		self._check(self._lib.pm_engine_get_stats(self._h, ctypes.byref(s)))
 		return s.as_dict()
 
+	def stage_clocks(self):
+		"""Cycles per front-end stage summed over CTAs since the last call (option stage_clocks=1); see the header."""
+		out = (ctypes.c_uint64 * 8)()
+		self._check(self._lib.pm_engine_stage_clocks(self._h, out))
+		return list(out)
+
 	def front_macs_per_sample(self):
 		return self._lib.pm_engine_front_macs_per_sample(self._h)
 

@@ -400,18 +400,19 @@ def test_sliding_correlator_matches_direct_fir(cuda_lib, tag):
 	that agree with each other far inside the FP32 budget (40/60-tap windows at 48 kHz, 37 taps -- odd -- at 44.1)."""
 	g = Golden(tag)
 	out, softs = [], []
-	for slide in (1, 0):
-		eng = engine(build_stack(g.sample_rate, g.lines), slide_correlator=slide, keep_soft=1)
+	for slide, fuse in ((1, 1), (0, 1), (1, 0)):       # mark+space of a pair in one pass, plain FIRs, tone by tone
+		eng = engine(build_stack(g.sample_rate, g.lines), slide_correlator=slide, fuse_pairs=fuse, keep_soft=1)
 		try:
 			pk = as_tuples(eng.run(g.audio()))
 			out.append((pk, [tuple(map(bytes, map(np.ndarray.tobytes, eng.stream(ci, 0)))) for ci in range(g.n_chains)]))
 			softs.append([eng.soft(ci).astype(np.float64) for ci in range(g.n_chains)])
 		finally:
 			eng.close()
-	assert out[0] == out[1]
+	assert out[0] == out[1] == out[2]
 	assert out[0][0] == g.all_packets()
-	for a, b in zip(*softs):
+	for a, b, c in zip(*softs):
 		assert np.max(np.abs(a - b)) <= 8e-6 * np.sqrt(np.mean(b ** 2))
+		assert np.max(np.abs(c - b)) <= 8e-6 * np.sqrt(np.mean(b ** 2))
 
 
 def test_long_noise_exercises_the_gap_filter(cuda_lib, oracle):
