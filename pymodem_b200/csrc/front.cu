@@ -9,6 +9,10 @@
 // The reference computes LPF(m_mark - m_space_gained); LPF is linear, so the
 // LPF of the unit-gain space magnitude is shared by every chain that differs
 // only in space_gain (afsk_1200_ax25_super_opt.json chains 2-8).
+// The tone correlators of the reference are rotations over a rectangular window
+// (afsk.py:134-144) of which only the magnitude is used, so m_j is computed as a
+// sliding window sum (SlideUnit / SlidePair below) unless a caller supplies
+// other taps (FirUnitPair).
 //
 // Only the SIGN of y reaches the rest of the chain (slicer.py:85, 99-102), so
 // the kernel's product is one bit per chain-sample.  A sample whose |y| is
@@ -403,9 +407,11 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	__syncthreads();
 	stage_done(1);
 
-	// tone correlators and magnitudes (afsk.py:153-160): I and Q of one tone in the two halves of an FFMA2
-	// (tone by tone, so that the tap operands are warp-uniform: an FFMA2 whose tap comes from a uniform register runs
-	// at the full FP32 rate, one with three vector-register operands only at ~78 % -- tools/ubench/ffma2.cu)
+	// tone correlators and magnitudes (afsk.py:153-160): I and Q of one tone in the two halves of an FFMA2.
+	// All threads of a warp work on the same tone(s), so that the tap / table operands are warp-uniform: an FFMA2 whose
+	// tap comes from a uniform register runs at the full FP32 rate, one with three vector-register operands only at
+	// ~78 % (tools/ubench/ffma2.cu) -- which is also why every table offset is indexed by the loop counter itself
+	// (an offset fetched through a second constant load makes the compiler give up on the uniform datapath)
 	for (int p = 0; p < P.n_pair; p++) {                                        // fused pairs: both tones in one pass
 		if (!P.pair_fused[p]) continue;
 		for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {   // warp-uniform control flow
