@@ -333,7 +333,7 @@ struct SlidePair {
 };
 
 // sqrt.approx.f32: one MUFU instead of the IEEE sequence with its slow path; maximum relative error 2^-23, far
-// inside the FP32 front end's error budget (the sign guard is 2^-16)
+// inside the FP32 front end's error budget (the sign guard is 2^-18)
 __device__ __forceinline__ float fast_sqrt(float x)
 {
 	float r;
