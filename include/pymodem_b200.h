@@ -311,6 +311,11 @@ int pm_measure_fp32_peak(int device, double *tflops);
 double pm_engine_front_macs_per_sample(const pm_engine *e);
 int pm_engine_front_tile(const pm_engine *e, int group);
 
+/* Host-side helper (no device): 1 when the correlator taps (i[k], q[k]), k < n, are a rotation a*e^{i(phi + step*k)} with
+ * n >= 16 -- the form afsk.py:134-144 generates -- which is what lets the engine compute the tone magnitudes as sliding
+ * window sums; *step receives the angle per tap.  0 otherwise (the engine then runs the taps as plain FIRs). */
+int pm_taps_are_rotation(const double *i, const double *q, int32_t n, double *step);
+
 /* Tracing (option "stage_clocks" = 1): SM cycles per stage of the AFSK front-end kernel, summed over the CTAs launched
  * since the last call: out8[0..3] = staging, band-pass, tone correlators, low-pass + epilogue (each including the
  * wait for the CTA's slowest warp), out8[4] = number of CTAs.  Resets the counters. */

@@ -123,6 +123,8 @@ PROTOTYPES = {
 	"pm_engine_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
 	"pm_engine_front_macs_per_sample": (ctypes.c_double, [_vp]),
 	"pm_engine_stage_clocks": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
+	"pm_taps_are_rotation": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int32,
+		ctypes.POINTER(ctypes.c_double)]),
 	"pm_engine_front_tile": (ctypes.c_int, [_vp, ctypes.c_int]),
 	"pm_measure_fp32_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 	"pm_host_alloc": (_vp, [ctypes.c_size_t]),

@@ -1822,6 +1822,16 @@ extern "C" double pm_engine_front_macs_per_sample(const pm_engine *e)
 	return m;
 }
 
+// host-side check behind the sliding-window correlators (no device needed): are (ti[k], tq[k]) = a e^{i(phi + w k)}?
+extern "C" int pm_taps_are_rotation(const double *ti, const double *tq, int32_t n, double *step)
+{
+	if (!ti || !tq || n <= 0) return 0;
+	double w = 0;
+	const bool ok = rotation_taps(std::vector<double>(ti, ti + n), std::vector<double>(tq, tq + n), w);
+	if (ok && step) *step = w;
+	return ok ? 1 : 0;
+}
+
 // cycles per stage of the AFSK front end summed over the CTAs launched since the last call (option "stage_clocks")
 extern "C" int pm_engine_stage_clocks(pm_engine *e, uint64_t *out8)
 {
