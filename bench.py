@@ -394,7 +394,8 @@ def run_b200_arm(args):
 				"hand-off, bit tails and packet records exchanged by the GPUs over NVLink peer memory (csrc/link.cu), "
 				"every rank ends the step with the merged records of all ranks on its host"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-			"h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"]},
+			"h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"],
+			"bytes_scope": "rank 0 (every rank copies its own shard of the recording plus the slicer's warm-up history)"},
 		"gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
 		"stage_ms": stage_ms, "shard_phase_ms_rank0": shard_phase, "link_fallbacks": link_fallbacks,
 		"pipelined": pipelined, "packets_per_step": n_packets,
