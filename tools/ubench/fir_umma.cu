@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(128, 1)
 fir_umma_kernel(const __nv_bfloat16 *__restrict__ x, const uint8_t *__restrict__ bt, float *__restrict__ out,
                 int base_offset_mode, int reps, long long *__restrict__ cycles, int *__restrict__ status)
 {
-	extern __shared__ __align__(1024) uint8_t smem[];
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	// the swizzle is a function of the address bits: make sure of the 1024-byte alignment (1 KB of slack is allocated)
+	uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	uint8_t *sA = smem;                              // A_BYTES rounded up to 1024
 	uint8_t *sB = smem + ((A_BYTES + 1023) / 1024) * 1024;
 	__shared__ __align__(8) unsigned long long bar;
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(128, 1)
 fir_umma_split_kernel(const float *__restrict__ x, const uint8_t *__restrict__ bt, float *__restrict__ out,
                       int base_offset_mode, long long *__restrict__ cycles, int *__restrict__ status)
 {
-	extern __shared__ __align__(1024) uint8_t smem[];
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	const uint32_t a_stride = ((A_BYTES + 1023) / 1024) * 1024;
 	uint8_t *sA = smem;                              // 3 pieces
 	uint8_t *sB = smem + 3 * a_stride;               // 3 pieces
