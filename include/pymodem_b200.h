@@ -32,6 +32,7 @@ extern "C" {
 #define PM_ERR_STATE      -5
 
 /* modem kinds -- chain_builder.py:17-38 */
+#define PM_MODEM_NONE      0   /* no modem: the chain only serves the per-stage calls (pm_engine_slice_soft, ...) */
 #define PM_MODEM_AFSK      1   /* afsk.py:13   AFSKModem  */
 #define PM_MODEM_FSK       2   /* fsk.py:15    FSKModem   */
 #define PM_MODEM_BPSK      3   /* psk.py:20    BPSKModem  */
@@ -173,11 +174,13 @@ int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_c
  * "warmup_exact_len" (samples of float64 tail of every slicer warm-up; the part before it runs in FP32 -- a warm-up
  *   only has to get near the true state; 0 = all float64), "verify_passes", "slicer_fast" (0: always the plain clock update),
  * "guard_eps" (relative width of the FP32 front end's sign guard band, default 2^-18; samples inside it are
- *   re-evaluated in float64), "guard_cap" (initial capacity of the guard list; grows on demand),
+ *   re-evaluated in float64), "guard_abs" (the guard's raw-input term: multiples, default 0.25, of 2^-24 max|audio of the tile|
+ *   sum|h_bpf| N_corr sum|h_lpf| (1 + space_gain) added to the band -- the band-pass rounds at the magnitude of the RAW
+ *   samples, DC / hum / out-of-band energy included), "guard_cap" (initial capacity of the guard list; grows on demand),
  * "slide_correlator" (0: tone correlators as plain FIRs even when their taps are a rotation), "fuse_pairs" (0: sliding
  *   windows tone by tone instead of mark and space of a pair together), "tile" (front-end outputs
  *   per CTA, 0 = cost model), "keep_soft" (1: keep the soft values for pm_engine_get_soft), "h2d_chunk" (samples per
- *   host-to-device copy of pm_engine_run), "stage_clocks" (1: trace the front end's stages, pm_engine_stage_clocks),
+ *   host-to-device copy of pm_engine_run), "copy_threads" (host threads that stage pageable input, default 4), "stage_clocks" (1: trace the front end's stages, pm_engine_stage_clocks),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
  *   close that |mark| - |space| cancels below FP32 resolution; set before pm_engine_load_chains). */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
@@ -215,8 +218,13 @@ int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_sampl
  *             return the last tail_bits own bits of every chain
  *   finish  : prepend the previous shard's tail, descramble, decode; a packet is
  *             emitted by the shard that holds its closing bit
- * PM_ERR_STATE from finish means a frame reached back past the hand-off tail
- * (or needs the sequential AX.25 replay): run unsharded or with a longer tail.
+ * PM_ERR_STATE from finish means a frame reached back past the hand-off tail or a
+ * gap is long enough to overflow max_packet_length (ax25.py:46-51; the sequential
+ * replay needs a known decoder state).  The shards then recover together: every
+ * rank exports what it holds of the sliced stream (pm_engine_shard_export), the
+ * exports are gathered, and the complete stream is decoded by
+ * pm_engine_unscramble_stream / pm_engine_decode_stream -- exactly what an
+ * unsharded run decodes (pymodem_b200/sharded.py: recover_from_bitstream).
  */
 typedef struct pm_shard_plan {
 	int64_t sample_base;
@@ -268,6 +276,8 @@ int pm_engine_shard_finish_il2p(pm_engine *e, const uint32_t *tail_in, const pm_
  * trip after the slicer; run_linked_end waits for it and leaves the MERGED records of all ranks (ordered like an
  * unsharded run: chain, then stream position; their `offset` fields point into an arena that holds rank 0's packet
  * bytes first, then rank 1's, ...) in the engine for pm_engine_get_packets.
+ *   *verified == 2: some rank could not finish its decode from what it holds (see PM_ERR_STATE above).  Every rank
+ *   learns it with the records, so all of them get 2 and recover through pm_engine_shard_export.
  *   *verified == 0: some rank's speculated slicer start state was wrong.  All ranks see the same states, so all
  *   of them get 0 and continue with the host-driven protocol: pm_engine_shard_states (what shard_begin would
  *   have returned) -> shard_handoff ... -> shard_gather -> shard_finish.
@@ -282,6 +292,27 @@ int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, int64_t n_sam
                                const pm_shard_plan *plan);
 int pm_engine_run_linked_end(pm_engine *e, int32_t *verified);
 int pm_engine_shard_states(pm_engine *e, pm_shard_state *out);
+/* What this shard holds of one chain's sliced stream after shard_gather (also after a finish that failed, or a linked
+ * run that ended with *verified == 2): bits[(info4[0] + 31) / 32] packed LSB-first in time, byte_addr[(info4[0] + 7) / 8]
+ * local sample addresses of the stream bytes (valid for the bytes whose last bit is an own bit; add info4[3]).
+ * info4 = {local stream bits, local position of the first own bit, own bits, sample_base}.  bits == byte_addr == NULL:
+ * only info4 is filled. */
+int pm_engine_shard_export(pm_engine *e, int32_t chain, uint32_t *bits, int64_t cap_words, uint32_t *byte_addr,
+                           int64_t cap_bytes, int64_t *info4);
+
+/*
+ * Per-stage entry points: the reference's duck-typed blocks one at a time (chain_execute.py:32-47), on the same
+ * kernels as the whole-chain run, for ONE chain of the loaded table.
+ *   slice_soft         slicer.slice(soft)  slicer.py:59-107 / 193-242: float64 soft values (I, and Q for the quadrature
+ *                      slicer) -> the AddressedData stream, read back with pm_engine_get_stream(stage 0)
+ *   unscramble_stream  stream.stream_unscramble_8bit(list[AddressedData])  lfsr.py:22-52 -> pm_engine_get_stream(stage 1)
+ *   decode_stream      codec.decode(list[AddressedData])  ax25.py:25-93 / il2p.py:360-519 (incl. the sequential replay
+ *                      after a max_packet_length overflow) -> pm_engine_get_packets
+ * bytes[i] / addresses[i] = AddressedData.data / .address; addresses must fit 32 bits.
+ */
+int pm_engine_slice_soft(pm_engine *e, int32_t chain, const double *soft_i, const double *soft_q, int64_t n);
+int pm_engine_unscramble_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const int64_t *addresses, int64_t n);
+int pm_engine_decode_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const int64_t *addresses, int64_t n);
 
 int64_t pm_engine_num_packets(const pm_engine *e);
 int64_t pm_engine_arena_bytes(const pm_engine *e);
@@ -294,6 +325,10 @@ int pm_engine_get_packets(const pm_engine *e, pm_packet_rec *recs, int64_t rec_c
 int64_t pm_engine_soft_len(const pm_engine *e, int32_t chain);
 int pm_engine_get_soft(const pm_engine *e, int32_t chain, int32_t component /*0=I/real,1=Q*/,
                        float *out, int64_t cap);
+/* The packed signs of the soft values (bit i of word w = soft[32 w + i] >= 0; slicer.py:85, 99-102 read nothing else of
+ * the demod output), after the float64 fix-up: (soft_len + 31) / 32 words.  Lets a test compare the FP32 front end's
+ * signs with the float64 route's (option "precise") over whole recordings. */
+int pm_engine_get_signs(const pm_engine *e, int32_t chain, int32_t component, uint32_t *out, int64_t cap_words);
 /* AddressedData streams: stage 0 = slicer output (slicer.py:97), 1 = after LFSR (lfsr.py:47-51). */
 int64_t pm_engine_stream_len(const pm_engine *e, int32_t chain);
 int pm_engine_get_stream(const pm_engine *e, int32_t chain, int32_t stage,
@@ -321,9 +356,16 @@ int pm_taps_are_rotation(const double *i, const double *q, int32_t n, double *st
  * wait for the CTA's slowest warp), out8[4] = number of CTAs.  Resets the counters. */
 int pm_engine_stage_clocks(pm_engine *e, uint64_t *out8);
 
-/* Pinned host memory for callers that want the overlapped H2D path. */
+/* Host memory the GPU can read directly.  pm_engine_run takes any host pointer: from pinned memory (pm_host_alloc,
+ * pm_host_register, torch pin_memory ...) the chunks are DMA'ed in place; from pageable memory they are staged through
+ * the engine's ring of pinned buffers by a few host threads (options "h2d_chunk", "copy_threads") -- correct but bounded
+ * by the host's memcpy rate.  pm_host_alloc: read a recording straight into pinned memory (what python -m pymodem_b200
+ * does with the WAV, pymodem.py:46).  pm_host_register: pin a buffer the caller already owns, once, for repeated runs
+ * (unregister before freeing it). */
 void *pm_host_alloc(size_t bytes);
 void pm_host_free(void *p);
+int pm_host_register(void *p, size_t bytes);
+int pm_host_unregister(void *p);
 
 const char *pm_version(void);
 

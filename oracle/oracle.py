@@ -588,7 +588,7 @@ class IL2PCodec:
 		data = np.ascontiguousarray(data, dtype=np.uint8)
 		addr = np.ascontiguousarray(addr, dtype=np.int64)
 		n = len(data)
-		rec_cap = n // 19 + 16
+		rec_cap = n // 17 + 16            # shortest frame: 3 sync bytes + a 15-byte header (no payload, no trailing CRC)
 		arena_cap = 2 * n + (1 << 16)
 		rec_addr = np.empty(rec_cap, dtype=np.int64)
 		rec_off = np.empty(rec_cap, dtype=np.int64)

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpymodem_b200.so")
 
 PM_OK, PM_ERR_ARG, PM_ERR_CUDA, PM_ERR_UNSUPPORTED, PM_ERR_CAPACITY, PM_ERR_STATE = 0, -1, -2, -3, -4, -5
-PM_MODEM_AFSK, PM_MODEM_FSK, PM_MODEM_BPSK, PM_MODEM_MPSK, PM_MODEM_AFSK_PLL = 1, 2, 3, 4, 5
+PM_MODEM_NONE, PM_MODEM_AFSK, PM_MODEM_FSK, PM_MODEM_BPSK, PM_MODEM_MPSK, PM_MODEM_AFSK_PLL = 0, 1, 2, 3, 4, 5
 PM_SLICER_BINARY, PM_SLICER_QUADRATURE = 1, 2
 PM_CODEC_AX25, PM_CODEC_IL2P = 1, 2
 
@@ -113,6 +113,11 @@ PROTOTYPES = {
 	"pm_engine_run_linked_begin": (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.POINTER(ShardPlan)]),
 	"pm_engine_run_linked_end": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
 	"pm_engine_shard_states": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState)]),
+	"pm_engine_shard_export": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, ctypes.POINTER(_i64)]),
+	"pm_engine_slice_soft": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64]),
+	"pm_engine_unscramble_stream": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64]),
+	"pm_engine_decode_stream": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64]),
+	"pm_engine_get_signs": (ctypes.c_int, [_vp, _i32, _i32, _vp, _i64]),
 	"pm_engine_num_packets": (_i64, [_vp]),
 	"pm_engine_arena_bytes": (_i64, [_vp]),
 	"pm_engine_get_packets": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64]),
@@ -129,6 +134,8 @@ PROTOTYPES = {
 	"pm_measure_fp32_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 	"pm_host_alloc": (_vp, [ctypes.c_size_t]),
 	"pm_host_free": (None, [_vp]),
+	"pm_host_register": (ctypes.c_int, [_vp, ctypes.c_size_t]),
+	"pm_host_unregister": (ctypes.c_int, [_vp]),
 	"pm_version": (_cp, []),
 }
 

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpymodem_b200.so")
 SOURCES = ["engine.cu", "front.cu", "slicer.cu", "bits.cu", "il2p.cu", "loops.cu", "link.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-	"-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--fmad=true", "-Xptxas", "-v"]
+	"-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-Xcompiler", "-pthread", "--fmad=true", "-Xptxas", "-v"]
 
 
 def needs_build():
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
 			sys.stderr.write(r.stdout + r.stderr)
 			raise RuntimeError(f"nvcc failed on {src}")
 		objs.append(obj)
-	cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+	cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-pthread"]
 	r = subprocess.run(cmd, capture_output=True, text=True)
 	if r.returncode != 0:
 		sys.stderr.write(r.stdout + r.stderr)

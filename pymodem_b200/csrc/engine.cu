@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pm_common.cuh"
@@ -49,7 +50,7 @@ cudaError_t pm_link_wait_states(LinkGeom, unsigned char *, int, unsigned int, co
 cudaError_t pm_link_set_flag(unsigned int *, unsigned int, cudaStream_t);
 cudaError_t pm_link_wait_flag(const unsigned int *, unsigned int, int *, cudaStream_t);
 cudaError_t pm_link_push_records(LinkGeom, LinkPeers, int, unsigned int, const PacketRecDev *, const uint8_t *,
-	const PacketTotals *, int *, cudaStream_t);
+	const PacketTotals *, const ChainCounters *, int *, cudaStream_t);
 cudaError_t pm_link_merge(LinkGeom, unsigned char *, int, unsigned int, unsigned int *, unsigned long long *,
 	unsigned long long *, PacketTotals *, PacketRecDev *, unsigned long long, uint8_t *, unsigned long long, int *,
 	cudaStream_t);
@@ -144,7 +145,9 @@ struct pm_engine {
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	int opt_warm_exact_words = 512; // float64 tail of a warm-up (16384 samples); the part before it runs in FP32 (0: all float64)
-	double opt_guard_eps = 3.814697265625e-06;  // 2^-18: 4x the largest guard that still changed a sign in 1.4e9 samples (tools/guard_sweep.py)
+	double opt_guard_eps = 3.814697265625e-06;  // 2^-18 of the in-band magnitude scale: 4x the largest error seen (tools/guard_sweep.py, guard_bound.py)
+	double opt_guard_abs = 0.25;                // c_abs of the raw-input term: 4x the largest error seen in units of
+	                                            // 2^-24 max|audio| sum|h_bpf| N_corr sum|h_lpf| (1 + g) (tools/guard_bound.py)
 	int opt_tile = 0;             // 0 = auto
 	int opt_keep_soft = 0;
 	int opt_fuse_pairs = 1;       // mark and space sliding windows of a pair in one pass (0: tone by tone)
@@ -218,6 +221,9 @@ struct pm_engine {
 	int *h_link_status = nullptr;         // pinned
 	PacketTotals *h_mtotals = nullptr;    // pinned
 	int il2p_cand_cap = 0;
+	double rec_scale = 1.0, il2p_cand_scale = 1.0;   // grown (and the run repeated) when packet buffers / IL2P candidate lists overflow
+	int grow_hint = 0;                    // what the last PM_ERR_CAPACITY asked for: 1 packet buffers, 2 IL2P candidates
+	bool skip_lfsr = false;               // pm_engine_decode_stream: the stream loaded is already descrambled
 	bool has_il2p = false, il2p_tables = false;
 	unsigned int *h_counters = nullptr;   // pinned
 	PacketTotals *h_totals = nullptr;     // pinned
@@ -233,6 +239,13 @@ struct pm_engine {
 	pm_stats stats;
 	cudaEvent_t ev[8] = {};
 	std::vector<cudaEvent_t> ev_chunks;
+	// pageable input: chunks are staged through a ring of pinned buffers (memcpy on host threads, then async H2D)
+	static const int RING = 3;
+	int16_t *h_ring[RING] = {nullptr, nullptr, nullptr};
+	size_t ring_samples = 0;
+	cudaEvent_t ev_ring[RING] = {nullptr, nullptr, nullptr};
+	int opt_copy_threads = 4;
+	int64_t staged_bytes = 0;             // bytes of the last run that went through the ring (0: the caller's buffer was pinned)
 	bool have_run = false;
 };
 
@@ -351,7 +364,7 @@ static int build_groups(pm_engine *e)
 	}
 	for (int c = 0; c < nc; c++) {
 		HostChain &hc = e->chains[c];
-		if (hc.group >= 0 || hc.p64) continue;
+		if (hc.group >= 0 || hc.p64 || hc.d.modem_kind == PM_MODEM_NONE) continue;
 		FrontGroup g;
 		g.kind = hc.d.modem_kind;
 		if (g.kind != PM_MODEM_AFSK && g.kind != PM_MODEM_FSK)
@@ -454,6 +467,19 @@ static int build_groups(pm_engine *e)
 			p.pair_first[p.n_pair] = ci;
 			p.n_chain = ci;
 			p.guard_eps = (float)e->opt_guard_eps;
+			{
+				// raw-input term of the guard (front.cu epilogue): the band-pass accumulates at the magnitude of the raw
+				// samples, so its rounding error -- carried through the window sum (N_corr terms) and the low-pass
+				// (sum|h_lpf|) into y = L_mark - g L_space -- scales with max|audio|, whatever the in-band level is
+				double hb = 0, hl = 0;
+				for (double v : hc.bpf) hb += std::fabs(v);
+				for (double v : hc.lpf) hl += std::fabs(v);
+				for (int i = 0; i < p.n_chain; i++) {
+					const HostChain &o = e->chains[p.chain_gid[i]];
+					p.chain_guard_abs[i] = (float)(e->opt_guard_abs * std::ldexp(1.0, -24) * hb * (double)o.mark_i.size() * hl *
+						(1.0 + std::fabs(o.d.space_gain)));
+				}
+			}
 			// pairs whose two tones are sliding-window tones of one length, each used by this pair only, are computed
 			// together (front.cu SlidePair)
 			for (int pi = 0; pi < p.n_pair; pi++) {
@@ -522,7 +548,9 @@ static int build_groups(pm_engine *e)
 				p.chain_gid[i] = g.chains[i];
 				p.chain_neg[i] = e->chains[g.chains[i]].d.invert_soft;
 			}
-			p.guard_eps = (float)(e->opt_guard_eps * abs_sum);
+			// |FP32 FIR - exact| <= (n + 1) 2^-24 sum|h| max|x| (one rounding per tap plus the tap's own conversion): the
+			// guard is never narrower than that worst case, so the single-FIR front end's signs are exact by bound
+			p.guard_eps = (float)(std::max(e->opt_guard_eps, 1.02 * (hc.bpf.size() + 2) * std::ldexp(1.0, -24)) * abs_sum);
 			int tile = e->opt_tile > 0 ? round_up(e->opt_tile, 32) : 4096;
 			p.tile = tile;
 			p.U_y = tile / 16;
@@ -602,6 +630,10 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->h_recs.release(); e->h_arena.release();
 	if (e->h_counters) cudaFreeHost(e->h_counters);
 	if (e->h_totals) cudaFreeHost(e->h_totals);
+	for (int i = 0; i < pm_engine::RING; i++) {
+		if (e->h_ring[i]) cudaFreeHost(e->h_ring[i]);
+		if (e->ev_ring[i]) cudaEventDestroy(e->ev_ring[i]);
+	}
 	cudaStreamDestroy(e->st);
 	cudaStreamDestroy(e->st_copy);
 	for (int i = 0; i < 2; i++) {
@@ -667,6 +699,8 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 			}
 			hc.loop.nco_wavetable = nullptr; hc.loop.pd_table = nullptr; hc.loop.hilbert = nullptr;
 			hc.p64 = true;
+		} else if (d.modem_kind == PM_MODEM_NONE) {
+			hc.trim = 0;                     // per-stage calls only (pm_engine_slice_soft / unscramble_stream / decode_stream)
 		} else {
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, d.modem_kind);
 		}
@@ -674,7 +708,7 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: slicer kind %d not supported by this build", c, d.slicer_kind);
 		// the reference's duck typing: MPSKModem.demod returns IQData (psk.py:748), which only
 		// QuadratureSlicer.slice can iterate (slicer.py:198); every other modem returns an ndarray
-		if ((d.slicer_kind == PM_SLICER_QUADRATURE) != (d.modem_kind == PM_MODEM_MPSK))
+		if (d.modem_kind != PM_MODEM_NONE && (d.slicer_kind == PM_SLICER_QUADRATURE) != (d.modem_kind == PM_MODEM_MPSK))
 			return fail(e, PM_ERR_ARG, "chain %d: the quadrature slicer goes with the mpsk modem (and only with it)", c);
 		if (d.slicer_kind == PM_SLICER_QUADRATURE &&
 		    (d.bits_per_symbol < 1 || d.bits_per_symbol > 2 || d.state_mask > 15 || 8 % d.bits_per_symbol))
@@ -804,6 +838,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "verify_passes") e->opt_verify_passes = std::max(0, (int)value);
 	else if (k == "warmup_exact_len") e->opt_warm_exact_words = std::max(0, (int)((value + 31) / 32));
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
+	else if (k == "guard_abs") { e->opt_guard_abs = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
 	else if (k == "keep_soft") e->opt_keep_soft = value != 0;
 	else if (k == "slicer_fast") e->opt_slicer_fast = value != 0;
@@ -822,6 +857,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 		}
 	}
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
+	else if (k == "copy_threads") e->opt_copy_threads = std::max(1, std::min(16, (int)value));
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
 	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);
 	if (replan && !e->chains.empty()) return build_groups(e);
@@ -832,7 +868,10 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 // One run = begin (front end + slicer) -> [handoff]* -> gather -> finish.
 // An unsharded run is the same pipeline with "everything is mine".
 // ---------------------------------------------------------------------------
-static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, bool sharded)
+// only_chain >= 0: a per-stage call (pm_engine_slice_soft / unscramble_stream / decode_stream) works on one chain, the
+// others see an empty recording; min_bits: stream bits the bit-level buffers have to hold whatever n says
+static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, bool sharded, int only_chain = -1,
+                       long long min_bits = 0)
 {
 	const int nc = (int)e->chains.size();
 	if (nc == 0) return fail(e, PM_ERR_STATE, "no chains loaded");
@@ -870,9 +909,9 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		if (sharded && (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK)))
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: chains with a carrier loop (AGC takes max() of the whole "
 				"recording, agc.py:67) cannot be sharded on the sample axis", c);
-		const long long nout = std::max<long long>(0, n - hc.trim);
+		const long long nout = (only_chain >= 0 && c != only_chain) ? 0 : std::max<long long>(0, n - hc.trim);
 		max_nout = std::max(max_nout, nout);
-		const int tile = hc.p64 ? P64_TILE : e->groups[hc.group].tile;
+		const int tile = (hc.p64 || hc.group < 0) ? P64_TILE : e->groups[hc.group].tile;
 		const long long tiles = (nout + tile - 1) / tile;
 		max_words = std::max(max_words, tiles * tile / 32);
 		SlicerChain &s = sl[c];
@@ -919,10 +958,13 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		b.il2p_min_dist = hc.d.il2p_min_dist; b.il2p_sync_tol = hc.d.il2p_sync_tol;
 		e->h_init[c].clock = 0.0; e->h_init[c].last = 1; e->h_init[c].last_q = 1;    // slicer.py:50,55
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(s.thr));
-		const long long mb = (nout / min_gap + 8) * b.bps + 64 + plan.tail_bits;
+		const long long mb = std::max((nout / min_gap + 8) * b.bps + 64 + plan.tail_bits, min_bits);
 		max_bits = std::max(max_bits, mb);
-		rec_cap += mb / 152 + 4;
-		arena_cap += mb / 8 + 64;
+		// shortest frame on the air: AX.25 18 bytes + a flag = 152 stream bits; IL2P a header-only frame without trailing
+		// CRC = 24 sync bits + 15 bytes = 144 (back to back, il2p.py:367-409); buffers grow and the run repeats when a
+		// recording still overflows them (rec_scale)
+		rec_cap += (long long)((mb / (hc.d.codec_kind == PM_CODEC_IL2P ? 144 : 152) + 4) * e->rec_scale);
+		arena_cap += (long long)((mb / 8 + 64) * e->rec_scale);
 	}
 	max_words = round_up((int)max_words, 4) + 4;
 	e->sign_stride = max_words;
@@ -976,7 +1018,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	CK(e->d_arena.ensure((size_t)arena_cap));
 	CK(e->d_guard_entries.ensure(e->guard_cap));
 	if (e->has_il2p) {
-		e->il2p_cand_cap = (int)std::min<long long>(e->flag_stride, max_bits / 256 + 64);
+		e->il2p_cand_cap = (int)std::min<long long>(e->flag_stride, (long long)((max_bits / 256 + 64) * e->il2p_cand_scale));
 		CK(e->d_il2p_slots.ensure((size_t)nc * (e->il2p_cand_cap + 1) * IL2P_SLOT));
 		CK(e->d_il2p_res.ensure((size_t)nc * e->il2p_cand_cap));
 		CK(e->d_il2p_hand.ensure((size_t)2 * nc));
@@ -1140,10 +1182,39 @@ static int fetch_shard_states(pm_engine *e)
 	return PM_OK;
 }
 
+// true when the driver can DMA straight out of [p, ...): cudaHostAlloc'ed, cudaHostRegister'ed or managed memory
+static bool host_pointer_is_pinned(const void *p)
+{
+	cudaPointerAttributes pa;
+	if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged;
+}
+
+// memcpy on a few host threads: one thread copies ~10 GB/s, the PCIe link takes 50
+static void parallel_copy(void *dst, const void *src, size_t bytes, int threads)
+{
+	if (threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	const size_t per = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+	for (int t = 1; t < threads; t++) {
+		const size_t off = per * t;
+		if (off >= bytes) break;
+		th.emplace_back([=]() { memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off)); });
+	}
+	memcpy(dst, src, std::min(per, bytes));
+	for (auto &t : th) t.join();
+}
+
 static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
                       bool sharded)
 {
 	const int nc = (int)e->chains.size();
+	for (int c = 0; c < nc; c++)
+		if (e->chains[c].d.modem_kind == PM_MODEM_NONE)
+			return fail(e, PM_ERR_STATE, "chain %d has no modem: it only serves the per-stage calls (slice_soft / unscramble_stream / decode_stream)", c);
 	memset(&e->stats, 0, sizeof(e->stats));
 	int rc = prepare_run(e, n, plan, sharded);
 	if (rc != PM_OK) return rc;
@@ -1174,12 +1245,36 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 		CK(cudaEventRecord(e->ev[6], e->st));
 		CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
 		for (int q = 0; q < 2; q++) CK(cudaStreamWaitEvent(e->st_front[q], e->ev[6], 0));
+		// pageable caller memory: the driver would stage it through its own small bounce buffers, synchronously.  Stage
+		// it ourselves through a ring of pinned buffers: the memcpy of chunk i+1 (host threads) overlaps the DMA of chunk i
+		const bool staged = !host_pointer_is_pinned(audio);
+		e->staged_bytes = staged ? (int64_t)n * 2 : 0;
+		if (staged) {
+			const size_t want = (size_t)std::min<long long>(e->opt_h2d_chunk, n);
+			if (want > e->ring_samples) {
+				for (int i = 0; i < pm_engine::RING; i++) {
+					if (e->h_ring[i]) cudaFreeHost(e->h_ring[i]);
+					e->h_ring[i] = nullptr;
+					CK(cudaHostAlloc((void **)&e->h_ring[i], want * sizeof(int16_t), cudaHostAllocDefault));
+					if (!e->ev_ring[i]) CK(cudaEventCreateWithFlags(&e->ev_ring[i], cudaEventDisableTiming));
+				}
+				e->ring_samples = want;
+			}
+		}
 		long long done = 0;
 		for (int i = 0; i < n_chunks; i++) {
 			const long long len = cuts[i] - done;
 			cudaStream_t fs = e->st_front[i & 1];
-			CK(cudaMemcpyAsync(e->d_audio.p + done, audio + done, (size_t)len * sizeof(int16_t),
+			const int16_t *src = audio + done;
+			if (staged) {
+				const int slot = i % pm_engine::RING;
+				if (i >= pm_engine::RING) CK(cudaEventSynchronize(e->ev_ring[slot]));      // its previous DMA has read the buffer
+				parallel_copy(e->h_ring[slot], audio + done, (size_t)len * sizeof(int16_t), e->opt_copy_threads);
+				src = e->h_ring[slot];
+			}
+			CK(cudaMemcpyAsync(e->d_audio.p + done, src, (size_t)len * sizeof(int16_t),
 				cudaMemcpyHostToDevice, e->st_copy));
+			if (staged) CK(cudaEventRecord(e->ev_ring[i % pm_engine::RING], e->st_copy));
 			CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
 			CK(cudaStreamWaitEvent(fs, e->ev_chunks[i], 0));
 			rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1, fs);
@@ -1357,9 +1452,11 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "tail inject launch failed: %s", cudaGetErrorString(ce));
 		e->stats.kernel_launches++;
 	}
-	ce = pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, e->st);
-	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "lfsr launch failed: %s", cudaGetErrorString(ce));
-	e->stats.kernel_launches++;
+	if (!e->skip_lfsr) {
+		ce = pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "lfsr launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+	}
 	ce = pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p,
 		e->d_blk_base.p, e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride,
 		e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->sharded ? 0 : 1,
@@ -1398,14 +1495,20 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 		if (e->h_cc[c].tail_short)
 			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
 				c, plan.tail_bits);
-		if (e->h_cc[c].seq_needed == 2)
+		if (e->h_cc[c].seq_needed == 2) {
+			e->grow_hint = 2;
 			return fail(e, PM_ERR_CAPACITY, "chain %d: IL2P sync candidates overflowed the candidate list", c);
+		}
+		// a gap long enough to overflow max_packet_length (ax25.py:46-51) needs the sequential replay from a known
+		// state: the shards recover through pm_engine_shard_export + pm_engine_decode_stream (sharded.py)
 		if (e->sharded && e->h_cc[c].seq_needed)
-			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (run unsharded)", c);
+			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (recover from the gathered bitstream)", c);
 	}
 	const unsigned long long np = e->h_totals->n_packets, nb = e->h_totals->n_bytes;
-	if (np > e->d_recs.n || nb > e->d_arena.n)
+	if (np > e->d_recs.n || nb > e->d_arena.n) {
+		e->grow_hint = 1;
 		return fail(e, PM_ERR_CAPACITY, "packet buffers too small (%llu records, %llu bytes)", np, nb);
+	}
 	CK(e->h_recs.resize(np));
 	CK(e->h_arena.resize(nb));
 	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
@@ -1429,16 +1532,30 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	return PM_OK;
 }
 
+// a finish that ran out of room says what to grow (grow_hint); true when the run should be repeated
+static bool grow_after_capacity(pm_engine *e, int rc)
+{
+	if (rc != PM_ERR_CAPACITY || !e->grow_hint) return false;
+	if (e->grow_hint == 1) e->rec_scale *= 2.0;
+	else e->il2p_cand_scale *= 4.0;
+	e->grow_hint = 0;
+	return e->rec_scale <= 64.0 && e->il2p_cand_scale <= 4096.0;
+}
+
 static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host)
 {
 	pm_shard_plan plan;
 	memset(&plan, 0, sizeof(plan));
 	plan.first = plan.last = 1;
-	int rc = shard_begin_impl(e, audio, n, on_host, plan, false);
-	if (rc != PM_OK) return rc;
-	rc = shard_gather_impl(e, nullptr, nullptr);
-	if (rc != PM_OK) return rc;
-	return shard_finish_impl(e, nullptr);
+	for (;;) {
+		if (e) e->grow_hint = 0;
+		int rc = shard_begin_impl(e, audio, n, on_host, plan, false);
+		if (rc != PM_OK) return rc;
+		rc = shard_gather_impl(e, nullptr, nullptr);
+		if (rc != PM_OK) return rc;
+		rc = shard_finish_impl(e, nullptr);
+		if (!grow_after_capacity(e, rc)) return rc;      // packet buffers / IL2P candidate list too small: grow, run again
+	}
 }
 
 extern "C" int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples)
@@ -1512,6 +1629,178 @@ extern "C" int pm_engine_shard_finish(pm_engine *e, const uint32_t *tail_in)
 	return shard_finish_impl(e, tail_in);
 }
 
+
+// ---------------------------------------------------------------------------
+// Per-stage entry points: the reference's duck-typed blocks one at a time (chain_execute.py:32-47) --
+// slicer.slice(soft), stream.stream_unscramble_8bit(AddressedData[]), codec.decode(AddressedData[]) -- on the same
+// kernels as the whole-chain run.  They work on ONE chain of the loaded table; the other chains see nothing.
+// ---------------------------------------------------------------------------
+extern "C" cudaError_t pm_launch_soft_signs(const double *, long long, uint32_t *, cudaStream_t);
+
+static int stage_chain_ok(pm_engine *e, int32_t chain)
+{
+	if (!e) return PM_ERR_ARG;
+	if (chain < 0 || chain >= (int)e->chains.size()) return fail(e, PM_ERR_ARG, "chain %d out of range", chain);
+	cudaSetDevice(e->device);
+	e->phase = 0;
+	e->have_run = false;
+	memset(&e->stats, 0, sizeof(e->stats));
+	return PM_OK;
+}
+
+static int fetch_counters(pm_engine *e)
+{
+	const int nc = (int)e->chains.size();
+	e->h_cc.resize(nc);
+	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
+	CK(cudaStreamSynchronize(e->st));
+	return PM_OK;
+}
+
+extern "C" int pm_engine_slice_soft(pm_engine *e, int32_t chain, const double *soft_i, const double *soft_q, int64_t n)
+{
+	int rc = stage_chain_ok(e, chain);
+	if (rc != PM_OK) return rc;
+	HostChain &hc = e->chains[chain];
+	const bool quad = hc.d.slicer_kind == PM_SLICER_QUADRATURE;
+	if (n < 0 || (n > 0 && !soft_i) || (quad && n > 0 && !soft_q))
+		return fail(e, PM_ERR_ARG, "slice_soft: soft values missing (the quadrature slicer needs I and Q, slicer.py:198-199)");
+	pm_shard_plan plan;
+	memset(&plan, 0, sizeof(plan));
+	plan.first = plan.last = 1;
+	rc = prepare_run(e, (long long)n + hc.trim, plan, false, chain);     // this chain's valid soft samples = n
+	if (rc != PM_OK) return rc;
+	const int nc = (int)e->chains.size();
+	DevBuf<double> d_x;
+	CK(d_x.ensure((size_t)std::max<int64_t>(n, 1)));
+	for (int comp = 0; comp < (quad ? 2 : 1); comp++) {
+		const int row = comp ? hc.sign_q_row : chain;
+		if (n) CK(cudaMemcpyAsync(d_x.p, comp ? soft_q : soft_i, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->st));
+		cudaError_t ce = pm_launch_soft_signs(d_x.p, n, e->d_sign.p + (size_t)row * e->sign_stride, e->st);
+		if (ce != cudaSuccess) { d_x.release(); return fail(e, PM_ERR_CUDA, "sign launch failed: %s", cudaGetErrorString(ce)); }
+		CK(cudaStreamSynchronize(e->st));       // the caller's buffer (pageable) has been read
+	}
+	d_x.release();
+	e->E_cur = e->d_E0.p; e->E_alt = e->d_E1.p;
+	cudaError_t ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+		e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches += 2;
+	rc = slicer_converge(e);
+	if (rc != PM_OK) return rc;
+	e->phase = 1;
+	rc = shard_gather_impl(e, nullptr, nullptr);
+	if (rc != PM_OK) return rc;
+	rc = fetch_counters(e);
+	if (rc != PM_OK) return rc;
+	e->phase = 0;
+	e->have_run = true;
+	return PM_OK;
+}
+
+// AddressedData list of one chain -> the device's packed stream (first bit of a byte = its MSB, bits.cu) + byte addresses
+static int load_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const int64_t *addresses, int64_t n, bool descrambled)
+{
+	int rc = stage_chain_ok(e, chain);
+	if (rc != PM_OK) return rc;
+	if (n < 0 || (n > 0 && (!bytes || !addresses))) return fail(e, PM_ERR_ARG, "stream: bytes/addresses missing");
+	if (n >= (1ll << 28)) return fail(e, PM_ERR_ARG, "stream too long");
+	pm_shard_plan plan;
+	memset(&plan, 0, sizeof(plan));
+	plan.first = plan.last = 1;
+	rc = prepare_run(e, (long long)e->chains[chain].trim + 64, plan, false, chain, 8 * (long long)n + 64);
+	if (rc != PM_OK) return rc;
+	const int nc = (int)e->chains.size();
+	std::vector<uint32_t> words((size_t)(n + 3) / 4 + 1, 0u), addr((size_t)n + 1, 0u);
+	for (int64_t b = 0; b < n; b++) {
+		uint32_t v = bytes[b];
+		v = ((v & 0xF0u) >> 4) | ((v & 0x0Fu) << 4);
+		v = ((v & 0xCCu) >> 2) | ((v & 0x33u) << 2);
+		v = ((v & 0xAAu) >> 1) | ((v & 0x55u) << 1);
+		words[(size_t)b >> 2] |= v << ((b & 3) * 8);
+		if (addresses[b] < 0 || addresses[b] > 0xFFFFFFFFll) return fail(e, PM_ERR_ARG, "stream: address %lld out of range", (long long)addresses[b]);
+		addr[(size_t)b] = (uint32_t)addresses[b];
+	}
+	uint32_t *row = (descrambled ? e->d_bits_lfsr.p : e->d_bits_raw.p) + (size_t)chain * e->bits_stride;
+	CK(cudaMemsetAsync(row, 0, (size_t)e->bits_stride * sizeof(uint32_t), e->st));
+	CK(cudaMemcpyAsync(row, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemcpyAsync(e->d_byte_addr.p + (size_t)chain * e->addr_stride, addr.data(), (size_t)n * sizeof(uint32_t) + 4,
+		cudaMemcpyHostToDevice, e->st));
+	std::vector<ChainCounters> cc(nc);
+	std::vector<ShardBits> sb(nc);
+	memset(cc.data(), 0, nc * sizeof(ChainCounters));
+	memset(sb.data(), 0, nc * sizeof(ShardBits));
+	for (int c = 0; c < nc; c++) { sb[c].first = 1; sb[c].own_hi = 0x7fffffffffffffffll; }
+	cc[chain].nbits = 8 * (long long)n;
+	cc[chain].nbytes = n;
+	CK(cudaMemcpyAsync(e->d_cc.p, cc.data(), nc * sizeof(ChainCounters), cudaMemcpyHostToDevice, e->st));
+	CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
+	CK(cudaEventRecord(e->ev[0], e->st));
+	for (int i = 1; i <= 3; i++) CK(cudaEventRecord(e->ev[i], e->st));
+	CK(cudaStreamSynchronize(e->st));           // the staging vectors go out of scope
+	e->h_A0.assign(nc, 0);
+	e->h_valid_from.assign(nc, 0);
+	e->phase = 2;
+	return PM_OK;
+}
+
+extern "C" int pm_engine_unscramble_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const int64_t *addresses, int64_t n)
+{
+	int rc = load_stream(e, chain, bytes, addresses, n, false);
+	if (rc != PM_OK) return rc;
+	const int nc = (int)e->chains.size();
+	cudaError_t ce = pm_launch_lfsr(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_raw.p, e->d_bits_lfsr.p, e->bits_stride, e->st);
+	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "lfsr launch failed: %s", cudaGetErrorString(ce));
+	e->stats.kernel_launches++;
+	rc = fetch_counters(e);
+	if (rc != PM_OK) return rc;
+	e->phase = 0;
+	e->have_run = true;
+	e->h_recs.resize(0);
+	e->h_arena.resize(0);
+	return PM_OK;
+}
+
+extern "C" int pm_engine_decode_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const int64_t *addresses, int64_t n)
+{
+	for (;;) {
+		if (e) e->grow_hint = 0;
+		int rc = load_stream(e, chain, bytes, addresses, n, true);
+		if (rc != PM_OK) return rc;
+		e->skip_lfsr = true;
+		rc = shard_finish_impl(e, nullptr);
+		e->skip_lfsr = false;
+		if (!grow_after_capacity(e, rc)) return rc;
+	}
+}
+
+// What a shard holds of one chain's sliced stream after shard_gather (also after a finish that failed): the local
+// packed bits and byte addresses, for the recovery path of sharded.py.  info4 = {local stream bits, local position of
+// the first own bit, own bits, sample_base}.  With bits == NULL only info4 is filled.
+extern "C" int pm_engine_shard_export(pm_engine *e, int32_t chain, uint32_t *bits, int64_t cap_words, uint32_t *byte_addr,
+                                      int64_t cap_bytes, int64_t *info4)
+{
+	if (!e || !info4) return PM_ERR_ARG;
+	if (chain < 0 || chain >= (int)e->chains.size()) return fail(e, PM_ERR_ARG, "chain %d out of range", chain);
+	if (e->phase != 2 && !(e->have_run && e->sharded)) return fail(e, PM_ERR_STATE, "shard_export: call shard_gather first");
+	cudaSetDevice(e->device);
+	ChainCounters cc;
+	ShardBits sb;
+	CK(cudaStreamSynchronize(e->st));
+	CK(cudaMemcpy(&cc, e->d_cc.p + chain, sizeof(cc), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(&sb, e->d_shardbits.p + chain, sizeof(sb), cudaMemcpyDeviceToHost));
+	const long long nbits = cc.nbits;
+	info4[0] = nbits;
+	info4[1] = sb.bit_off;
+	info4[2] = (sb.own_hi == 0x7fffffffffffffffll) ? nbits - sb.bit_off : sb.own_hi - sb.bit_off;
+	info4[3] = e->sample_base;
+	if (!bits && !byte_addr) return PM_OK;
+	const long long nw = (nbits + 31) / 32, nby = (nbits + 7) / 8;
+	if (!bits || !byte_addr || cap_words < nw || cap_bytes < nby) return fail(e, PM_ERR_CAPACITY, "shard_export: buffers too small");
+	if (nw) CK(cudaMemcpy(bits, e->d_bits_raw.p + (size_t)chain * e->bits_stride, (size_t)nw * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if (nby) CK(cudaMemcpy(byte_addr, e->d_byte_addr.p + (size_t)chain * e->addr_stride, (size_t)nby * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return PM_OK;
+}
 
 // ---------------------------------------------------------------------------
 // Shard link: the hand-off done on the devices over peer memory (csrc/link.cu)
@@ -1653,10 +1942,11 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p, e->d_recs.n,
 		e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base, st));
 	CK(cudaEventRecord(e->ev[4], st));
-	CKL(pm_link_push_records(G, e->lp, parity, epoch, (const PacketRecDev *)e->d_recs.p, e->d_arena.p, e->d_totals.p, status, st));
+	CKL(pm_link_push_records(G, e->lp, parity, epoch, (const PacketRecDev *)e->d_recs.p, e->d_arena.p, e->d_totals.p, e->d_cc.p,
+		status, st));
 	CKL(pm_link_merge(G, own, parity, epoch, e->d_link_lb.p, e->d_link_obase.p, e->d_link_obase.p + (size_t)G.world * (nc + 1),
 		e->d_mtotals.p, (PacketRecDev *)e->d_mrecs.p, e->d_mrecs.n, e->d_marena.p, e->d_marena.n, status, st));
-	e->stats.kernel_launches += 12;
+	e->stats.kernel_launches += 13;
 	CK(cudaMemcpyAsync(e->h_link_status, status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(e->h_mtotals, e->d_mtotals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, st));
 	// (nothing here may block the host: a copy into pageable memory would wait for the stream, i.e. for the peers)
@@ -1686,6 +1976,14 @@ extern "C" int pm_engine_run_linked_end(pm_engine *e, int32_t *verified)
 		e->phase = 1;
 		return PM_OK;
 	}
+	if (e->h_link_status[3] != 0) {
+		// some rank could not finish its decode from what it holds (a frame longer than the hand-off tail, or the
+		// max_packet_length overflow of ax25.py:46-51): every rank was told with the records, all of them export
+		// their bits (pm_engine_shard_export) and decode the gathered stream (pm_engine_decode_stream)
+		*verified = 2;
+		e->phase = 2;
+		return PM_OK;
+	}
 	const unsigned long long np = e->h_mtotals->n_packets, nb = e->h_mtotals->n_bytes;
 	if (np > e->d_mrecs.n || nb > e->d_marena.n)
 		return fail(e, PM_ERR_CAPACITY, "merged packet buffers too small (%llu records, %llu bytes)", np, nb);
@@ -1697,13 +1995,6 @@ extern "C" int pm_engine_run_linked_end(pm_engine *e, int32_t *verified)
 	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_marena.p, nb, cudaMemcpyDeviceToHost, e->st));
 	CK(cudaEventRecord(e->ev[5], e->st));
 	CK(cudaStreamSynchronize(e->st));
-	for (int c = 0; c < nc; c++) {
-		if (e->h_cc[c].tail_short)
-			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",
-				c, e->plan.tail_bits);
-		if (e->h_cc[c].seq_needed)
-			return fail(e, PM_ERR_STATE, "chain %d: needs the sequential AX.25 replay (run unsharded)", c);
-	}
 	e->stats.d2h_bytes = (int64_t)(np * sizeof(pm_packet_rec) + nb + sizeof(PacketTotals) + nc * sizeof(ChainCounters) + 16);
 	e->stats.n_packets = (int64_t)np;
 	e->stats.n_stream_bits = 0;
@@ -1771,6 +2062,24 @@ extern "C" int pm_engine_get_soft(const pm_engine *ce, int32_t chain, int32_t co
 	else if (component != 0) return fail(e, PM_ERR_ARG, "component %d not available", component);
 	cudaSetDevice(e->device);
 	CK(cudaMemcpy(out, e->d_soft.p + (size_t)row * e->soft_stride, (size_t)len * sizeof(float), cudaMemcpyDeviceToHost));
+	return PM_OK;
+}
+
+// packed sign words of a chain's soft values as the slicer reads them (after the float64 fix-up)
+extern "C" int pm_engine_get_signs(const pm_engine *ce, int32_t chain, int32_t component, uint32_t *out, int64_t cap_words)
+{
+	pm_engine *e = const_cast<pm_engine *>(ce);
+	if (!e || !e->have_run) return PM_ERR_STATE;
+	const int64_t len = pm_engine_soft_len(e, chain);
+	if (len < 0 || !out) return PM_ERR_ARG;
+	const int64_t words = (len + 31) / 32;
+	if (cap_words < words) return PM_ERR_CAPACITY;
+	int row = chain;
+	if (component == 1 && e->chains[chain].d.slicer_kind == PM_SLICER_QUADRATURE) row = e->chains[chain].sign_q_row;
+	else if (component != 0) return fail(e, PM_ERR_ARG, "component %d not available", component);
+	cudaSetDevice(e->device);
+	if (words) CK(cudaMemcpy(out, e->d_sign.p + (size_t)row * e->sign_stride, (size_t)words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if (len & 31) out[words - 1] &= (1u << (len & 31)) - 1u;      // bits past the last soft sample are not defined
 	return PM_OK;
 }
 
@@ -1875,6 +2184,28 @@ extern "C" int pm_measure_fp32_peak(int device, double *tflops)
 	cudaEventDestroy(a); cudaEventDestroy(b);
 	cudaFree(d);
 	*tflops = best;
+	return PM_OK;
+}
+
+// Pin a caller-owned buffer in place (page-locks it: ~20 ms per 100 MB, once), so that pm_engine_run can DMA straight
+// out of it on every later call.  Read-only mappings (a memory-mapped WAV) are registered read-only.
+extern "C" int pm_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return PM_ERR_ARG;
+	if (host_pointer_is_pinned(p)) return PM_OK;
+	cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+	if (ce != cudaSuccess) {
+		cudaGetLastError();
+		ce = cudaHostRegister(p, bytes, cudaHostRegisterReadOnly);
+	}
+	if (ce != cudaSuccess) { cudaGetLastError(); return PM_ERR_CUDA; }
+	return PM_OK;
+}
+
+extern "C" int pm_host_unregister(void *p)
+{
+	if (!p) return PM_ERR_ARG;
+	if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return PM_ERR_CUDA; }
 	return PM_OK;
 }
 

@@ -343,9 +343,11 @@ __device__ __forceinline__ float fast_sqrt(float x)
 
 // Stage a_len int16 samples starting at n0 into shared memory as floats
 // (zero beyond the end of the recording).
-__device__ __forceinline__ void stage_audio(float *s_a, const int16_t *__restrict__ audio,
-                                            long long n0, long long n_audio, int a_len)
+// Returns the largest |sample| this thread staged (the raw-input term of the sign guard, see afsk_front_kernel).
+__device__ __forceinline__ float stage_audio(float *s_a, const int16_t *__restrict__ audio,
+                                             long long n0, long long n_audio, int a_len)
 {
+	float amax = 0.f;
 	for (int i = threadIdx.x * 8; i < a_len; i += blockDim.x * 8) {
 		long long g = n0 + i;
 		float f[8];
@@ -363,7 +365,10 @@ __device__ __forceinline__ void stage_audio(float *s_a, const int16_t *__restric
 		}
 		sts4(s_a, i, f[0], f[1], f[2], f[3]);
 		sts4(s_a, i + 4, f[4], f[5], f[6], f[7]);
+#pragma unroll
+		for (int q = 0; q < 8; q++) amax = fmaxf(amax, fabsf(f[q]));
 	}
+	return amax;
 }
 
 template <bool WRITE_SOFT>
@@ -389,7 +394,14 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 		}
 	};
 
-	stage_audio(s_a, audio, n0, n_audio, P.a_len);
+	// Largest raw |sample| of the tile: the band-pass rounds at the magnitude of its RAW input (DC, hum and anything else
+	// out of band included), so the sign guard carries a term proportional to it (epilogue below)
+	__shared__ float s_wmax[PM_FRONT_THREADS / 32];
+	{
+		float amax = stage_audio(s_a, audio, n0, n_audio, P.a_len);
+		amax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));      // non-negative floats order like their bit patterns
+		if ((tid & 31) == 0) s_wmax[tid >> 5] = amax;
+	}
 	__syncthreads();
 	stage_done(0);
 
@@ -457,6 +469,9 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	// sign packing (afsk.py:162-166 -> slicer.py:85,99)
 	const int lane = tid & 31;
 	const int total = P.n_pair * P.U_l;
+	float tile_amax = s_wmax[0];
+#pragma unroll
+	for (int q = 1; q < PM_FRONT_THREADS / 32; q++) tile_amax = fmaxf(tile_amax, s_wmax[q]);
 	for (int ub = tid - lane; ub < total; ub += PM_FRONT_THREADS) {
 		const int u = ub + lane;
 		const bool active = u < total;
@@ -480,7 +495,11 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 				c = P.pair_first[p] + ci;
 				const float g = P.chain_gain[c];
 				const float neg_eps = -P.guard_eps;
-				// five instructions per sample: y, the magnitude scale, |y| - eps * scale, and one funnel shift each to
+				// guard: |y| < eps * (|L_mark| + g |L_space|) + abs_c, where abs_c = c_abs * 2^-24 * max|audio of the tile| *
+				// sum|h_bpf| * N_corr * sum|h_lpf| * (1 + g) bounds what the band-pass's rounding at raw-input magnitude can
+				// leave in y (host: build_groups; calibration: tools/guard_bound.py, tests/test_gpu_guard.py)
+				const float abs_c = P.chain_guard_abs[c] * tile_amax;
+				// six instructions per sample: y, the magnitude scale, |y| - abs_c - eps * scale, and one funnel shift each to
 				// collect the sign bits of y and of the guard test (y is never -0: the accumulators start at +0)
 				unsigned int neg = 0, near = 0;
 #pragma unroll
@@ -488,7 +507,7 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 					const float lm = fp.lo(r), ls = fp.hi(r);
 					const float y = fmaf(-g, ls, lm);
 					const float scale = fmaf(g, fabsf(ls), fabsf(lm));
-					const float d = fmaf(neg_eps, scale, fabsf(y));
+					const float d = fmaf(neg_eps, scale, fabsf(y) - abs_c);
 					neg = __funnelshift_l(__float_as_uint(y), neg, 1);
 					near = __funnelshift_l(__float_as_uint(d), near, 1);
 				}
@@ -540,7 +559,7 @@ fir_front_kernel(const __grid_constant__ FirPlan P, const int16_t *__restrict__ 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 
-	stage_audio(s_a, audio, n0, n_audio, P.a_len);
+	(void)stage_audio(s_a, audio, n0, n_audio, P.a_len);
 	__syncthreads();
 
 	for (int ub = tid - lane; ub < P.U_y; ub += PM_FRONT_THREADS) {

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256)
 link_push_records_kernel(LinkGeom G, LinkPeers peers, int parity, const PacketRecDev *__restrict__ recs,
                          const uint8_t *__restrict__ arena, const PacketTotals *__restrict__ totals, int *status)
 {
+	if (status[3] != 0) return;                    // nothing to trust in this shard's records
 	const unsigned long long n = totals->n_packets, nb = totals->n_bytes;
 	const unsigned long long rec_bytes = n * sizeof(PacketRecDev);
 	if (rec_bytes + nb > (unsigned long long)G.rec_region) {
@@ -179,6 +180,20 @@ link_push_records_kernel(LinkGeom G, LinkPeers peers, int parity, const PacketRe
 	for (unsigned long long i = t; i < nb; i += stride) da[i] = arena[i];
 }
 
+// A shard whose decode could not be completed from what it holds -- a frame reaching back past the hand-off tail, or a
+// gap long enough to overflow max_packet_length (ax25.py:46-51: the sequential replay needs a known state) -- says so
+// in status[3]; every rank learns it with the records and all of them recover together from the gathered bitstream
+// (sharded.py: pm_engine_shard_export -> pm_engine_decode_stream).
+#define LINK_HDR_FAILED  (~0ull)
+#define LINK_HDR_RECOVER (~0ull - 1ull)
+__global__ void link_check_decode_kernel(const ChainCounters *__restrict__ cc, int nc, int *status)
+{
+	int bad = 0;
+	for (int c = threadIdx.x; c < nc; c += blockDim.x)
+		if (cc[c].tail_short || cc[c].seq_needed) bad = 1;
+	if (__any_sync(0xffffffffu, bad) && threadIdx.x == 0) status[3] = 1;
+}
+
 __global__ void link_publish_records_kernel(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch,
                                             const PacketTotals *__restrict__ totals, const int *status)
 {
@@ -186,8 +201,8 @@ __global__ void link_publish_records_kernel(LinkGeom G, LinkPeers peers, int par
 	if (q >= G.world) return;
 	unsigned char *slot = slot_of(peers.base[q], G, parity);
 	unsigned long long *hdr = reinterpret_cast<unsigned long long *>(slot + G.off_rhdr) + 2 * G.rank;
-	const bool ok = status[1] == 0;
-	hdr[0] = ok ? totals->n_packets : ~0ull;       // ~0: this rank failed, do not trust its region
+	const bool ok = status[1] == 0 && status[3] == 0;
+	hdr[0] = ok ? totals->n_packets : (status[1] != 0 ? LINK_HDR_FAILED : LINK_HDR_RECOVER);   // not ok: do not trust the region
 	hdr[1] = ok ? totals->n_bytes : 0ull;
 	__threadfence_system();
 	st_flag(reinterpret_cast<unsigned int *>(slot + G.off_rflag) + G.rank, epoch);
@@ -211,11 +226,13 @@ link_merge_plan_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int 
 	const unsigned long long *hdr = reinterpret_cast<const unsigned long long *>(slot + G.off_rhdr);
 	if (threadIdx.x == 0) {
 		if (!s_ok) { status[1] = PM_ERR_STATE; status[2] = 4; }
-		for (int q = 0; q < G.world; q++)
-			if (s_ok && hdr[2 * q] == ~0ull && status[1] == 0) { status[1] = PM_ERR_STATE; status[2] = 5; }
+		for (int q = 0; q < G.world; q++) {
+			if (s_ok && hdr[2 * q] == LINK_HDR_FAILED && status[1] == 0) { status[1] = PM_ERR_STATE; status[2] = 5; }
+			if (s_ok && hdr[2 * q] == LINK_HDR_RECOVER) status[3] = 1;
+		}
 	}
 	__syncthreads();
-	if (status[1] != 0) {
+	if (status[1] != 0 || status[3] != 0) {
 		if (threadIdx.x == 0) { merged_totals->n_packets = 0; merged_totals->n_bytes = 0; }
 		return;
 	}
@@ -251,7 +268,7 @@ link_merge_write_kernel(LinkGeom G, unsigned char *own, int parity, const unsign
                         PacketRecDev *__restrict__ out_recs, unsigned long long rec_cap,
                         uint8_t *__restrict__ out_arena, unsigned long long arena_cap, const int *status)
 {
-	if (status[1] != 0) return;
+	if (status[1] != 0 || status[3] != 0) return;
 	unsigned char *slot = slot_of(own, G, parity);
 	const int q = blockIdx.y, nc1 = G.nc + 1;
 	const unsigned long long *hdr = reinterpret_cast<const unsigned long long *>(slot + G.off_rhdr);
@@ -285,6 +302,7 @@ cudaError_t pm_link_preload(void)
 	if ((e = cudaFuncGetAttributes(&a, link_set_flag_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_wait_flag_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_push_records_kernel)) != cudaSuccess) return e;
+	if ((e = cudaFuncGetAttributes(&a, link_check_decode_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_publish_records_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_merge_plan_kernel)) != cudaSuccess) return e;
 	return cudaFuncGetAttributes(&a, link_merge_write_kernel);
@@ -317,8 +335,9 @@ cudaError_t pm_link_wait_flag(const unsigned int *flag, unsigned int epoch, int 
 }
 
 cudaError_t pm_link_push_records(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch, const PacketRecDev *recs,
-	const uint8_t *arena, const PacketTotals *totals, int *status, cudaStream_t st)
+	const uint8_t *arena, const PacketTotals *totals, const ChainCounters *cc, int *status, cudaStream_t st)
 {
+	link_check_decode_kernel<<<1, 32, 0, st>>>(cc, G.nc, status);
 	link_push_records_kernel<<<dim3(32, G.world), 256, 0, st>>>(G, peers, parity, recs, arena, totals, status);
 	link_publish_records_kernel<<<1, 32, 0, st>>>(G, peers, parity, epoch, totals, status);
 	return cudaGetLastError();

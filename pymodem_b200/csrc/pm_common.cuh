@@ -51,6 +51,8 @@ struct AfskPlan {
 	int mag_dst_first[PM_MAX_MAG + 1]; // tone j feeds mag_dst[mag_dst_first[j] .. mag_dst_first[j+1])
 	int mag_dst[2 * PM_MAX_PAIR];      // pair * 2 + slot (0: mark, 1: space)
 	float guard_eps;
+	float chain_guard_abs[PM_MAX_GCH];  // raw-input term of the sign guard per unit of max|audio| over the tile:
+	                                    // c_abs * 2^-24 * sum|h_bpf| * N_corr * sum|h_lpf| * (1 + space_gain)
 	alignas(16) float taps[PM_MAX_TAPS];   // every tap set starts at a multiple of 4 floats: read as float4
 };
 

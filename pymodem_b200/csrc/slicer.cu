@@ -22,6 +22,7 @@
 // Output: one rollover mask bit per sample (bit i of word w = "a symbol was
 // taken at sample 32w+i"); bits and byte addresses are produced from
 // (sign, mask) by the gather kernels in bits.cu.
+#include <algorithm>
 #include "pm_common.cuh"
 
 __device__ __forceinline__ bool seg_state_equal(const SegState &a, const SegState &b)
@@ -95,9 +96,10 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 			if (WRITE) m = __brev(m);
 		} else {
 			for (int i = 0; i < cnt; i++) {
-				c += 1.0;                                // slicer.py:77
-				if (c >= thr) { c -= sps; m |= (1u << i); }   // slicer.py:79-81
-				if ((z >> i) & 1u) c *= lam;                 // slicer.py:104
+				// one rounding per operation, as in CPython: the compiler must not contract c * lam with the next + 1.0 (--fmad)
+				c = __dadd_rn(c, 1.0);                                    // slicer.py:77
+				if (c >= thr) { c = __dsub_rn(c, sps); m |= (1u << i); }   // slicer.py:79-81
+				if ((z >> i) & 1u) c = __dmul_rn(c, lam);                 // slicer.py:104
 			}
 			// state after a partial word: last signs are those of sample cnt-1
 			last = (s >> (cnt - 1)) & 1u;
@@ -335,6 +337,29 @@ slicer_count_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__re
 	}
 	cnt = __reduce_add_sync(0xffffffffu, cnt);
 	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&out[ch], (unsigned long long)cnt);
+}
+
+// soft values -> the packed sign stream the slicer reads (bit = sample >= 0.0: slicer.py:85, 99-102; NaN counts as negative,
+// as it does in the reference's comparisons).  For pm_engine_slice_soft.
+__global__ void __launch_bounds__(256) soft_sign_kernel(const double *__restrict__ x, long long n, uint32_t *__restrict__ out)
+{
+	const long long words = (n + 31) >> 5;
+	const int lane = threadIdx.x & 31;
+	for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < words;
+	     w += (long long)gridDim.x * (blockDim.x >> 5)) {
+		const long long i = (w << 5) + lane;
+		const unsigned int m = __ballot_sync(0xffffffffu, i < n && x[i] >= 0.0);
+		if (lane == 0) out[w] = m;
+	}
+}
+
+extern "C" cudaError_t pm_launch_soft_signs(const double *x, long long n, uint32_t *out, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	const long long words = (n + 31) >> 5;
+	const int blocks = (int)std::min<long long>((words + 7) / 8, 148 * 8);
+	soft_sign_kernel<<<blocks, 256, 0, st>>>(x, n, out);
+	return cudaGetLastError();
 }
 
 extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int n_chains, const uint32_t *sign,

@@ -4,6 +4,9 @@ pm_engine_run -> list[PacketMeta] per chain.
 No CPU fallback: everything here calls libpymodem_b200.so through ctypes and
 raises if the library or an sm_100 GPU is missing."""
 import ctypes
+import hashlib
+import weakref
+from collections.abc import Sequence
 
 import numpy as np
 
@@ -21,6 +24,56 @@ REC_DTYPE = np.dtype([
 	('valid_crc', 'u1'), ('valid_header', 'u1'), ('pad', 'u1', (6,)),
 ])
 assert REC_DTYPE.itemsize == ctypes.sizeof(_lib.PacketRec) == 40
+
+
+class PacketList(Sequence):
+	"""The decode() result of one chain: a read-only sequence of PacketMeta in stream order, backed by the engine's
+	record block (numpy structured array + byte arena).  Packets are built when they are first touched -- one hour of
+	the 8-chain config is ~5400 records, and a Python object per record with a list-of-int payload costs more host time
+	than the GPU needs for the whole decode -- so bulk consumers can stay on the arrays (.records, .arena) while
+	code written against the reference's list[PacketMeta] (PacketMetaArray.add, iteration, indexing, len, ==) sees
+	exactly that."""
+	__slots__ = ('records', 'arena', 'name', '_raw', '_items')
+
+	def __init__(self, records, arena, name, raw=None):
+		self.records, self.arena, self.name = records, arena, name
+		self._raw = raw
+		self._items = None
+
+	def __len__(self):
+		return len(self.records)
+
+	def _build(self):
+		r = self.records
+		raw = self._raw if self._raw is not None else self.arena.tobytes()
+		name = self.name
+		items = []
+		for off, ln, sa, bc, calc, carried, vc, vh in zip(r['offset'].tolist(), r['len'].tolist(), r['streamaddress'].tolist(),
+				r['bytes_corrected'].tolist(), r['calculated_crc'].tolist(), r['carried_crc'].tolist(),
+				r['valid_crc'].tolist(), r['valid_header'].tolist()):
+			p = PacketMeta.__new__(PacketMeta)
+			p.__dict__ = {'data': list(raw[off:off + ln]), 'streamaddress': sa, 'source_sample_rate': 0.0,
+				'CalculatedCRC': calc, 'CarriedCRC': carried, 'ValidCRC': bool(vc), 'SourceDecoder': name,
+				'BytesCorrected': bc, 'CorrelatedDecoders': [], 'SlicedIQSamples': [], 'ValidHeader': bool(vh),
+				'_device_checked': True}
+			items.append(p)
+		self._items = items
+		return items
+
+	def __getitem__(self, i):
+		items = self._items if self._items is not None else self._build()
+		return items[i]
+
+	def __iter__(self):
+		return iter(self._items if self._items is not None else self._build())
+
+	def __eq__(self, other):
+		if isinstance(other, (list, PacketList)):
+			return len(self) == len(other) and all(a is b or a == b for a, b in zip(self, other))
+		return NotImplemented
+
+	def __repr__(self):
+		return f"PacketList({self.name!r}, {len(self)} packets)"
 
 
 def describe_chain(chain, keep):
@@ -58,6 +111,8 @@ class Engine:
 		descs = (_lib.ChainDesc * len(demod_stack))()
 		for i, chain in enumerate(demod_stack):
 			descs[i] = describe_chain(chain, keep)
+		self.fingerprint = stack_fingerprint(demod_stack)
+		self._registered = {}
 		self._check(self._lib.pm_engine_load_chains(self._h, descs, len(demod_stack)))
 		self.n_chains = len(demod_stack)
 		self.has_il2p = any(getattr(chain[4], 'codec_kind', None) == _lib.PM_CODEC_IL2P for chain in demod_stack)
@@ -162,11 +217,12 @@ class Engine:
 		self._check(self._lib.pm_engine_run_linked_begin(self._h, audio_ptr, int(n), int(bool(on_device)), ctypes.byref(p)))
 
 	def run_linked_end(self):
-		"""-> True when every hand-off verified (merged records of all ranks are ready for fetch());
-		False when the ranks have to fall back to the host-driven repair protocol."""
+		"""-> 1 when every hand-off verified (merged records of all ranks are ready for fetch()); 0 when the ranks have
+		to fall back to the host-driven slicer repair protocol; 2 when some rank could not finish its decode from what
+		it holds and all ranks recover from the gathered bitstream (sharded.recover_from_bitstream)."""
 		v = ctypes.c_int32(0)
 		self._check(self._lib.pm_engine_run_linked_end(self._h, ctypes.byref(v)))
-		return bool(v.value)
+		return int(v.value)
 
 	def shard_states(self):
 		out = (_lib.ShardState * self.n_chains)()
@@ -178,30 +234,74 @@ class Engine:
 		nb = self._lib.pm_engine_arena_bytes(self._h)
 		if n < 0:
 			raise EngineError("no results: run the engine first")
-		recs = np.zeros(n, dtype=REC_DTYPE)
-		arena = np.zeros(max(nb, 1), dtype=np.uint8)
+		recs = np.empty(n, dtype=REC_DTYPE)
+		arena = np.empty(max(nb, 1), dtype=np.uint8)
 		self._check(self._lib.pm_engine_get_packets(self._h, recs.ctypes.data, n, arena.ctypes.data, arena.shape[0]))
 		return recs, arena[:nb]
 
 	def packets(self, recs, arena):
-		"""records -> [list[PacketMeta]] per chain, in config order (the order the
-		reference's deterministic driver produces)."""
-		out = [[] for _ in range(self.n_chains)]
+		"""records -> one PacketList (a sequence of PacketMeta) per chain, in config order (the order the reference's
+		deterministic driver produces).  The records are ordered by (chain, stream position), so every chain is a
+		contiguous block: no per-record work happens here."""
+		bounds = np.searchsorted(recs['chain'], np.arange(self.n_chains + 1, dtype=np.uint32))
 		raw = arena.tobytes()
-		for r in recs:
-			p = PacketMeta()
-			off = int(r['offset'])
-			p.data = list(raw[off:off + int(r['len'])])
-			p.streamaddress = int(r['streamaddress'])
-			p.SourceDecoder = self.names[int(r['chain'])]
-			p.BytesCorrected = int(r['bytes_corrected'])
-			p.CalculatedCRC = int(r['calculated_crc'])
-			p.CarriedCRC = int(r['carried_crc'])
-			p.ValidCRC = bool(r['valid_crc'])
-			p.ValidHeader = bool(r['valid_header'])
-			p._device_checked = True
-			out[int(r['chain'])].append(p)
-		return out
+		return [PacketList(recs[bounds[c]:bounds[c + 1]], arena, self.names[c], raw) for c in range(self.n_chains)]
+
+	# -- host memory ---------------------------------------------------------------
+	def pin(self, audio):
+		"""Page-lock a NumPy buffer in place (cudaHostRegister), once: every later run() on it is DMA'ed straight from
+		the caller's memory.  The registration is dropped when the array is garbage collected."""
+		key = (audio.ctypes.data, audio.nbytes)
+		if key in self._registered or audio.nbytes == 0:
+			return True
+		if self._lib.pm_host_register(audio.ctypes.data, audio.nbytes) != _lib.PM_OK:
+			return False
+		self._registered[key] = weakref.finalize(audio, _unregister, self._lib, audio.ctypes.data, self._registered, key)
+		return True
+
+	# -- the reference's blocks one at a time (chain_execute.py:32-47) -------------
+	def slice_soft(self, chain, soft_i, soft_q=None):
+		"""slicer.slice(): float64 soft values -> (bytes uint8[n], addresses int64[n]) of the AddressedData stream."""
+		i = np.ascontiguousarray(soft_i, dtype=np.float64)
+		q = None if soft_q is None else np.ascontiguousarray(soft_q, dtype=np.float64)
+		if q is not None and len(q) != len(i):
+			raise EngineError("slice_soft: I and Q lengths differ")
+		self._check(self._lib.pm_engine_slice_soft(self._h, chain, i.ctypes.data, None if q is None else q.ctypes.data, len(i)))
+		return self.stream(chain, 0)
+
+	def unscramble_stream(self, chain, data, addresses):
+		"""stream.stream_unscramble_8bit(): (bytes, addresses) -> (bytes, addresses)"""
+		b = np.ascontiguousarray(data, dtype=np.uint8)
+		a = np.ascontiguousarray(addresses, dtype=np.int64)
+		self._check(self._lib.pm_engine_unscramble_stream(self._h, chain, b.ctypes.data, a.ctypes.data, len(b)))
+		return self.stream(chain, 1)
+
+	def decode_stream(self, chain, data, addresses):
+		"""codec.decode(): (bytes, addresses) -> (records, arena)"""
+		b = np.ascontiguousarray(data, dtype=np.uint8)
+		a = np.ascontiguousarray(addresses, dtype=np.int64)
+		self._check(self._lib.pm_engine_decode_stream(self._h, chain, b.ctypes.data, a.ctypes.data, len(b)))
+		return self.fetch()
+
+	def shard_export(self, chain):
+		"""What this shard holds of a chain's sliced stream after shard_gather: (bit words uint32[], byte addresses
+		uint32[], info = [local bits, first own bit, own bits, sample_base])."""
+		info = (ctypes.c_int64 * 4)()
+		self._check(self._lib.pm_engine_shard_export(self._h, chain, None, 0, None, 0, info))
+		nw, nby = (info[0] + 31) // 32, (info[0] + 7) // 8
+		bits = np.zeros(max(nw, 1), dtype=np.uint32)
+		addr = np.zeros(max(nby, 1), dtype=np.uint32)
+		self._check(self._lib.pm_engine_shard_export(self._h, chain, bits.ctypes.data, len(bits), addr.ctypes.data, len(addr), info))
+		return bits[:nw], addr[:nby], [int(x) for x in info]
+
+	def signs(self, chain, component=0):
+		"""Packed signs of the soft values as the slicer reads them: uint32[(soft_len + 31) // 32]."""
+		n = self._lib.pm_engine_soft_len(self._h, chain)
+		if n < 0:
+			raise EngineError("no signs: run the engine first")
+		out = np.zeros(max((n + 31) // 32, 1), dtype=np.uint32)
+		self._check(self._lib.pm_engine_get_signs(self._h, chain, component, out.ctypes.data, len(out)))
+		return out[:(n + 31) // 32]
 
 	def run(self, audio):
 		recs, arena = self.run_raw(audio)
@@ -242,19 +342,83 @@ class Engine:
 		return self._lib.pm_engine_front_macs_per_sample(self._h)
 
 
+def _unregister(lib, ptr, table, key):
+	table.pop(key, None)
+	lib.pm_host_unregister(ptr)
+
+
+def stack_fingerprint(demod_stack):
+	"""Digest of everything describe() hands to the engine -- the pm_chain_desc scalars and every tap / table array.
+	The reference reads its blocks' state on every call (chain_execute.py:32-47), so a retune() or
+	StringOptionsRetune() between two calls must take effect: engine_for() compares this, not object identities."""
+	h = hashlib.blake2b(digest_size=16)
+	ptr_types = (ctypes._Pointer,)
+	for chain in demod_stack:
+		keep = []
+		desc = describe_chain(chain, keep)
+		for name, _ in _lib.ChainDesc._fields_:
+			v = getattr(desc, name)
+			if isinstance(v, ptr_types):
+				continue
+			h.update(bytes(v) if isinstance(v, ctypes.Array) else repr(v).encode())
+		if desc.loop:
+			lp = desc.loop.contents
+			for name, _ in _lib.LoopDesc._fields_:
+				v = getattr(lp, name)
+				if not isinstance(v, ptr_types):
+					h.update(repr(v).encode())
+		for a in keep:
+			if isinstance(a, np.ndarray):
+				h.update(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes())
+		h.update(str(chain[0]).encode() + b"|")
+	return h.hexdigest()
+
+
 _cache = {}
 
 
 def engine_for(demod_stack, device=0, **options):
-	"""Engines are cached per (chain objects, device, options): building one uploads taps."""
-	key = (tuple(id(b) for chain in demod_stack for b in chain[1:]), device, tuple(sorted(options.items())))
+	"""One cached engine per (chain parameters, device, options): building an engine uploads taps and allocates its
+	buffers.  The key is the digest of the described parameters, so retuned blocks get a new engine."""
+	key = (stack_fingerprint(demod_stack), device, tuple(sorted(options.items())))
 	eng = _cache.get(key)
 	if eng is None:
 		eng = Engine(demod_stack, device=device, **options)
+		for old in _cache.values():
+			old.close()
 		_cache.clear()
 		_cache[key] = eng
-		eng._stack_ref = demod_stack      # keep ids alive
 	return eng
+
+
+class _NoModem:
+	"""Stands in for the modem of a chain that only serves the per-stage calls."""
+	modem_kind = _lib.PM_MODEM_NONE
+
+	def describe(self, desc, keep):
+		desc.modem_kind = self.modem_kind
+
+
+def stage_engine(slicer=None, stream=None, codec=None, name="stage"):
+	"""A one-chain engine around the block(s) a per-stage call needs (the others are defaults that stay unused)."""
+	from .modems_codecs import ax25, lfsr, slicer as slicer_mod
+	chain = [name, _NoModem(), slicer or slicer_mod.BinarySlicer(sample_rate=48000, config='1200'), stream or lfsr.LFSR(),
+		codec or ax25.AX25Codec(ident=name)]
+	return engine_for([chain])
+
+
+def addressed_arrays(stream):
+	"""list[AddressedData] (or a (bytes, addresses) pair of arrays) -> (uint8[n], int64[n])"""
+	if isinstance(stream, tuple) and len(stream) == 2:
+		return np.ascontiguousarray(stream[0], dtype=np.uint8), np.ascontiguousarray(stream[1], dtype=np.int64)
+	n = len(stream)
+	return (np.fromiter((int(s.data) & 0xFF for s in stream), dtype=np.uint8, count=n),
+		np.fromiter((int(s.address) for s in stream), dtype=np.int64, count=n))
+
+
+def addressed_list(data, addresses):
+	from .modems_codecs.data_classes import AddressedData
+	return [AddressedData(d, a) for d, a in zip(data.tolist(), addresses.tolist())]
 
 
 def demod_only(modem, audio):

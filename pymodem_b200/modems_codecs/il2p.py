@@ -21,6 +21,14 @@ class IL2PCodec:
 		self.min_distance = int(options.get('min_dist', self.min_distance))
 		self.sync_tolerance = int(options.get('sync_tol', self.sync_tolerance))
 
+	def decode(self, stream):
+		"""il2p.py:360-519 on the GPU: list[AddressedData] -> list of PacketMeta (SourceDecoder = ident), decoded from the
+		initial state; CalculatedCRC / CarriedCRC / ValidCRC / ValidHeader are already filled in."""
+		from ..engine import addressed_arrays, stage_engine
+		data, addresses = addressed_arrays(stream)
+		eng = stage_engine(codec=self, name=self.identifier)
+		return eng.packets(*eng.decode_stream(0, data, addresses))[0]
+
 	def describe(self, desc):
 		desc.codec_kind = self.codec_kind
 		desc.il2p_crc = 1 if self.collect_trailing_crc else 0

@@ -1,5 +1,6 @@
-"""Feed-forward descrambler parameters (reference modems_codecs/lfsr.py:10-20);
-the GF(2) FIR itself runs on the GPU (csrc/bits.cu lfsr_kernel)."""
+"""Feed-forward descrambler (reference modems_codecs/lfsr.py:10-52): parameters on the host, the GF(2) FIR on the GPU
+(csrc/bits.cu lfsr_kernel).  stream_unscramble_8bit() is the reference's duck-typed stage call
+(chain_execute.py:40-43); it starts from an empty shift register on every call (see slicer.py of this package)."""
 from .string_ops import check_boolean
 
 
@@ -12,6 +13,12 @@ class LFSR:
 	def StringOptionsRetune(self, options):      # lfsr.py:18-20: poly is a hex string
 		self.polynomial = int(options.get('poly', 0x1), 16)
 		self.invert = check_boolean(options.get('invert', "false"))
+
+	def stream_unscramble_8bit(self, stream):
+		"""lfsr.py:22-52 on the GPU: list[AddressedData] -> list[AddressedData] (addresses pass through)."""
+		from ..engine import addressed_arrays, addressed_list, stage_engine
+		data, addresses = addressed_arrays(stream)
+		return addressed_list(*stage_engine(stream=self).unscramble_stream(0, data, addresses))
 
 	def describe(self, desc):
 		if self.polynomial <= 0 or self.polynomial >= (1 << 64):

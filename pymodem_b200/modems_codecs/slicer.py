@@ -1,7 +1,17 @@
-"""Symbol-timing slicers -- parameter holders for the GPU slicer kernels.
-Mirrors reference modems_codecs/slicer.py (BinarySlicer 9-107, QuadratureSlicer
-109-242): constructor kwargs, presets, StringOptionsRetune, tune()."""
+"""Symbol-timing slicers -- parameters on the host, the timing loop on the GPU (csrc/slicer.cu + the gather kernels
+of csrc/bits.cu).  Mirrors reference modems_codecs/slicer.py (BinarySlicer 9-107, QuadratureSlicer 109-242):
+constructor kwargs, presets, StringOptionsRetune, tune(), slice().
+
+slice() is the reference's duck-typed stage call (chain_execute.py:36-39).  One difference, shared by the other
+per-stage methods of this package: a call processes a complete recording from the state tune() sets (the reference's
+blocks carry their state from one call to the next, slicer.py:50-56; chain_execute.py calls each block once)."""
 from .. import _lib
+
+
+def _slice(slicer, soft_i, soft_q=None):
+	from ..engine import addressed_list, stage_engine
+	data, addresses = stage_engine(slicer=slicer).slice_soft(0, soft_i, soft_q)
+	return addressed_list(data, addresses)
 
 _QPSK_DEMAP = [3, 1, 2, 0, 2, 3, 0, 1, 1, 0, 3, 2, 0, 2, 1, 3]
 _BPSK_DEMAP = [0, 0, 1, 1]
@@ -39,6 +49,10 @@ class BinarySlicer:
 		self.working_bit_count = 0
 		self.last_sample = 0.0
 		self.streamaddress = 0
+
+	def slice(self, samples):
+		"""slicer.py:59-107 on the GPU: float64 soft values -> list[AddressedData]."""
+		return _slice(self, samples)
 
 	def describe(self, desc):
 		desc.slicer_kind = self.slicer_kind
@@ -91,6 +105,10 @@ class QuadratureSlicer:
 		self.last_q_sample = 0.0
 		self.streamaddress = 0
 		self.state_register = 0
+
+	def slice(self, samples):
+		"""slicer.py:193-242 on the GPU: IQData (i_data, q_data) -> list[AddressedData]."""
+		return _slice(self, samples.i_data, samples.q_data)
 
 	def describe(self, desc):
 		desc.slicer_kind = self.slicer_kind

@@ -124,21 +124,116 @@ class ShardWorker:
 
 	def finish(self, all_tails, il2p_prev=None, il2p=False):
 		"""il2p: the engine has IL2P chains -- il2p_prev is the previous rank's decoder-state blob (None on rank 0) and
-		self.il2p_blob becomes this rank's."""
+		self.il2p_blob becomes this rank's.  A shard that cannot finish from what it holds (a frame reaching back
+		past the hand-off tail, the max_packet_length overflow of ax25.py:46-51, an IL2P frame longer than the tail)
+		answers RECOVER: the ranks then decode the gathered bitstream together (recover_from_bitstream)."""
+		from .engine import EngineError
 		tail_in = None
 		if self.rank > 0 and self.plan['tail_bits'] > 0:
 			tail_in = np.frombuffer(all_tails[self.rank - 1], dtype=np.uint32).reshape(self.n_chains, -1)
-		if il2p:
-			prev = None
-			if il2p_prev is not None:
-				prev = (_lib.Il2pState * self.n_chains)()
-				ctypes.memmove(ctypes.addressof(prev), il2p_prev, ctypes.sizeof(prev))
-			out = self.engine.shard_finish_il2p(tail_in, prev)
-			self.il2p_blob = bytes(ctypes.string_at(ctypes.addressof(out), ctypes.sizeof(out)))
-		else:
-			self.engine.shard_finish(tail_in)
+		try:
+			if il2p:
+				self.il2p_blob = bytes(ctypes.sizeof(_lib.Il2pState) * self.n_chains)
+				prev = None
+				if il2p_prev is not None:
+					prev = (_lib.Il2pState * self.n_chains)()
+					ctypes.memmove(ctypes.addressof(prev), il2p_prev, ctypes.sizeof(prev))
+				out = self.engine.shard_finish_il2p(tail_in, prev)
+				self.il2p_blob = bytes(ctypes.string_at(ctypes.addressof(out), ctypes.sizeof(out)))
+			else:
+				self.engine.shard_finish(tail_in)
+		except EngineError as exc:
+			if f"error {_lib.PM_ERR_STATE}:" not in str(exc):
+				raise
+			return RECOVER
 		recs, arena = self.engine.fetch()
 		return struct.pack("<qq", len(recs), len(arena)) + recs.tobytes() + arena.tobytes()
+
+
+RECOVER = b"RECOVER!" * 2       # in place of a rank's result blob (16 bytes: never a valid header + records)
+
+
+def export_blob(engine):
+	"""What one rank contributes to the recovery: for every chain the local stream bits, byte addresses and their
+	placement (Engine.shard_export)."""
+	parts = [struct.pack("<q", engine.n_chains)]
+	for c in range(engine.n_chains):
+		bits, addr, info = engine.shard_export(c)
+		parts.append(struct.pack("<6q", *info, len(bits), len(addr)) + bits.tobytes() + addr.tobytes())
+	return b"".join(parts)
+
+
+def assemble_streams(blobs):
+	"""Export blobs of all ranks in rank order -> per chain (bytes uint8[n], addresses int64[n]): the AddressedData
+	stream the unsharded slicer produces (slicer.py:92-97): every rank's own bits back to back, cut into bytes every 8
+	bits counted from the start of the recording, each byte carrying the address of the sample that completed it
+	(held by the rank that owns the byte's last bit); a trailing partial byte is dropped."""
+	n_chains = struct.unpack_from("<q", blobs[0], 0)[0]
+	offs = [8] * len(blobs)
+	out = []
+	for _c in range(n_chains):
+		pieces, placed, pos = [], [], 0
+		for r, blob in enumerate(blobs):
+			nbits, bit_off, n_own, base, nw, na = struct.unpack_from("<6q", blob, offs[r])
+			o = offs[r] + 48
+			words = np.frombuffer(blob, dtype=np.uint32, count=nw, offset=o)
+			addr = np.frombuffer(blob, dtype=np.uint32, count=na, offset=o + 4 * nw)
+			offs[r] = o + 4 * nw + 4 * na
+			local = np.unpackbits(words.view(np.uint8), bitorder='little')
+			pieces.append(local[bit_off:bit_off + n_own])
+			a0 = pos - bit_off                      # global index of local bit 0: a multiple of 8 (byte cuts are global)
+			assert a0 % 8 == 0 and a0 >= 0, "shard placement is not byte aligned"
+			j_lo, j_hi = bit_off // 8, (bit_off + n_own) // 8      # local bytes whose last bit is an own bit
+			placed.append((a0 // 8 + j_lo, addr[j_lo:j_hi].astype(np.int64) + base))
+			pos += n_own
+		nbytes = pos // 8
+		bits = np.concatenate(pieces)[:8 * nbytes] if pieces else np.zeros(0, dtype=np.uint8)
+		data = np.packbits(bits, bitorder='big')
+		addresses = np.zeros(nbytes, dtype=np.int64)
+		for first, vals in placed:
+			vals = vals[:max(0, nbytes - first)]
+			addresses[first:first + len(vals)] = vals
+		out.append((data, addresses))
+	return out
+
+
+def decode_streams(engine, streams):
+	"""Per-chain AddressedData streams -> (records, arena) ordered like an unsharded run, through the engine's own
+	descrambler and codec kernels (Engine.unscramble_stream / decode_stream)."""
+	recs_all, arenas, base = [], [], 0
+	for c, (data, addresses) in enumerate(streams):
+		d1, a1 = engine.unscramble_stream(c, data, addresses)
+		recs, arena = engine.decode_stream(c, d1, a1)
+		recs = recs.copy()
+		recs['offset'] += base
+		base += len(arena)
+		recs_all.append(recs)
+		arenas.append(arena.copy())
+	recs = np.concatenate(recs_all) if recs_all else np.zeros(0, dtype=REC_DTYPE)
+	arena = np.concatenate(arenas) if arenas else np.zeros(0, dtype=np.uint8)
+	return recs, arena
+
+
+def recover_from_bitstream(engines, exchange_var):
+	"""The always-exact way out of a sharded run: every rank exports its part of the sliced stream, the parts are
+	gathered (a few MB per chain-hour), and the complete stream of every chain is descrambled and decoded from the
+	start -- the same bit-level work an unsharded run does, including the sequential AX.25 replay.  Every rank ends
+	with the same (records, arena)."""
+	blobs = exchange_var([export_blob(e) for e in engines])
+	return decode_streams(engines[0], assemble_streams(blobs))
+
+
+class Recovered:
+	"""Result of a run that went through recover_from_bitstream, shaped like Gathered."""
+
+	def __init__(self, recs, arena):
+		self.recs, self.arena = recs, arena
+
+	def n_packets(self):
+		return len(self.recs)
+
+	def merge(self):
+		return self.recs, self.arena
 
 
 def _unpack_result(blob):
@@ -261,6 +356,13 @@ def run_protocol(workers, exchange, exchange_var=None, timing=None, merge=True, 
 	lap("finish")
 	results = exchange_var(results)
 	lap("exchange")
+	if any(r == RECOVER for r in results):
+		# every rank sees the same blobs, so every rank takes this branch
+		recs, arena = recover_from_bitstream([w.engine for w in workers], exchange_var)
+		lap("recover")
+		if timing is not None:
+			timing['recovered'] = timing.get('recovered', 0) + 1
+		return (recs, arena) if merge else Recovered(recs, arena)
 	if not merge:
 		return Gathered(results)
 	merged = merge_results(results)
@@ -384,6 +486,7 @@ class LinkedRun:
 			raise ValueError("LinkedRun: ranks disagree on max_samples / tail_bits / chain count")
 		engine.link_connect(handles=[b[:64] for b in blobs])
 		self.fallbacks = 0
+		self.recoveries = 0
 
 	def run(self, plan, audio_ptr, n_local, on_device=False, timing=None, fetch=True):
 		"""-> (records, arena) of ALL ranks, ordered like an unsharded run.  fetch=False leaves them in the engine
@@ -397,8 +500,12 @@ class LinkedRun:
 		if timing is not None:
 			timing['linked_begin'] = timing.get('linked_begin', 0.0) + (t1 - t0) * 1e3
 			timing['linked_end'] = timing.get('linked_end', 0.0) + (t2 - t1) * 1e3
-		if ok:
+		if ok == 1:
 			return self.engine.fetch() if fetch else None
+		if ok == 2:
+			# some rank could not finish its decode from what it holds: all ranks decode the gathered bitstream
+			self.recoveries += 1
+			return recover_from_bitstream([self.engine], self.exchange_var)
 		self.fallbacks += 1
 		worker = ShardWorker(self.engine, plan, audio_ptr, n_local, on_device)
 		return run_protocol([worker], self.exchange, self.exchange_var, timing=timing, resume=True)
@@ -431,6 +538,10 @@ def run_linked_local(demod_stack, audio, world, device=0, tail_bits=16384, **opt
 			e.run_linked_begin(l.ctypes.data, len(l), p)
 		verified = [e.run_linked_end() for e in engines]
 		info = dict(verified=verified, plans=plans, repairs=[e.stats()['slicer_repairs'] for e in engines])
+		if all(v == 2 for v in verified):
+			info['recovered'] = True
+			return engines[0].packets(*recover_from_bitstream(engines, local_exchange)), info
+		assert 2 not in verified, "ranks disagree on the recovery verdict"
 		if all(verified):
 			results = [e.fetch() for e in engines]
 			info['all_ranks_equal'] = all(np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1])

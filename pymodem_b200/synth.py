@@ -80,10 +80,12 @@ def _default_payload(k, rng):
 
 def afsk1200_ax25(duration_s, sample_rate=48000, frame_interval_s=3.1, amplitude=0.5,
 		noise_start=0.0, noise_end=1.6, seed=0, noise_seed=1, mark=1200.0, space=2200.0,
-		baud=1200.0, first_frame_s=0.5, deemphasis=False):
+		baud=1200.0, first_frame_s=0.5, deemphasis=False, payload_len=None):
 	"""int16 mono audio: AX.25 UI frames 'MODEM-0 < NOISE-0' every
 	frame_interval_s, Bell-202 continuous-phase AFSK, AWGN sigma ramped linearly
 	from noise_start to noise_end (in units of the signal amplitude).
+	payload_len: information-field bytes per frame (an int, or a list cycled through) instead of the default 40-odd --
+	frames beyond 1023 bytes exercise the max_packet_length overflow of ax25.py:46-51.
 	Returns (audio int16[N], frames list of bytes, frame start samples)."""
 	rng = np.random.default_rng(seed)
 	n = int(round(duration_s * sample_rate))
@@ -94,7 +96,13 @@ def afsk1200_ax25(duration_s, sample_rate=48000, frame_interval_s=3.1, amplitude
 	sps = sample_rate / baud
 	while True:
 		start = int(round(t * sample_rate))
-		frame = ax25_ui_frame("MODEM", "NOISE", _default_payload(k, rng))
+		if payload_len is None:
+			payload = _default_payload(k, rng)
+		else:
+			want = payload_len[k % len(payload_len)] if isinstance(payload_len, (list, tuple)) else payload_len
+			head = (f"packet {k} ").encode()
+			payload = head + bytes(int(c) for c in rng.integers(0, 256, size=max(0, int(want) - len(head))))
+		frame = ax25_ui_frame("MODEM", "NOISE", payload)
 		line = nrzi(hdlc_bits(frame))
 		nsamp = int(np.floor(len(line) * sps))
 		if start + nsamp >= n:

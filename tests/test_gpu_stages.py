@@ -1,0 +1,125 @@
+"""The reference's duck-typed stage calls (chain_execute.py:32-47) one at a time on the GPU -- slicer.slice(),
+stream.stream_unscramble_8bit(), codec.decode() of the mirror classes -- against the oracle's restatement of the
+same blocks fed with the same intermediate data, and the engine cache against retuned blocks."""
+import numpy as np
+import pytest
+
+from util import Golden, as_tuples
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(stream):
+	return [(s.data, s.address) for s in stream]
+
+
+def _zip(b, a):
+	return list(zip(b.tolist(), a.tolist()))
+
+
+@pytest.mark.parametrize("tag,ci", [("afsk1200_superopt_48k", 0), ("afsk1200_superopt_48k", 5), ("afsk1200_ax25_44k1", 0),
+	("fsk9600_ax25_48k", 0)])
+def test_binary_slicer_slice(cuda_lib, oracle, tag, ci):
+	from pymodem_b200.modems_codecs import chain_builder
+	g = Golden(tag)
+	line = g.chain_lines()[ci]
+	oc = oracle.Chain(g.sample_rate, line)
+	soft = oc.modem.demod(g.audio())
+	want = oc.slicer.slice(soft)
+	chain = chain_builder.build_chain(g.sample_rate, line)
+	got = chain[2].slice(soft)
+	assert _pairs(got) == _zip(*want) and len(got) > 100
+	# the reference's other per-stage methods on the result
+	want_u = oc.stream.stream_unscramble_8bit(*want)
+	got_u = chain[3].stream_unscramble_8bit(got)
+	assert _pairs(got_u) == _zip(*want_u)
+	want_p = oc.codec.decode(*want_u)
+	got_p = chain[4].decode(got_u)
+	assert as_tuples([got_p])[0] == want_p
+	assert all(p.SourceDecoder == line['object_name'] for p in got_p)
+
+
+@pytest.mark.parametrize("tag", ["qpsk2400_il2p_8k", "qpsk2400_il2p_22k"])
+def test_quadrature_slicer_slice_and_il2p_decode(cuda_lib, oracle, tag):
+	from pymodem_b200.modems_codecs import chain_builder
+	from pymodem_b200.modems_codecs.data_classes import IQData
+	g = Golden(tag)
+	line = g.chain_lines()[1]
+	oc = oracle.Chain(g.sample_rate, line)
+	i_s, q_s = oc.modem.demod(g.audio())
+	want = oc.slicer.slice((i_s, q_s))
+	chain = chain_builder.build_chain(g.sample_rate, line)
+	got = chain[2].slice(IQData(i_s, q_s))
+	assert _pairs(got) == _zip(*want) and len(got) > 100
+	want_u = oc.stream.stream_unscramble_8bit(*want)
+	got_u = chain[3].stream_unscramble_8bit(got)
+	assert _pairs(got_u) == _zip(*want_u)
+	want_p = oc.codec.decode(*want_u)
+	got_p = chain[4].decode(got_u)
+	assert as_tuples([got_p])[0] == want_p and len(want_p) > 0
+
+
+@pytest.mark.parametrize("poly,invert", [("0x3", "true"), ("0x63003", "true"), ("0x1", "false"), ("0x211", "false")])
+def test_lfsr_unscramble(cuda_lib, oracle, poly, invert):
+	from pymodem_b200.modems_codecs import chain_builder
+	rng = np.random.default_rng(11)
+	for n in (0, 1, 3, 4, 5, 1000, 4097):
+		data = rng.integers(0, 256, n).astype(np.uint8)
+		addr = np.cumsum(rng.integers(280, 360, n)).astype(np.int64)
+		opts = {"poly": poly, "invert": invert}
+		want = oracle.LFSR(opts).stream_unscramble_8bit(data, addr)
+		blk = chain_builder.StreamConfigurator({"type": "lfsr", "options": opts})
+		got = blk.stream_unscramble_8bit((data, addr))
+		assert _pairs(got) == _zip(*want)
+	# SURVEY Appendix B.2 known answers
+	kat = chain_builder.StreamConfigurator({"type": "lfsr", "options": {"poly": "0x3", "invert": "true"}})
+	from pymodem_b200.modems_codecs.data_classes import AddressedData
+	out = kat.stream_unscramble_8bit([AddressedData(b, i + 1) for i, b in enumerate([0x00, 0xFF, 0xAA, 0x0F, 0x7E])])
+	assert [s.data for s in out] == [0xFF, 0x7F, 0x80, 0xF7, 0x3E]
+
+
+def test_empty_inputs(cuda_lib):
+	from pymodem_b200.modems_codecs import chain_builder
+	assert chain_builder.SlicerConfigurator(48000, {"type": "binary", "config": "1200", "options": {}}).slice(np.zeros(0)) == []
+	assert chain_builder.CodecConfigurator({"type": "ax25"}, "x").decode([]) == []
+	assert chain_builder.CodecConfigurator({"type": "il2p", "options": {}}, "x").decode([]) == []
+
+
+def test_engine_cache_follows_retuned_blocks(cuda_lib, oracle):
+	"""engine_for() used to key on object identities; a retune between two process_chains calls must take
+	effect, as it does in the reference (the blocks' state is read on every call)."""
+	from pymodem_b200.modems_codecs import chain_builder, chain_execute
+	g = Golden("afsk1200_superopt_48k")
+	audio = g.audio()
+	lines = g.chain_lines()[2:4]
+	stack = [chain_builder.build_chain(g.sample_rate, l) for l in lines]
+	first = as_tuples(chain_execute.process_chains(stack, audio))
+	assert first == [g.packets(2), g.packets(3)]
+	import copy
+	changed = copy.deepcopy(lines)
+	changed[0]['modem']['options']['space_gain'] = "2.75"
+	changed[0]['slicer']['options']['lock_rate'] = "0.6"
+	stack[0][1].StringOptionsRetune(changed[0]['modem']['options'])
+	stack[0][2].StringOptionsRetune(changed[0]['slicer']['options'])
+	second = as_tuples(chain_execute.process_chains(stack, audio))
+	assert second == oracle.run_config(g.sample_rate, changed, audio)
+	assert second[0] != first[0] and second[1] == first[1]
+
+
+def test_pageable_and_pinned_input_agree(cuda_lib):
+	"""pm_engine_run takes any host pointer: pageable memory goes through the engine's pinned ring, registered memory
+	is read in place; the chunked copy must not change a bit."""
+	from pymodem_b200.engine import Engine
+	from pymodem_b200.modems_codecs import chain_builder
+	g = Golden("afsk1200_superopt_48k")
+	audio = g.audio()
+	stack = [chain_builder.build_chain(g.sample_rate, l) for l in g.chain_lines()]
+	for opts in ({}, {"h2d_chunk": 1 << 16, "copy_threads": 1}, {"h2d_chunk": 100000, "copy_threads": 3}):
+		eng = Engine(stack, **opts)
+		try:
+			a = as_tuples(eng.run(audio))
+			assert eng.pin(audio)
+			b = as_tuples(eng.run(audio))
+		finally:
+			eng.close()
+		assert a == b == g.all_packets()
