@@ -335,6 +335,11 @@ int pm_engine_get_stream(const pm_engine *e, int32_t chain, int32_t stage,
                          uint8_t *bytes, int64_t *addresses, int64_t cap);
 
 int pm_engine_get_stats(const pm_engine *e, pm_stats *out);
+/* Per-kernel times of the last pm_engine_run / pm_engine_run_device when option "kernel_times" was 1: a CUDA event is
+ * recorded before every kernel launch and copy of the run; buf receives one line per kernel name,
+ * "name<TAB>launches<TAB>milliseconds" (the time up to the next launch on the stream), in order of first launch.  Returns
+ * the bytes written or PM_ERR_CAPACITY.  The events cost a few microseconds each: a timing pass is not a benchmark run. */
+int64_t pm_engine_kernel_times(const pm_engine *e, char *buf, int64_t cap);
 
 /* FP32 FFMA peak microbenchmark (roofline denominator for the FIR kernels):
  * returns achieved TFLOP/s of a register-resident FFMA loop on the device. */

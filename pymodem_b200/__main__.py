@@ -3,14 +3,13 @@
 The reference's command line (pymodem.py:25-183) with the per-chain process fan-out (pymodem.py:140-166) replaced by
 one GPU engine call: JSON-lines config -> chain objects (chain_builder) -> libpymodem_b200.so -> PacketMeta lists in
 config order -> PacketMetaArray.CalcCRCs / Correlate(address_distance = sample_rate / 40) -> report.  Exit codes follow
-the reference: 2 usage, 3 config file, 4 audio file.  The WAV is memory-mapped (16-bit PCM mono, as the reference's
-sample files) and handed to the engine as a host buffer; the engine streams it to the GPU in chunks that overlap the
-front-end kernels.  There is no CPU fallback."""
+the reference: 2 usage, 3 config file, 4 audio file.  The WAV (16-bit PCM mono, as the reference's sample files) is
+memory-mapped and copied once, into page-locked memory (engine.read_wav_pinned); the engine DMAs it to the GPU in chunks
+that overlap the front-end kernels.  There is no CPU fallback."""
 import json
 import sys
 import time
 
-import numpy as np
 
 
 def main(argv):
@@ -24,10 +23,8 @@ def main(argv):
 		print('Unable to open config json file.')
 		return 3
 	try:
-		from scipy.io.wavfile import read as readwav
-		input_sample_rate, input_audio = readwav(argv[2], mmap=True)
-		if input_audio.ndim != 1 or input_audio.dtype != np.int16:
-			raise ValueError("16-bit mono PCM expected")
+		from .engine import read_wav_pinned
+		input_sample_rate, input_audio = read_wav_pinned(argv[2])      # the one copy of the samples: file -> pinned memory
 	except Exception:
 		print('Unable to open audio file.')
 		return 4
@@ -50,7 +47,7 @@ def main(argv):
 		return 3
 	print("Executing demod stack plan.")
 	start_time = time.time()
-	decoded_datas = chain_execute.process_chains(demod_stack, np.ascontiguousarray(input_audio))
+	decoded_datas = chain_execute.process_chains(demod_stack, input_audio)
 	print("Correlating results.")
 	results = PacketMetaArray()
 	for decoded_data in decoded_datas:

@@ -801,10 +801,15 @@ cudaError_t pm_launch_gather(const BitChain *chains, int n_chains, ChainCounters
 {
 	const int n_blocks = (int)((n_words + GB_WORDS - 1) / GB_WORDS);
 	dim3 grid(n_blocks, n_chains);
+	pm_kt_mark("gather_count_kernel", st);
 	gather_count_kernel<<<grid, GB_THREADS, 0, st>>>(chains, mask, mask_stride, blk_count, n_blocks, w_origin);
+	pm_kt_mark("row_scan_kernel", st);
 	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, sym_totals);
+	pm_kt_mark("finalize_counts_kernel", st);
 	finalize_counts_kernel<<<(n_chains + 31) / 32, 32, 0, st>>>(chains, sym_totals, cc, n_chains, sb);
+	pm_kt_mark("memset bits", st);
 	cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)bits_stride * n_chains, st);
+	pm_kt_mark("gather_write_kernel", st);
 	gather_write_kernel<<<grid, GB_THREADS, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, blk_base,
 		n_blocks, bits, bits_stride, byte_addr, addr_stride, init_state, w_origin, sb);
 	return cudaGetLastError();
@@ -814,6 +819,7 @@ cudaError_t pm_launch_tail_extract(const uint32_t *bits, long long bits_stride, 
 	int k_words, uint32_t *out, cudaStream_t st)
 {
 	dim3 grid((k_words + 255) / 256, n_chains);
+	pm_kt_mark("tail_extract_kernel", st);
 	tail_extract_kernel<<<grid, 256, 0, st>>>(bits, bits_stride, sb, k_words, out);
 	return cudaGetLastError();
 }
@@ -822,6 +828,7 @@ cudaError_t pm_launch_tail_inject(uint32_t *bits, long long bits_stride, const S
 	int k_words, const uint32_t *in, cudaStream_t st)
 {
 	dim3 grid((k_words + 255) / 256, n_chains);
+	pm_kt_mark("tail_inject_kernel", st);
 	tail_inject_kernel<<<grid, 256, 0, st>>>(bits, bits_stride, sb, k_words, in);
 	return cudaGetLastError();
 }
@@ -832,6 +839,7 @@ cudaError_t pm_launch_lfsr(const BitChain *chains, int n_chains, const ChainCoun
 	int bx = (int)((bits_stride + 255) / 256);
 	if (bx > 1024) bx = 1024;
 	dim3 grid(bx, n_chains);
+	pm_kt_mark("lfsr_kernel", st);
 	lfsr_kernel<<<grid, 256, 0, st>>>(chains, cc, in, out, bits_stride, (int)bits_stride);
 	return cudaGetLastError();
 }
@@ -844,19 +852,26 @@ cudaError_t pm_launch_ax25(const BitChain *chains, int n_chains, ChainCounters *
 {
 	const int n_blocks = (int)((bits_stride + FL_WORDS - 1) / FL_WORDS);
 	dim3 grid(n_blocks, n_chains);
+	pm_kt_mark("flag_count_kernel", st);
 	flag_count_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_count, n_blocks);
+	pm_kt_mark("row_scan_kernel", st);
 	row_scan_kernel<<<n_chains, 1024, 0, st>>>(blk_count, blk_base, n_blocks, n_blocks, flag_totals);
+	pm_kt_mark("flag_write_kernel", st);
 	flag_write_kernel<<<grid, 256, 0, st>>>(chains, cc, d, bits_stride, blk_base, n_blocks, flag_pos, flag_stride);
 	// gaps: at most flag_stride per chain
 	dim3 ggrid((unsigned int)std::min<long long>((flag_stride + 127) / 128, 148 * 16), n_chains);
 	cudaMemsetAsync(gap_ncand, 0, sizeof(unsigned int) * n_chains, st);
+	pm_kt_mark("ax25_gap_filter_kernel", st);
 	ax25_gap_filter_kernel<<<ggrid, 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, flag_totals, gaps,
 		gap_stride, sb, gap_cand, gap_ncand);
+	pm_kt_mark("ax25_gap_kernel", st);
 	ax25_gap_kernel<<<dim3(148 * 2, n_chains), 128, 0, st>>>(chains, cc, d, bits_stride, flag_pos, flag_stride, byte_addr,
 		addr_stride, scratch, scratch_stride, gaps, gap_stride, sb, gap_cand, gap_ncand);
-	if (allow_sequential)
+	if (allow_sequential) {
+		pm_kt_mark("ax25_sequential_kernel", st);
 		ax25_sequential_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, byte_addr, addr_stride, scratch,
 			scratch_stride, gaps, gap_stride);
+	}
 	return cudaGetLastError();
 }
 
@@ -865,9 +880,12 @@ cudaError_t pm_launch_packets(int n_chains, ChainCounters *cc, const GapRec *gap
 	PacketTotals *totals, const uint8_t *scratch, long long scratch_stride, uint8_t *arena,
 	unsigned long long arena_cap, long long sample_base, cudaStream_t st)
 {
+	pm_kt_mark("packet_count_kernel", st);
 	packet_count_kernel<<<n_chains, 1024, 0, st>>>(cc, gaps, gap_stride);
+	pm_kt_mark("packet_index_kernel", st);
 	packet_index_kernel<<<n_chains, 1024, 0, st>>>(cc, n_chains, gaps, gap_stride, recs, rec_src, rec_cap, totals,
 		sample_base);
+	pm_kt_mark("packet_copy_kernel", st);
 	packet_copy_kernel<<<296, 256, 0, st>>>(recs, rec_src, totals, 0, rec_cap, scratch, scratch_stride, arena,
 		arena_cap);
 	return cudaGetLastError();
@@ -877,6 +895,7 @@ cudaError_t pm_launch_stream_export(const ChainCounters *cc, int ch, const uint3
 	const uint32_t *byte_addr, long long addr_stride, uint8_t *out_bytes, long long *out_addr,
 	long long sample_base, cudaStream_t st)
 {
+	pm_kt_mark("stream_export_kernel", st);
 	stream_export_kernel<<<296, 256, 0, st>>>(cc, ch, bits, bits_stride, byte_addr, addr_stride, out_bytes, out_addr,
 		sample_base);
 	return cudaGetLastError();

@@ -14,6 +14,31 @@
 
 static_assert(sizeof(pm_packet_rec) == 40 && sizeof(PacketRecDev) == 40, "pm_packet_rec layout");
 
+// ---- per-kernel timing pass (option "kernel_times") --------------------------------------------------
+struct KernelTimer {
+	struct Mark { const char *name; cudaEvent_t ev; };
+	std::vector<Mark> marks;
+	std::vector<cudaEvent_t> pool;
+	size_t used = 0;
+	void reset() { marks.clear(); used = 0; }
+	~KernelTimer() { for (auto ev : pool) cudaEventDestroy(ev); }
+};
+static thread_local KernelTimer *g_kt = nullptr;      // set while a timing pass runs on this host thread
+
+extern "C" void pm_kt_mark(const char *name, cudaStream_t st)
+{
+	KernelTimer *t = g_kt;
+	if (!t) return;
+	if (t->used == t->pool.size()) {
+		cudaEvent_t ev;
+		if (cudaEventCreate(&ev) != cudaSuccess) return;
+		t->pool.push_back(ev);
+	}
+	cudaEvent_t ev = t->pool[t->used++];
+	cudaEventRecord(ev, st);
+	t->marks.push_back({name, ev});
+}
+
 extern "C" {
 cudaError_t pm_launch_afsk_front(const AfskPlan *, size_t, const int16_t *, long long, long long, int, uint32_t *,
 	long long, float *, long long, GuardList, cudaStream_t);
@@ -224,6 +249,9 @@ struct pm_engine {
 	double rec_scale = 1.0, il2p_cand_scale = 1.0;   // grown (and the run repeated) when packet buffers / IL2P candidate lists overflow
 	int grow_hint = 0;                    // what the last PM_ERR_CAPACITY asked for: 1 packet buffers, 2 IL2P candidates
 	bool skip_lfsr = false;               // pm_engine_decode_stream: the stream loaded is already descrambled
+	int opt_kernel_times = 0;             // record an event before every kernel of a run (pm_engine_kernel_times)
+	KernelTimer kt;
+	std::string kt_report;
 	bool has_il2p = false, il2p_tables = false;
 	unsigned int *h_counters = nullptr;   // pinned
 	PacketTotals *h_totals = nullptr;     // pinned
@@ -857,6 +885,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 		}
 	}
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
+	else if (k == "kernel_times") e->opt_kernel_times = value != 0;
 	else if (k == "copy_threads") e->opt_copy_threads = std::max(1, std::min(16, (int)value));
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
 	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);
@@ -1132,6 +1161,7 @@ static int slicer_converge(pm_engine *e)
 		}
 		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
 		e->stats.kernel_launches++;
+		pm_kt_mark("d2h counters + host sync", e->st);
 		CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
 		CK(cudaStreamSynchronize(e->st));
 		e->stats.slicer_repairs += e->h_counters[1];
@@ -1220,6 +1250,7 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 	if (rc != PM_OK) return rc;
 	const int16_t *d_audio = audio;
 	CK(cudaEventRecord(e->ev[0], e->st));
+	pm_kt_mark("(launch gap)", e->st);
 	if (on_host) {
 		CK(e->d_audio.ensure((size_t)n + 64));
 		d_audio = e->d_audio.p;
@@ -1395,6 +1426,7 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 			b.own_hi = b.bit_off + n_own;
 		}
 	}
+	pm_kt_mark("(launch gap)", e->st);
 	CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
 	cudaError_t ce = pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p,
 		e->sign_stride, e->own_w0, std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p,
@@ -1481,6 +1513,7 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	CK(cudaEventRecord(e->ev[4], e->st));
 
 	// results to host
+	pm_kt_mark("d2h counters + host sync", e->st);
 	CK(cudaMemcpyAsync(e->h_totals, e->d_totals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, e->st));
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
@@ -1511,6 +1544,7 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	}
 	CK(e->h_recs.resize(np));
 	CK(e->h_arena.resize(nb));
+	pm_kt_mark("d2h records", e->st);
 	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
 	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, nb, cudaMemcpyDeviceToHost, e->st));
 	CK(cudaEventRecord(e->ev[5], e->st));
@@ -1532,6 +1566,30 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	return PM_OK;
 }
 
+// elapsed time between consecutive marks of a timing pass, summed per name in order of first appearance
+static void kt_finish(pm_engine *e)
+{
+	cudaStreamSynchronize(e->st);
+	std::vector<std::string> names;
+	std::vector<double> ms;
+	std::vector<int> cnt;
+	auto &m = e->kt.marks;
+	for (size_t i = 0; i + 1 < m.size(); i++) {
+		float dt = 0;
+		if (cudaEventElapsedTime(&dt, m[i].ev, m[i + 1].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+		size_t k = 0;
+		while (k < names.size() && names[k] != m[i].name) k++;
+		if (k == names.size()) { names.push_back(m[i].name); ms.push_back(0); cnt.push_back(0); }
+		ms[k] += dt; cnt[k]++;
+	}
+	e->kt_report.clear();
+	char line[160];
+	for (size_t k = 0; k < names.size(); k++) {
+		snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", names[k].c_str(), cnt[k], ms[k]);
+		e->kt_report += line;
+	}
+}
+
 // a finish that ran out of room says what to grow (grow_hint); true when the run should be repeated
 static bool grow_after_capacity(pm_engine *e, int rc)
 {
@@ -1549,11 +1607,16 @@ static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_hos
 	plan.first = plan.last = 1;
 	for (;;) {
 		if (e) e->grow_hint = 0;
+		const bool timing = e && e->opt_kernel_times;
+		if (timing) { e->kt.reset(); g_kt = &e->kt; }
 		int rc = shard_begin_impl(e, audio, n, on_host, plan, false);
-		if (rc != PM_OK) return rc;
-		rc = shard_gather_impl(e, nullptr, nullptr);
-		if (rc != PM_OK) return rc;
-		rc = shard_finish_impl(e, nullptr);
+		if (rc == PM_OK) rc = shard_gather_impl(e, nullptr, nullptr);
+		if (rc == PM_OK) rc = shard_finish_impl(e, nullptr);
+		if (timing) {
+			pm_kt_mark("end", e->st);
+			g_kt = nullptr;
+			kt_finish(e);
+		}
 		if (!grow_after_capacity(e, rc)) return rc;      // packet buffers / IL2P candidate list too small: grow, run again
 	}
 }
@@ -2113,6 +2176,17 @@ extern "C" int pm_engine_get_stream(const pm_engine *ce, int32_t chain, int32_t 
 	if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess)
 		return fail(e, PM_ERR_CUDA, "stream export failed");
 	return PM_OK;
+}
+
+// The last run's per-kernel times (option "kernel_times" = 1 before the run): one line per kernel name,
+// "name<TAB>launches<TAB>milliseconds", in order of first launch.  Returns the number of bytes written (without the
+// terminating 0) or PM_ERR_CAPACITY.
+extern "C" int64_t pm_engine_kernel_times(const pm_engine *e, char *buf, int64_t cap)
+{
+	if (!e || !buf) return PM_ERR_ARG;
+	if ((int64_t)e->kt_report.size() + 1 > cap) return PM_ERR_CAPACITY;
+	memcpy(buf, e->kt_report.c_str(), e->kt_report.size() + 1);
+	return (int64_t)e->kt_report.size();
 }
 
 extern "C" int pm_engine_get_stats(const pm_engine *e, pm_stats *out)

@@ -731,6 +731,7 @@ extern "C" cudaError_t pm_launch_afsk_front(const AfskPlan *plan, size_t smem_by
 		cudaFuncSetAttribute(afsk_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 		attr_done = true;
 	}
+	pm_kt_mark("afsk_front_kernel", st);
 	if (soft)
 		afsk_front_kernel<true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
 			sign, sign_stride, soft, soft_stride, guard);
@@ -751,6 +752,7 @@ extern "C" cudaError_t pm_launch_fir_front(const FirPlan *plan, size_t smem_byte
 		cudaFuncSetAttribute(fir_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 		attr_done = true;
 	}
+	pm_kt_mark("fir_front_kernel", st);
 	if (soft)
 		fir_front_kernel<true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
 			sign, sign_stride, soft, soft_stride, guard);
@@ -770,6 +772,7 @@ extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int warp_d
 		cudaFuncSetAttribute(guard_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		attr = smem;
 	}
+	pm_kt_mark("guard_fixup_kernel", st);
 	guard_fixup_kernel<<<grid, PM_FIX_THREADS, smem, st>>>(chains, audio, n_audio, sign, sign_stride, soft,
 		soft_stride, guard, warp_doubles);
 	return cudaGetLastError();

@@ -442,8 +442,10 @@ extern "C" cudaError_t pm_launch_il2p(const BitChain *chains, int n_chains, Chai
 	GapRec *gaps, long long gap_stride, const ShardBits *sb, const Il2pHand *hand_in, Il2pHand *hand_out, cudaStream_t st)
 {
 	dim3 grid((cand_cap + 63) / 64, n_chains);
+	pm_kt_mark("il2p_decode_kernel", st);
 	il2p_decode_kernel<<<grid, 64, 0, st>>>(chains, cc, d, bits_stride, cand_pos, cand_stride, cand_totals, cand_cap,
 		cand_scratch, cand_scratch_stride, results);
+	pm_kt_mark("il2p_resolve_kernel", st);
 	il2p_resolve_kernel<<<n_chains, 32, 0, st>>>(chains, cc, d, bits_stride, cand_pos, cand_stride, cand_totals,
 		cand_cap, cand_scratch, cand_scratch_stride, results, byte_addr, addr_stride, scratch, scratch_stride,
 		gaps, gap_stride, sb, hand_in, hand_out);

@@ -311,6 +311,7 @@ cudaError_t pm_link_preload(void)
 cudaError_t pm_link_push_states(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch, const SegState *S,
 	const SegState *E, int n_seg, int k_end, const unsigned long long *symcount, cudaStream_t st)
 {
+	pm_kt_mark("link_push_states_kernel", st);
 	link_push_states_kernel<<<1, 256, 0, st>>>(G, peers, parity, epoch, S, E, n_seg, k_end, symcount);
 	return cudaGetLastError();
 }
@@ -318,18 +319,21 @@ cudaError_t pm_link_push_states(LinkGeom G, LinkPeers peers, int parity, unsigne
 cudaError_t pm_link_wait_states(LinkGeom G, unsigned char *own, int parity, unsigned int epoch, const BitChain *chains,
 	int first, int last, int tail_bits, ShardBits *sb, int *status, cudaStream_t st)
 {
+	pm_kt_mark("link_wait_states_kernel", st);
 	link_wait_states_kernel<<<1, 256, 0, st>>>(G, own, parity, epoch, chains, first, last, tail_bits, sb, status);
 	return cudaGetLastError();
 }
 
 cudaError_t pm_link_set_flag(unsigned int *flag, unsigned int epoch, cudaStream_t st)
 {
+	pm_kt_mark("link_set_flag_kernel", st);
 	link_set_flag_kernel<<<1, 1, 0, st>>>(flag, epoch);
 	return cudaGetLastError();
 }
 
 cudaError_t pm_link_wait_flag(const unsigned int *flag, unsigned int epoch, int *status, cudaStream_t st)
 {
+	pm_kt_mark("link_wait_flag_kernel", st);
 	link_wait_flag_kernel<<<1, 1, 0, st>>>(flag, epoch, status);
 	return cudaGetLastError();
 }
@@ -337,8 +341,11 @@ cudaError_t pm_link_wait_flag(const unsigned int *flag, unsigned int epoch, int 
 cudaError_t pm_link_push_records(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch, const PacketRecDev *recs,
 	const uint8_t *arena, const PacketTotals *totals, const ChainCounters *cc, int *status, cudaStream_t st)
 {
+	pm_kt_mark("link_check_decode_kernel", st);
 	link_check_decode_kernel<<<1, 32, 0, st>>>(cc, G.nc, status);
+	pm_kt_mark("link_push_records_kernel", st);
 	link_push_records_kernel<<<dim3(32, G.world), 256, 0, st>>>(G, peers, parity, recs, arena, totals, status);
+	pm_kt_mark("link_publish_records_kernel", st);
 	link_publish_records_kernel<<<1, 32, 0, st>>>(G, peers, parity, epoch, totals, status);
 	return cudaGetLastError();
 }
@@ -347,7 +354,9 @@ cudaError_t pm_link_merge(LinkGeom G, unsigned char *own, int parity, unsigned i
 	unsigned long long *obase, unsigned long long *abase, PacketTotals *merged_totals, PacketRecDev *out_recs,
 	unsigned long long rec_cap, uint8_t *out_arena, unsigned long long arena_cap, int *status, cudaStream_t st)
 {
+	pm_kt_mark("link_merge_plan_kernel", st);
 	link_merge_plan_kernel<<<1, 256, 0, st>>>(G, own, parity, epoch, lb, obase, abase, merged_totals, status);
+	pm_kt_mark("link_merge_write_kernel", st);
 	link_merge_write_kernel<<<dim3(64, G.world), 256, 0, st>>>(G, own, parity, lb, obase, abase, out_recs, rec_cap,
 		out_arena, arena_cap, status);
 	return cudaGetLastError();

@@ -432,14 +432,23 @@ extern "C" cudaError_t pm_launch_p64(const P64Chain *d_chains, const P64Chain *h
 	}
 	if (L1 <= 0) L1 = 1;
 	cudaMemsetAsync(max_slots, 0, sizeof(unsigned long long) * n_chains, st);
+	pm_kt_mark("p64_bpf_kernel", st);
 	p64_bpf_kernel<<<dim3(tiles(L1), n_chains), P64_THREADS, sizeof(double) * (P64_TILE + 2 * m_bpf), st>>>(d_chains, audio);
 	if (any_loop) {
+		pm_kt_mark("p64_max_kernel", st);
 		p64_max_kernel<<<dim3(min(tiles(L1) * 4u, 1184u), n_chains), P64_THREADS, 0, st>>>(d_chains);
+		pm_kt_mark("p64_seq_kernel", st);
 		p64_seq_kernel<<<n_chains, 64, 0, st>>>(d_chains, 0);
 	}
-	if (any_mid && L2 > 0)
+	if (any_mid && L2 > 0) {
+		pm_kt_mark("p64_mid_kernel", st);
 		p64_mid_kernel<<<dim3(tiles(L2), n_chains), P64_THREADS, sizeof(double) * (P64_TILE + m_mid), st>>>(d_chains);
-	if (any_mpsk) p64_seq_kernel<<<n_chains, 64, 0, st>>>(d_chains, 1);
+	}
+	if (any_mpsk) {
+		pm_kt_mark("p64_seq_kernel", st);
+		p64_seq_kernel<<<n_chains, 64, 0, st>>>(d_chains, 1);
+	}
+	pm_kt_mark("p64_out_kernel", st);
 	p64_out_kernel<<<dim3(max(tiles(L3), 1u), n_chains, any_mpsk ? 2 : 1), P64_THREADS,
 		sizeof(double) * (P64_TILE + 2 * m_out), st>>>(d_chains, sign, sign_stride, soft, soft_stride);
 	return cudaGetLastError();

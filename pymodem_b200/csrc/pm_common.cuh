@@ -3,6 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Per-kernel timing (option "kernel_times", pm_engine_kernel_times): every launcher announces the kernel it is about to
+// launch; the engine records a CUDA event on that stream when a timing pass is active on the calling thread, and does
+// nothing otherwise (csrc/engine.cu).
+extern "C" void pm_kt_mark(const char *name, cudaStream_t st);
+
 #define PM_MAX_MAG     8      // tone-magnitude streams per AFSK front-end group
 #define PM_MAX_PAIR    8      // (mark stream, space stream) pairs per group
 #define PM_MAX_GCH     16     // chains per front-end group

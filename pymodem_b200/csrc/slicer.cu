@@ -358,6 +358,7 @@ extern "C" cudaError_t pm_launch_soft_signs(const double *x, long long n, uint32
 	if (n <= 0) return cudaSuccess;
 	const long long words = (n + 31) >> 5;
 	const int blocks = (int)std::min<long long>((words + 7) / 8, 148 * 8);
+	pm_kt_mark("soft_sign_kernel", st);
 	soft_sign_kernel<<<blocks, 256, 0, st>>>(x, n, out);
 	return cudaGetLastError();
 }
@@ -367,6 +368,7 @@ extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int 
 	const SegState *init, SlicerGeom G, cudaStream_t st)
 {
 	dim3 grid((G.n_seg + 127) / 128, n_chains);
+	pm_kt_mark("slicer_segments_kernel", st);
 	slicer_segments_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, chk, init, G);
 	return cudaGetLastError();
 }
@@ -376,6 +378,7 @@ extern "C" cudaError_t pm_launch_slicer_verify(const SlicerChain *chains, int n_
 	SegState *E_out, SegState *chk, const SegState *init, SlicerGeom G, unsigned int *repairs, cudaStream_t st)
 {
 	dim3 grid((G.n_seg + 127) / 128, n_chains);
+	pm_kt_mark("slicer_verify_kernel", st);
 	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, chk,
 		init, G, repairs);
 	return cudaGetLastError();
@@ -385,6 +388,7 @@ extern "C" cudaError_t pm_launch_slicer_sweep(const SlicerChain *chains, int n_c
 	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, SegState *E, SegState *chk,
 	const SegState *init, SlicerGeom G, unsigned int *repairs, cudaStream_t st)
 {
+	pm_kt_mark("slicer_sweep_kernel", st);
 	slicer_sweep_kernel<<<n_chains, 32, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, chk, init, G,
 		repairs);
 	return cudaGetLastError();
@@ -398,6 +402,7 @@ extern "C" cudaError_t pm_launch_slicer_count(const SlicerChain *chains, int n_c
 	if (nb < 1) nb = 1;
 	if (nb > 1184) nb = 1184;
 	dim3 grid((unsigned int)nb, n_chains);
+	pm_kt_mark("slicer_count_kernel", st);
 	slicer_count_kernel<<<grid, 256, 0, st>>>(chains, mask, mask_stride, w0, w1, out);
 	return cudaGetLastError();
 }

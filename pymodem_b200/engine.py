@@ -332,6 +332,18 @@ class Engine:
 		self._check(self._lib.pm_engine_get_stats(self._h, ctypes.byref(s)))
 		return s.as_dict()
 
+	def kernel_times(self):
+		"""Per-kernel times of the last run (option kernel_times=1): [(name, launches, ms)] in order of first launch."""
+		buf = ctypes.create_string_buffer(1 << 16)
+		n = self._lib.pm_engine_kernel_times(self._h, buf, len(buf))
+		if n < 0:
+			raise EngineError(f"pm_engine_kernel_times failed ({n})")
+		out = []
+		for line in buf.value.decode().splitlines():
+			name, cnt, ms = line.split("\t")
+			out.append((name, int(cnt), float(ms)))
+		return out
+
 	def stage_clocks(self):
 		"""Cycles per front-end stage summed over CTAs since the last call (option stage_clocks=1); see the header."""
 		out = (ctypes.c_uint64 * 8)()
@@ -347,29 +359,27 @@ def _unregister(lib, ptr, table, key):
 	lib.pm_host_unregister(ptr)
 
 
+_SCALAR_FIELDS = [n for n, t in _lib.ChainDesc._fields_ if not issubclass(t, (ctypes._Pointer, ctypes.Array))]
+_LOOP_SCALARS = [n for n, t in _lib.LoopDesc._fields_ if not issubclass(t, ctypes._Pointer)]
+
+
 def stack_fingerprint(demod_stack):
 	"""Digest of everything describe() hands to the engine -- the pm_chain_desc scalars and every tap / table array.
 	The reference reads its blocks' state on every call (chain_execute.py:32-47), so a retune() or
 	StringOptionsRetune() between two calls must take effect: engine_for() compares this, not object identities."""
 	h = hashlib.blake2b(digest_size=16)
-	ptr_types = (ctypes._Pointer,)
 	for chain in demod_stack:
 		keep = []
 		desc = describe_chain(chain, keep)
-		for name, _ in _lib.ChainDesc._fields_:
-			v = getattr(desc, name)
-			if isinstance(v, ptr_types):
-				continue
-			h.update(bytes(v) if isinstance(v, ctypes.Array) else repr(v).encode())
+		scal = [getattr(desc, n) for n in _SCALAR_FIELDS]
 		if desc.loop:
 			lp = desc.loop.contents
-			for name, _ in _lib.LoopDesc._fields_:
-				v = getattr(lp, name)
-				if not isinstance(v, ptr_types):
-					h.update(repr(v).encode())
+			scal += [getattr(lp, n) for n in _LOOP_SCALARS]
+		h.update(repr(scal).encode())
+		h.update(bytes(desc.demap))
 		for a in keep:
 			if isinstance(a, np.ndarray):
-				h.update(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes())
+				h.update(a.dtype.char.encode() + a.tobytes() + b"|")
 		h.update(str(chain[0]).encode() + b"|")
 	return h.hexdigest()
 
@@ -419,6 +429,33 @@ def addressed_arrays(stream):
 def addressed_list(data, addresses):
 	from .modems_codecs.data_classes import AddressedData
 	return [AddressedData(d, a) for d, a in zip(data.tolist(), addresses.tolist())]
+
+
+def pinned_empty(n, dtype=np.int16):
+	"""A NumPy array in page-locked host memory (pm_host_alloc): pm_engine_run DMAs straight out of it.  Read a
+	recording into one of these (python -m pymodem_b200 does, pymodem.py:46) instead of into pageable memory.
+	The memory is released when the last view of it goes away."""
+	lib = _lib.load()
+	dtype = np.dtype(dtype)
+	nbytes = max(int(n) * dtype.itemsize, 1)
+	ptr = lib.pm_host_alloc(nbytes)
+	if not ptr:
+		raise EngineError(f"pm_host_alloc({nbytes}) failed: a CUDA device is required")
+	buf = (ctypes.c_char * nbytes).from_address(ptr)
+	weakref.finalize(buf, lib.pm_host_free, ptr)
+	return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+def read_wav_pinned(path):
+	"""scipy.io.wavfile.read (pymodem.py:46) with the samples landing in pinned memory: the file is memory-mapped and
+	copied once, straight into the buffer the GPU reads.  -> (sample_rate, int16 ndarray)"""
+	from scipy.io.wavfile import read as readwav
+	rate, mapped = readwav(path, mmap=True)
+	if mapped.ndim != 1 or mapped.dtype != np.int16:
+		raise ValueError("16-bit mono PCM expected")
+	out = pinned_empty(len(mapped), np.int16)
+	out[:] = mapped
+	return int(rate), out
 
 
 def demod_only(modem, audio):

@@ -1,0 +1,81 @@
+"""Real multi-rank parity: torchrun with one process per GPU (NCCL for the IPC-handle exchange, the shard link over
+NVLink peer memory for everything else).  ONE recording split over the ranks must leave, on every rank, exactly the
+records an unsharded engine produces for the whole recording.  Skipped on a box with fewer than two GPUs; the
+one-GPU emulation of the same protocol is tests/test_gpu_sharded.py, its CPU logic tests/test_sharded_cpu.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import hashlib, json, os, sys
+sys.path.insert(0, %(repo)r)
+import numpy as np, torch, torch.distributed as dist
+from pymodem_b200 import configs, synth
+from pymodem_b200.engine import Engine
+from pymodem_b200.modems_codecs import chain_builder
+from pymodem_b200.sharded import LinkedRun, TorchExchange, plan_shards
+sys.path.insert(0, os.path.join(%(repo)r))
+from bench import records_digest
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+out = {}
+for case, kw in (("noise_ramp", dict(duration_s=240.0, frame_interval_s=1.7, noise_start=0.0, noise_end=1.5, seed=81, noise_seed=82)),
+		("long_frames", dict(duration_s=120.0, frame_interval_s=9.0, noise_start=0.0, noise_end=0.3, seed=83, noise_seed=84,
+			payload_len=[1100, 60, 1300, 40, 1500]))):
+	audio = synth.afsk1200_ax25(sample_rate=48000, **kw)[0]
+	stack = [chain_builder.build_chain(48000, l) for l in configs.demod_chains(configs.afsk_1200_ax25_super_opt())]
+	plans = plan_shards(len(audio), world, trim_max=305, samples_per_symbol=40.0)
+	plan = plans[rank]
+	local_audio = np.ascontiguousarray(audio[plan['audio_begin']:plan['audio_end']])
+	eng = Engine(stack, device=local)
+	ex = TorchExchange(torch.device("cuda", local))
+	link = LinkedRun(eng, rank, world, max(p['audio_end'] - p['audio_begin'] for p in plans), ex, ex.var)
+	digests = []
+	for rep in range(2):
+		recs, arena = link.run(plan, local_audio.ctypes.data, len(local_audio))
+		digests.append(records_digest(recs, arena))
+	everyone = [None] * world
+	dist.all_gather_object(everyone, (digests, int(len(recs)), link.fallbacks, link.recoveries))
+	if rank == 0:
+		solo = Engine(stack, device=local)
+		r2, a2 = solo.run_raw(audio)
+		out[case] = dict(ranks=everyone, unsharded=records_digest(r2, a2), n_unsharded=int(len(r2)))
+		solo.close()
+	eng.close()
+if rank == 0:
+	print("RESULT " + json.dumps(out), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def _gpu_count():
+	import torch
+	return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_torchrun_ranks_equal_unsharded(cuda_lib, tmp_path, world):
+	if _gpu_count() < world:
+		pytest.skip(f"needs {world} GPUs")
+	script = tmp_path / "worker.py"
+	script.write_text(WORKER % {"repo": REPO})
+	port = 29400 + world
+	r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+		"--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900, cwd=REPO)
+	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+	line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+	res = json.loads(line[len("RESULT "):])
+	for case, d in res.items():
+		assert d["n_unsharded"] > 0, case
+		for digests, n, fallbacks, recoveries in d["ranks"]:
+			assert n == d["n_unsharded"], (case, d)
+			assert all(x == d["unsharded"] for x in digests), (case, d)
+	# frames beyond 1023 bytes force the bitstream recovery on every rank, every run
+	assert all(r[3] == 2 for r in res["long_frames"]["ranks"]), res["long_frames"]

@@ -13,7 +13,8 @@ SOFT_RTOL = 1e-5          # BASELINE.json north_star: "within a stated relative 
 CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
 	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k",
 	# recursive modems (float64 pipeline: AGC + Costas / decision-directed / PLL loops)
-	"bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k"]
+	"bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k",
+	"qpsk600_il2p_8k", "qpsk3600_il2p_16k", "mpsk_bpsk300_il2p_8k", "mpsk_bpsk1200_il2p_12k"]
 
 
 def build_stack(sample_rate, lines):

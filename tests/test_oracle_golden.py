@@ -12,7 +12,8 @@ CASES = ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_ax25_48k",
 	"afsk1200_il2p_48k", "fsk9600_il2p_48k", "afsk300_real_8k"]
 # recursive modems (AGC + Costas / decision-directed / PLL loops): no chunked form, AGC.apply takes
 # max(buffer) of the whole recording (agc.py:67)
-PSK_CASES = ["bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k"]
+PSK_CASES = ["bpsk300_il2p_8k", "qpsk2400_il2p_8k", "qpsk2400_il2p_22k", "afsk300_full_8k", "bpsk1200_il2p_12k",
+	"qpsk600_il2p_8k", "qpsk3600_il2p_16k", "mpsk_bpsk300_il2p_8k", "mpsk_bpsk1200_il2p_12k"]
 
 
 @pytest.mark.parametrize("tag", CASES + PSK_CASES)

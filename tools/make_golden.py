@@ -147,6 +147,7 @@ def main():
 	run_case("fsk9600_ax25_48k", "fsk_9600.json", lines, 48000, audio, meta, stage_chains=(0,))
 	more_cases()
 	psk_cases()
+	preset_cases()
 
 
 def more_cases():
@@ -202,6 +203,47 @@ def psk_cases():
 	run_case("bpsk1200_il2p_12k", "bpsk_1200.json", load_config("bpsk_1200.json"), 12000, audio, meta, stage_chains=(0,))
 
 
+def _mpsk_line(name, config, carrier, lock_rate):
+	"""A demod_chain line for an MPSKModem preset that no shipped config uses (psk.py:570-628: 'bpsk_300', 'bpsk_1200'),
+	in the shape of configs/qpsk_2400.json: differential decoding is the stream's job (LFSR poly 0x3 + invert), the
+	quadrature slicer's 'bpsk_*' presets demap the I sign (slicer.py:124-141)."""
+	return {"object_name": name, "object_type": "demod_chain",
+		"modem": {"type": "mpsk", "config": config, "options": {"carrier_freq": carrier}},
+		"slicer": {"type": "quadrature", "config": config, "options": {"lock_rate": lock_rate}},
+		"stream": {"type": "lfsr", "options": {"poly": "0x3", "invert": "True"}},
+		"codec": {"type": "il2p", "options": {"crc": "yes", "disable_rs": "no", "min_dist": "0", "sync_tol": "2"}}}
+
+
+def preset_cases():
+	"""The presets round 1 left without a fixture (VERDICT r1 missing #3): psk.py:485-541 (qpsk_3600, qpsk_600),
+	psk.py:570-628 (MPSK bpsk_300, bpsk_1200), slicer.py:124-165 (their quadrature-slicer presets)."""
+	# (12) qpsk_600.json as shipped: 300 symbols/s, RRC 0.6, carrier 1500, at 8 kHz (26.67 samples per symbol)
+	meta = dict(gen="qpsk2400_il2p", duration_s=50.0, sample_rate=8000, frame_interval_s=4.0, noise_start=0.0,
+		noise_end=0.5, seed=20, noise_seed=21, carrier=1501.5, baud=300.0, rolloff=0.6, first_frame_s=2.0,
+		payload_len=[None, 100, 0, 30])
+	audio, _, _ = synth.qpsk2400_il2p(**meta_args(meta))
+	run_case("qpsk600_il2p_8k", "qpsk_600.json", load_config("qpsk_600.json"), 8000, audio, meta, stage_chains=(0,))
+	# (13) qpsk_3600.json as shipped: 1800 symbols/s, RRC 0.3, carrier 1650, at 16 kHz (8.89 samples per symbol)
+	meta = dict(gen="qpsk2400_il2p", duration_s=14.0, sample_rate=16000, frame_interval_s=0.8, noise_start=0.0,
+		noise_end=0.4, seed=22, noise_seed=23, carrier=1648.0, baud=1800.0, rolloff=0.3, first_frame_s=1.0,
+		payload_len=[None, 200, 0, 40])
+	audio, _, _ = synth.qpsk2400_il2p(**meta_args(meta))
+	run_case("qpsk3600_il2p_16k", "qpsk_3600.json", load_config("qpsk_3600.json"), 16000, audio, meta, stage_chains=(0,))
+	# (14) MPSKModem preset 'bpsk_300' (decision-directed loop on a two-point constellation) at 8 kHz
+	meta = dict(gen="bpsk300_il2p", duration_s=50.0, sample_rate=8000, frame_interval_s=3.0, noise_start=0.0,
+		noise_end=0.7, seed=24, noise_seed=25, carrier=1502.0, first_frame_s=1.5, payload_len=[None, 60, 0, 30])
+	audio, _, _ = synth.bpsk300_il2p(**meta_args(meta))
+	lines = [_mpsk_line("MPSK2 300 IL2P+CRC 1500", "bpsk_300", "1500", "0.815")]
+	run_case("mpsk_bpsk300_il2p_8k", None, lines, 8000, audio, meta, stage_chains=(0,))
+	# (15) MPSKModem preset 'bpsk_1200' at 12 kHz
+	meta = dict(gen="bpsk300_il2p", duration_s=14.0, sample_rate=12000, frame_interval_s=0.8, noise_start=0.0,
+		noise_end=0.5, seed=26, noise_seed=27, carrier=1497.0, baud=1200.0, rolloff=0.9, first_frame_s=0.6,
+		payload_len=[None, 50])
+	audio, _, _ = synth.bpsk300_il2p(**meta_args(meta))
+	lines = [_mpsk_line("MPSK2 1200 IL2P+CRC 1500", "bpsk_1200", "1500", "0.9")]
+	run_case("mpsk_bpsk1200_il2p_12k", None, lines, 12000, audio, meta, stage_chains=(0,))
+
+
 def meta_args(meta):
 	return {k: v for k, v in meta.items() if k != "gen"}
 
@@ -211,5 +253,7 @@ if __name__ == "__main__":
 		more_cases()
 	elif "--psk" in sys.argv:
 		psk_cases()
+	elif "--presets" in sys.argv:
+		preset_cases()
 	else:
 		main()
