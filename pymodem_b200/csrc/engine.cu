@@ -50,7 +50,8 @@ cudaError_t pm_launch_ffma_peak(float *, int, int, cudaStream_t);
 cudaError_t pm_launch_slicer_segments(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
 	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, cudaStream_t);
 cudaError_t pm_launch_slicer_verify(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
-	SegState *, const SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *, cudaStream_t);
+	SegState *, const SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *,
+	const unsigned int *, cudaStream_t);
 cudaError_t pm_launch_slicer_sweep(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
 	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *, cudaStream_t);
 cudaError_t pm_launch_slicer_count(const SlicerChain *, int, const uint32_t *, long long, long long, long long,
@@ -69,7 +70,7 @@ cudaError_t pm_launch_p64(const P64Chain *, const P64Chain *, int, const int16_t
 	long long, unsigned long long *, cudaStream_t);
 cudaError_t pm_link_preload(void);
 cudaError_t pm_link_push_states(LinkGeom, LinkPeers, int, unsigned int, const SegState *, const SegState *, int, int,
-	const unsigned long long *, cudaStream_t);
+	const unsigned long long *, const unsigned int *, int, unsigned int, cudaStream_t);
 cudaError_t pm_link_wait_states(LinkGeom, unsigned char *, int, unsigned int, const BitChain *, int, int, int, ShardBits *,
 	int *, cudaStream_t);
 cudaError_t pm_link_set_flag(unsigned int *, unsigned int, cudaStream_t);
@@ -249,6 +250,15 @@ struct pm_engine {
 	double rec_scale = 1.0, il2p_cand_scale = 1.0;   // grown (and the run repeated) when packet buffers / IL2P candidate lists overflow
 	int grow_hint = 0;                    // what the last PM_ERR_CAPACITY asked for: 1 packet buffers, 2 IL2P candidates
 	bool skip_lfsr = false;               // pm_engine_decode_stream: the stream loaded is already descrambled
+	int fast_passes = 0;                  // verify passes enqueued without a host round trip (slicer_enqueue_fast)
+	bool fast_pending = false;            // ... whose counters have not been looked at yet
+	size_t spec_recs = 4096, spec_arena = 1 << 18;   // records / packet bytes copied back before their count is known
+	std::vector<ShardBits> h_sb;
+	std::vector<SlicerChain> up_sl;       // what the device tables hold (prepare_run uploads only what changed)
+	std::vector<BitChain> up_bc;
+	std::vector<SegState> up_init;
+	std::vector<P64Chain> up_p64;
+	std::vector<ShardBits> up_sb;
 	int opt_kernel_times = 0;             // record an event before every kernel of a run (pm_engine_kernel_times)
 	KernelTimer kt;
 	std::string kt_report;
@@ -296,6 +306,12 @@ static int fail(pm_engine *e, int code, const char *fmt, ...)
 	} while (0)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+static bool same_bytes(const std::vector<T> &a, const std::vector<T> &b)
+{
+	return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(T)) == 0);
+}
 
 static bool same_taps(const std::vector<double> &a, const std::vector<double> &b)
 {
@@ -686,6 +702,7 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 	cudaSetDevice(e->device);
 	e->chains.clear();
 	e->have_run = false;
+	e->up_sl.clear(); e->up_bc.clear(); e->up_init.clear(); e->up_p64.clear(); e->up_sb.clear();
 	for (int c = 0; c < n; c++) {
 		HostChain hc;
 		hc.d = descs[c];
@@ -931,6 +948,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	long long max_words = 0, max_bits = 0, max_nout = 0;
 	std::vector<SlicerChain> sl(nc);
 	std::vector<BitChain> bc(nc);
+	memset(sl.data(), 0, nc * sizeof(SlicerChain));
 	e->h_init.assign(nc, SegState());
 	long long rec_cap = 16, arena_cap = 64;
 	for (int c = 0; c < nc; c++) {
@@ -1078,14 +1096,27 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 			if (P.kind == PM_MODEM_MPSK) { P.C = w; w += n; P.D = w; w += n; }
 			P.max_slot = e->d_p64_max.p + i;
 		}
-		CK(cudaMemcpyAsync(e->d_p64.p, e->h_p64.data(), e->h_p64.size() * sizeof(P64Chain), cudaMemcpyHostToDevice, e->st));
+		if (!same_bytes(e->up_p64, e->h_p64)) {
+			CK(cudaMemcpyAsync(e->d_p64.p, e->h_p64.data(), e->h_p64.size() * sizeof(P64Chain), cudaMemcpyHostToDevice, e->st));
+			e->up_p64 = e->h_p64;
+		}
 	}
-	CK(cudaMemcpyAsync(e->d_slicer.p, sl.data(), nc * sizeof(SlicerChain), cudaMemcpyHostToDevice, e->st));
-	CK(cudaMemcpyAsync(e->d_bitchain.p, bc.data(), nc * sizeof(BitChain), cudaMemcpyHostToDevice, e->st));
-	CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+	// the per-run tables only travel when they changed (same recording length and plan as last time: nothing to upload;
+	// a copy from pageable memory returns once the source has been staged, so the vectors may go out of scope)
+	if (!same_bytes(e->up_sl, sl)) {
+		CK(cudaMemcpyAsync(e->d_slicer.p, sl.data(), nc * sizeof(SlicerChain), cudaMemcpyHostToDevice, e->st));
+		e->up_sl = sl;
+	}
+	if (!same_bytes(e->up_bc, bc)) {
+		CK(cudaMemcpyAsync(e->d_bitchain.p, bc.data(), nc * sizeof(BitChain), cudaMemcpyHostToDevice, e->st));
+		e->up_bc = bc;
+	}
+	if (!same_bytes(e->up_init, e->h_init)) {
+		CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+		e->up_init = e->h_init;
+	}
 	CK(cudaMemsetAsync(e->d_counters.p, 0, 16 * sizeof(unsigned int), e->st));
 	CK(cudaMemsetAsync(e->d_totals.p, 0, sizeof(PacketTotals), e->st));
-	CK(cudaStreamSynchronize(e->st));      // the staging vectors above go out of scope
 	for (auto &g : e->groups) {
 		if (g.kind == PM_MODEM_AFSK)
 			for (int i = 0; i < g.afsk.n_chain; i++)
@@ -1153,7 +1184,7 @@ static int slicer_converge(pm_engine *e)
 		CK(cudaMemsetAsync(e->d_counters.p + 1, 0, sizeof(unsigned int), e->st));
 		if (pass < e->opt_verify_passes) {
 			ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-				e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, e->st);
+				e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, nullptr, e->st);
 			std::swap(e->E_cur, e->E_alt);
 		} else {
 			ce = pm_launch_slicer_sweep(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
@@ -1169,6 +1200,39 @@ static int slicer_converge(pm_engine *e)
 		if (e->h_counters[1] == 0) break;
 	}
 	return PM_OK;
+}
+
+// The same passes without asking the host in between: up to FAST_PASSES verify passes are enqueued back to back, each
+// one skipping itself when its predecessor repaired nothing (d_counters[2 + p] = repairs of pass p).  Whether that was
+// enough is read from the counters with the run's results (slicer_fast_converged); almost always it is -- pass 0
+// repairs the ~0.15 % of hand-offs whose warm-up did not become bit-identical, pass 1 finds nothing.
+#define FAST_PASSES 3
+static int slicer_enqueue_fast(pm_engine *e)
+{
+	const int nc = (int)e->chains.size();
+	e->fast_passes = std::min(e->opt_verify_passes, FAST_PASSES);
+	for (int p = 0; p < e->fast_passes; p++) {
+		cudaError_t ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+			e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 2 + p,
+			p ? e->d_counters.p + 2 + p - 1 : nullptr, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
+		std::swap(e->E_cur, e->E_alt);
+		e->stats.kernel_launches++;
+	}
+	e->fast_pending = true;
+	return PM_OK;
+}
+
+// after the counters came back: did some enqueued pass find nothing to repair?
+static bool slicer_fast_converged(pm_engine *e)
+{
+	bool ok = false;
+	for (int p = 0; p < e->fast_passes; p++) {
+		e->stats.slicer_repairs += e->h_counters[2 + p];
+		if (e->h_counters[2 + p] == 0) ok = true;
+	}
+	e->fast_pending = false;
+	return ok;
 }
 
 // start state (S of the first own segment k0), end state (E of segment k_end-1) and own symbol count of every chain
@@ -1239,7 +1303,7 @@ static void parallel_copy(void *dst, const void *src, size_t bytes, int threads)
 }
 
 static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
-                      bool sharded)
+                      bool sharded, bool defer)
 {
 	const int nc = (int)e->chains.size();
 	for (int c = 0; c < nc; c++)
@@ -1355,6 +1419,15 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 		// the state at own_begin is only speculated so far: take it as given until the hand-off
 		CK(cudaMemcpy2DAsync(e->d_init.p, sizeof(SegState), e->d_S.p, (size_t)e->geom.n_seg * sizeof(SegState),
 			sizeof(SegState), nc, cudaMemcpyDeviceToDevice, e->st));
+		e->up_init.clear();
+	}
+	if (defer) {
+		// no host round trip: the verify passes are enqueued blind, the guard and repair counters come back with the
+		// results (run_impl / run_linked_end look at them)
+		rc = slicer_enqueue_fast(e);
+		if (rc != PM_OK) return rc;
+		CK(cudaEventRecord(e->ev[3], e->st));
+		return PM_OK;
 	}
 	rc = slicer_converge(e);
 	if (rc != PM_OK) return rc;
@@ -1372,8 +1445,10 @@ static int shard_begin_impl(pm_engine *e, const int16_t *audio, long long n, boo
 	cudaSetDevice(e->device);
 	e->phase = 0;
 	e->have_run = false;
+	e->fast_pending = false;
+	const bool defer = !sharded || !read_states;        // unsharded and linked runs: one host synchronisation, at the end
 	for (int attempt = 0; attempt < 4; attempt++) {
-		int rc = begin_once(e, audio, n, on_host, plan, sharded);
+		int rc = begin_once(e, audio, n, on_host, plan, sharded, defer);
 		if (rc == PM_ERR_CAPACITY && e->h_counters[0] > e->guard_cap) {
 			// guard list overflowed: grow it and run again
 			e->guard_cap = e->h_counters[0] + e->h_counters[0] / 4 + 1024;
@@ -1396,7 +1471,9 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 	if (!e || e->phase != 1) return fail(e, PM_ERR_STATE, "shard_gather: call shard_begin first");
 	const int nc = (int)e->chains.size();
 	const pm_shard_plan &plan = e->plan;
-	std::vector<ShardBits> sb(nc);
+	std::vector<ShardBits> &sb = e->h_sb;
+	sb.assign(nc, ShardBits());
+	memset(sb.data(), 0, nc * sizeof(ShardBits));
 	e->h_A0.assign(nc, 0);
 	e->h_valid_from.assign(nc, 0);
 	for (int c = 0; c < nc; c++) {
@@ -1427,7 +1504,10 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 		}
 	}
 	pm_kt_mark("(launch gap)", e->st);
-	CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
+	if (!same_bytes(e->up_sb, sb)) {
+		CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
+		e->up_sb = sb;
+	}
 	cudaError_t ce = pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p,
 		e->sign_stride, e->own_w0, std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p,
 		e->d_sym_totals.p, e->d_bits_raw.p, e->bits_stride, e->d_byte_addr.p, e->addr_stride, nullptr,
@@ -1442,7 +1522,7 @@ static int shard_gather_impl(pm_engine *e, const int64_t *symbols_before, uint32
 		CK(cudaMemcpyAsync(tail_out, e->d_tail.p, (size_t)nc * (plan.tail_bits / 32) * sizeof(uint32_t),
 			cudaMemcpyDeviceToHost, e->st));
 	}
-	CK(cudaStreamSynchronize(e->st));       // sb goes out of scope; tail_out is ready
+	if (e->sharded && tail_out) CK(cudaStreamSynchronize(e->st));       // tail_out is ready
 	e->phase = 2;
 	return PM_OK;
 }
@@ -1512,11 +1592,20 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	e->stats.kernel_launches += 3;
 	CK(cudaEventRecord(e->ev[4], e->st));
 
-	// results to host
-	pm_kt_mark("d2h counters + host sync", e->st);
+	// results to host: ONE synchronisation.  The record count is not known yet, so as many records / packet bytes as the
+	// last run produced (plus a quarter) are copied back blind with the counters; only a run that produced more
+	// pays a second copy.
+	pm_kt_mark("d2h results + host sync", e->st);
 	CK(cudaMemcpyAsync(e->h_totals, e->d_totals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, e->st));
+	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
+	const size_t spec_np = std::min(e->spec_recs, e->d_recs.n), spec_nb = std::min(e->spec_arena, e->d_arena.n);
+	CK(e->h_recs.resize(spec_np));
+	CK(e->h_arena.resize(spec_nb));
+	if (spec_np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, spec_np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
+	if (spec_nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, spec_nb, cudaMemcpyDeviceToHost, e->st));
+	CK(cudaEventRecord(e->ev[5], e->st));
 	CK(cudaStreamSynchronize(e->st));
 	if (e->has_il2p && il2p_out)
 		for (int c = 0; c < nc; c++) {
@@ -1542,13 +1631,21 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 		e->grow_hint = 1;
 		return fail(e, PM_ERR_CAPACITY, "packet buffers too small (%llu records, %llu bytes)", np, nb);
 	}
-	CK(e->h_recs.resize(np));
-	CK(e->h_arena.resize(nb));
-	pm_kt_mark("d2h records", e->st);
-	if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
-	if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, nb, cudaMemcpyDeviceToHost, e->st));
-	CK(cudaEventRecord(e->ev[5], e->st));
-	CK(cudaStreamSynchronize(e->st));
+	if (np > spec_np || nb > spec_nb) {
+		// more than was copied blind: fetch everything again (the pinned buffers may have to grow)
+		CK(e->h_recs.resize(np));
+		CK(e->h_arena.resize(nb));
+		pm_kt_mark("d2h records (second copy)", e->st);
+		if (np) CK(cudaMemcpyAsync(e->h_recs.data(), e->d_recs.p, np * sizeof(pm_packet_rec), cudaMemcpyDeviceToHost, e->st));
+		if (nb) CK(cudaMemcpyAsync(e->h_arena.data(), e->d_arena.p, nb, cudaMemcpyDeviceToHost, e->st));
+		CK(cudaEventRecord(e->ev[5], e->st));
+		CK(cudaStreamSynchronize(e->st));
+	} else {
+		CK(e->h_recs.resize(np));           // shrinks the logical size only: the data stays
+		CK(e->h_arena.resize(nb));
+	}
+	e->spec_recs = np + np / 4 + 256;
+	e->spec_arena = nb + nb / 4 + 16384;
 	e->stats.d2h_bytes = (int64_t)(np * sizeof(pm_packet_rec) + nb + sizeof(PacketTotals) + nc * sizeof(ChainCounters) + 8);
 	e->stats.n_packets = (int64_t)np;
 	e->stats.n_stream_bits = 0;
@@ -1612,6 +1709,26 @@ static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_hos
 		int rc = shard_begin_impl(e, audio, n, on_host, plan, false);
 		if (rc == PM_OK) rc = shard_gather_impl(e, nullptr, nullptr);
 		if (rc == PM_OK) rc = shard_finish_impl(e, nullptr);
+		if (e && e->fast_pending && (rc == PM_OK || rc == PM_ERR_CAPACITY)) {
+			// the one synchronisation of the run is behind us: now look at what the blind part assumed
+			const unsigned int flagged = e->h_counters[0];
+			const bool converged = slicer_fast_converged(e);
+			e->stats.guard_flagged = flagged;
+			if (flagged > e->guard_cap) {
+				// guard list overflowed (samples went without their float64 re-evaluation): grow it, run again
+				e->guard_cap = flagged + flagged / 4 + 1024;
+				if (timing) g_kt = nullptr;
+				continue;
+			}
+			if (!converged && rc == PM_OK) {
+				// rare (stretches without zero crossings): finish the verify/repair passes with the host in the loop,
+				// then redo the bit-level stages on the now exact roll-over mask
+				rc = slicer_converge(e);
+				if (rc == PM_OK) { e->phase = 1; rc = shard_gather_impl(e, nullptr, nullptr); }
+				if (rc == PM_OK) rc = shard_finish_impl(e, nullptr);
+				e->stats.guard_flagged = flagged;
+			}
+		}
 		if (timing) {
 			pm_kt_mark("end", e->st);
 			g_kt = nullptr;
@@ -1663,6 +1780,7 @@ extern "C" int pm_engine_shard_handoff(pm_engine *e, const pm_shard_state *prev,
 			const std::vector<pm_shard_state> before = e->shard_out;
 			e->geom.k_init = e->k0;      // the true state enters at the first own segment; the history before it is final
 			CK(cudaMemcpyAsync(e->d_init.p, e->h_init.data(), nc * sizeof(SegState), cudaMemcpyHostToDevice, e->st));
+			e->up_init.clear();
 			int rc = slicer_converge(e);
 			if (rc != PM_OK) return rc;
 			rc = read_shard_states(e);
@@ -1798,6 +1916,7 @@ static int load_stream(pm_engine *e, int32_t chain, const uint8_t *bytes, const 
 	cc[chain].nbytes = n;
 	CK(cudaMemcpyAsync(e->d_cc.p, cc.data(), nc * sizeof(ChainCounters), cudaMemcpyHostToDevice, e->st));
 	CK(cudaMemcpyAsync(e->d_shardbits.p, sb.data(), nc * sizeof(ShardBits), cudaMemcpyHostToDevice, e->st));
+	e->up_sb.clear();
 	CK(cudaEventRecord(e->ev[0], e->st));
 	for (int i = 1; i <= 3; i++) CK(cudaEventRecord(e->ev[i], e->st));
 	CK(cudaStreamSynchronize(e->st));           // the staging vectors go out of scope
@@ -1977,9 +2096,11 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	int *status = e->d_link_status.p;
 	CK(cudaMemsetAsync(status, 0, 8 * sizeof(int), st));
 	CKL(pm_launch_slicer_count(e->d_slicer.p, nc, e->d_mask.p, e->sign_stride, e->own_w0, e->own_w1, e->d_symcount.p, st));
-	CKL(pm_link_push_states(G, e->lp, parity, epoch, e->d_S.p + e->k0, e->E_cur, e->geom.n_seg, e->k_end, e->d_symcount.p, st));
+	CKL(pm_link_push_states(G, e->lp, parity, epoch, e->d_S.p + e->k0, e->E_cur, e->geom.n_seg, e->k_end, e->d_symcount.p,
+		e->d_counters.p, e->fast_passes, e->guard_cap, st));
 	CKL(pm_link_wait_states(G, own, parity, epoch, e->d_bitchain.p, plan->first, plan->last, plan->tail_bits,
 		e->d_shardbits.p, status, st));
+	e->up_sb.clear();                       // the placement was written on the device
 	CKL(pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride, e->own_w0,
 		std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p, e->d_sym_totals.p, e->d_bits_raw.p,
 		e->bits_stride, e->d_byte_addr.p, e->addr_stride, nullptr, e->d_shardbits.p, st));
@@ -2010,6 +2131,7 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_link_merge(G, own, parity, epoch, e->d_link_lb.p, e->d_link_obase.p, e->d_link_obase.p + (size_t)G.world * (nc + 1),
 		e->d_mtotals.p, (PacketRecDev *)e->d_mrecs.p, e->d_mrecs.n, e->d_marena.p, e->d_marena.n, status, st));
 	e->stats.kernel_launches += 13;
+	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(e->h_link_status, status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(e->h_mtotals, e->d_mtotals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, st));
 	// (nothing here may block the host: a copy into pageable memory would wait for the stream, i.e. for the peers)
@@ -2025,6 +2147,12 @@ extern "C" int pm_engine_run_linked_end(pm_engine *e, int32_t *verified)
 	const int nc = (int)e->chains.size();
 	CK(cudaStreamSynchronize(e->st));
 	*verified = e->h_link_status[0];
+	if (*verified && e->fast_pending) {
+		// all hand-offs verified implies every rank's own passes converged and no guard list overflowed (a rank for
+		// which that does not hold publishes n_symbols = -1, which un-verifies the run for everybody)
+		e->stats.guard_flagged = e->h_counters[0];
+		slicer_fast_converged(e);
+	}
 	if (e->h_link_status[1] != 0) {
 		e->phase = 0;
 		static const char *where[] = {"", "waiting for the slicer states of the other ranks", "waiting for the previous rank's bit tail",
@@ -2081,6 +2209,23 @@ extern "C" int pm_engine_shard_states(pm_engine *e, pm_shard_state *out)
 	if (!e || !out) return fail(e, PM_ERR_ARG, "shard_states: bad arguments");
 	if (e->phase != 1 || !e->sharded) return fail(e, PM_ERR_STATE, "shard_states: no sharded run in progress");
 	cudaSetDevice(e->device);
+	if (e->fast_pending) {
+		// the linked run was enqueued blind (run_linked_begin): settle what it left open before the host-driven protocol
+		// takes over -- a guard list that overflowed means starting over, verify passes that did not converge are finished
+		const unsigned int flagged = e->h_counters[0];
+		const bool converged = slicer_fast_converged(e);
+		e->stats.guard_flagged = flagged;
+		if (flagged > e->guard_cap) {
+			e->guard_cap = flagged + flagged / 4 + 1024;
+			const pm_shard_plan plan = e->plan;
+			int rc = begin_once(e, e->run_audio, e->n_samples, false, plan, true, false);
+			if (rc != PM_OK) return rc;
+			e->phase = 1;
+		} else if (!converged) {
+			int rc = slicer_converge(e);
+			if (rc != PM_OK) return rc;
+		}
+	}
 	int rc = fetch_shard_states(e);
 	if (rc != PM_OK) return rc;
 	memcpy(out, e->shard_out.data(), e->shard_out.size() * sizeof(pm_shard_state));

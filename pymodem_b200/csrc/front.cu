@@ -727,8 +727,12 @@ extern "C" cudaError_t pm_launch_afsk_front(const AfskPlan *plan, size_t smem_by
 	if (n_tiles <= 0) return cudaSuccess;
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaFuncSetAttribute(afsk_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-		cudaFuncSetAttribute(afsk_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+		// 227 KB per CTA in all, static shared memory (the per-warp raw-sample maxima) included: the engine plans
+		// tiles of at most 226 KB of dynamic shared memory
+		cudaError_t e1 = cudaFuncSetAttribute(afsk_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		cudaError_t e2 = cudaFuncSetAttribute(afsk_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		if (e1 != cudaSuccess) return e1;
+		if (e2 != cudaSuccess) return e2;
 		attr_done = true;
 	}
 	pm_kt_mark("afsk_front_kernel", st);

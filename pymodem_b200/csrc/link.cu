@@ -62,14 +62,24 @@ __device__ __forceinline__ unsigned char *slot_of(unsigned char *base, const Lin
 __global__ void __launch_bounds__(256)
 link_push_states_kernel(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch,
                         const SegState *__restrict__ S, const SegState *__restrict__ E, int n_seg, int k_end,
-                        const unsigned long long *__restrict__ symcount)
+                        const unsigned long long *__restrict__ symcount, const unsigned int *__restrict__ counters,
+                        int fast_passes, unsigned int guard_cap)
 {
+	// The run was enqueued without a host round trip: whether this rank's own verify passes converged (some pass
+	// repaired nothing) and whether its guard list held is only known here, on the device.  If not, the states below are
+	// not final: n_symbols = -1 tells every rank to take the host-driven protocol (link_wait_states_kernel).
+	bool unsettled = false;
+	if (counters) {
+		bool conv = false;
+		for (int p = 0; p < fast_passes; p++) conv = conv || counters[2 + p] == 0u;
+		unsettled = !conv || counters[0] > guard_cap;
+	}
 	for (int c = threadIdx.x; c < G.nc; c += blockDim.x) {
 		pm_shard_state st;
 		const SegState s0 = S[(long long)c * n_seg], e1 = E[(long long)c * n_seg + (k_end - 1)];
 		st.start_clock = s0.clock; st.start_last = s0.last; st.start_last_q = s0.last_q;
 		st.end_clock = e1.clock; st.end_last = e1.last; st.end_last_q = e1.last_q;
-		st.n_symbols = (long long)symcount[c];
+		st.n_symbols = unsettled ? -1ll : (long long)symcount[c];
 		for (int q = 0; q < G.world; q++) {
 			pm_shard_state *dst = reinterpret_cast<pm_shard_state *>(slot_of(peers.base[q], G, parity) + G.off_states);
 			dst[(long long)G.rank * G.nc + c] = st;
@@ -114,15 +124,22 @@ link_wait_states_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int
 		    a.end_last_q != b.start_last_q)
 			atomicExch(&s_bad, 1);
 	}
+	for (int i = threadIdx.x; i < G.world * G.nc; i += blockDim.x)
+		if (st[i].n_symbols < 0) atomicExch(&s_bad, 1);          // some rank's own slicer pass is not settled yet
+	__syncthreads();                                             // s_bad is final: the placement below reads it
 	for (int c = threadIdx.x; c < G.nc; c += blockDim.x) {
 		long long P = 0;
-		for (int q = 0; q < G.rank; q++) P += st[(long long)q * G.nc + c].n_symbols;
-		const long long n_own = st[(long long)G.rank * G.nc + c].n_symbols;
+		for (int q = 0; q < G.rank; q++) {
+			const long long v = st[(long long)q * G.nc + c].n_symbols;
+			if (v > 0) P += v;
+		}
+		long long n_own = st[(long long)G.rank * G.nc + c].n_symbols;
+		if (n_own < 0) n_own = 0;
 		ShardBits b;
 		b.first = first; b.pad = 0; b.valid_from = 0;
 		if (first) { b.bit_off = 0; b.own_lo = 0; }
 		else {
-			if (P < tail_bits) atomicExch(&s_err, 1);
+			if (P < tail_bits && !s_bad) atomicExch(&s_err, 1);
 			const long long A0 = ((P - tail_bits) >> 3) << 3;          // global bit index of local bit 0
 			b.bit_off = P - A0;
 			b.own_lo = b.bit_off;
@@ -309,10 +326,12 @@ cudaError_t pm_link_preload(void)
 }
 
 cudaError_t pm_link_push_states(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch, const SegState *S,
-	const SegState *E, int n_seg, int k_end, const unsigned long long *symcount, cudaStream_t st)
+	const SegState *E, int n_seg, int k_end, const unsigned long long *symcount, const unsigned int *counters,
+	int fast_passes, unsigned int guard_cap, cudaStream_t st)
 {
 	pm_kt_mark("link_push_states_kernel", st);
-	link_push_states_kernel<<<1, 256, 0, st>>>(G, peers, parity, epoch, S, E, n_seg, k_end, symcount);
+	link_push_states_kernel<<<1, 256, 0, st>>>(G, peers, parity, epoch, S, E, n_seg, k_end, symcount, counters, fast_passes,
+		guard_cap);
 	return cudaGetLastError();
 }
 

@@ -235,12 +235,18 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
                      long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
                      SegState *__restrict__ S, const SegState *__restrict__ E_in, SegState *__restrict__ E_out,
                      SegState *__restrict__ chk, const SegState *__restrict__ init, SlicerGeom G,
-                     unsigned int *repairs)
+                     unsigned int *repairs, const unsigned int *__restrict__ skip_if_zero)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int ch = blockIdx.y;
 	if (k >= G.n_seg) return;
 	const long long idx = (long long)ch * G.n_seg + k;
+	// passes are enqueued back to back without asking the host: a pass whose predecessor repaired nothing has
+	// nothing to do either (every hand-off already verified) and only keeps the double buffer in step
+	if (skip_if_zero && *skip_if_zero == 0u) {
+		E_out[idx] = E_in[idx];
+		return;
+	}
 	if (k < G.k_init) {                 // history segments before a repaired hand-off: already final
 		E_out[idx] = E_in[idx];
 		return;
@@ -375,12 +381,13 @@ extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int 
 
 extern "C" cudaError_t pm_launch_slicer_verify(const SlicerChain *chains, int n_chains, const uint32_t *sign,
 	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, const SegState *E_in,
-	SegState *E_out, SegState *chk, const SegState *init, SlicerGeom G, unsigned int *repairs, cudaStream_t st)
+	SegState *E_out, SegState *chk, const SegState *init, SlicerGeom G, unsigned int *repairs,
+	const unsigned int *skip_if_zero, cudaStream_t st)
 {
 	dim3 grid((G.n_seg + 127) / 128, n_chains);
 	pm_kt_mark("slicer_verify_kernel", st);
 	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, chk,
-		init, G, repairs);
+		init, G, repairs, skip_if_zero);
 	return cudaGetLastError();
 }
 

@@ -122,8 +122,11 @@ def test_linked_frame_straddling_a_boundary(cuda_lib, oracle):
 	stack = build_stack(48000, lines)
 	got, info = run_linked_local(stack, audio, 2, tail_bits=2048, segment_len=4096, warmup_len=16384)
 	assert as_tuples(got) == want
-	with pytest.raises(EngineError):
-		run_linked_local(stack, audio, 2, tail_bits=128, segment_len=4096, warmup_len=16384)
+	# a hand-off tail far shorter than a frame: the shard that holds the closing flag cannot decode it from what it has --
+	# round 1 gave up with an error here; now all shards recover from the gathered bitstream
+	got, info = run_linked_local(stack, audio, 2, tail_bits=128, segment_len=4096, warmup_len=16384)
+	assert as_tuples(got) == want
+	assert info.get('recovered')
 
 
 def test_linked_engine_is_reusable(cuda_lib):
