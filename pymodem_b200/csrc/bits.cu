@@ -121,17 +121,39 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 	const long long w0 = w_origin + (long long)blockIdx.x * GB_WORDS + threadIdx.x * 4;
 	const long long bit_off = sb[ch].bit_off;
 
-	uint32_t m[4];
+	// everything the block needs from global memory is requested up front, in one round trip: the four mask words and
+	// the four sign words of the thread as 128-bit loads (rows and the thread's first word are 16-byte aligned), and the
+	// block's symbol base -- the scan and the scatter below then run out of registers
+	uint32_t m[4], sv[4] = {0u, 0u, 0u, 0u}, qv[4] = {0u, 0u, 0u, 0u};
 	unsigned int cnt = 0;
+	const bool vec = ((w0 & 3) == 0) && (((w0 + 3) << 5) < C.nout) && ((mask_stride & 3) == 0) && ((sign_stride & 3) == 0);
+	if (vec) {
+		const uint4 mv = *reinterpret_cast<const uint4 *>(mk + w0);
+		const uint4 s4 = *reinterpret_cast<const uint4 *>(sg + w0);
+		m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+		sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+		if (sq) {
+			const uint4 q4 = *reinterpret_cast<const uint4 *>(sq + w0);
+			qv[0] = q4.x; qv[1] = q4.y; qv[2] = q4.z; qv[3] = q4.w;
+		}
 #pragma unroll
-	for (int q = 0; q < 4; q++) {
-		const long long w = w0 + q;
-		m[q] = ((w << 5) < C.nout) ? valid_mask_word(mk[w], w, C.nout) : 0;
-		cnt += __popc(m[q]);
+		for (int q = 0; q < 4; q++) {
+			m[q] = valid_mask_word(m[q], w0 + q, C.nout);
+			cnt += __popc(m[q]);
+		}
+	} else {
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const long long w = w0 + q;
+			const bool in = (w << 5) < C.nout;
+			m[q] = in ? valid_mask_word(mk[w], w, C.nout) : 0;
+			if (in) { sv[q] = sg[w]; if (sq) qv[q] = sq[w]; }
+			cnt += __popc(m[q]);
+		}
 	}
+	const unsigned int sym_block = block_base[(long long)ch * n_blocks + blockIdx.x];   // symbols before block
 	unsigned int total;
 	const unsigned int ex = block_excl_scan(cnt, s_warp, total);
-	const unsigned int sym_block = block_base[(long long)ch * n_blocks + blockIdx.x];   // symbols before block
 	const long long bit_block = (long long)sym_block * C.bps + bit_off;                  // stream bits before block
 	const unsigned int nbits_block = total * C.bps;
 	const int stage_shift = (int)(bit_block & 31);
@@ -162,11 +184,12 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 			}
 		}
 		long long sym = (long long)sym_block + ex;          // shard-local symbol index
+#pragma unroll
 		for (int q = 0; q < 4; q++) {
 			uint32_t mm = m[q];
 			const long long w = w0 + q;
-			const uint32_t s = mm ? sg[w] : 0;
-			const uint32_t sqw = (mm && sq) ? sq[w] : 0;
+			const uint32_t s = sv[q];
+			const uint32_t sqw = qv[q];
 			while (mm) {
 				const int i = __ffs(mm) - 1;
 				mm &= mm - 1;
@@ -410,52 +433,105 @@ __device__ __forceinline__ unsigned int crc16_x25_dev(const uint8_t *p, unsigned
 // emitted at the flag.  `aborted` reports whether an abort (seven or more ones,
 // ax25.py:35-38) was seen, i.e. whether the emission decision is independent of
 // anything before `start`.
-__device__ bool ax25_replay(const uint32_t *__restrict__ d, long long start, long long end, uint8_t *dst,
-                            unsigned int &len_out, int &overflow, bool &aborted)
+//
+// Four stream bits per step where nothing special happens inside them -- no seventh one in a row, no flag: 97 % of
+// the nibbles of noise, all but two per frame of a clean signal -- from a table indexed by (run of ones so far,
+// nibble): the run after the nibble, how many data bits it holds (stuffed zeros dropped) and the bits themselves.
+// `hist` is the reference's working_byte as it stands when a byte is appended (the newest bit in bit 7, ax25.py:32/44:
+// OR in 0x80, append, then shift), i.e. the last eight bits shifted in; the nibbles the table marks as complex and the
+// last bits before the flag go through the bit-by-bit form of the reference's statements.
+//   table entry: bits 0-2 run of ones after the nibble, 3-5 data bits in it, 6-9 the bits (first one lowest), bit 10 complex
+#define HDLC_COMPLEX 0x400u
+__device__ __forceinline__ unsigned int hdlc_replay_entry(unsigned int oc, unsigned int nib)
 {
-	unsigned int wb = 0, one_count = 0, bit_index = 0, byte_index = 0, len = 0;
+	unsigned int n = 0, bits = 0, complex_ = 0;
+	for (int b = 0; b < 4; b++) {
+		if ((nib >> b) & 1u) {
+			oc++;
+			if (oc > 6u) complex_ = 1;                     // abort: bit_index / byte_index reset in the middle
+			bits |= 1u << n; n++;
+		} else {
+			if (oc < 5u) n++;                              // a data zero
+			else if (oc >= 6u) complex_ = 1;               // flag (or the zero that ends an abort run)
+			oc = 0;                                        // oc == 5: stuffed zero, dropped
+		}
+	}
+	return (oc & 7u) | (n << 3) | (bits << 6) | (complex_ ? HDLC_COMPLEX : 0u);
+}
+
+__device__ bool ax25_replay(const uint32_t *__restrict__ d, const unsigned short *__restrict__ tab, long long start,
+                            long long end, uint8_t *dst, unsigned int &len_out, int &overflow, bool &aborted)
+{
+	unsigned int hist = 0, one_count = 0, bit_index = 0, byte_index = 0, len = 0;
 	bool emit = false;
 	aborted = false;
-	for (long long g = start; g <= end; g++) {
-		// inside a long run of ones nothing changes any more (bit_index = byte_index = 0,
-		// wb = 0x7F): skip whole all-ones words
-		if (one_count >= 8 && (g & 31) == 0) {
-			while (g + 32 <= end && d[g >> 5] == 0xFFFFFFFFu) {
-				g += 32;
-				if (one_count < (1u << 30)) one_count += 32;
+	long long g = start;
+	long long nw = (g >> 5) + 1;                          // next word to fetch
+	unsigned long long buf = (unsigned long long)(d[g >> 5] >> (g & 31));
+	int avail = 32 - (int)(g & 31);
+	while (g <= end) {
+		if (avail <= 32) {                                 // keep at least 32 bits in the window while the gap lasts
+			buf |= (unsigned long long)d[nw++] << avail;   // (the rows are padded: reading one word past `end` is in bounds)
+			avail += 32;
+		}
+		if (one_count <= 6u && end - g >= 8) {
+			const unsigned int e = tab[one_count * 16u + ((unsigned int)buf & 15u)];
+			if (!(e & HDLC_COMPLEX)) {
+				const unsigned int nb = (e >> 3) & 7u, bits = (e >> 6) & 15u;
+				const unsigned int tot = bit_index + nb;
+				if (tot >= 8u) {
+					const unsigned int j = 8u - bit_index;     // the byte completes with the first j data bits of the nibble
+					dst[len++] = (uint8_t)((hist >> j) | ((bits & ((1u << j) - 1u)) << (8u - j)));
+					byte_index++;
+					if (byte_index > 1023u) { overflow = 1; len_out = len; return false; }   // replayed sequentially by the caller's fallback
+					bit_index = tot - 8u;
+				} else {
+					bit_index = tot;
+				}
+				hist = ((hist >> nb) | (bits << (8u - nb))) & 0xFFu;
+				one_count = e & 7u;
+				g += 4; buf >>= 4; avail -= 4;
+				continue;
 			}
 		}
-		const unsigned int bit = (d[g >> 5] >> (g & 31)) & 1u;
+		// inside a long run of ones nothing changes any more (bit_index = byte_index = 0, hist = 0xFF): skip 32 at once
+		if (one_count >= 8u && end - g >= 32 && (unsigned int)buf == 0xFFFFFFFFu) {
+			g += 32; buf >>= 32; avail -= 32;
+			if (one_count < (1u << 30)) one_count += 32;
+			continue;
+		}
+		const unsigned int bit = (unsigned int)buf & 1u;
+		buf >>= 1; avail--;
 		if (bit) {
-			wb |= 0x80;
+			hist = (hist >> 1) | 0x80u;
 			one_count++;
 			bit_index++;
-			if (one_count > 6) { bit_index = 0; byte_index = 0; aborted = true; }   // abort: data not cleared
-			if (bit_index == 8) {
+			if (one_count > 6u) { bit_index = 0; byte_index = 0; aborted = true; }   // abort: data not cleared
+			if (bit_index == 8u) {
 				bit_index = 0;
-				dst[len++] = (uint8_t)wb;
+				dst[len++] = (uint8_t)hist;
 				byte_index++;
-				if (byte_index > 1023) { byte_index = 0; one_count = 0; overflow = 1; }
+				if (byte_index > 1023u) { byte_index = 0; one_count = 0; overflow = 1; }
 			}
-			wb >>= 1;
 		} else {
-			if (one_count < 5) {
+			if (one_count < 5u) {
+				hist >>= 1;
 				bit_index++;
-				if (bit_index == 8) {
+				if (bit_index == 8u) {
 					bit_index = 0;
-					dst[len++] = (uint8_t)wb;
+					dst[len++] = (uint8_t)hist;
 					byte_index++;
-					if (byte_index > 1023) byte_index = 0;
+					if (byte_index > 1023u) { byte_index = 0; overflow = 1; }
 				}
-				wb >>= 1;
-			} else if (one_count == 6) {
-				if (g == end) emit = (byte_index >= 18 && bit_index == 7);
+			} else if (one_count == 6u) {
+				if (g == end) emit = (byte_index >= 18u && bit_index == 7u);
 				// (a flag strictly inside the range cannot happen: ranges end at the first flag)
 				byte_index = 0;
 				bit_index = 0;
 			}
 			one_count = 0;
 		}
+		g++;
 	}
 	len_out = len;
 	return emit;
@@ -574,6 +650,9 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
                 GapRec *__restrict__ gaps, long long gap_stride, const ShardBits *__restrict__ sb,
                 const unsigned int *__restrict__ cand, const unsigned int *__restrict__ ncand)
 {
+	__shared__ unsigned short s_rep[7 * 16];
+	if (threadIdx.x < 7 * 16) s_rep[threadIdx.x] = (unsigned short)hdlc_replay_entry(threadIdx.x >> 4, threadIdx.x & 15u);
+	__syncthreads();
 	const int ch = blockIdx.y;
 	if (chains[ch].codec != 1) return;
 	const unsigned int n = ncand[ch];
@@ -593,7 +672,7 @@ ax25_gap_kernel(const BitChain *__restrict__ chains, ChainCounters *__restrict__
 		int overflow = 0;
 		unsigned int len = 0;
 		bool aborted = false;
-		const bool emit = ax25_replay(d + (long long)ch * bits_stride, start, end,
+		const bool emit = ax25_replay(d + (long long)ch * bits_stride, s_rep, start, end,
 			scratch + (long long)ch * scratch_stride + r.scratch_off, len, overflow, aborted);
 		if (overflow) atomicExch(&cc[ch].seq_needed, 1);
 		if (open_start && (emit || !aborted)) {

@@ -149,7 +149,7 @@ link_wait_states_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int
 		}
 		if (last) b.own_hi = 0x7fffffffffffffffll;
 		else {
-			if (n_own < tail_bits) atomicExch(&s_err, 1);
+			if (n_own < tail_bits && !s_bad) atomicExch(&s_err, 1);
 			b.own_hi = b.bit_off + n_own;
 		}
 		sb[c] = b;

@@ -549,7 +549,9 @@ def run_linked_local(demod_stack, audio, world, device=0, tail_bits=16384, **opt
 			return engines[0].packets(*results[0]), info
 		assert not any(verified), "ranks disagree on the hand-off verdict"
 		workers = [ShardWorker(e, p, l.ctypes.data, len(l)) for e, p, l in zip(engines, plans, locals_)]
-		recs, arena = run_protocol(workers, local_exchange, resume=True)
+		timing = {}
+		recs, arena = run_protocol(workers, local_exchange, resume=True, timing=timing)
+		info['recovered'] = bool(timing.get('recovered'))
 		return engines[0].packets(recs, arena), info
 	finally:
 		for e in engines:
@@ -575,8 +577,9 @@ def run_sharded_local(demod_stack, audio, world, device=0, tail_bits=16384, **op
 			local = audio[plan['audio_begin']:plan['audio_end']]
 			workers.append(ShardWorker(eng, plan, local.ctypes.data, len(local)))
 			workers[-1]._keep = local
-		recs, arena = run_protocol(workers, local_exchange)
-		info = dict(rounds=[w.rounds for w in workers], plans=plans,
+		timing = {}
+		recs, arena = run_protocol(workers, local_exchange, timing=timing)
+		info = dict(rounds=[w.rounds for w in workers], plans=plans, recovered=bool(timing.get('recovered')),
 			repairs=[e.stats()['slicer_repairs'] for e in engines])
 		return engines[0].packets(recs, arena), info
 	finally:

@@ -87,6 +87,7 @@ def test_long_frames_sharded_recover(cuda_lib, oracle, world, tail_bits):
 	stack = [chain_builder.build_chain(48000, l) for l in lines]
 	got, info = run_sharded_local(stack, audio, world, tail_bits=tail_bits)
 	assert as_tuples(got) == want
+	assert info.get('recovered')
 	got, info = run_linked_local(stack, audio, world, tail_bits=tail_bits)
 	assert as_tuples(got) == want
 	assert info.get('recovered')
