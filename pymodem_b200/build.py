@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpymodem_b200.so")
-SOURCES = ["engine.cu", "front.cu", "slicer.cu", "bits.cu", "il2p.cu", "loops.cu", "link.cu"]
+SOURCES = ["engine.cu", "front.cu", "lpf_tc.cu", "slicer.cu", "bits.cu", "il2p.cu", "loops.cu", "link.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
 	"-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-Xcompiler", "-pthread", "--fmad=true", "-Xptxas", "-v"]
 

@@ -41,7 +41,9 @@ extern "C" void pm_kt_mark(const char *name, cudaStream_t st)
 
 extern "C" {
 cudaError_t pm_launch_afsk_front(const AfskPlan *, size_t, const int16_t *, long long, long long, int, uint32_t *,
-	long long, float *, long long, GuardList, cudaStream_t);
+	long long, float *, long long, GuardList, MagOut, cudaStream_t);
+cudaError_t pm_launch_lpf_tc(const LpfTcPlan *, const unsigned char *, long long, const unsigned char *, const float *,
+	long long, long long, uint32_t *, long long, float *, long long, GuardList, int *, int, cudaStream_t);
 cudaError_t pm_launch_fir_front(const FirPlan *, size_t, const int16_t *, long long, long long, int, uint32_t *,
 	long long, float *, long long, GuardList, cudaStream_t);
 cudaError_t pm_launch_guard_fixup(const Fp64Chain *, int, const int16_t *, long long, uint32_t *, long long,
@@ -154,6 +156,14 @@ struct FrontGroup {
 	int tile = 0;
 	int trim_max = 0;
 	double macs_per_sample = 0;   // executed FP32 MACs per input sample (after sharing)
+	// tensor-core low-pass (csrc/lpf_tc.cu): the front kernel stops at the magnitudes, lpf_tc_kernel does the rest
+	bool tensor = false;
+	LpfTcPlan tc;
+	std::vector<unsigned char> btaps;   // the banded-Toeplitz tap matrix, three bf16 pieces, operand layout
+	long long n_tile_a = 0, n_tile_b = 0, a_done = 0, b_done = 0;
+	long long mag_rows = 0, mag_off = 0, amax_off = 0;     // this group's part of d_mag (bytes) / d_amax (floats)
+	double tc_macs_per_sample = 0;      // executed bf16 multiply-adds per input sample on the tensor cores
+	double lpf_macs_per_sample = 0;     // the FP32 multiply-adds they replace
 };
 
 struct pm_engine {
@@ -179,6 +189,8 @@ struct pm_engine {
 	int opt_fuse_pairs = 1;       // mark and space sliding windows of a pair in one pass (0: tone by tone)
 	int opt_slide = 1;            // rotation-tap correlators as sliding window sums (0: always the direct FIR)
 	int opt_slicer_fast = 1;      // shortened slicer clock update where it is exact (0: always the plain form)
+	int opt_tensor_lpf = 1;       // low-pass of the AFSK front end on the tensor cores where the group qualifies
+	int sm_count = 148;
 	int opt_precise = 0;          // all AFSK chains through the float64 pipeline
 	double opt_precise_ratio = 0.2;
 	long long opt_h2d_chunk = 8 << 20;
@@ -197,6 +209,9 @@ struct pm_engine {
 	DevBuf<unsigned long long> d_guard_entries;
 	DevBuf<unsigned int> d_counters;      // [0] guard count, [1] repairs
 	DevBuf<unsigned long long> d_stage_clk;   // option "stage_clocks": GuardList::stage_clk
+	DevBuf<unsigned char> d_mag;          // tone magnitudes as bf16 pieces (MagOut), tensor-core low-pass only
+	DevBuf<float> d_amax;
+	std::vector<DevBuf<unsigned char>> d_btaps;   // per front group
 	int opt_stage_clocks = 0;
 	DevBuf<SegState> d_S, d_E0, d_E1, d_chk;
 	DevBuf<ShardBits> d_shardbits;
@@ -259,6 +274,8 @@ struct pm_engine {
 	std::vector<SegState> up_init;
 	std::vector<P64Chain> up_p64;
 	std::vector<ShardBits> up_sb;
+	int opt_tc_debug = 0;
+	int opt_debug_sync = 0;               // synchronise after every front-end launch and name the kernel that failed
 	int opt_kernel_times = 0;             // record an event before every kernel of a run (pm_engine_kernel_times)
 	KernelTimer kt;
 	std::string kt_report;
@@ -361,6 +378,22 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 	int cmax = 0;
 	double corr_sum = 0;
 	for (int j = 0; j < p.n_mag; j++) { cmax = std::max(cmax, p.mag_n[j]); corr_sum += p.mag_n[j]; }
+	auto warps = [](int units) { return (units + 31) / 32 * 32; };
+	if (p.tensor_lpf) {
+		// the kernel stops at the magnitudes (low-pass on the tensor cores): no low-pass halo, no pair streams
+		g.U_l = 0;
+		g.U_m = tile / 16;
+		g.U_x = (16 * g.U_m + cmax + 15) / 16;
+		g.a_len = round_up(16 * g.U_x + p.n_bpf, 8);
+		const int a_phys = round_up(pm_phys(g.a_len) + 4, 4);
+		const int x_phys = round_up(2 * pm_phys2(16 * g.U_x) + 8, 4);
+		g.s_m_stride = 0;
+		g.s_m_off = 0;
+		g.s_x1_off = a_phys;
+		g.smem = sizeof(float) * (size_t)(g.s_x1_off + x_phys);
+		g.cost = ((double)warps(g.U_x) * p.n_bpf + (double)warps(g.U_m) * 1.15 * corr_sum) / tile;
+		return g;
+	}
 	g.U_l = tile / 16;
 	g.U_m = (tile + p.n_lpf + 15) / 16;
 	g.U_x = (16 * g.U_m + cmax + 15) / 16;
@@ -373,7 +406,6 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 	g.s_x1_off = std::max(a_phys, p.n_pair * g.s_m_stride);
 	g.smem = sizeof(float) * (size_t)(g.s_x1_off + x_phys);
 	// issue-slot cost per output sample (warp granular)
-	auto warps = [](int units) { return (units + 31) / 32 * 32; };
 	double c = (double)warps(g.U_x) * p.n_bpf;
 	// magnitude units are laid out stream after stream
 	// the correlator (I, Q) and the low-pass (mark, space) stages run packed FFMA2: one issue slot per tap and pair
@@ -557,6 +589,15 @@ static int build_groups(pm_engine *e)
 			p.lpf2_off = used;
 			for (int j = 0; j < p.n_lpf; j++) p.taps[used + 2 * j] = p.taps[used + 2 * j + 1] = p.taps[p.lpf_off + j];
 			used += 2 * p.n_lpf;
+			// Tensor-core low-pass (csrc/lpf_tc.cu) where the group qualifies: every pair a fused sliding-window pair (the
+			// magnitudes then leave the correlator stage pair by pair), at most TC_MAX_TONES tones, taps within K = 192
+			{
+				bool all_fused = p.n_pair > 0;
+				for (int pi = 0; pi < p.n_pair; pi++) all_fused = all_fused && p.pair_fused[pi] > 0;
+				g.tensor = e->opt_tensor_lpf && all_fused && p.n_mag <= TC_MAX_TONES && (int)hc.lpf.size() <= TC_MAX_LPF &&
+					(int)hc.lpf.size() >= 8;
+				p.tensor_lpf = g.tensor ? 1 : 0;
+			}
 			// tile: cheapest issue-slot cost that still fits two CTAs per SM
 			int best = 0;
 			double best_cost = 1e300;
@@ -575,10 +616,58 @@ static int build_groups(pm_engine *e)
 			p.s_x1_off = gg.s_x1_off; p.s_m_off = gg.s_m_off; p.s_m_stride = gg.s_m_stride;
 			g.smem = gg.smem;
 			g.tile = best;
-			double macs = hc.bpf.size() + 2.0 * p.n_pair * hc.lpf.size();
+			double macs = hc.bpf.size() + (g.tensor ? 0.0 : 2.0 * p.n_pair * hc.lpf.size());
 			for (int t = 0; t < p.n_mag; t++)
 				macs += p.mag_slide[t] ? 2.0 * (p.mag_slide[t] + 30) / 16.0 : 2.0 * tones[t].i->size();
 			g.macs_per_sample = macs;
+			g.lpf_macs_per_sample = 2.0 * p.n_pair * hc.lpf.size();
+			if (g.tensor) {
+				LpfTcPlan &T = g.tc;
+				memset(&T, 0, sizeof(T));
+				T.n_mag = p.n_mag; T.n_pair = p.n_pair; T.n_chain = p.n_chain;
+				for (int pi = 0; pi < p.n_pair; pi++) { T.pair_mark[pi] = p.pair_mark[pi]; T.pair_space[pi] = p.pair_space[pi]; }
+				for (int pi = 0; pi <= p.n_pair; pi++) T.pair_first[pi] = p.pair_first[pi];
+				for (int i = 0; i < p.n_chain; i++) {
+					T.chain_gid[i] = p.chain_gid[i]; T.chain_gain[i] = p.chain_gain[i]; T.chain_guard_abs[i] = p.chain_guard_abs[i];
+				}
+				T.guard_eps = p.guard_eps;
+				T.n_lpf = (int)hc.lpf.size();
+				T.debug_mask = e->opt_tc_debug;
+				T.tile_a = p.tile;
+				int cmax = 0;
+				for (int t = 0; t < p.n_mag; t++) cmax = std::max(cmax, (int)tones[t].i->size());
+				T.reach = ((int)hc.bpf.size() - 1) + (cmax - 1) + ((int)hc.lpf.size() - 1);
+				// B[d][n] = hr[d - n] (hr = the taps in correlation order), three bf16 pieces, per piece three K blocks of
+				// 64 rows (n) x 64 columns (d within the block), K-major rows of 128 bytes, SWIZZLE_128B
+				const int M = (int)hc.lpf.size();
+				g.btaps.assign(3 * TC_B_BYTES, 0);
+				auto bf16_rn = [](float f) -> uint16_t {
+					uint32_t u;
+					memcpy(&u, &f, 4);
+					u = u + 0x7FFFu + ((u >> 16) & 1u);
+					return (uint16_t)(u >> 16);
+				};
+				for (int kb = 0; kb < TC_KBLK; kb++)
+					for (int nn = 0; nn < TC_N; nn++)
+						for (int kk = 0; kk < 64; kk++) {
+							const int t = 64 * kb + kk - nn;
+							float rest = (t >= 0 && t < M) ? (float)hc.lpf[M - 1 - t] : 0.0f;
+							for (int q = 0; q < 3; q++) {
+								const uint16_t h16 = bf16_rn(rest);
+								uint32_t back = (uint32_t)h16 << 16;
+								float pq;
+								memcpy(&pq, &back, 4);
+								const uint32_t o = (uint32_t)nn * 128u + (uint32_t)kk * 2u;
+								const uint32_t sw = o ^ (((o >> 7) & 7u) << 4);
+								memcpy(&g.btaps[(size_t)q * TC_B_BYTES + (size_t)kb * TC_N * 128 + sw], &h16, 2);
+								rest -= pq;                      // exact
+							}
+						}
+				// executed on the tensor cores per input sample: six piece products x the K steps that hold taps x 64 columns
+				int ksteps = 0;
+				for (int k0 = 0; k0 < 64 * TC_KBLK; k0 += 16) if (k0 < M + 63) ksteps++;
+				g.tc_macs_per_sample = 6.0 * ksteps * 16.0 * p.n_mag;
+			}
 		} else {
 			FirPlan &p = g.fir;
 			memset(&p, 0, sizeof(p));
@@ -611,6 +700,14 @@ static int build_groups(pm_engine *e)
 		}
 		e->groups.push_back(g);
 	}
+	for (auto &b : e->d_btaps) b.release();
+	e->d_btaps.assign(e->groups.size(), DevBuf<unsigned char>());
+	for (size_t gi = 0; gi < e->groups.size(); gi++) {
+		FrontGroup &g = e->groups[gi];
+		if (!g.tensor) continue;
+		CK(e->d_btaps[gi].ensure(g.btaps.size()));
+		CK(cudaMemcpy(e->d_btaps[gi].p, g.btaps.data(), g.btaps.size(), cudaMemcpyHostToDevice));
+	}
 	return PM_OK;
 }
 
@@ -629,6 +726,7 @@ extern "C" int pm_engine_create(int device, pm_engine **out)
 	if (prop.major != 10) return PM_ERR_CUDA;          // sm_100a code only: no fallback path
 	pm_engine *e = new pm_engine();
 	e->device = device;
+	e->sm_count = prop.multiProcessorCount;
 	memset(&e->stats, 0, sizeof(e->stats));
 	if (cudaSetDevice(device) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
@@ -657,6 +755,8 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_cc.release(); e->d_init.release(); e->d_audio.release(); e->d_sign.release(); e->d_mask.release();
 	e->d_bits_raw.release(); e->d_bits_lfsr.release(); e->d_byte_addr.release(); e->d_soft.release();
 	e->d_chk.release(); e->d_shardbits.release(); e->d_symcount.release(); e->d_tail.release();
+	e->d_mag.release(); e->d_amax.release();
+	for (auto &b : e->d_btaps) b.release();
 	e->d_guard_entries.release(); e->d_counters.release(); e->d_stage_clk.release(); e->d_S.release(); e->d_E0.release();
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
@@ -889,6 +989,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "slicer_fast") e->opt_slicer_fast = value != 0;
 	else if (k == "slide_correlator") { e->opt_slide = value != 0; replan = true; }
 	else if (k == "fuse_pairs") { e->opt_fuse_pairs = value != 0; replan = true; }
+	else if (k == "tensor_lpf") { e->opt_tensor_lpf = value != 0; replan = true; }
 	else if (k == "precise") {
 		if (!e->chains.empty()) return fail(e, PM_ERR_STATE, "set 'precise' before loading chains");
 		e->opt_precise = value != 0;
@@ -903,6 +1004,8 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	}
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
 	else if (k == "kernel_times") e->opt_kernel_times = value != 0;
+	else if (k == "debug_sync") e->opt_debug_sync = value != 0;
+	else if (k == "tc_debug") { e->opt_tc_debug = (int)value; replan = true; }
 	else if (k == "copy_threads") e->opt_copy_threads = std::max(1, std::min(16, (int)value));
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
 	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);
@@ -1117,6 +1220,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	}
 	CK(cudaMemsetAsync(e->d_counters.p, 0, 16 * sizeof(unsigned int), e->st));
 	CK(cudaMemsetAsync(e->d_totals.p, 0, sizeof(PacketTotals), e->st));
+	long long mag_bytes = 0, amax_floats = 0;
 	for (auto &g : e->groups) {
 		if (g.kind == PM_MODEM_AFSK)
 			for (int i = 0; i < g.afsk.n_chain; i++)
@@ -1124,6 +1228,27 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		else
 			for (int i = 0; i < g.fir.n_chain; i++)
 				g.fir.chain_nout[i] = std::max<long long>(0, n - e->chains[g.fir.chain_gid[i]].trim);
+		g.a_done = g.b_done = 0;
+		if (g.tensor) {
+			long long nout_max = 0;
+			for (int i = 0; i < g.afsk.n_chain; i++) {
+				g.tc.chain_nout[i] = (only_chain >= 0) ? 0 : g.afsk.chain_nout[i];
+				nout_max = std::max(nout_max, g.tc.chain_nout[i]);
+			}
+			// low-pass tiles of TC_TILE outputs; the front tiles have to cover their inputs: TC_KBLK more rows of 64
+			g.n_tile_b = (nout_max + TC_TILE - 1) / TC_TILE;
+			g.n_tile_a = g.n_tile_b ? (g.n_tile_b * TC_TILE + 64 * TC_KBLK + g.tile - 1) / g.tile : 0;
+			g.tc.n_tile_a = g.n_tile_a;
+			g.mag_rows = ((g.n_tile_a * g.tile + 63) / 64 + 8 + 7) / 8 * 8;
+			g.mag_off = mag_bytes;
+			g.amax_off = amax_floats;
+			mag_bytes += (long long)g.afsk.n_mag * 3 * g.mag_rows * 128;
+			amax_floats += g.n_tile_a + 1;
+		}
+	}
+	if (mag_bytes) {
+		CK(e->d_mag.ensure((size_t)mag_bytes));
+		CK(e->d_amax.ensure((size_t)amax_floats));
 	}
 	return PM_OK;
 }
@@ -1148,7 +1273,7 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 		const int a_len = (g.kind == PM_MODEM_AFSK) ? g.afsk.a_len : g.fir.a_len;
 		long long nout_max = 0;
 		for (int k : g.chains) nout_max = std::max(nout_max, std::max<long long>(0, n - e->chains[k].trim));
-		const long long tiles_total = (nout_max + g.tile - 1) / g.tile;
+		const long long tiles_total = g.tensor ? g.n_tile_a : (nout_max + g.tile - 1) / g.tile;
 		auto ready = [&](long long upto, bool fin) -> long long {
 			if (fin) return tiles_total;
 			long long t = (upto - a_len) / g.tile + 1;      // tiles with t*tile + a_len <= upto
@@ -1160,16 +1285,41 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 		while (t < t1) {
 			const int cnt = (int)std::min<long long>(t1 - t, 1 << 30);
 			cudaError_t ce;
+			MagOut mo;
+			mo.base = g.tensor ? e->d_mag.p + g.mag_off : nullptr;
+			mo.rows = g.mag_rows;
+			mo.tile_amax = g.tensor ? e->d_amax.p + g.amax_off : nullptr;
 			if (g.kind == PM_MODEM_AFSK)
 				ce = pm_launch_afsk_front(&g.afsk, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
-					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), stream);
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), mo, stream);
 			else
 				ce = pm_launch_fir_front(&g.fir, g.smem, d_audio, n, t, cnt, e->d_sign.p, e->sign_stride,
 					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), stream);
 			if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "front-end launch failed: %s", cudaGetErrorString(ce));
+			if (e->opt_debug_sync && (ce = cudaStreamSynchronize(stream)) != cudaSuccess)
+				return fail(e, PM_ERR_CUDA, "front-end kernel (tiles %lld..%lld of %lld) failed: %s", t, t + cnt, tiles_total, cudaGetErrorString(ce));
 			e->stats.kernel_launches++;
 			e->stats.front_launches++;
 			t += cnt;
+		}
+		if (g.tensor) {
+			// low-pass tiles whose input rows are all written now: tile k reads the magnitudes [TC_TILE k, TC_TILE (k + 1) + 64 TC_KBLK)
+			g.a_done = std::max(g.a_done, t1);
+			long long b_ready = (g.a_done >= g.n_tile_a) ? g.n_tile_b : (g.a_done * g.tile - 64 * TC_KBLK) / TC_TILE;
+			b_ready = std::min(std::max<long long>(b_ready, 0), g.n_tile_b);
+			if (b_ready > g.b_done) {
+				const size_t gi = (size_t)(&g - e->groups.data());
+				cudaError_t ce = pm_launch_lpf_tc(&g.tc, e->d_mag.p + g.mag_off, g.mag_rows, e->d_btaps[gi].p,
+					e->d_amax.p + g.amax_off, g.b_done, b_ready - g.b_done, e->d_sign.p, e->sign_stride,
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), (int *)(e->d_counters.p + 7),
+					e->sm_count, stream);
+				if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "tensor-core low-pass launch failed: %s", cudaGetErrorString(ce));
+				if (e->opt_debug_sync && (ce = cudaStreamSynchronize(stream)) != cudaSuccess)
+					return fail(e, PM_ERR_CUDA, "tensor-core low-pass kernel (tiles %lld..%lld of %lld, %lld rows, %lld front tiles of %d) failed: %s",
+						g.b_done, b_ready, g.n_tile_b, g.mag_rows, g.n_tile_a, g.tile, cudaGetErrorString(ce));
+				e->stats.kernel_launches++;
+				g.b_done = b_ready;
+			}
 		}
 	}
 	return PM_OK;
@@ -1356,10 +1506,13 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 				e->ring_samples = want;
 			}
 		}
+		bool any_tensor = false;
+		for (auto &g : e->groups) any_tensor = any_tensor || g.tensor;
 		long long done = 0;
 		for (int i = 0; i < n_chunks; i++) {
 			const long long len = cuts[i] - done;
-			cudaStream_t fs = e->st_front[i & 1];
+			// (a low-pass tile reads magnitudes of front tiles from earlier chunks: one launch stream keeps them ordered)
+			cudaStream_t fs = e->st_front[any_tensor ? 0 : (i & 1)];
 			const int16_t *src = audio + done;
 			if (staged) {
 				const int slot = i % pm_engine::RING;
@@ -1613,6 +1766,8 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 			il2p_out[c].mode = hand[c].mode;
 			il2p_out[c].leak = hand[c].leak;
 		}
+	if (e->h_counters[7] != 0)
+		return fail(e, PM_ERR_CUDA, "tensor-core low-pass: a pipeline barrier timed out (internal error)");
 	for (int c = 0; c < nc; c++) {
 		if (e->h_cc[c].tail_short)
 			return fail(e, PM_ERR_STATE, "chain %d: a frame closing in this shard reaches back past the %d-bit hand-off tail",

@@ -254,10 +254,65 @@ struct SlideUnit {
 // parallelism of a stage that is bound by the latency of its chains, not by their number of operations (stage
 // tracing: as many cycles per CTA as the band-pass with a tenth of its multiply-adds) -- and the magnitudes leave
 // as (mark, space) pairs, two samples per 128-bit store, instead of one 32-bit store per tone and sample.
+// Where the magnitudes of a SlidePair go.  EmitSmem: the (mark, space) pair stream in shared memory that the FFMA2
+// low-pass reads (even outputs wait for their odd neighbour, then both leave in one 128-bit store).
+struct EmitSmem {
+	float *dst;               // the pair stream at the unit's first sample (16 (mark, space) float2 in a row, 16-byte aligned)
+	float pa, pb;
+	__device__ __forceinline__ void put(int r, float ma, float mb)
+	{
+		if (r & 1) *reinterpret_cast<float4 *>(dst + 2 * (r - 1)) = make_float4(pa, pb, ma, mb);
+		else { pa = ma; pb = mb; }
+	}
+};
+
+// two floats -> two bf16 in one word (the second operand in the low half: the lower address)
+__device__ __forceinline__ uint32_t bf16x2_rn(float hi, float lo)
+{
+	uint32_t d;
+	asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+	return d;
+}
+
+// Eight consecutive FP32 samples -> three 16-byte chunks of bf16 pieces, v = p0 + p1 + p2 exactly (each residual is
+// exactly representable: it has at most 16, then 8 significant bits left)
+__device__ __forceinline__ void split_store8(const float *v, unsigned char *b0, unsigned char *b1, unsigned char *b2, long long off)
+{
+	uint32_t a[4], b[4], c[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const float lo = v[2 * j], hi = v[2 * j + 1];
+		a[j] = bf16x2_rn(hi, lo);
+		float rl = lo - __uint_as_float(a[j] << 16), rh = hi - __uint_as_float(a[j] & 0xFFFF0000u);
+		b[j] = bf16x2_rn(rh, rl);
+		rl -= __uint_as_float(b[j] << 16); rh -= __uint_as_float(b[j] & 0xFFFF0000u);
+		c[j] = bf16x2_rn(rh, rl);
+	}
+	*reinterpret_cast<uint4 *>(b0 + off) = make_uint4(a[0], a[1], a[2], a[3]);
+	*reinterpret_cast<uint4 *>(b1 + off) = make_uint4(b[0], b[1], b[2], b[3]);
+	*reinterpret_cast<uint4 *>(b2 + off) = make_uint4(c[0], c[1], c[2], c[3]);
+}
+
+// EmitPieces: the tensor-core route -- both magnitude streams leave for global memory as bf16 pieces in the operand
+// layout of csrc/lpf_tc.cu (MagOut), eight samples = one 16-byte chunk per piece at a time.
+struct EmitPieces {
+	unsigned char *ma[3], *mb[3];     // piece arrays of the mark and of the space tone
+	long long off[2];                 // byte offsets of the unit's two chunks
+	float va[8], vb[8];
+	__device__ __forceinline__ void put(int r, float a, float b)
+	{
+		va[r & 7] = a; vb[r & 7] = b;
+		if ((r & 7) == 7) {
+			split_store8(va, ma[0], ma[1], ma[2], off[r >> 3]);
+			split_store8(vb, mb[0], mb[1], mb[2], off[r >> 3]);
+		}
+	}
+};
+
 struct SlidePair {
-	// dst: the pair stream at sample `base` (16 (mark, space) float2 in a row, 16-byte aligned)
+	template <typename EMIT>
 	__device__ __forceinline__ static void run(const float *__restrict__ s, int base, const float *__restrict__ EA,
-	                                           const float *__restrict__ EB, int N, float *__restrict__ dst)
+	                                           const float *__restrict__ EB, int N, EMIT &em)
 	{
 		const unsigned long long *__restrict__ A2 = reinterpret_cast<const unsigned long long *>(EA);
 		const unsigned long long *__restrict__ B2 = reinterpret_cast<const unsigned long long *>(EB);
@@ -284,12 +339,8 @@ struct SlidePair {
 		}
 		const unsigned long long *__restrict__ An = A2 + N, *__restrict__ Bn = B2 + N;
 		unsigned long long DA = 0ull, DB = 0ull, SA, SB;
-		float pa = 0.f, pb = 0.f;
-		// output r: even ones wait for their odd neighbour, then both leave in one 128-bit store
 		auto emit = [&](int r) {
-			const float ma = SlideUnit::mag(SlideUnit::add2(SA, DA)), mb = SlideUnit::mag(SlideUnit::add2(SB, DB));
-			if (r & 1) *reinterpret_cast<float4 *>(dst + 2 * (r - 1)) = make_float4(pa, pb, ma, mb);
-			else { pa = ma; pb = mb; }
+			em.put(r, SlideUnit::mag(SlideUnit::add2(SA, DA)), SlideUnit::mag(SlideUnit::add2(SB, DB)));
 		};
 		auto slide = [&](int r, unsigned long long xin) {          // window r -> r + 1
 			fma2(DA, xin, An[r]); fma2(DB, xin, Bn[r]);
@@ -371,11 +422,11 @@ __device__ __forceinline__ float stage_audio(float *s_a, const int16_t *__restri
 	return amax;
 }
 
-template <bool WRITE_SOFT>
+template <bool WRITE_SOFT, bool MAGS>
 __global__ void __launch_bounds__(PM_FRONT_THREADS, 2)
 afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict__ audio, long long n_audio,
                   long long tile_first, uint32_t *__restrict__ sign, long long sign_stride,
-                  float *__restrict__ soft, long long soft_stride, GuardList guard)
+                  float *__restrict__ soft, long long soft_stride, GuardList guard, MagOut mags)
 {
 	extern __shared__ __align__(16) float smem[];
 	float *s_a = smem;
@@ -404,6 +455,12 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	}
 	__syncthreads();
 	stage_done(0);
+	if (MAGS && tid == 0) {
+		float m = s_wmax[0];
+#pragma unroll
+		for (int q = 1; q < PM_FRONT_THREADS / 32; q++) m = fmaxf(m, s_wmax[q]);
+		mags.tile_amax[tile_first + blockIdx.x] = m;
+	}
 
 	// input band-pass (afsk.py:151); the result is stored as (x, x) pairs: the window operand of the packed correlators
 	for (int ub = tid - (tid & 31); ub < P.U_x; ub += PM_FRONT_THREADS) {        // warp-uniform control flow: uniform taps
@@ -429,9 +486,32 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 		for (int ub = tid - (tid & 31); ub < P.U_m; ub += PM_FRONT_THREADS) {   // warp-uniform control flow
 			const int ui = ub + (tid & 31);
 			if (ui >= P.U_m) continue;
-			SlidePair::run(s_x1, 16 * ui, P.taps + P.pair_ea[p], P.taps + P.pair_eb[p], P.pair_fused[p],
-				s_m + p * P.s_m_stride + 2 * pm_phys2(16 * ui));
+			if (MAGS) {
+				EmitPieces em;
+				const long long rows128 = mags.rows * 128;
+#pragma unroll
+				for (int q = 0; q < 3; q++) {
+					em.ma[q] = mags.base + (long long)(P.pair_mark[p] * 3 + q) * rows128;
+					em.mb[q] = mags.base + (long long)(P.pair_space[p] * 3 + q) * rows128;
+				}
+				em.off[0] = pm_mag_offset(n0 + 16 * ui);
+				em.off[1] = pm_mag_offset(n0 + 16 * ui + 8);
+				SlidePair::run(s_x1, 16 * ui, P.taps + P.pair_ea[p], P.taps + P.pair_eb[p], P.pair_fused[p], em);
+			} else {
+				EmitSmem em;
+				em.dst = s_m + p * P.s_m_stride + 2 * pm_phys2(16 * ui);
+				em.pa = em.pb = 0.f;
+				SlidePair::run(s_x1, 16 * ui, P.taps + P.pair_ea[p], P.taps + P.pair_eb[p], P.pair_fused[p], em);
+			}
 		}
+	}
+	if (MAGS) {                       // the low-pass and the epilogue are csrc/lpf_tc.cu's
+		if (trace) {
+			__syncwarp();
+			stage_done(2);
+			atomicAdd(&guard.stage_clk[4], 1ull);
+		}
+		return;
 	}
 	for (int j = 0; j < P.n_mag; j++) {
 	if (P.mag_dst_first[j] == P.mag_dst_first[j + 1]) continue;                 // both uses of the tone are fused pairs
@@ -722,26 +802,34 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, f
 // ---------------------------------------------------------------------------
 extern "C" cudaError_t pm_launch_afsk_front(const AfskPlan *plan, size_t smem_bytes, const int16_t *audio,
 	long long n_audio, long long tile_first, int n_tiles, uint32_t *sign, long long sign_stride,
-	float *soft, long long soft_stride, GuardList guard, cudaStream_t st)
+	float *soft, long long soft_stride, GuardList guard, MagOut mags, cudaStream_t st)
 {
 	if (n_tiles <= 0) return cudaSuccess;
 	static bool attr_done = false;
 	if (!attr_done) {
 		// 227 KB per CTA in all, static shared memory (the per-warp raw-sample maxima) included: the engine plans
 		// tiles of at most 226 KB of dynamic shared memory
-		cudaError_t e1 = cudaFuncSetAttribute(afsk_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-		cudaError_t e2 = cudaFuncSetAttribute(afsk_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		cudaError_t e1 = cudaFuncSetAttribute(afsk_front_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		cudaError_t e2 = cudaFuncSetAttribute(afsk_front_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+		cudaError_t e3 = cudaFuncSetAttribute(afsk_front_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 		if (e1 != cudaSuccess) return e1;
 		if (e2 != cudaSuccess) return e2;
+		if (e3 != cudaSuccess) return e3;
 		attr_done = true;
+	}
+	if (plan->tensor_lpf) {
+		pm_kt_mark("afsk_front_kernel (magnitudes)", st);
+		afsk_front_kernel<false, true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard, mags);
+		return cudaGetLastError();
 	}
 	pm_kt_mark("afsk_front_kernel", st);
 	if (soft)
-		afsk_front_kernel<true><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
-			sign, sign_stride, soft, soft_stride, guard);
+		afsk_front_kernel<true, false><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard, mags);
 	else
-		afsk_front_kernel<false><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
-			sign, sign_stride, soft, soft_stride, guard);
+		afsk_front_kernel<false, false><<<n_tiles, PM_FRONT_THREADS, smem_bytes, st>>>(*plan, audio, n_audio, tile_first,
+			sign, sign_stride, soft, soft_stride, guard, mags);
 	return cudaGetLastError();
 }
 

@@ -55,10 +55,66 @@ struct AfskPlan {
 	int s_x1_off, s_m_off, s_m_stride; // shared-memory carve-up, in floats; s_m_stride = one PAIR stream (float2 per sample)
 	int mag_dst_first[PM_MAX_MAG + 1]; // tone j feeds mag_dst[mag_dst_first[j] .. mag_dst_first[j+1])
 	int mag_dst[2 * PM_MAX_PAIR];      // pair * 2 + slot (0: mark, 1: space)
+	int tensor_lpf;           // 1: the kernel stops after the tone magnitudes and writes them, split into three bf16 pieces
+	                          // each, to global memory (MagOut); the low-pass and the epilogue run on the tensor cores
+	                          // (csrc/lpf_tc.cu).  The tile then has no low-pass halo: U_m = tile / 16.
 	float guard_eps;
 	float chain_guard_abs[PM_MAX_GCH];  // raw-input term of the sign guard per unit of max|audio| over the tile:
 	                                    // c_abs * 2^-24 * sum|h_bpf| * N_corr * sum|h_lpf| * (1 + space_gain)
 	alignas(16) float taps[PM_MAX_TAPS];   // every tap set starts at a multiple of 4 floats: read as float4
+};
+
+// ---- tensor-core low-pass (csrc/lpf_tc.cu) ------------------------------------------------------------
+// The 100-tap low-pass of every tone magnitude as a tcgen05 GEMM: D[128 x 64] (FP32, TMEM) = A[128 x 192] * B[192 x 64],
+// A[i][d] = m[64 i + d] (the magnitude stream itself, rows of 64 samples), B[d][n] = h[d - n] (banded Toeplitz matrix
+// of the taps), so D[i][n] = sum_t h[t] m[64 i + n + t] = output 64 i + n.  FP32 accuracy from bf16 operands: every
+// magnitude and every tap is split into three bf16 pieces (x = x1 + x2 + x3 exactly) and the six largest piece
+// products are accumulated into one TMEM tile (tools/ubench/fir_umma.cu: error 6.5e-8 of sum|h||m| rms, below the
+// sequential FP32 FMA's 1.5e-7).
+//
+// Magnitude streams in global memory (written by afsk_front_kernel<.., MAGS = true>, read by lpf_tc_kernel with bulk
+// copies): per tone t and piece q an array of `rows` rows of 128 bytes; row r holds samples [64 r, 64 r + 64) as bf16,
+// its 16-byte chunks XOR-swizzled with r & 7 (the shared-memory SWIZZLE_128B pattern, so a run of rows starting at a
+// multiple of 8 can be copied verbatim into a 1024-byte aligned operand buffer).
+#define TC_ROWS 128                      // M: rows (of 64 outputs) per tile
+#define TC_N 64
+#define TC_KBLK 3                        // K = 192 = 3 x 64 >= n_lpf + 63
+#define TC_TILE (TC_ROWS * TC_N)         // 8192 outputs of every tone per tile
+#define TC_A_ROWS (TC_ROWS + TC_KBLK)    // rows of one operand buffer: K block kb of row i is row i + kb
+#define TC_A_BYTES (TC_A_ROWS * 128)     // 16768
+#define TC_A_STRIDE 17408                // ... rounded up to 1024
+#define TC_B_BYTES (TC_KBLK * TC_N * 128)    // one tap piece: 24576
+#define TC_MAX_TONES 4                   // TMEM: 2 sets x 4 tones x 64 columns = 512
+#define TC_MAX_LPF (TC_KBLK * 64 - 16 - 63)   // 113 taps: eleven K steps of 16 (see lpf_tc.cu on the twelfth)
+
+struct MagOut {
+	unsigned char *base;      // piece array (t, q) starts at base + (t * 3 + q) * rows * 128
+	long long rows;
+	float *tile_amax;         // largest raw |sample| staged by front tile i (the guard's raw-input term), one float per tile
+};
+
+__host__ __device__ __forceinline__ long long pm_mag_offset(long long sample)
+{
+	const long long r = sample >> 6;
+	const int c = (int)((sample & 63) >> 3);
+	return r * 128 + (long long)((c ^ (int)(r & 7)) << 4);        // byte offset of the 16-byte chunk holding `sample`
+}
+
+struct LpfTcPlan {
+	int n_mag;                         // tones = TMEM accumulators per tile
+	int n_pair, n_chain;
+	int pair_mark[PM_MAX_PAIR], pair_space[PM_MAX_PAIR];
+	int pair_first[PM_MAX_PAIR + 1];
+	int chain_gid[PM_MAX_GCH];
+	float chain_gain[PM_MAX_GCH];
+	float chain_guard_abs[PM_MAX_GCH];
+	long long chain_nout[PM_MAX_GCH];
+	float guard_eps;
+	int n_lpf;                         // taps of the low-pass (K steps beyond n_lpf + 63 hold only zeros and are skipped)
+	int tile_a;                        // outputs per front tile (granularity of tile_amax)
+	int reach;                         // raw samples an output depends on beyond its own index: sum of (taps - 1)
+	long long n_tile_a;                // front tiles per run
+	int debug_mask;                    // development aid (option "tc_debug", tools/tc_debug.py): 1 no epilogue stores, 2 no bulk copies, 4 no MMAs, 8 no tile_amax reads
 };
 
 // Plan of a single-FIR front end (FSK: fsk.py:149-159).
