@@ -1006,6 +1006,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "kernel_times") e->opt_kernel_times = value != 0;
 	else if (k == "debug_sync") e->opt_debug_sync = value != 0;
 	else if (k == "tc_debug") { e->opt_tc_debug = (int)value; replan = true; }
+	else if (k == "tc_grid") e->sm_count = std::max(1, (int)value);          // CTAs of the persistent low-pass kernel (default: one per SM)
 	else if (k == "copy_threads") e->opt_copy_threads = std::max(1, std::min(16, (int)value));
 	else if (k == "guard_cap") e->guard_cap = (unsigned int)std::max(1024.0, value);
 	else return fail(e, PM_ERR_ARG, "unknown option '%s'", key);

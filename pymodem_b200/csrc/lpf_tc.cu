@@ -9,12 +9,14 @@
 // largest piece products (measured on B200, tools/ubench/fir_umma.cu: 576 cycles per 12-MMA product, error 6.5e-8 rms
 // of sum|h||m| against 1.5e-7 for the sequential FP32 FMAs it replaces).
 //
-// One persistent CTA per SM, five warps:
-//   warp 4, one lane   producer + MMA issuer: bulk-copies (cp.async.bulk, mbarrier complete_tx) the three piece
-//                      buffers of one (tile, tone) item into a shared-memory slot -- two slots, the copy for item
-//                      i + 1 is issued when item i - 1 has left its slot, i.e. it has the duration of item i to land --
-//                      and issues the 6 x 11 tcgen05.mma of an item into that tone's 64 TMEM columns; tcgen05.commit
-//                      releases the slot and, after a tile's last tone, hands the accumulators to the epilogue.
+// One persistent CTA per SM, six warps:
+//   warp 5, one lane   producer: bulk-copies (cp.async.bulk, mbarrier complete_tx) the three piece buffers of one
+//                      (tile, tone) item into a shared-memory slot.  Three slots: the copy for item i + 2 is issued as
+//                      soon as item i - 1 has left its slot, so it has two items' time to land.
+//   warp 4             MMA issuer: the whole warp runs the control loop (barrier waits, operand descriptors: warp-uniform
+//                      values in uniform registers), one elected lane issues the 6 x NK tcgen05.mma of an item into that
+//                      tone's 64 TMEM columns; tcgen05.commit releases the slot and, after a tile's last tone, hands the
+//                      accumulators to the epilogue.
 //   warps 0-3          epilogue: thread = TMEM lane = one row of 64 consecutive outputs.  Per tone pair and half row
 //                      the mark and the space accumulators come out with tcgen05.ld (32 columns each), every chain of
 //                      the pair forms y = L_mark - g L_space, the sign word (32 outputs = exactly one word of the
@@ -23,8 +25,9 @@
 // TMEM: 2 sets x 4 tones x 64 columns, so the MMAs of tile k + 1 run while the epilogue reads tile k.
 #include "pm_common.cuh"
 
-#define TC_THREADS 160
-#define TC_SMEM_BYTES (3 * TC_B_BYTES + 2 * 3 * TC_A_STRIDE + 1024)
+#define TC_THREADS 192
+#define TC_SLOTS 3                        // operand slots: the copy for item i + 2 is in flight while item i + 1 waits and item i runs
+#define TC_SMEM_BYTES (3 * TC_B_BYTES + TC_SLOTS * 3 * TC_A_STRIDE + 1024 + 128)   // + alignment slack + barriers: 231552 of the 232448 a CTA may have
 #define TC_SPIN_LIMIT (1ll << 24)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +54,20 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 		"setp.ne.b32 p, %4, 0;\n\t"
 		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
 		"}\n" :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// one lane of the (converged) warp, the way CUTLASS's elect_one_sync() asks for it: ptxas knows that the region this
+// predicate guards has a single active thread
+__device__ __forceinline__ bool tc_elect()
+{
+	uint32_t pred = 0;
+	asm volatile(
+		"{\n\t"
+		".reg .pred P;\n\t"
+		"elect.sync _|P, 0xFFFFFFFF;\n\t"
+		"@P mov.s32 %0, 1;\n\t"
+		"}\n" : "+r"(pred));
+	return pred != 0;
 }
 
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -90,7 +107,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *v)
 		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
 }
 
-template <bool WRITE_SOFT>
+// NK: K steps of 16 per piece product, ceil((n_lpf + 63) / 16) -- the steps past the last tap hold only zeros and are not
+// issued; a template parameter so that the issue loop is a straight run of tcgen05.mma with immediate descriptor offsets
+template <bool WRITE_SOFT, int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restrict__ mag, long long mag_rows,
               const unsigned char *__restrict__ btaps, const float *__restrict__ tile_amax, long long tile_first,
@@ -101,13 +120,15 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 	// the swizzle is a function of the address bits: 1024-byte alignment (1 KB of slack is allocated)
 	unsigned char *smem = tc_smem_raw + ((1024u - (tc_smem_u32(tc_smem_raw) & 1023u)) & 1023u);
 	unsigned char *sB = smem;                                   // 3 tap pieces x 3 K blocks x 64 rows x 128 bytes
-	unsigned char *sA = smem + 3 * TC_B_BYTES;                  // 2 slots x 3 data pieces x TC_A_STRIDE
-	__shared__ __align__(8) unsigned long long bars[8];         // full_a[2], free_a[2], d_full[2], d_free[2]
-	__shared__ uint32_t tmem_slot;
-	__shared__ int s_abort;
+	unsigned char *sA = smem + 3 * TC_B_BYTES;                  // TC_SLOTS slots x 3 data pieces x TC_A_STRIDE
+	// barriers and two words of bookkeeping behind the operand buffers (no static shared memory: the kernel uses all but
+	// 900 bytes of what a CTA can have): full_a[3], free_a[3], d_full[2], d_free[2]
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(sA + TC_SLOTS * 3 * TC_A_STRIDE);
+	uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(bars + 12);
+	int &s_abort = *reinterpret_cast<int *>(bars + 13);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t bar_full_a = tc_smem_u32(&bars[0]), bar_free_a = tc_smem_u32(&bars[2]);
-	const uint32_t bar_d_full = tc_smem_u32(&bars[4]), bar_d_free = tc_smem_u32(&bars[6]);
+	const uint32_t bar_full_a = tc_smem_u32(&bars[0]), bar_free_a = tc_smem_u32(&bars[3]);
+	const uint32_t bar_d_full = tc_smem_u32(&bars[6]), bar_d_free = tc_smem_u32(&bars[8]);
 
 	// tiles of this CTA: tile_first + blockIdx.x, + gridDim.x, ...
 	const long long my_tiles = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -116,8 +137,8 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 		*reinterpret_cast<uint4 *>(sB + i * 16) = *reinterpret_cast<const uint4 *>(btaps + i * 16);
 	if (tid == 0) {
 		s_abort = 0;
-		for (int b = 0; b < 6; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tc_smem_u32(&bars[b])) : "memory");
-		for (int b = 6; b < 8; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tc_smem_u32(&bars[b])) : "memory");
+		for (int b = 0; b < 8; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tc_smem_u32(&bars[b])) : "memory");
+		for (int b = 8; b < 10; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tc_smem_u32(&bars[b])) : "memory");
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 4) {
@@ -132,74 +153,114 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 	volatile int *abort_flag = &s_abort;
 
 	if (warp == 4) {
-		if (lane == 0 && my_tiles > 0) {
+		if (my_tiles > 0) {
+			// The whole warp runs the control loop -- loop counters, barrier waits and operand descriptors are then
+			// warp-uniform values that stay in uniform registers -- and one lane issues the copies, MMAs and commits.
+			// (Issued from inside an `if (lane == 0)` region every tcgen05.mma had its operands moved from vector to uniform
+			// registers through an elect/broadcast loop: 85 cycles of issue per MMA against the 48 the tensor core needs.)
+			const bool leader = lane == 0;
 			// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = BF16 [7,10) = 1, B = BF16 [10,13) = 1,
 			// both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 			const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
 			const long long n_items = my_tiles * P.n_mag;
 			const uint64_t descB0 = tc_desc(tc_smem_u32(sB));
-			auto issue_load = [&](long long it) -> bool {
-				const int slot = (int)(it & 1);
-				// the slot's previous tenant (item it - 2) has been consumed; the first two uses pass at once
-				if (!tc_wait(bar_free_a + 8u * slot, (uint32_t)(((it >> 1) & 1) ^ 1), abort_flag)) return false;
-				const long long tile = tile_first + blockIdx.x + (it / P.n_mag) * gridDim.x;
-				const int tone = (int)(it % P.n_mag);
-				const uint32_t bar = bar_full_a + 8u * slot;
-				if (P.debug_mask & 2) {
-					asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-					return true;
-				}
-				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(3u * TC_A_BYTES) : "memory");
-#pragma unroll
-				for (int q = 0; q < 3; q++) {
-					const unsigned char *src = mag + ((long long)(tone * 3 + q) * mag_rows + tile * TC_ROWS) * 128;
-					const uint32_t dst = tc_smem_u32(sA + (slot * 3 + q) * TC_A_STRIDE);
-					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-						:: "r"(dst), "l"(src), "r"((uint32_t)TC_A_BYTES), "r"(bar) : "memory");
-				}
-				return true;
-			};
-			bool ok = issue_load(0);
+			// tracing (option "stage_clocks"): cycles spent waiting for data / for a slot / for the epilogue, and issuing
+			const bool trace = guard.stage_clk != nullptr && leader;
+			long long c_full = 0, c_free = 0, c_dfree = 0, c_issue = 0, t_a = 0;
+			auto tick = [&]() { if (trace) t_a = clock64(); };
+			auto tock = [&](long long &acc_c) { if (trace) acc_c += clock64() - t_a; };
+			const long long t_loop0 = trace ? clock64() : 0;
+			bool ok = true;
 			for (long long it = 0; ok && it < n_items; it++) {
-				const int slot = (int)(it & 1);
+				const int slot = (int)(it % TC_SLOTS);
 				const long long k = it / P.n_mag;
 				const int tone = (int)(it % P.n_mag), set = (int)(k & 1);
-				if (!tc_wait(bar_full_a + 8u * slot, (uint32_t)((it >> 1) & 1), abort_flag)) break;
+				tick();
+				if (!tc_wait(bar_full_a + 8u * slot, (uint32_t)((it / TC_SLOTS) & 1), abort_flag)) break;
+				tock(c_full);
 				// the epilogue has read this TMEM set (tile k - 2); the first two tiles pass at once
-				if (tone == 0 && !tc_wait(bar_d_free + 8u * set, (uint32_t)(((k >> 1) & 1) ^ 1), abort_flag)) break;
+				tick();
+				if (tone == 0 && !(P.debug_mask & 512) && !tc_wait(bar_d_free + 8u * set, (uint32_t)(((k >> 1) & 1) ^ 1), abort_flag)) break;
+				tock(c_dfree);
+				tick();
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				const uint32_t d_tmem = tmem_base + (uint32_t)((set * TC_MAX_TONES + tone) * TC_N);
 				const uint64_t descA0 = tc_desc(tc_smem_u32(sA + slot * 3 * TC_A_STRIDE));
-				// (tap piece, data piece): the small products first, the leading one last
-				const int order[6][2] = {{2, 0}, {1, 1}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
-				uint32_t acc = 0;
+				// (tap piece, data piece): the small products first, the leading one last.  Plain loops over the products, the K
+				// steps of a product unrolled with immediate descriptor offsets; the accumulate flag is off only for the very
+				// first MMA of the item.
+				if (!(P.debug_mask & 4)) {
+#pragma unroll 1
+					for (int o = 0; o < 6; o++) {
+						const int tq = (0x210100 >> (4 * (5 - o))) & 3;          // tap piece of product o:  2 1 0 1 0 0
+						const int dq = (0x012010 >> (4 * (5 - o))) & 3;          // data piece of product o: 0 1 2 0 1 0
+						const uint64_t da0 = descA0 + (uint64_t)((dq * TC_A_STRIDE) >> 4);
+						const uint64_t db0 = descB0 + (uint64_t)((tq * TC_B_BYTES) >> 4);
+						if (tc_elect()) {
 #pragma unroll
-				for (int o = 0; o < 6; o++)
-#pragma unroll
-					for (int kb = 0; kb < TC_KBLK; kb++)
-#pragma unroll
-						for (int ks = 0; ks < 4; ks++) {
-							// K steps past the last tap hold only zeros.  The twelfth (third shifted row, 96 bytes in) is never
-							// issued: on B200 it added a spurious contribution to the last three columns in the one
-							// configuration tried (all-zero B block, tools/tc_debug.py), so plans are limited to TC_MAX_LPF taps
-							if (64 * kb + 16 * ks >= P.n_lpf + 63) continue;
-							const uint64_t da = descA0 + (uint64_t)((order[o][1] * TC_A_STRIDE + 128 * kb + 32 * ks) >> 4);
-							const uint64_t db = descB0 + (uint64_t)((order[o][0] * TC_B_BYTES + TC_N * 128 * kb + 32 * ks) >> 4);
-							if (!(P.debug_mask & 4)) tc_mma(d_tmem, da, db, idesc, acc);
-							acc = 1;
+							for (int kk = 0; kk < NK; kk++) {
+								const int kb = kk >> 2, ks = kk & 3;
+								tc_mma(d_tmem, da0 + (uint64_t)((128 * kb + 32 * ks) >> 4), db0 + (uint64_t)((TC_N * 128 * kb + 32 * ks) >> 4),
+									idesc, (kk == 0 && o == 0) ? 0u : 1u);
+							}
 						}
-				tc_commit(bar_free_a + 8u * slot);                      // the slot is free once these MMAs have read it
-				if (tone == P.n_mag - 1) tc_commit(bar_d_full + 8u * set);
-				if (it + 1 < n_items) ok = issue_load(it + 1);
+						__syncwarp();
+					}
+				}
+				if (leader) {
+					tc_commit(bar_free_a + 8u * slot);                  // the slot is free once these MMAs have read it
+					if (tone == P.n_mag - 1) tc_commit(bar_d_full + 8u * set);
+				}
+				__syncwarp();
+				tock(c_issue);
+			}
+			if (trace) {
+				atomicAdd(&guard.stage_clk[0], (unsigned long long)c_full);
+				atomicAdd(&guard.stage_clk[1], (unsigned long long)c_free);
+				atomicAdd(&guard.stage_clk[2], (unsigned long long)c_dfree);
+				atomicAdd(&guard.stage_clk[3], (unsigned long long)c_issue);
+				atomicAdd(&guard.stage_clk[4], (unsigned long long)n_items);
+				atomicAdd(&guard.stage_clk[7], (unsigned long long)(clock64() - t_loop0));     // the whole control loop of this CTA
+			}
+		}
+	} else if (warp == 5) {
+		// ---- producer warp: keeps the operand slots full, TC_SLOTS - 1 items ahead of the MMAs ----
+		if (my_tiles > 0) {
+			const bool leader = lane == 0;
+			const long long n_items = my_tiles * P.n_mag;
+			for (long long it = 0; it < n_items; it++) {
+				const int slot = (int)(it % TC_SLOTS);
+				// the slot's previous tenant (item it - TC_SLOTS) has been consumed; the first uses pass at once
+				if (!tc_wait(bar_free_a + 8u * slot, (uint32_t)(((it / TC_SLOTS) & 1) ^ 1), abort_flag)) break;
+				const long long tile = tile_first + blockIdx.x + (it / P.n_mag) * gridDim.x;
+				const int tone = (int)(it % P.n_mag);
+				const uint32_t bar = bar_full_a + 8u * slot;
+				if (leader) {
+					if (P.debug_mask & 2) {
+						asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+					} else {
+						asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(3u * TC_A_BYTES) : "memory");
+#pragma unroll
+						for (int q = 0; q < 3; q++) {
+							const unsigned char *src = mag + ((long long)(tone * 3 + q) * mag_rows + tile * TC_ROWS) * 128;
+							const uint32_t dst = tc_smem_u32(sA + (slot * 3 + q) * TC_A_STRIDE);
+							asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+								:: "r"(dst), "l"(src), "r"((uint32_t)TC_A_BYTES), "r"(bar) : "memory");
+						}
+					}
+				}
+				__syncwarp();
 			}
 		}
 	} else {
 		// ---- epilogue warps: thread = TMEM lane = row of 64 outputs ----
 		const int row = tid;                                         // 0 .. 127 (warp w reads lanes [32 w, 32 w + 32))
-		for (long long k = 0; k < my_tiles; k++) {
+		for (long long k = 0; k < ((P.debug_mask & 512) ? 0 : my_tiles); k++) {      // (512: the epilogue warps leave at once, timing experiments)
 			const int set = (int)(k & 1);
 			const long long tile = tile_first + blockIdx.x + k * gridDim.x;
+			const long long t_e0 = (guard.stage_clk && tid == 0) ? clock64() : 0;
 			if (!tc_wait(bar_d_full + 8u * set, (uint32_t)((k >> 1) & 1), abort_flag)) break;
+			const long long t_e1 = (guard.stage_clk && tid == 0) ? clock64() : 0;
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			const long long n_row = tile * TC_TILE + (long long)row * TC_N;      // first output of this row
 			// raw-input term of the guard: largest |sample| of the front tiles this row's outputs depend on
@@ -210,7 +271,7 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 				if (!(P.debug_mask & 8))
 					for (long long t = t0; t <= t1; t++) amax = fmaxf(amax, tile_amax[t]);
 			}
-			for (int p = 0; p < P.n_pair; p++) {
+			for (int p = 0; p < ((P.debug_mask & 64) ? 0 : P.n_pair); p++) {      // (64: no epilogue at all, timing experiments)
 				const uint32_t t_mark = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)((set * TC_MAX_TONES + P.pair_mark[p]) * TC_N);
 				const uint32_t t_space = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)((set * TC_MAX_TONES + P.pair_space[p]) * TC_N);
 #pragma unroll 1
@@ -261,6 +322,10 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 			// this thread's loads of the set are complete (wait::ld above): hand the accumulators back
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_d_free + 8u * set) : "memory");
+			if (guard.stage_clk && tid == 0) {
+				atomicAdd(&guard.stage_clk[5], (unsigned long long)(t_e1 - t_e0));          // waiting for the accumulators
+				atomicAdd(&guard.stage_clk[6], (unsigned long long)(clock64() - t_e1));    // epilogue work of one tile
+			}
 		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -271,26 +336,40 @@ lpf_tc_kernel(const __grid_constant__ LpfTcPlan P, const unsigned char *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
+template <int NK>
+static cudaError_t launch_lpf_tc_nk(const LpfTcPlan *plan, const unsigned char *mag, long long mag_rows, const unsigned char *btaps,
+	const float *tile_amax, long long tile_first, long long n_tiles, uint32_t *sign, long long sign_stride, float *soft,
+	long long soft_stride, GuardList guard, int *status, int grid, cudaStream_t st)
+{
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e1 = cudaFuncSetAttribute(lpf_tc_kernel<false, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+		cudaError_t e2 = cudaFuncSetAttribute(lpf_tc_kernel<true, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+		if (e1 != cudaSuccess) return e1;
+		if (e2 != cudaSuccess) return e2;
+		attr_done = true;
+	}
+	if (soft)
+		lpf_tc_kernel<true, NK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(*plan, mag, mag_rows, btaps, tile_amax, tile_first,
+			n_tiles, sign, sign_stride, soft, soft_stride, guard, status);
+	else
+		lpf_tc_kernel<false, NK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(*plan, mag, mag_rows, btaps, tile_amax, tile_first,
+			n_tiles, sign, sign_stride, soft, soft_stride, guard, status);
+	return cudaGetLastError();
+}
+
 extern "C" cudaError_t pm_launch_lpf_tc(const LpfTcPlan *plan, const unsigned char *mag, long long mag_rows,
 	const unsigned char *btaps, const float *tile_amax, long long tile_first, long long n_tiles, uint32_t *sign,
 	long long sign_stride, float *soft, long long soft_stride, GuardList guard, int *status, int sm_count, cudaStream_t st)
 {
 	if (n_tiles <= 0) return cudaSuccess;
-	static bool attr_done = false;
-	if (!attr_done) {
-		cudaError_t e1 = cudaFuncSetAttribute(lpf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-		cudaError_t e2 = cudaFuncSetAttribute(lpf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-		if (e1 != cudaSuccess) return e1;
-		if (e2 != cudaSuccess) return e2;
-		attr_done = true;
-	}
 	const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+	const int nk = (plan->n_lpf + 63 + 15) >> 4;          // 5 (8 taps) .. 11 (TC_MAX_LPF taps)
 	pm_kt_mark("lpf_tc_kernel", st);
-	if (soft)
-		lpf_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(*plan, mag, mag_rows, btaps, tile_amax, tile_first,
-			n_tiles, sign, sign_stride, soft, soft_stride, guard, status);
-	else
-		lpf_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(*plan, mag, mag_rows, btaps, tile_amax, tile_first,
-			n_tiles, sign, sign_stride, soft, soft_stride, guard, status);
-	return cudaGetLastError();
+#define TC_CASE(N) case N: return launch_lpf_tc_nk<N>(plan, mag, mag_rows, btaps, tile_amax, tile_first, n_tiles, sign, sign_stride, soft, soft_stride, guard, status, grid, st)
+	switch (nk) {
+		TC_CASE(5); TC_CASE(6); TC_CASE(7); TC_CASE(8); TC_CASE(9); TC_CASE(10); TC_CASE(11);
+	}
+#undef TC_CASE
+	return cudaErrorInvalidValue;
 }
