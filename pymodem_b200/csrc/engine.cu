@@ -2002,6 +2002,15 @@ extern "C" int pm_engine_slice_soft(pm_engine *e, int32_t chain, const double *s
 	const bool quad = hc.d.slicer_kind == PM_SLICER_QUADRATURE;
 	if (n < 0 || (n > 0 && !soft_i) || (quad && n > 0 && !soft_q))
 		return fail(e, PM_ERR_ARG, "slice_soft: soft values missing (the quadrature slicer needs I and Q, slicer.py:198-199)");
+	if (n == 0) {                         // slicing nothing gives nothing (slicer.py:75: the loop body never runs)
+		ChainCounters zero;
+		memset(&zero, 0, sizeof(zero));
+		e->h_cc.assign(e->chains.size(), zero);
+		CK(e->h_recs.resize(0));
+		CK(e->h_arena.resize(0));
+		e->have_run = true;
+		return PM_OK;
+	}
 	pm_shard_plan plan;
 	memset(&plan, 0, sizeof(plan));
 	plan.first = plan.last = 1;

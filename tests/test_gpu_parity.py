@@ -412,7 +412,9 @@ def test_sliding_correlator_matches_direct_fir(cuda_lib, tag):
 	assert out[0] == out[1] == out[2]
 	assert out[0][0] == g.all_packets()
 	for a, b, c in zip(*softs):
-		assert np.max(np.abs(a - b)) <= 8e-6 * np.sqrt(np.mean(b ** 2))
+		# each variant is within 1e-5 of the RMS of the reference's float64 values (the fixture tests); the first runs its
+		# low-pass on the tensor cores (three bf16 pieces, FP32 accumulation in TMEM), the others on the FP32 pipe
+		assert np.max(np.abs(a - b)) <= 2e-5 * np.sqrt(np.mean(b ** 2))
 		assert np.max(np.abs(c - b)) <= 8e-6 * np.sqrt(np.mean(b ** 2))
 
 
