@@ -253,7 +253,7 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------
-def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3):
+def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3, tc_macs=0.0):
 	"""A timing pass (option kernel_times: a CUDA event before every launch) after the timed region: every kernel with
 	at least 2 % of the step gets a roofline line.  The bound named is the one the kernel is built against; `frac` is
 	achieved / peak for that bound; for the latency-bound kernels the HBM fraction says how far the bytes are from
@@ -282,6 +282,11 @@ def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3):
 	sign_mask = n_chains * words * 4.0
 	work = {
 		"afsk_front_kernel": ("fp32", 2.0 * macs * n / 1e12, fp32_peak, "TFLOP/s"),
+		# tensor-core route: the front kernel stops at the magnitudes (band-pass + sliding correlators + piece split), the
+		# low-pass is a tcgen05 GEMM: executed bf16 flops against the measured cuBLAS bf16 peak (burst figure: the kernel is
+		# timed alone)
+		"afsk_front_kernel (magnitudes)": ("fp32", 2.0 * macs * n / 1e12, fp32_peak, "TFLOP/s"),
+		"lpf_tc_kernel": ("tensor", 2.0 * tc_macs * n / 1e12, peaks.get("bf16_tflops") or 1590.0, "TFLOP/s"),
 		"guard_fixup_kernel": ("fp64", flagged * 2.0 * (320 * 148 + 4 * 100 * 60 + 100) / 1e12, FP64_NOMINAL_TFLOPS, "TFLOP/s"),
 		"slicer_segments_kernel": ("alu-issue", (3.0 * sign_mask + sign_mask) / 1e9, hbm, "GB/s"),
 		"slicer_verify_kernel": ("latency", 0.0, hbm, "GB/s"),
@@ -386,9 +391,12 @@ def run_b200_arm(args):
 	else:
 		# ONE recording sharded on the sample axis: rank r gets its slice + FIR/warm-up history + a few forward symbols
 		# (pymodem_b200/sharded.py).  weak: world x seconds (the synthetic hour repeated); strong: the hour itself.
-		from pymodem_b200.sharded import LinkedRun, TorchExchange, plan_shards
+		from pymodem_b200.sharded import LinkedRun, TorchExchange, choose_segment_len, plan_shards
 		n_total = n_hour if strong else n_hour * world
-		plans = plan_shards(n_total, world, trim_max=305, samples_per_symbol=40.0, tail_bits=16384)
+		# shorter slicer segments when a rank's shard is small (strong scaling): see sharded.choose_segment_len
+		seg_len = int(float(opts["segment_len"])) if "segment_len" in opts else choose_segment_len(n_total // world, n_chains)
+		eng.set_option("segment_len", seg_len)
+		plans = plan_shards(n_total, world, segment_len=seg_len, trim_max=305, samples_per_symbol=40.0, tail_bits=16384)
 		plan = plans[rank]
 		max_local = max(p['audio_end'] - p['audio_begin'] for p in plans)      # the link layout must be the same on every rank
 		idx = np.arange(plan['audio_begin'], plan['audio_end'], dtype=np.int64) % n_hour
@@ -556,7 +564,8 @@ def run_b200_arm(args):
 		traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n / tr["samples_per_launch"]) / max(front_launches, 1)
 	except (OSError, ValueError, KeyError):
 		pass
-	roofline = {"kernel": "afsk_front_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+	tc_macs = eng.front_tensor_macs_per_sample()
+	roofline = {"kernel": "afsk_front_kernel" + (" (magnitudes) + lpf_tc_kernel" if tc_macs else ""), "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
 		"unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
 		"peak_source": "pm_measure_fp32_peak: register-resident FFMA loop timed in this run "
 			f"(nominal {FP32_NOMINAL_TFLOPS:.1f} at max clocks; MEASURED_PEAKS.json has no FP32 entry)",
@@ -569,7 +578,24 @@ def run_b200_arm(args):
 	roofline_all = None
 	if world == 1:
 		try:
-			roofline_all = kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats)
+			roofline_all = kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, tc_macs=tc_macs)
+			# the headline roofline is that of the kernel with the largest share of the step, timed in that pass (with the
+			# tensor-core low-pass the front end is two kernels and front_ms above covers both)
+			top = max((k for k in roofline_all["kernels"] if k.get("frac")), key=lambda k: k["ms"])
+			roofline.update({"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+				"unit": top["unit"], "frac": top["frac"], "kernel_ms": top["ms"], "launches_per_step": top["launches"],
+				"share_of_step": top["share"]})
+			if top["bound"] != "fp32":
+				roofline["peak_source"] = peaks_src
+			if tc_macs:
+				tck = next((k for k in roofline_all["kernels"] if k["kernel"] == "lpf_tc_kernel"), None)
+				if tck:
+					roofline["tensor"] = {"kernel": "lpf_tc_kernel", "bound": "tensor", "achieved": tck["achieved"], "peak": tck["peak"],
+						"unit": "TFLOP/s", "frac": tck["frac"], "kernel_ms": tck["ms"], "peak_sustained": peaks.get("bf16_tflops_sustained"),
+						"executed_bf16_mac_per_sample": tc_macs,
+						"useful_mac_per_sample": eng._lib.pm_engine_front_lpf_macs_per_sample(eng._h),
+						"note": "three bf16 pieces per operand, six piece products, K padded to the Toeplitz band: executed flops, "
+							"not useful ones; peak = cuBLAS bf16 burst figure of MEASURED_PEAKS.json"}
 		except Exception as exc:                 # the timing pass is informational: never lose the line over it
 			roofline_all = {"error": f"{type(exc).__name__}: {exc}"}
 

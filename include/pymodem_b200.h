@@ -178,7 +178,8 @@ int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_c
  *   sum|h_bpf| N_corr sum|h_lpf| (1 + space_gain) added to the band -- the band-pass rounds at the magnitude of the RAW
  *   samples, DC / hum / out-of-band energy included), "guard_cap" (initial capacity of the guard list; grows on demand),
  * "slide_correlator" (0: tone correlators as plain FIRs even when their taps are a rotation), "fuse_pairs" (0: sliding
- *   windows tone by tone instead of mark and space of a pair together), "tile" (front-end outputs
+ *   windows tone by tone instead of mark and space of a pair together), "tensor_lpf" (0: the AFSK low-pass on the FP32
+ *   pipe, fused into the front kernel, even where the tensor-core route applies), "tile" (front-end outputs
  *   per CTA, 0 = cost model), "keep_soft" (1: keep the soft values for pm_engine_get_soft), "h2d_chunk" (samples per
  *   host-to-device copy of pm_engine_run), "copy_threads" (host threads that stage pageable input, default 4), "stage_clocks" (1: trace the front end's stages, pm_engine_stage_clocks),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
@@ -349,6 +350,14 @@ int pm_measure_fp32_peak(int device, double *tflops);
  * the sharing of common filter passes) and the tile length of a front-end
  * launch group -- reported by bench.py next to the roofline. */
 double pm_engine_front_macs_per_sample(const pm_engine *e);
+/* Executed bf16 multiply-adds per input sample on the tensor cores when the AFSK low-pass runs there (option
+ * "tensor_lpf", default on where a chain group qualifies: every tone pair a sliding-window pair, at most 4 tones, 8..113
+ * low-pass taps): three bf16 pieces per operand, six piece products, K padded to the Toeplitz band -- about eleven
+ * times the useful multiply-adds, on a pipe with thirty times the FP32 rate.  0 when no group takes that route. */
+double pm_engine_front_tensor_macs_per_sample(const pm_engine *e);
+/* The useful multiply-adds per input sample of the AFSK low-pass (2 x tone pairs x taps): what the FP32 route executes
+ * for it and what the tensor-core figure above should be compared with. */
+double pm_engine_front_lpf_macs_per_sample(const pm_engine *e);
 int pm_engine_front_tile(const pm_engine *e, int group);
 
 /* Host-side helper (no device): 1 when the correlator taps (i[k], q[k]), k < n, are a rotation a*e^{i(phi + step*k)} with

@@ -128,6 +128,8 @@ PROTOTYPES = {
 	"pm_engine_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
 	"pm_engine_kernel_times": (_i64, [_vp, ctypes.c_char_p, _i64]),
 	"pm_engine_front_macs_per_sample": (ctypes.c_double, [_vp]),
+	"pm_engine_front_tensor_macs_per_sample": (ctypes.c_double, [_vp]),
+	"pm_engine_front_lpf_macs_per_sample": (ctypes.c_double, [_vp]),
 	"pm_engine_stage_clocks": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
 	"pm_taps_are_rotation": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int32,
 		ctypes.POINTER(ctypes.c_double)]),

@@ -2515,6 +2515,23 @@ extern "C" double pm_engine_front_macs_per_sample(const pm_engine *e)
 	return m;
 }
 
+// executed bf16 multiply-adds per input sample on the tensor cores (csrc/lpf_tc.cu: six piece products x the K steps
+// issued x 16 per output and tone; about eleven times the 100 useful ones), 0 when no group takes that route
+extern "C" double pm_engine_front_tensor_macs_per_sample(const pm_engine *e)
+{
+	double m = 0;
+	if (e) for (auto &g : e->groups) if (g.tensor) m += g.tc_macs_per_sample;
+	return m;
+}
+
+// the FP32 multiply-adds per input sample the low-pass takes on the FP32 pipe (what the tensor-core route replaces)
+extern "C" double pm_engine_front_lpf_macs_per_sample(const pm_engine *e)
+{
+	double m = 0;
+	if (e) for (auto &g : e->groups) m += g.lpf_macs_per_sample;
+	return m;
+}
+
 // host-side check behind the sliding-window correlators (no device needed): are (ti[k], tq[k]) = a e^{i(phi + w k)}?
 extern "C" int pm_taps_are_rotation(const double *ti, const double *tq, int32_t n, double *step)
 {

@@ -353,6 +353,9 @@ class Engine:
 	def front_macs_per_sample(self):
 		return self._lib.pm_engine_front_macs_per_sample(self._h)
 
+	def front_tensor_macs_per_sample(self):
+		return self._lib.pm_engine_front_tensor_macs_per_sample(self._h)
+
 
 def _unregister(lib, ptr, table, key):
 	table.pop(key, None)

@@ -32,6 +32,17 @@ DEFAULT_SEGMENT_LEN = 24576
 DEFAULT_WARMUP_LEN = 49152
 
 
+def choose_segment_len(n_local, n_chains, target_threads=49152, lo=4096, hi=DEFAULT_SEGMENT_LEN):
+	"""Slicer segment length for a shard of n_local samples: the slicer kernel is one thread per (chain, segment) and
+	bound by the latency of a thread's dependent chain (warm-up + segment), so a small shard -- one hour split over 8
+	GPUs -- wants shorter segments than the 24576 samples that are best when a GPU has the whole hour: enough threads
+	to fill the machine, a shorter chain per thread.  Results do not depend on it (every hand-off is verified).  All
+	ranks of a run must use the same value (shard boundaries are segment aligned): compute it from the largest shard."""
+	want = max(1, n_local * max(n_chains, 1) // target_threads)
+	seg = max(lo, min(hi, want))
+	return max(1024, seg // 1024 * 1024)
+
+
 def plan_shards(n_samples, world, segment_len=DEFAULT_SEGMENT_LEN, warm_len=DEFAULT_WARMUP_LEN, trim_max=305, samples_per_symbol=40.0,
 		tail_bits=16384, pre_segments=4):
 	"""Split n_samples over `world` ranks.  Returns one dict per rank:

@@ -77,5 +77,7 @@ def test_torchrun_ranks_equal_unsharded(cuda_lib, tmp_path, world):
 		for digests, n, fallbacks, recoveries in d["ranks"]:
 			assert n == d["n_unsharded"], (case, d)
 			assert all(x == d["unsharded"] for x in digests), (case, d)
-	# frames beyond 1023 bytes force the bitstream recovery on every rank, every run
-	assert all(r[3] == 2 for r in res["long_frames"]["ranks"]), res["long_frames"]
+	# frames beyond 1023 bytes cannot be finished shard by shard: every run leaves the fast path -- straight into the
+	# bitstream recovery (recoveries), or through the host-driven protocol when the quiet stretches between the frames
+	# also left the slicer passes unsettled (fallbacks), which then recovers the same way
+	assert all(r[2] + r[3] == 2 for r in res["long_frames"]["ranks"]), res["long_frames"]
