@@ -666,6 +666,7 @@ def main():
 	ap.add_argument("--no-cpu", action="store_true")
 	ap.add_argument("--in-flight", type=int, default=2, help="recordings in flight for e2e.pipelined (N=1 only; 1 = skip)")
 	ap.add_argument("--opt", action="append", default=[], help="engine option key=value (pm_engine_set_option)")
+	ap.add_argument("--batch", type=int, default=0, help="--config lines: recordings per engine call (0 = the config's default)")
 	args = ap.parse_args()
 	args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 	if args.config != "super_opt":

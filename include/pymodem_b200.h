@@ -99,7 +99,8 @@ typedef struct pm_chain_desc {
 	double space_gain;              /* afsk.py:143 */
 	const double *lpf;              /* afsk.py:122 output_lpf / psk.py rrc taps */
 	int32_t n_lpf;
-	int32_t reserved0;
+	int32_t recording;              /* batch slot: which recording of pm_engine_run_batch this chain decodes (0 for the
+	                                   single-recording calls).  Chains of different recordings never share a front-end pass. */
 
 	/* --- slicer (slicer.py:49-56, 181-191) --- */
 	double slicer_sample_rate;      /* pymodem.py:86-90 */
@@ -196,6 +197,16 @@ int pm_engine_set_option(pm_engine *e, const char *key, double value);
  */
 int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_samples);
 int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples);
+
+/*
+ * Batched form: R recordings x the chains that name them (pm_chain_desc.recording = 0 .. R-1) in one engine call.  Row r of
+ * audio_host ([R][row_stride] int16, host memory) holds recording r, n_samples[r] <= row_stride of it valid.  Every
+ * stage runs over all chains of all recordings at once -- this is what fills a B200 when one recording cannot: the
+ * carrier-loop modems (psk.py:162-195, 705-773; afsk_pll.py:140-170) are sequential per chain, so 64 short recordings
+ * x their chains are 64+ loops side by side.  Records come back ordered by chain index as usual.
+ */
+int pm_engine_run_batch(pm_engine *e, const int16_t *audio_host, int64_t row_stride, const int64_t *n_samples,
+                        int32_t n_recordings);
 
 /*
  * Sharded form used by the multi-GPU host (one engine per rank; ONE recording is

@@ -38,7 +38,7 @@ class ChainDesc(ctypes.Structure):
 		("bpf", _dp), ("n_bpf", ctypes.c_int32), ("n_corr", ctypes.c_int32),
 		("mark_i", _dp), ("mark_q", _dp), ("space_i", _dp), ("space_q", _dp),
 		("space_unit_i", _dp), ("space_unit_q", _dp), ("space_gain", ctypes.c_double),
-		("lpf", _dp), ("n_lpf", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+		("lpf", _dp), ("n_lpf", ctypes.c_int32), ("recording", ctypes.c_int32),
 		("slicer_sample_rate", ctypes.c_double), ("symbol_rate", ctypes.c_double),
 		("lock_rate", ctypes.c_double), ("state_mask", ctypes.c_uint32),
 		("bits_per_symbol", ctypes.c_uint32), ("demap", ctypes.c_uint32 * 16),
@@ -103,6 +103,7 @@ PROTOTYPES = {
 	"pm_engine_set_option": (ctypes.c_int, [_vp, _cp, ctypes.c_double]),
 	"pm_engine_run": (ctypes.c_int, [_vp, _vp, _i64]),
 	"pm_engine_run_device": (ctypes.c_int, [_vp, _vp, _i64]),
+	"pm_engine_run_batch": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64), _i32]),
 	"pm_engine_shard_begin": (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.POINTER(ShardPlan), ctypes.POINTER(ShardState)]),
 	"pm_engine_shard_handoff": (ctypes.c_int, [_vp, ctypes.POINTER(ShardState), ctypes.POINTER(ShardState), ctypes.POINTER(_i32)]),
 	"pm_engine_shard_gather": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _vp]),

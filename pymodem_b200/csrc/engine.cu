@@ -265,6 +265,10 @@ struct pm_engine {
 	double rec_scale = 1.0, il2p_cand_scale = 1.0;   // grown (and the run repeated) when packet buffers / IL2P candidate lists overflow
 	int grow_hint = 0;                    // what the last PM_ERR_CAPACITY asked for: 1 packet buffers, 2 IL2P candidates
 	bool skip_lfsr = false;               // pm_engine_decode_stream: the stream loaded is already descrambled
+	// batched runs (pm_engine_run_batch): chain c decodes recording chains[c].d.recording = row of the audio buffer
+	long long batch_stride = 0;           // samples per row; 0: a single recording
+	std::vector<long long> batch_n;       // valid samples of every recording
+	std::vector<Fp64Chain> h_fp64, up_fp64;
 	int fast_passes = 0;                  // verify passes enqueued without a host round trip (slicer_enqueue_fast)
 	bool fast_pending = false;            // ... whose counters have not been looked at yet
 	size_t spec_recs = 4096, spec_arena = 1 << 18;   // records / packet bytes copied back before their count is known
@@ -303,6 +307,16 @@ struct pm_engine {
 	int64_t staged_bytes = 0;             // bytes of the last run that went through the ring (0: the caller's buffer was pinned)
 	bool have_run = false;
 };
+
+// audio of chain c: length and offset in the run's audio buffer (a single recording unless the run is batched)
+static inline long long chain_n(const pm_engine *e, int c, long long n)
+{
+	return e->batch_stride ? e->batch_n[e->chains[c].d.recording] : n;
+}
+static inline long long chain_aoff(const pm_engine *e, int c)
+{
+	return e->batch_stride ? (long long)e->chains[c].d.recording * e->batch_stride : 0;
+}
 
 static int fail(pm_engine *e, int code, const char *fmt, ...)
 {
@@ -447,7 +461,7 @@ static int build_groups(pm_engine *e)
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: modem kind %d not supported by this build", c, g.kind);
 		for (int k = c; k < nc; k++) {
 			HostChain &o = e->chains[k];
-			if (o.group >= 0 || o.p64 || o.d.modem_kind != g.kind) continue;
+			if (o.group >= 0 || o.p64 || o.d.modem_kind != g.kind || o.d.recording != hc.d.recording) continue;
 			if (!same_taps(o.bpf, hc.bpf)) continue;
 			if (g.kind == PM_MODEM_AFSK && !same_taps(o.lpf, hc.lpf)) continue;
 			if ((int)g.chains.size() >= PM_MAX_GCH) break;
@@ -799,6 +813,8 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 {
 	if (!e || !descs || n <= 0) return fail(e, PM_ERR_ARG, "load_chains: bad arguments");
 	if (n >= 65536) return fail(e, PM_ERR_ARG, "too many chains");
+	for (int c = 0; c < n; c++)
+		if (descs[c].recording < 0 || descs[c].recording >= 65536) return fail(e, PM_ERR_ARG, "chain %d: recording index out of range", c);
 	cudaSetDevice(e->device);
 	e->chains.clear();
 	e->have_run = false;
@@ -882,6 +898,7 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 	// FP64 taps (reversed = correlation order) for the guard-band fix-up and the float64 pipeline
 	std::vector<double> flat;
 	std::vector<Fp64Chain> f64(n);
+	memset(f64.data(), 0, n * sizeof(Fp64Chain));
 	auto push = [&](const std::vector<double> &h, bool reverse = true) {
 		size_t off = flat.size();
 		for (size_t j = 0; j < h.size(); j++) flat.push_back(reverse ? h[h.size() - 1 - j] : h[j]);
@@ -916,7 +933,8 @@ extern "C" int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *descs, i
 		f.lpf = e->d_taps64.p + o[c].lpf;
 	}
 	CK(e->d_fp64.ensure(n));
-	CK(cudaMemcpy(e->d_fp64.p, f64.data(), n * sizeof(Fp64Chain), cudaMemcpyHostToDevice));
+	e->h_fp64 = f64;                    // audio_off / n_audio are filled in per run (prepare_run)
+	e->up_fp64.clear();
 	// float64 pipeline table (buffers and lengths are filled in per run)
 	e->h_p64.clear();
 	for (int c = 0; c < n; c++) {
@@ -1060,7 +1078,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 		if (sharded && (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK)))
 			return fail(e, PM_ERR_UNSUPPORTED, "chain %d: chains with a carrier loop (AGC takes max() of the whole "
 				"recording, agc.py:67) cannot be sharded on the sample axis", c);
-		const long long nout = (only_chain >= 0 && c != only_chain) ? 0 : std::max<long long>(0, n - hc.trim);
+		const long long nout = (only_chain >= 0 && c != only_chain) ? 0 : std::max<long long>(0, chain_n(e, c, n) - hc.trim);
 		max_nout = std::max(max_nout, nout);
 		const int tile = (hc.p64 || hc.group < 0) ? P64_TILE : e->groups[hc.group].tile;
 		const long long tiles = (nout + tile - 1) / tile;
@@ -1189,8 +1207,9 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 			const HostChain &hc = e->chains[P.gid];
 			P.sign_row = P.gid;
 			P.sign_q_row = hc.sign_q_row;
-			P.n_audio = n;
-			P.L1 = std::max<long long>(0, n - (P.n_bpf - 1));
+			P.n_audio = chain_n(e, P.gid, n);
+			P.audio_off = chain_aoff(e, P.gid);
+			P.L1 = std::max<long long>(0, P.n_audio - (P.n_bpf - 1));
 			if (P.kind == PM_MODEM_AFSK || P.kind == PM_MODEM_MPSK) P.L2 = std::max<long long>(0, P.L1 - (P.n_mid - 1));
 			else P.L2 = P.L1;
 			P.L3 = std::max<long long>(0, P.L2 - (P.n_out - 1));
@@ -1221,14 +1240,22 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	}
 	CK(cudaMemsetAsync(e->d_counters.p, 0, 16 * sizeof(unsigned int), e->st));
 	CK(cudaMemsetAsync(e->d_totals.p, 0, sizeof(PacketTotals), e->st));
+	for (int c = 0; c < nc; c++) {
+		e->h_fp64[c].audio_off = chain_aoff(e, c);
+		e->h_fp64[c].n_audio = chain_n(e, c, n);
+	}
+	if (!same_bytes(e->up_fp64, e->h_fp64)) {
+		CK(cudaMemcpyAsync(e->d_fp64.p, e->h_fp64.data(), nc * sizeof(Fp64Chain), cudaMemcpyHostToDevice, e->st));
+		e->up_fp64 = e->h_fp64;
+	}
 	long long mag_bytes = 0, amax_floats = 0;
 	for (auto &g : e->groups) {
 		if (g.kind == PM_MODEM_AFSK)
 			for (int i = 0; i < g.afsk.n_chain; i++)
-				g.afsk.chain_nout[i] = std::max<long long>(0, n - e->chains[g.afsk.chain_gid[i]].trim);
+				g.afsk.chain_nout[i] = std::max<long long>(0, chain_n(e, g.afsk.chain_gid[i], n) - e->chains[g.afsk.chain_gid[i]].trim);
 		else
 			for (int i = 0; i < g.fir.n_chain; i++)
-				g.fir.chain_nout[i] = std::max<long long>(0, n - e->chains[g.fir.chain_gid[i]].trim);
+				g.fir.chain_nout[i] = std::max<long long>(0, chain_n(e, g.fir.chain_gid[i], n) - e->chains[g.fir.chain_gid[i]].trim);
 		g.a_done = g.b_done = 0;
 		if (g.tensor) {
 			long long nout_max = 0;
@@ -1270,8 +1297,13 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
                         bool last, cudaStream_t stream = nullptr)
 {
 	if (!stream) stream = e->st;
+	const int16_t *audio_all = d_audio;
+	const long long n_all = n;
 	for (auto &g : e->groups) {
 		const int a_len = (g.kind == PM_MODEM_AFSK) ? g.afsk.a_len : g.fir.a_len;
+		// the group's recording (all its chains share it)
+		const long long n = chain_n(e, g.chains[0], n_all);
+		const int16_t *d_audio = audio_all + chain_aoff(e, g.chains[0]);
 		long long nout_max = 0;
 		for (int k : g.chains) nout_max = std::max(nout_max, std::max<long long>(0, n - e->chains[k].trim));
 		const long long tiles_total = g.tensor ? g.n_tile_a : (nout_max + g.tile - 1) / g.tile;
@@ -1853,8 +1885,14 @@ static bool grow_after_capacity(pm_engine *e, int rc)
 	return e->rec_scale <= 64.0 && e->il2p_cand_scale <= 4096.0;
 }
 
-static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host)
+static int run_impl(pm_engine *e, const int16_t *audio, long long n, bool on_host, bool batched = false)
 {
+	if (e && !batched) {
+		e->batch_stride = 0;
+		for (size_t c = 0; c < e->chains.size(); c++)
+			if (e->chains[c].d.recording != 0)
+				return fail(e, PM_ERR_STATE, "chain %zu decodes recording %d of a batch: use pm_engine_run_batch", c, e->chains[c].d.recording);
+	}
 	pm_shard_plan plan;
 	memset(&plan, 0, sizeof(plan));
 	plan.first = plan.last = 1;
@@ -1902,6 +1940,32 @@ extern "C" int pm_engine_run(pm_engine *e, const int16_t *audio_host, int64_t n_
 extern "C" int pm_engine_run_device(pm_engine *e, const int16_t *audio_dev, int64_t n_samples)
 {
 	return run_impl(e, audio_dev, n_samples, false);
+}
+
+// R recordings x their chains in one run: the rows travel in one copy, then every stage runs over all chains at once
+extern "C" int pm_engine_run_batch(pm_engine *e, const int16_t *audio_host, int64_t row_stride, const int64_t *n_samples,
+                                   int32_t n_recordings)
+{
+	if (!e || !audio_host || !n_samples || n_recordings <= 0 || row_stride <= 0)
+		return fail(e, PM_ERR_ARG, "run_batch: bad arguments");
+	cudaSetDevice(e->device);
+	long long n_max = 0;
+	e->batch_n.assign(n_samples, n_samples + n_recordings);
+	for (int r = 0; r < n_recordings; r++) {
+		if (n_samples[r] <= 0 || n_samples[r] > row_stride) return fail(e, PM_ERR_ARG, "run_batch: recording %d has %lld samples (row stride %lld)", r, (long long)n_samples[r], (long long)row_stride);
+		n_max = std::max<long long>(n_max, n_samples[r]);
+	}
+	for (size_t c = 0; c < e->chains.size(); c++)
+		if (e->chains[c].d.recording >= n_recordings)
+			return fail(e, PM_ERR_ARG, "run_batch: chain %zu names recording %d of %d", c, e->chains[c].d.recording, n_recordings);
+	const size_t total = (size_t)row_stride * n_recordings;
+	if (total >= (1ull << 32)) return fail(e, PM_ERR_ARG, "run_batch: more than 2^32 samples in a batch");
+	CK(e->d_audio.ensure(total + 64));
+	CK(cudaMemcpyAsync(e->d_audio.p, audio_host, total * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+	e->batch_stride = row_stride;
+	const int rc = run_impl(e, e->d_audio.p, n_max, false, true);
+	e->stats.h2d_bytes = (int64_t)total * 2;
+	return rc;
 }
 
 extern "C" int pm_engine_shard_begin(pm_engine *e, const int16_t *audio, int64_t n_samples, int32_t audio_on_device,
@@ -2420,7 +2484,7 @@ extern "C" int pm_engine_get_packets(const pm_engine *e, pm_packet_rec *recs, in
 extern "C" int64_t pm_engine_soft_len(const pm_engine *e, int32_t chain)
 {
 	if (!e || !e->have_run || chain < 0 || chain >= (int)e->chains.size()) return -1;
-	return std::max<long long>(0, e->n_samples - e->chains[chain].trim);
+	return std::max<long long>(0, chain_n(e, chain, e->n_samples) - e->chains[chain].trim);
 }
 
 extern "C" int pm_engine_get_soft(const pm_engine *ce, int32_t chain, int32_t component, float *out, int64_t cap)

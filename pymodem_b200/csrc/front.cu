@@ -696,7 +696,7 @@ fir_front_kernel(const __grid_constant__ FirPlan P, const int16_t *__restrict__ 
 // The audio window is staged once as doubles; each lane slides a small register window over the taps (one tap load
 // and one sample load per FIX_OB multiply-adds), the low-pass is a warp reduction.
 __global__ void __launch_bounds__(PM_FIX_THREADS)
-guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restrict__ audio, long long n_audio,
+guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restrict__ audio_all, long long /* n_audio: per chain */,
                    uint32_t *__restrict__ sign, long long sign_stride, float *__restrict__ soft,
                    long long soft_stride, GuardList guard, int warp_doubles)
 {
@@ -710,6 +710,8 @@ guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restri
 		const int gid = (int)(ent >> 48);
 		const long long n = (long long)(ent & 0xFFFFFFFFFFFFull);
 		const Fp64Chain C = chains[gid];
+		const int16_t *__restrict__ audio = audio_all + C.audio_off;      // this chain's recording
+		const long long n_audio = C.n_audio;
 		double part = 0.0;
 		if (C.kind == 2) {
 			// y[n] = sum_j hr[j] a[n+j]

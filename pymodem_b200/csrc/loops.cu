@@ -63,7 +63,7 @@ p64_bpf_kernel(const P64Chain *__restrict__ chains, const int16_t *__restrict__ 
 	if (base >= C.L1) return;
 	double *s_h = sm, *s_x = sm + C.n_bpf;
 	p64_stage_taps(C.bpf, C.n_bpf, s_h);
-	p64_stage_tile(audio, C.n_audio, base, P64_TILE + C.n_bpf - 1, s_x);
+	p64_stage_tile(audio + C.audio_off, C.n_audio, base, P64_TILE + C.n_bpf - 1, s_x);
 	__syncthreads();
 	double acc[4];
 	p64_fir4(s_x, s_h, C.n_bpf, acc);
@@ -218,24 +218,6 @@ __device__ __forceinline__ double agc_envelope(const LoopConst &L, LoopState &s,
 __device__ __forceinline__ double agc_scale(const LoopConst &L, double sample, double envelope)
 {
 	return envelope != 0.0 ? __ddiv_rn(__dmul_rn(L.agc_target, sample), envelope) : sample;
-}
-
-// (fused form, kept for reference: envelope + scaling of one sample)
-__device__ __forceinline__ double agc_step(const LoopConst &L, LoopState &s, double sample)
-{
-	const double compare_value = fabs(sample);
-	if (compare_value > s.envelope) {
-		s.envelope = __dadd_rn(s.envelope, s.attack_step);
-		if (s.envelope > compare_value) s.envelope = compare_value;
-		s.sustain_count = 0.0;
-	}
-	if (s.sustain_count >= L.agc_sustain_time) {
-		s.envelope = __dsub_rn(s.envelope, s.decay_step);
-		if (s.envelope < 0.0) s.envelope = 0.0;
-	}
-	s.sustain_count = __dadd_rn(s.sustain_count, L.agc_sustain_increment);
-	if (s.envelope != 0.0) return __ddiv_rn(__dmul_rn(L.agc_target, sample), s.envelope);
-	return sample;
 }
 
 // NCO.update -- nco.py:34-53 (an index of wavetable_size raises IndexError there: the old sine is kept)

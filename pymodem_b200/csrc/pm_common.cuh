@@ -146,6 +146,8 @@ struct Fp64Chain {            // float64 taps for the guard-band fix-up
 	int kind;                 // PM_MODEM_AFSK (1) or PM_MODEM_FSK (2)
 	int n_bpf, n_corr, n_lpf;
 	int neg;
+	long long audio_off;      // where this chain's recording starts in the audio buffer (batched runs), and its length
+	long long n_audio;
 	const double *bpf;        // reversed (correlation order)
 	const double *mark_i, *mark_q, *space_i, *space_q;
 	const double *lpf;
@@ -255,6 +257,7 @@ struct P64Chain {
 	int sign_row, sign_q_row;
 	int n_bpf, n_mid, n_out, mid_delay;
 	long long n_audio;
+	long long audio_off;       // where this chain's recording starts in the audio buffer (batched runs)
 	long long L1, L2, L3;      // samples after the input FIR, after the middle stage, final soft samples
 	const double *bpf;         // all taps reversed (correlation order)
 	const double *mid0, *mid1, *mid2, *mid3;   // AFSK: mark_i, mark_q, space_i, space_q; MPSK: mid0 = Hilbert

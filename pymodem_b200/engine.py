@@ -95,9 +95,15 @@ def describe_chain(chain, keep):
 class Engine:
 	"""One engine = one GPU + one chain table (a demod_stack)."""
 
-	def __init__(self, demod_stack, device=0, **options):
+	def __init__(self, demod_stack, device=0, recordings=1, **options):
+		"""recordings > 1: a batch engine -- the chain table is laid out `recordings` times, copy r decoding recording r of
+		run_batch() (pm_chain_desc.recording); everything else about the engine is the same."""
 		self._lib = _lib.load()
 		self._h = ctypes.c_void_p()
+		self.recordings = int(recordings)
+		self.chains_per_recording = len(demod_stack)
+		stack_in = demod_stack
+		demod_stack = [chain for _ in range(self.recordings) for chain in stack_in]
 		self.names = [chain[0] for chain in demod_stack]
 		rc = self._lib.pm_engine_create(int(device), ctypes.byref(self._h))
 		if rc != _lib.PM_OK:
@@ -111,7 +117,8 @@ class Engine:
 		descs = (_lib.ChainDesc * len(demod_stack))()
 		for i, chain in enumerate(demod_stack):
 			descs[i] = describe_chain(chain, keep)
-		self.fingerprint = stack_fingerprint(demod_stack)
+			descs[i].recording = i // self.chains_per_recording
+		self.fingerprint = stack_fingerprint(stack_in)
 		self._registered = {}
 		self._check(self._lib.pm_engine_load_chains(self._h, descs, len(demod_stack)))
 		self.n_chains = len(demod_stack)
@@ -307,6 +314,24 @@ class Engine:
 		recs, arena = self.run_raw(audio)
 		return self.packets(recs, arena)
 
+	def run_batch(self, audios):
+		"""One engine call for len(audios) == recordings recordings (int16 arrays, lengths may differ):
+		-> [per recording [per chain PacketList]].  All stages run over every chain of every recording at once."""
+		if len(audios) != self.recordings:
+			raise EngineError(f"run_batch: this engine was built for {self.recordings} recordings, got {len(audios)}")
+		lens = np.array([len(a) for a in audios], dtype=np.int64)
+		stride = int(max(int(lens.max()), 1) + 63) // 64 * 64
+		buf = getattr(self, '_batch_buf', None)
+		if buf is None or buf.shape != (self.recordings, stride):
+			buf = self._batch_buf = pinned_empty(self.recordings * stride).reshape(self.recordings, stride)
+		for r, a in enumerate(audios):
+			buf[r, :len(a)] = a
+		self._check(self._lib.pm_engine_run_batch(self._h, buf.ctypes.data, stride,
+			lens.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.recordings))
+		per_chain = self.packets(*self.fetch())
+		c = self.chains_per_recording
+		return [per_chain[r * c:(r + 1) * c] for r in range(self.recordings)]
+
 	# -- intermediates (parity tests) -------------------------------------------
 	def soft(self, chain, component=0):
 		n = self._lib.pm_engine_soft_len(self._h, chain)
@@ -390,13 +415,13 @@ def stack_fingerprint(demod_stack):
 _cache = {}
 
 
-def engine_for(demod_stack, device=0, **options):
-	"""One cached engine per (chain parameters, device, options): building an engine uploads taps and allocates its
-	buffers.  The key is the digest of the described parameters, so retuned blocks get a new engine."""
-	key = (stack_fingerprint(demod_stack), device, tuple(sorted(options.items())))
+def engine_for(demod_stack, device=0, recordings=1, **options):
+	"""One cached engine per (chain parameters, device, recordings, options): building an engine uploads taps and allocates
+	its buffers.  The key is the digest of the described parameters, so retuned blocks get a new engine."""
+	key = (stack_fingerprint(demod_stack), device, recordings, tuple(sorted(options.items())))
 	eng = _cache.get(key)
 	if eng is None:
-		eng = Engine(demod_stack, device=device, **options)
+		eng = Engine(demod_stack, device=device, recordings=recordings, **options)
 		for old in _cache.values():
 			old.close()
 		_cache.clear()

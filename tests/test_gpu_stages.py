@@ -123,3 +123,24 @@ def test_pageable_and_pinned_input_agree(cuda_lib):
 		finally:
 			eng.close()
 		assert a == b == g.all_packets()
+
+
+@pytest.mark.parametrize("tag,count", [("bpsk300_il2p_8k", 5), ("qpsk2400_il2p_8k", 3), ("afsk1200_superopt_48k", 3), ("afsk300_full_8k", 2)])
+def test_batched_recordings_equal_single_runs(cuda_lib, oracle, tag, count):
+	"""pm_engine_run_batch: several recordings of different lengths x all chains in one call == one call per recording
+	(and == the fixture for the unmodified one)."""
+	from pymodem_b200.modems_codecs import chain_builder, chain_execute
+	g = Golden(tag)
+	audio = g.audio()
+	stack = [chain_builder.build_chain(g.sample_rate, l) for l in g.chain_lines()]
+	rng = np.random.default_rng(5)
+	recs = [audio]
+	for k in range(1, count):
+		cut = audio[int(rng.integers(0, len(audio) // 3)): len(audio) - int(rng.integers(0, len(audio) // 3))].copy()
+		if k % 2:
+			cut = np.clip(cut.astype(np.int32) + rng.normal(0, 400, len(cut)).astype(np.int32), -32768, 32767).astype(np.int16)
+		recs.append(cut)
+	got = chain_execute.process_recordings(stack, recs)
+	assert as_tuples(got[0]) == g.all_packets()
+	for r in range(1, count):
+		assert as_tuples(got[r]) == oracle.run_config(g.sample_rate, g.chain_lines(), recs[r]), r
