@@ -32,19 +32,22 @@ DEFAULT_SEGMENT_LEN = 24576
 DEFAULT_WARMUP_LEN = 49152
 
 
-def choose_segment_len(n_local, n_chains, target_threads=49152, lo=4096, hi=DEFAULT_SEGMENT_LEN):
+def choose_segment_len(n_local, n_chains, target_threads=49152, lo=8192, hi=DEFAULT_SEGMENT_LEN):
 	"""Slicer segment length for a shard of n_local samples: the slicer kernel is one thread per (chain, segment) and
 	bound by the latency of a thread's dependent chain (warm-up + segment), so a small shard -- one hour split over 8
 	GPUs -- wants shorter segments than the 24576 samples that are best when a GPU has the whole hour: enough threads
 	to fill the machine, a shorter chain per thread.  Results do not depend on it (every hand-off is verified).  All
-	ranks of a run must use the same value (shard boundaries are segment aligned): compute it from the largest shard."""
+	ranks of a run must use the same value (shard boundaries are segment aligned): compute it from the largest shard.
+	Measured on a 450 s shard (tools/slicer_sweep_short.py, profiles/r02_slicer_sweep_short.txt): 24576 -> 1.36 ms, 8192 -> 1.10 ms,
+	4096 -> 1.02 ms of slicer but more segments to gather; shorter warm-ups than 49152 samples cost more in repairs than they
+	save (a warm-up has to see ~90 zero crossings before the clock is bit-identical)."""
 	want = max(1, n_local * max(n_chains, 1) // target_threads)
 	seg = max(lo, min(hi, want))
 	return max(1024, seg // 1024 * 1024)
 
 
 def plan_shards(n_samples, world, segment_len=DEFAULT_SEGMENT_LEN, warm_len=DEFAULT_WARMUP_LEN, trim_max=305, samples_per_symbol=40.0,
-		tail_bits=16384, pre_segments=4):
+		tail_bits=16384, pre_segments=None, pre_samples=4 * DEFAULT_SEGMENT_LEN):
 	"""Split n_samples over `world` ranks.  Returns one dict per rank:
 	audio_begin/audio_end (the slice of the recording the rank needs) + the pm_shard_plan fields.
 
@@ -55,6 +58,10 @@ def plan_shards(n_samples, world, segment_len=DEFAULT_SEGMENT_LEN, warm_len=DEFA
 	0.1 % more front-end work per rank."""
 	if world < 1:
 		raise ValueError("world must be >= 1")
+	if pre_segments is None:
+		# the verified history before a shard is a number of SAMPLES (98304 by default: four default segments), whatever
+		# the segment length: with short segments and the same count the hand-off would rest on too little and fall back
+		pre_segments = int(math.ceil(pre_samples / segment_len))
 	per = int(math.ceil(n_samples / world / segment_len)) * segment_len
 	if world > 1 and per * (world - 1) >= n_samples - trim_max:
 		raise ValueError(f"recording too short ({n_samples} samples) for {world} shards of segment_len {segment_len}")
