@@ -557,13 +557,17 @@ def run_b200_arm(args):
 	achieved = executed_flop / max(front_launches, 1) / t_front / 1e12
 	peaks, peaks_src = measured_peaks()
 	algo_bytes = 2.0 * n + n_chains * n / 8.0        # int16 audio in, 1 sign bit per chain-sample out
-	traffic = None
-	try:      # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this launch's samples
-		with open(os.path.join(REPO, "profiles", "front_traffic.json")) as f:
-			tr = json.load(f)
-		traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n / tr["samples_per_launch"]) / max(front_launches, 1)
-	except (OSError, ValueError, KeyError):
-		pass
+	def committed_traffic(kernel):
+		"""DRAM bytes of a kernel from the committed ncu --set full capture (profiles/kernel_traffic.json), scaled to this
+		launch's samples; None when the capture does not have it."""
+		try:
+			with open(os.path.join(REPO, "profiles", "kernel_traffic.json")) as f:
+				tr = json.load(f)
+			k = tr["kernels"][kernel]
+			return (k["dram_bytes_read"] + k["dram_bytes_write"]) * (n / tr["samples_per_launch"])
+		except (OSError, ValueError, KeyError):
+			return None
+	traffic = committed_traffic("afsk_front_kernel")
 	tc_macs = eng.front_tensor_macs_per_sample()
 	roofline = {"kernel": "afsk_front_kernel" + (" (magnitudes) + lpf_tc_kernel" if tc_macs else ""), "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
 		"unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
@@ -584,7 +588,11 @@ def run_b200_arm(args):
 			top = max((k for k in roofline_all["kernels"] if k.get("frac")), key=lambda k: k["ms"])
 			roofline.update({"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
 				"unit": top["unit"], "frac": top["frac"], "kernel_ms": top["ms"], "launches_per_step": top["launches"],
-				"share_of_step": top["share"]})
+				"share_of_step": top["share"], "traffic": committed_traffic(top["kernel"])})
+			if top["kernel"] == "afsk_front_kernel (magnitudes)":
+				# what the kernel has to move: int16 audio in, four tone magnitudes out as three bf16 pieces each
+				roofline["hbm"]["algorithmic_bytes"] = 2.0 * n + 4 * 3 * 2.0 * n
+				roofline["hbm"]["achieved_gbs"] = roofline["hbm"]["algorithmic_bytes"] / (top["ms"] * 1e-3) / 1e9
 			if top["bound"] != "fp32":
 				roofline["peak_source"] = peaks_src
 			if tc_macs:

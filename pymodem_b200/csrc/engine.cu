@@ -397,9 +397,10 @@ static AfskGeom afsk_geom(const AfskPlan &p, int tile)
 		// the kernel stops at the magnitudes (low-pass on the tensor cores): no low-pass halo, no pair streams
 		g.U_l = 0;
 		g.U_m = tile / 16;
-		g.U_x = (16 * g.U_m + cmax + 15) / 16;
-		g.a_len = round_up(16 * g.U_x + p.n_bpf, 8);
-		const int a_phys = round_up(pm_phys(g.a_len) + 4, 4);
+		g.U_x = round_up((16 * g.U_m + cmax + 15) / 16, 2);      // two half tiles side by side in the band-pass
+		g.a_len = round_up(16 * g.U_x + p.n_bpf + 16, 8);
+		// the staged audio: (a[i], a[i + 8 U_x]) pairs for i < 8 U_x + n_bpf + 16
+		const int a_phys = round_up(2 * pm_phys2(8 * g.U_x + p.n_bpf + 16) + 8, 4);
 		const int x_phys = round_up(2 * pm_phys2(16 * g.U_x) + 8, 4);
 		g.s_m_stride = 0;
 		g.s_m_off = 0;
@@ -598,6 +599,11 @@ static int build_groups(pm_engine *e)
 				}
 				p.mag_dst_first[p.n_mag] = k;
 			}
+			// band-pass taps twice in a row each, for the route that runs two half tiles on FFMA2
+			if (used + 2 * p.n_bpf > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
+			p.bpf2_off = used;
+			for (int j = 0; j < p.n_bpf; j++) p.taps[used + 2 * j] = p.taps[used + 2 * j + 1] = p.taps[p.bpf_off + j];
+			used += 2 * p.n_bpf;
 			// low-pass taps once more, each twice in a row: the (h, h) operand of the packed FFMA2
 			if (used + 2 * p.n_lpf > PM_MAX_TAPS) return fail(e, PM_ERR_CAPACITY, "too many FIR taps");
 			p.lpf2_off = used;
@@ -627,6 +633,7 @@ static int build_groups(pm_engine *e)
 			AfskGeom gg = afsk_geom(p, best);
 			if (gg.smem > smem_max) return fail(e, PM_ERR_CAPACITY, "tile %d needs %zu B shared memory", best, gg.smem);
 			p.tile = best; p.U_x = gg.U_x; p.U_m = gg.U_m; p.U_l = gg.U_l; p.a_len = gg.a_len;
+			p.bpf_half = gg.U_x / 2;
 			p.s_x1_off = gg.s_x1_off; p.s_m_off = gg.s_m_off; p.s_m_stride = gg.s_m_stride;
 			g.smem = gg.smem;
 			g.tile = best;

@@ -422,6 +422,40 @@ __device__ __forceinline__ float stage_audio(float *s_a, const int16_t *__restri
 	return amax;
 }
 
+// The same for the route whose band-pass runs two half tiles side by side (MAGS): sample i and sample i + half travel as
+// one float2, the window operand of the packed FFMA2.  cnt = pairs to stage (a multiple of 8).
+__device__ __forceinline__ float stage_audio_pairs(float *s_a2, const int16_t *__restrict__ audio, long long n0,
+                                                   long long n_audio, int half, int cnt)
+{
+	float amax = 0.f;
+	for (int i = threadIdx.x * 8; i < cnt; i += blockDim.x * 8) {
+		float f[2][8];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const long long g = n0 + i + (h ? half : 0);
+			if (g + 8 <= n_audio) {
+				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(audio + g));
+				const unsigned int u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					f[h][2 * q] = (float)(short)(u[q] & 0xFFFFu);
+					f[h][2 * q + 1] = (float)(short)(u[q] >> 16);
+				}
+			} else {
+#pragma unroll
+				for (int q = 0; q < 8; q++) f[h][q] = (g + q < n_audio) ? (float)audio[g + q] : 0.f;
+			}
+		}
+		float *dst = s_a2 + 2 * pm_phys2(i);
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+			*reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(f[0][2 * q], f[1][2 * q], f[0][2 * q + 1], f[1][2 * q + 1]);
+#pragma unroll
+		for (int q = 0; q < 8; q++) amax = fmaxf(amax, fmaxf(fabsf(f[0][q]), fabsf(f[1][q])));
+	}
+	return amax;
+}
+
 template <bool WRITE_SOFT, bool MAGS>
 __global__ void __launch_bounds__(PM_FRONT_THREADS, 2)
 afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict__ audio, long long n_audio,
@@ -449,7 +483,8 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	// out of band included), so the sign guard carries a term proportional to it (epilogue below)
 	__shared__ float s_wmax[PM_FRONT_THREADS / 32];
 	{
-		float amax = stage_audio(s_a, audio, n0, n_audio, P.a_len);
+		float amax = MAGS ? stage_audio_pairs(s_a, audio, n0, n_audio, 16 * P.bpf_half, (16 * P.bpf_half + P.n_bpf + 16 + 7) & ~7)
+		                  : stage_audio(s_a, audio, n0, n_audio, P.a_len);
 		amax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));      // non-negative floats order like their bit patterns
 		if ((tid & 31) == 0) s_wmax[tid >> 5] = amax;
 	}
@@ -463,6 +498,22 @@ afsk_front_kernel(const __grid_constant__ AfskPlan P, const int16_t *__restrict_
 	}
 
 	// input band-pass (afsk.py:151); the result is stored as (x, x) pairs: the window operand of the packed correlators
+	if (MAGS) {
+		// two half tiles side by side: unit u and unit u + bpf_half share one packed FFMA2 per tap (the taps stored twice,
+		// a uniform operand) -- half the issue slots of the scalar form, which leaves room for the window loads
+		for (int ub = tid - (tid & 31); ub < P.bpf_half; ub += PM_FRONT_THREADS) {
+			const int u = ub + (tid & 31);
+			if (u >= P.bpf_half) continue;
+			FirUnitPair f;
+			f.run(s_a, 16 * u, P.taps + P.bpf2_off, P.n_bpf);
+			float *d0 = s_x1 + 2 * pm_phys2(16 * u), *d1 = s_x1 + 2 * pm_phys2(16 * (u + P.bpf_half));
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				*reinterpret_cast<float4 *>(d0 + 4 * q) = make_float4(f.lo(2 * q), f.lo(2 * q), f.lo(2 * q + 1), f.lo(2 * q + 1));
+				*reinterpret_cast<float4 *>(d1 + 4 * q) = make_float4(f.hi(2 * q), f.hi(2 * q), f.hi(2 * q + 1), f.hi(2 * q + 1));
+			}
+		}
+	} else
 	for (int ub = tid - (tid & 31); ub < P.U_x; ub += PM_FRONT_THREADS) {        // warp-uniform control flow: uniform taps
 		const int u = ub + (tid & 31);
 		if (u >= P.U_x) continue;

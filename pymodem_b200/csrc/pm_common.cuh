@@ -40,6 +40,9 @@ struct AfskPlan {
 	int mag_e_off[PM_MAX_MAG];    // (cos wk, sin wk) for k in [0, N + 16), then (-cos wk, -sin wk) for k in [0, 16)
 	int n_lpf, lpf_off;
 	int lpf2_off;             // the low-pass taps, each stored twice in a row: (h, h) operands of the packed FFMA2
+	int bpf2_off;             // the band-pass taps likewise (tensor_lpf route: the band-pass runs two half tiles side by side on FFMA2)
+	int bpf_half;             // that route: 16-output units per half tile (U_x = 2 * bpf_half); the staged audio is an array of
+	                          // (a[i], a[i + 16 * bpf_half]) pairs
 	int n_pair;
 	int pair_mark[PM_MAX_PAIR];
 	int pair_space[PM_MAX_PAIR];
