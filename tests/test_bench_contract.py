@@ -15,7 +15,8 @@ REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 
 def _latest_lines():
-	files = sorted(glob.glob(os.path.join(REPO, "profiles", "r01[f-z]_bench_n*.json")))
+	files = sorted(glob.glob(os.path.join(REPO, "profiles", "r01[f-z]_bench_n*.json")) +
+		glob.glob(os.path.join(REPO, "profiles", "r02[a-z]_bench_n*.json")))
 	assert files, "no committed bench lines"
 	return [(os.path.basename(f), json.load(open(f))) for f in files]
 
@@ -42,6 +43,14 @@ def test_committed_bench_lines_carry_the_contract(name, line):
 	roof = line["roofline"]
 	for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
 		assert key in roof, (name, key)
+	if name.startswith("r02"):
+		# round 2 lines: parity digest of what the timed steps produced, and the per-kernel rooflines at N = 1
+		assert line["parity"]["match"] is True, name
+		assert "frac_of_value" in e2e and "call" in e2e
+		if line["n_gpus"] == 1:
+			kernels = {k["kernel"]: k for k in line["roofline_all"]["kernels"]}
+			assert any(k.get("share", 0) >= 0.02 and "frac" in k for k in kernels.values())
+			assert e2e["h2d_ceiling"]["gbs"] > 0 and 0 < e2e["pcie_frac"] <= 1.05
 	assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and 0.0 < roof["frac"] < 1.0
 	clocks = line["clocks"]
 	assert clocks["sm_mhz"] > 0.8 * clocks["sm_max_mhz"]
