@@ -1351,7 +1351,7 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 				const size_t gi = (size_t)(&g - e->groups.data());
 				cudaError_t ce = pm_launch_lpf_tc(&g.tc, e->d_mag.p + g.mag_off, g.mag_rows, e->d_btaps[gi].p,
 					e->d_amax.p + g.amax_off, g.b_done, b_ready - g.b_done, e->d_sign.p, e->sign_stride,
-					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), (int *)(e->d_counters.p + 7),
+					e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), (int *)(e->d_counters.p + 15),
 					e->sm_count, stream);
 				if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "tensor-core low-pass launch failed: %s", cudaGetErrorString(ce));
 				if (e->opt_debug_sync && (ce = cudaStreamSynchronize(stream)) != cudaSuccess)
@@ -1395,8 +1395,9 @@ static int slicer_converge(pm_engine *e)
 // The same passes without asking the host in between: up to FAST_PASSES verify passes are enqueued back to back, each
 // one skipping itself when its predecessor repaired nothing (d_counters[2 + p] = repairs of pass p).  Whether that was
 // enough is read from the counters with the run's results (slicer_fast_converged); almost always it is -- pass 0
-// repairs the ~0.15 % of hand-offs whose warm-up did not become bit-identical, pass 1 finds nothing.
-#define FAST_PASSES 3
+// repairs the ~0.15 % of hand-offs whose warm-up did not become bit-identical, pass 1 finds nothing; the later passes
+// are there for short segments, where a repaired segment more often ends in a different state than the first run did.
+#define FAST_PASSES 8      // d_counters[2 .. 10): a repair whose segment does not merge with a checkpoint moves the next hand-off, one segment per pass
 static int slicer_enqueue_fast(pm_engine *e)
 {
 	const int nc = (int)e->chains.size();
@@ -1790,7 +1791,7 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 	// pays a second copy.
 	pm_kt_mark("d2h results + host sync", e->st);
 	CK(cudaMemcpyAsync(e->h_totals, e->d_totals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, e->st));
-	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
+	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
 	e->h_cc.resize(nc);
 	CK(cudaMemcpyAsync(e->h_cc.data(), e->d_cc.p, nc * sizeof(ChainCounters), cudaMemcpyDeviceToHost, e->st));
 	const size_t spec_np = std::min(e->spec_recs, e->d_recs.n), spec_nb = std::min(e->spec_arena, e->d_arena.n);
@@ -1806,7 +1807,7 @@ static int shard_finish_impl(pm_engine *e, const uint32_t *tail_in, const pm_il2
 			il2p_out[c].mode = hand[c].mode;
 			il2p_out[c].leak = hand[c].leak;
 		}
-	if (e->h_counters[7] != 0)
+	if (e->h_counters[15] != 0)
 		return fail(e, PM_ERR_CUDA, "tensor-core low-pass: a pipeline barrier timed out (internal error)");
 	for (int c = 0; c < nc; c++) {
 		if (e->h_cc[c].tail_short)
@@ -2367,7 +2368,7 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_link_merge(G, own, parity, epoch, e->d_link_lb.p, e->d_link_obase.p, e->d_link_obase.p + (size_t)G.world * (nc + 1),
 		e->d_mtotals.p, (PacketRecDev *)e->d_mrecs.p, e->d_mrecs.n, e->d_marena.p, e->d_marena.n, status, st));
 	e->stats.kernel_launches += 13;
-	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(e->h_link_status, status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(e->h_mtotals, e->d_mtotals.p, sizeof(PacketTotals), cudaMemcpyDeviceToHost, st));
 	// (nothing here may block the host: a copy into pageable memory would wait for the stream, i.e. for the peers)
