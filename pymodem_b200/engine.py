@@ -387,29 +387,45 @@ def _unregister(lib, ptr, table, key):
 	lib.pm_host_unregister(ptr)
 
 
-_SCALAR_FIELDS = [n for n, t in _lib.ChainDesc._fields_ if not issubclass(t, (ctypes._Pointer, ctypes.Array))]
-_LOOP_SCALARS = [n for n, t in _lib.LoopDesc._fields_ if not issubclass(t, ctypes._Pointer)]
+_SCALARS = (int, float, str, bool, type(None))
+
+
+def _state_bytes(obj, out, depth=0):
+	"""Everything a block object holds, as bytes: arrays by content, scalars and plain lists through one repr of the lot,
+	nested helper objects (AGC, NCO, IIR_1, PI_control, RRC, Hilbert ...) recursively."""
+	plain = []
+	for name, v in vars(obj).items():
+		t = type(v)
+		if t is np.ndarray:
+			out.append(name.encode() + v.dtype.char.encode())
+			out.append(v.tobytes())
+		elif t in _SCALARS:
+			plain.append((name, v))
+		elif t in (list, tuple):
+			plain.append((name, v if (not v or type(v[0]) in _SCALARS) else repr(v)))
+		elif hasattr(v, '__dict__') and depth < 4:
+			out.append(name.encode())
+			_state_bytes(v, out, depth + 1)
+		else:
+			plain.append((name, repr(v)))
+	out.append(repr(plain).encode())
 
 
 def stack_fingerprint(demod_stack):
-	"""Digest of everything describe() hands to the engine -- the pm_chain_desc scalars and every tap / table array.
-	The reference reads its blocks' state on every call (chain_execute.py:32-47), so a retune() or
-	StringOptionsRetune() between two calls must take effect: engine_for() compares this, not object identities."""
-	h = hashlib.blake2b(digest_size=16)
+	"""Digest of the complete state of every block of every chain (parameters, tap and table arrays).  The reference
+	reads its blocks' state on every call (chain_execute.py:32-47), so a retune() or StringOptionsRetune() between two
+	calls must take effect: engine_for() compares this, not object identities.  (Any attribute change gives a new
+	engine, also one describe() would not look at: conservative, never stale.)"""
+	out = []
 	for chain in demod_stack:
-		keep = []
-		desc = describe_chain(chain, keep)
-		scal = [getattr(desc, n) for n in _SCALAR_FIELDS]
-		if desc.loop:
-			lp = desc.loop.contents
-			scal += [getattr(lp, n) for n in _LOOP_SCALARS]
-		h.update(repr(scal).encode())
-		h.update(bytes(desc.demap))
-		for a in keep:
-			if isinstance(a, np.ndarray):
-				h.update(a.dtype.char.encode() + a.tobytes() + b"|")
-		h.update(str(chain[0]).encode() + b"|")
-	return h.hexdigest()
+		out.append(str(chain[0]).encode())
+		for block in chain[1:]:
+			if block == [] or block is None:
+				out.append(b"<missing>")
+			else:
+				out.append(type(block).__name__.encode())
+				_state_bytes(block, out)
+	return hashlib.blake2b(b"\0".join(out), digest_size=16).hexdigest()
 
 
 _cache = {}
