@@ -132,6 +132,19 @@ def main(args):
 			"sample": f"{len(sample)} recording(s) x first {len(sample[0]) / rate:g} s x {n_chains} chains, oracle port, one process per "
 				f"(recording, chain) over {procs} processes, {dt:.1f} s"}
 	loop_kind = lines[0]["modem"]["type"]
+	# the carrier loops against their floor: operations on the per-sample dependency chain x the latency of one dependent
+	# float64 operation (control -> NCO phase -> index -> wavetable -> mixer -> [rotation, phase table] -> IIR -> PI -> control)
+	from pymodem_b200.engine import measure_fp64_chain
+	chain_ops = {"bpsk": 17, "afsk_pll": 15, "mpsk": 21}.get(loop_kind)
+	loop_floor = None
+	if chain_ops:
+		ns_op, cyc_op = measure_fp64_chain(0)
+		per_sample = solo_stats["front_ms"] * 1e6 / len(recordings[0])
+		loop_floor = {"fp64_dependent_op_ns": ns_op, "fp64_dependent_op_cycles": cyc_op, "ops_on_the_chain_per_sample": chain_ops,
+			"floor_ns_per_sample": chain_ops * ns_op, "measured_ns_per_sample": per_sample,
+			"frac_of_floor": chain_ops * ns_op / per_sample if per_sample else None,
+			"note": "measured = the modem stages of one recording alone (FIRs included) per sample; the chain also crosses two "
+				"shared-memory table look-ups and integer conversions, which the floor does not count"}
 	line = {"metric": "demod chain-samples/sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
 		"ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f64" if loop_kind in ("bpsk", "mpsk", "afsk_pll") else "f32", "data": "synthetic",
@@ -145,7 +158,7 @@ def main(args):
 			"ns_per_sample_per_chain": solo_ms * 1e6 / len(recordings[0]),
 			"note": "one recording alone: for the carrier-loop modems this is the latency of one thread's float64 dependency chain "
 				"(NCO, mixer, IIR, PI: ~25 dependent operations per sample), not a throughput"},
-		"cpu_baseline": cpu, "packets_per_step": n_packets,
+		"loop_latency": loop_floor, "cpu_baseline": cpu, "packets_per_step": n_packets,
 		"parity": {"recording_0_equals_oracle": got == want, "n_packets_recording_0": sum(len(p) for p in got)},
 		"stage_ms": {k: statistics.mean(s[k] for s in stats) for k in ("total_ms", "front_ms", "fixup_ms", "slicer_ms", "bits_ms", "d2h_ms")},
 		"host_cpus": os.cpu_count()}

@@ -357,6 +357,11 @@ int64_t pm_engine_kernel_times(const pm_engine *e, char *buf, int64_t cap);
  * returns achieved TFLOP/s of a register-resident FFMA loop on the device. */
 int pm_measure_fp32_peak(int device, double *tflops);
 
+/* Latency of one dependent float64 operation on the device (alternating add / multiply on its own result, one thread):
+ * the floor under the sequential carrier loops of psk.py:173-189, 727-747 and afsk_pll.py:147-166, whose operations per
+ * sample form one dependency chain.  bench.py --config reports a loop's measured time per sample against it. */
+int pm_measure_fp64_chain(int device, double *ns_per_op, double *cycles_per_op);
+
 /* Executed FP32 multiply-adds per input sample over all loaded chains (after
  * the sharing of common filter passes) and the tile length of a front-end
  * launch group -- reported by bench.py next to the roofline. */

@@ -136,6 +136,7 @@ PROTOTYPES = {
 		ctypes.POINTER(ctypes.c_double)]),
 	"pm_engine_front_tile": (ctypes.c_int, [_vp, ctypes.c_int]),
 	"pm_measure_fp32_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+	"pm_measure_fp64_chain": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 	"pm_host_alloc": (_vp, [ctypes.c_size_t]),
 	"pm_host_free": (None, [_vp]),
 	"pm_host_register": (ctypes.c_int, [_vp, ctypes.c_size_t]),

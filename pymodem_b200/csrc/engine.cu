@@ -2682,6 +2682,38 @@ extern "C" int pm_host_unregister(void *p)
 	return PM_OK;
 }
 
+// Dependent float64 operation latency in nanoseconds (and SM cycles): the floor under the sequential carrier loops,
+// whose ~25 operations per sample form one dependency chain (csrc/loops.cu)
+extern "C" cudaError_t pm_launch_fp64_chain(double *, long long *, int, cudaStream_t);
+extern "C" int pm_measure_fp64_chain(int device, double *ns_per_op, double *cycles_per_op)
+{
+	if (!ns_per_op || !cycles_per_op) return PM_ERR_ARG;
+	if (cudaSetDevice(device) != cudaSuccess) return PM_ERR_CUDA;
+	double *d = nullptr;
+	long long *c = nullptr;
+	if (cudaMalloc((void **)&d, 8) != cudaSuccess || cudaMalloc((void **)&c, 8) != cudaSuccess) return PM_ERR_CUDA;
+	cudaMemset(d, 0, 8);
+	cudaEvent_t a, b;
+	cudaEventCreate(&a); cudaEventCreate(&b);
+	const int iters = 20000;                       // 320 000 dependent operations
+	pm_launch_fp64_chain(d, c, 100, 0);
+	cudaDeviceSynchronize();
+	cudaEventRecord(a, 0);
+	pm_launch_fp64_chain(d, c, iters, 0);
+	cudaEventRecord(b, 0);
+	int rc = PM_OK;
+	if (cudaEventSynchronize(b) != cudaSuccess) rc = PM_ERR_CUDA;
+	float ms = 0;
+	long long cyc = 0;
+	cudaEventElapsedTime(&ms, a, b);
+	cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
+	*ns_per_op = (double)ms * 1e6 / (16.0 * iters);
+	*cycles_per_op = (double)cyc / (16.0 * iters);
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	cudaFree(d); cudaFree(c);
+	return rc;
+}
+
 // pinned host memory for callers without torch
 extern "C" void *pm_host_alloc(size_t bytes)
 {

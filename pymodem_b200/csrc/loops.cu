@@ -386,6 +386,29 @@ p64_seq_kernel(const P64Chain *__restrict__ chains, int pass)
 	}
 }
 
+// Latency of one dependent float64 operation (the floor under a carrier loop: its ~25 operations per sample form one
+// chain): a single thread alternates __dadd_rn / __dmul_rn on its own result and reports cycles per operation.
+__global__ void fp64_chain_kernel(double *out, long long *cycles, int iters, double a, double b)
+{
+	double x = out[0];
+	const long long t0 = clock64();
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			x = __dadd_rn(x, a);
+			x = __dmul_rn(x, b);
+		}
+	}
+	cycles[0] = clock64() - t0;
+	out[0] = x;
+}
+
+extern "C" cudaError_t pm_launch_fp64_chain(double *out, long long *cycles, int iters, cudaStream_t st)
+{
+	fp64_chain_kernel<<<1, 1, 0, st>>>(out, cycles, iters, 1.0e-9, 0.999999999);
+	return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" cudaError_t pm_launch_p64(const P64Chain *d_chains, const P64Chain *h_chains, int n_chains,
 	const int16_t *audio, uint32_t *sign, long long sign_stride, float *soft, long long soft_stride,

@@ -527,6 +527,15 @@ def demod_only(modem, audio):
 		eng.close()
 
 
+def measure_fp64_chain(device=0):
+	"""(nanoseconds, SM cycles) per dependent float64 operation: the floor under the sequential carrier loops."""
+	ns, cyc = ctypes.c_double(), ctypes.c_double()
+	rc = _lib.load().pm_measure_fp64_chain(device, ctypes.byref(ns), ctypes.byref(cyc))
+	if rc != _lib.PM_OK:
+		raise EngineError(f"pm_measure_fp64_chain failed ({rc})")
+	return ns.value, cyc.value
+
+
 def measure_fp32_peak(device=0):
 	t = ctypes.c_double()
 	rc = _lib.load().pm_measure_fp32_peak(device, ctypes.byref(t))
