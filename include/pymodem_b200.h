@@ -352,6 +352,10 @@ int pm_engine_get_stats(const pm_engine *e, pm_stats *out);
  * "name<TAB>launches<TAB>milliseconds" (the time up to the next launch on the stream), in order of first launch.  Returns
  * the bytes written or PM_ERR_CAPACITY.  The events cost a few microseconds each: a timing pass is not a benchmark run. */
 int64_t pm_engine_kernel_times(const pm_engine *e, char *buf, int64_t cap);
+/* Timeline of the last pm_engine_run on a host buffer when option "trace" was 1: "label milliseconds" lines (chunk i
+ * copied / its front end done / its guard fix-up done / its batch of slicer segments done), relative to the start of the
+ * run.  Synchronises the device.  Returns the length of the text (it is cut at cap - 1). */
+int64_t pm_engine_trace(pm_engine *e, char *buf, int64_t cap);
 
 /* FP32 FFMA peak microbenchmark (roofline denominator for the FIR kernels):
  * returns achieved TFLOP/s of a register-resident FFMA loop on the device. */

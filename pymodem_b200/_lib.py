@@ -128,6 +128,7 @@ PROTOTYPES = {
 	"pm_engine_get_stream": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i64]),
 	"pm_engine_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
 	"pm_engine_kernel_times": (_i64, [_vp, ctypes.c_char_p, _i64]),
+	"pm_engine_trace": (_i64, [_vp, ctypes.c_char_p, _i64]),
 	"pm_engine_front_macs_per_sample": (ctypes.c_double, [_vp]),
 	"pm_engine_front_tensor_macs_per_sample": (ctypes.c_double, [_vp]),
 	"pm_engine_front_lpf_macs_per_sample": (ctypes.c_double, [_vp]),

@@ -1,6 +1,7 @@
 // engine.cu -- host side of libpymodem_b200.so: chain table -> launch plans,
 // device memory, the run pipeline, and the C ABI of include/pymodem_b200.h.
 #include <algorithm>
+#include <limits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -49,6 +50,7 @@ cudaError_t pm_launch_fir_front(const FirPlan *, size_t, const int16_t *, long l
 cudaError_t pm_launch_guard_fixup(const Fp64Chain *, int, const int16_t *, long long, uint32_t *, long long,
 	float *, long long, GuardList, int, cudaStream_t);
 cudaError_t pm_launch_ffma_peak(float *, int, int, cudaStream_t);
+cudaError_t pm_launch_guard_snapshot(const unsigned int *, unsigned int *, cudaStream_t);
 cudaError_t pm_launch_slicer_segments(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
 	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, cudaStream_t);
 cudaError_t pm_launch_slicer_verify(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
@@ -172,15 +174,29 @@ struct pm_engine {
 	cudaStream_t st_front[2] = {nullptr, nullptr};   // chunk launches of the host-buffer path alternate between these, so
 	                                                 // that the last partial wave of one launch overlaps the next launch
 	cudaEvent_t ev_front[2] = {nullptr, nullptr};
+	// host-buffer runs start the tail while the copy is still going: guard fix-up (st_tail[0]) and slicer segments
+	// (st_tail[1], st_tail[2] in turn) of the part of the recording whose sign words are final
+	cudaStream_t st_tail[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t ev_tail[3] = {nullptr, nullptr, nullptr};
+	std::vector<cudaEvent_t> ev_steps;               // front end of a chunk done / its fix-up done
+	DevBuf<unsigned int> d_snap;                     // guard count after the front-end launches of chunk i: d_snap[i + 1]
+	int opt_early_tail = 1;                          // host-buffer runs: 1 guard fix-up chunk by chunk beside the copy, 2 slicer segments too, 0 neither
+	int opt_trace = 0;                               // option "trace": timing events at the steps of a host-buffer run (pm_engine_trace)
+	std::vector<cudaEvent_t> ev_trace;
+	std::vector<std::string> trace_label;
+	size_t trace_used = 0;
+	int opt_early_batches = 12;                      // segments are launched in about this many batches
+	bool early_fix = false, early_seg = false;       // this run's fix-up / segments were launched chunk by chunk
 	std::string err;
 	std::vector<HostChain> chains;
 	std::vector<FrontGroup> groups;
 	// options
 	int opt_seg_words = 768;      // 24576 samples  (sweeps: profiles/r01_slicer_sweep.txt, tools/slicer_sweep2.py)
-	int opt_warm_words = 1536;    // 49152 samples, of which the last 16384 in float64
+	int opt_warm_words = 1536;    // 49152 samples, of which the last 4096 sample by sample (profiles/r02aa_slicer_sweep3.txt)
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
-	int opt_warm_exact_words = 512; // float64 tail of a warm-up (16384 samples); the part before it runs in FP32 (0: all float64)
+	int opt_warm_exact_words = 128; // exact sample-by-sample tail of a warm-up (4096 samples; 16384 before the float64 far part); the part before it runs crossing by crossing (0: all exact)
+	int opt_warm_far_f64 = 1;     // the crossing-by-crossing part in float64 (0: FP32, round 1's form, needs a 16384-sample tail)
 	double opt_guard_eps = 3.814697265625e-06;  // 2^-18 of the in-band magnitude scale: 4x the largest error seen (tools/guard_sweep.py, guard_bound.py)
 	double opt_guard_abs = 0.25;                // c_abs of the raw-input term: 4x the largest error seen in units of
 	                                            // 2^-24 max|audio| sum|h_bpf| N_corr sum|h_lpf| (1 + g) (tools/guard_bound.py)
@@ -749,6 +765,7 @@ extern "C" int pm_engine_create(int device, pm_engine **out)
 	e->device = device;
 	e->sm_count = prop.multiProcessorCount;
 	memset(&e->stats, 0, sizeof(e->stats));
+	int prio_lo = 0, prio_hi = 0;
 	if (cudaSetDevice(device) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
@@ -756,6 +773,14 @@ extern "C" int pm_engine_create(int device, pm_engine **out)
 	    cudaStreamCreateWithFlags(&e->st_front[1], cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&e->ev_front[0], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&e->ev_front[1], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+	    // (highest priority: their few blocks are placed as soon as a front-end CTA retires instead of after the whole grid)
+	    cudaStreamCreateWithPriority(&e->st_tail[0], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+	    cudaStreamCreateWithPriority(&e->st_tail[1], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+	    cudaStreamCreateWithPriority(&e->st_tail[2], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&e->ev_tail[2], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaHostAlloc((void **)&e->h_counters, 64, cudaHostAllocDefault) != cudaSuccess ||
 	    cudaHostAlloc((void **)&e->h_totals, sizeof(PacketTotals), cudaHostAllocDefault) != cudaSuccess) {
 		delete e;
@@ -787,6 +812,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_p64_work.release(); e->d_p64_tabs.release(); e->d_p64_pd.release(); e->d_p64.release(); e->d_p64_max.release();
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
+	for (auto &ev : e->ev_trace) cudaEventDestroy(ev);
 	for (void *p : e->link_opened) cudaIpcCloseMemHandle(p);
 	e->d_link.release(); e->d_link_status.release(); e->d_link_lb.release(); e->d_link_obase.release();
 	e->d_mrecs.release(); e->d_marena.release(); e->d_mtotals.release();
@@ -805,6 +831,11 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 		if (e->st_front[i]) cudaStreamDestroy(e->st_front[i]);
 		if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
 	}
+	for (int i = 0; i < 3; i++) {
+		if (e->st_tail[i]) cudaStreamDestroy(e->st_tail[i]);
+		if (e->ev_tail[i]) cudaEventDestroy(e->ev_tail[i]);
+	}
+	for (auto ev : e->ev_steps) cudaEventDestroy(ev);
 	delete e;
 }
 
@@ -1007,6 +1038,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "checkpoint_len") e->opt_chk_words = std::max(1, (int)(value / 32));
 	else if (k == "verify_passes") e->opt_verify_passes = std::max(0, (int)value);
 	else if (k == "warmup_exact_len") e->opt_warm_exact_words = std::max(0, (int)((value + 31) / 32));
+	else if (k == "warmup_far_f64") e->opt_warm_far_f64 = value != 0;
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "guard_abs") { e->opt_guard_abs = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
@@ -1027,6 +1059,9 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 			CK(cudaMemset(e->d_stage_clk.p, 0, 8 * sizeof(unsigned long long)));
 		}
 	}
+	else if (k == "early_tail") e->opt_early_tail = std::max(0, std::min(2, (int)value));
+	else if (k == "trace") e->opt_trace = (int)value;
+	else if (k == "early_batches") e->opt_early_batches = std::max(1, (int)value);
 	else if (k == "h2d_chunk") e->opt_h2d_chunk = std::max<long long>(1 << 16, (long long)value);
 	else if (k == "kernel_times") e->opt_kernel_times = value != 0;
 	else if (k == "debug_sync") e->opt_debug_sync = value != 0;
@@ -1154,14 +1189,17 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	e->k0 = plan.pre_segments;
 	G.origin_w = e->own_w0 - (long long)e->k0 * seg_words;
 	G.k_init = 0;
-	G.warm_f32_words = (e->opt_warm_exact_words > 0 && e->opt_warm_exact_words < G.warm_words) ?
-		G.warm_words - e->opt_warm_exact_words : 0;
 	G.seg_words = seg_words;
 	G.warm_words = e->opt_warm_words;
+	G.warm_f32_words = (e->opt_warm_exact_words > 0 && e->opt_warm_exact_words < G.warm_words) ?
+		G.warm_words - e->opt_warm_exact_words : 0;
+	G.warm_far_f64 = e->opt_warm_far_f64;
 	G.chk_words = chk_words;
 	G.n_chk = seg_words / chk_words;
 	G.n_seg = e->k0 + (int)std::max<long long>(1, (e->end_w - e->own_w0 + seg_words - 1) / seg_words);
 	G.true_start = plan.first ? 1 : 0;
+	G.k_first = 0;
+	G.k_count = G.n_seg;
 	e->k_end = e->k0 + (int)std::min<long long>(G.n_seg - e->k0,
 		std::max<long long>(1, (e->own_w1 - e->own_w0 + seg_words - 1) / seg_words));
 	e->n_seg = G.n_seg;
@@ -1295,6 +1333,7 @@ static GuardList guard_of(pm_engine *e)
 	g.count = e->d_counters.p;
 	g.cap = e->guard_cap;
 	g.stage_clk = e->opt_stage_clocks ? e->d_stage_clk.p : nullptr;
+	g.from = g.to = nullptr;
 	return g;
 }
 
@@ -1342,9 +1381,9 @@ static int launch_front(pm_engine *e, const int16_t *d_audio, long long n, long 
 			e->stats.front_launches++;
 			t += cnt;
 		}
+		g.a_done = std::max(g.a_done, t1);
 		if (g.tensor) {
 			// low-pass tiles whose input rows are all written now: tile k reads the magnitudes [TC_TILE k, TC_TILE (k + 1) + 64 TC_KBLK)
-			g.a_done = std::max(g.a_done, t1);
 			long long b_ready = (g.a_done >= g.n_tile_a) ? g.n_tile_b : (g.a_done * g.tile - 64 * TC_KBLK) / TC_TILE;
 			b_ready = std::min(std::max<long long>(b_ready, 0), g.n_tile_b);
 			if (b_ready > g.b_done) {
@@ -1493,6 +1532,34 @@ static void parallel_copy(void *dst, const void *src, size_t bytes, int threads)
 	for (auto &t : th) t.join();
 }
 
+// option "trace": a timing event on a stream, reported by pm_engine_trace relative to the start of the run
+static void trace_mark(pm_engine *e, const char *what, int i, cudaStream_t st)
+{
+	if (!e->opt_trace) return;
+	if (e->trace_used == e->ev_trace.size()) {
+		cudaEvent_t ev;
+		if (cudaEventCreate(&ev) != cudaSuccess) return;
+		e->ev_trace.push_back(ev);
+		e->trace_label.emplace_back();
+	}
+	char buf[64];
+	snprintf(buf, sizeof(buf), "%s %d", what, i);
+	e->trace_label[e->trace_used] = buf;
+	cudaEventRecord(e->ev_trace[e->trace_used++], st);
+}
+
+// guard_fixup_kernel, doubles per warp: audio window, band-passed window, 2 magnitude rows
+static int fixup_doubles(const pm_engine *e)
+{
+	int max_sum = 8;
+	for (auto &hc : e->chains) {
+		const int nx = (int)(hc.mark_i.size() + hc.lpf.size());
+		const int nx_pad = (nx + 159) / 160 * 160, mrow = ((int)hc.lpf.size() + 223) / 224 * 224;
+		max_sum = std::max(max_sum, nx_pad + (int)hc.bpf.size() + nx_pad + (int)hc.mark_i.size() + 7 * 32 + 2 * mrow + 8);
+	}
+	return max_sum;
+}
+
 static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_host, const pm_shard_plan &plan,
                       bool sharded, bool defer)
 {
@@ -1504,6 +1571,8 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 	int rc = prepare_run(e, n, plan, sharded);
 	if (rc != PM_OK) return rc;
 	const int16_t *d_audio = audio;
+	e->early_fix = e->early_seg = false;
+	e->trace_used = 0;
 	CK(cudaEventRecord(e->ev[0], e->st));
 	pm_kt_mark("(launch gap)", e->st);
 	if (on_host) {
@@ -1527,10 +1596,34 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 			CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 			e->ev_chunks.push_back(ev);
 		}
+		// Early tail (option early_tail).  1: the guard fix-up does not wait for the last chunk.  After the front-end launches
+		// of a chunk the guard count is snapshot on the launch stream and the fix-up of the entries since the previous
+		// snapshot runs on st_tail[0], beside the front end of the following chunks: what follows the last byte of the
+		// recording is one chunk's front end, a small fix-up, then slicer and bit level as on the device-resident path.
+		// 2: the slicer's speculative segments are launched early too, in batches, on st_tail[1] / st_tail[2], as soon as
+		// all sign words below them are final.  Measured and NOT the default: a batch of segments takes as long as ALL of
+		// them (a thread's chain of ~74000 dependent steps is 1.1 ms, the whole kernel 1.1 ms), so the batch after the
+		// last chunk costs what the single launch costs, and the earlier ones hold the front end back while they share its
+		// SMs (profiles/r02ad_e2e_trace.txt: 9.4-11.9 ms against 8.9).
+		const int early = (defer && e->h_p64.empty() && n_chunks > 2) ? e->opt_early_tail : 0;
+		int k_done = 0, n_slc = 0, snap_prev = 0;
+		const int k_batch = std::max(1, e->geom.n_seg / std::max(1, e->opt_early_batches));
+		if (early) {
+			CK(e->d_snap.ensure((size_t)n_chunks + 2));
+			CK(cudaMemsetAsync(e->d_snap.p, 0, sizeof(unsigned int), e->st));
+			while ((int)e->ev_steps.size() < 2 * n_chunks) {
+				cudaEvent_t ev;
+				CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+				e->ev_steps.push_back(ev);
+			}
+			e->E_cur = e->d_E0.p; e->E_alt = e->d_E1.p;
+		}
 		// the copy stream must not start before the engine stream reached this point
 		CK(cudaEventRecord(e->ev[6], e->st));
 		CK(cudaStreamWaitEvent(e->st_copy, e->ev[6], 0));
 		for (int q = 0; q < 2; q++) CK(cudaStreamWaitEvent(e->st_front[q], e->ev[6], 0));
+		if (early)
+			for (int q = 0; q < 3; q++) CK(cudaStreamWaitEvent(e->st_tail[q], e->ev[6], 0));
 		// pageable caller memory: the driver would stage it through its own small bounce buffers, synchronously.  Stage
 		// it ourselves through a ring of pinned buffers: the memcpy of chunk i+1 (host threads) overlaps the DMA of chunk i
 		const bool staged = !host_pointer_is_pinned(audio);
@@ -1553,7 +1646,7 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 		for (int i = 0; i < n_chunks; i++) {
 			const long long len = cuts[i] - done;
 			// (a low-pass tile reads magnitudes of front tiles from earlier chunks: one launch stream keeps them ordered)
-			cudaStream_t fs = e->st_front[any_tensor ? 0 : (i & 1)];
+			cudaStream_t fs = e->st_front[(any_tensor || early) ? 0 : (i & 1)];
 			const int16_t *src = audio + done;
 			if (staged) {
 				const int slot = i % pm_engine::RING;
@@ -1565,10 +1658,57 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 				cudaMemcpyHostToDevice, e->st_copy));
 			if (staged) CK(cudaEventRecord(e->ev_ring[i % pm_engine::RING], e->st_copy));
 			CK(cudaEventRecord(e->ev_chunks[i], e->st_copy));
+			trace_mark(e, "copied", i, e->st_copy);
 			CK(cudaStreamWaitEvent(fs, e->ev_chunks[i], 0));
 			rc = launch_front(e, d_audio, n, done, done + len, i == n_chunks - 1, fs);
 			if (rc != PM_OK) return rc;
 			done += len;
+			trace_mark(e, "front", i, fs);
+			if (early) {
+				const bool last = i == n_chunks - 1;
+				const SlicerGeom &G = e->geom;
+				long long upto = std::numeric_limits<long long>::max();     // sign words below this sample are written
+				for (auto &g : e->groups) upto = std::min(upto, g.tensor ? g.b_done * (long long)TC_TILE : g.a_done * (long long)g.tile);
+				const int k_ready = last ? G.n_seg
+					: (int)std::min<long long>(G.n_seg, std::max<long long>(0, (upto / 32 - G.origin_w) / G.seg_words));
+				if (last || early == 1 || k_ready - k_done >= k_batch) {
+					if (pm_launch_guard_snapshot(e->d_counters.p, e->d_snap.p + i + 1, fs) != cudaSuccess)
+						return fail(e, PM_ERR_CUDA, "guard snapshot launch failed");
+					CK(cudaEventRecord(e->ev_steps[2 * i], fs));
+					CK(cudaStreamWaitEvent(e->st_tail[0], e->ev_steps[2 * i], 0));
+					GuardList gl = guard_of(e);
+					gl.from = e->d_snap.p + snap_prev;
+					gl.to = e->d_snap.p + i + 1;
+					snap_prev = i + 1;
+					cudaError_t ce = pm_launch_guard_fixup(e->d_fp64.p, fixup_doubles(e), d_audio, n, e->d_sign.p, e->sign_stride,
+						e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, gl, last ? 148 * 5 : 148, e->st_tail[0]);
+					if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));
+					e->stats.kernel_launches++;
+					CK(cudaEventRecord(e->ev_steps[2 * i + 1], e->st_tail[0]));
+					trace_mark(e, "fixup", i, e->st_tail[0]);
+					if (early == 2 && k_ready > k_done) {
+						cudaStream_t ss = e->st_tail[1 + (n_slc++ & 1)];
+						CK(cudaStreamWaitEvent(ss, e->ev_steps[2 * i + 1], 0));
+						SlicerGeom G2 = G;
+						G2.k_first = k_done;
+						G2.k_count = k_ready - k_done;
+						ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+							e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, G2, ss);
+						if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
+						e->stats.kernel_launches++;
+						trace_mark(e, "segments", i, ss);
+						k_done = k_ready;
+					}
+				}
+			}
+		}
+		if (early) {
+			for (int q = 0; q < 3; q++) {
+				CK(cudaEventRecord(e->ev_tail[q], e->st_tail[q]));
+				CK(cudaStreamWaitEvent(e->st, e->ev_tail[q], 0));
+			}
+			e->early_fix = true;
+			e->early_seg = early == 2;
 		}
 		for (int q = 0; q < 2; q++) {          // the engine stream continues when both launch streams are done
 			CK(cudaEventRecord(e->ev_front[q], e->st_front[q]));
@@ -1589,25 +1729,24 @@ static int begin_once(pm_engine *e, const int16_t *audio, long long n, bool on_h
 	e->run_audio = d_audio;
 	CK(cudaEventRecord(e->ev[1], e->st));
 
-	// FP64 guard-band fix-up
-	int max_sum = 8;
-	for (auto &hc : e->chains) {     // guard_fixup_kernel, doubles per warp: audio window, band-passed window, 2 magnitude rows
-		const int nx = (int)(hc.mark_i.size() + hc.lpf.size());
-		const int nx_pad = (nx + 159) / 160 * 160, mrow = ((int)hc.lpf.size() + 223) / 224 * 224;
-		max_sum = std::max(max_sum, nx_pad + (int)hc.bpf.size() + nx_pad + (int)hc.mark_i.size() + 7 * 32 + 2 * mrow + 8);
+	cudaError_t ce;
+	if (!e->early_fix) {
+		// FP64 guard-band fix-up
+		ce = pm_launch_guard_fixup(e->d_fp64.p, fixup_doubles(e), d_audio, n, e->d_sign.p, e->sign_stride,
+			e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 5, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
 	}
-	cudaError_t ce = pm_launch_guard_fixup(e->d_fp64.p, max_sum, d_audio, n, e->d_sign.p, e->sign_stride,
-		e->opt_keep_soft ? e->d_soft.p : nullptr, e->soft_stride, guard_of(e), 148 * 5, e->st);
-	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "fixup launch failed: %s", cudaGetErrorString(ce));
-	e->stats.kernel_launches++;
 	CK(cudaEventRecord(e->ev[2], e->st));
 
 	// slicer: speculative segments, then verify/repair
-	e->E_cur = e->d_E0.p; e->E_alt = e->d_E1.p;
-	ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-		e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->st);
-	if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
-	e->stats.kernel_launches++;
+	if (!e->early_seg) {
+		e->E_cur = e->d_E0.p; e->E_alt = e->d_E1.p;
+		ce = pm_launch_slicer_segments(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
+			e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->st);
+		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer launch failed: %s", cudaGetErrorString(ce));
+		e->stats.kernel_launches++;
+	}
 	e->stats.slicer_segments = (int64_t)nc * e->geom.n_seg;
 	if (!plan.first) {
 		// the state at own_begin is only speculated so far: take it as given until the hand-off
@@ -2569,6 +2708,26 @@ extern "C" int64_t pm_engine_kernel_times(const pm_engine *e, char *buf, int64_t
 	if ((int64_t)e->kt_report.size() + 1 > cap) return PM_ERR_CAPACITY;
 	memcpy(buf, e->kt_report.c_str(), e->kt_report.size() + 1);
 	return (int64_t)e->kt_report.size();
+}
+
+// option "trace": "label ms" lines of the last host-buffer run, times relative to its start
+extern "C" int64_t pm_engine_trace(pm_engine *e, char *buf, int64_t cap)
+{
+	if (!e || !buf || cap <= 0) return -1;
+	cudaSetDevice(e->device);
+	cudaDeviceSynchronize();
+	std::string out;
+	for (size_t i = 0; i < e->trace_used; i++) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, e->ev[0], e->ev_trace[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+		char line[96];
+		snprintf(line, sizeof(line), "%s %.3f\n", e->trace_label[i].c_str(), ms);
+		out += line;
+	}
+	const int64_t n = std::min<int64_t>((int64_t)out.size(), cap - 1);
+	memcpy(buf, out.data(), (size_t)n);
+	buf[n] = 0;
+	return (int64_t)out.size();
 }
 
 extern "C" int pm_engine_get_stats(const pm_engine *e, pm_stats *out)

@@ -754,9 +754,10 @@ guard_fixup_kernel(const Fp64Chain *__restrict__ chains, const int16_t *__restri
 	extern __shared__ __align__(16) double sm64[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	double *base = sm64 + (long long)wid * warp_doubles;
-	const unsigned int n_entries = min(*guard.count, guard.cap);
+	const unsigned int n_entries = min(guard.to ? *guard.to : *guard.count, guard.cap);
+	const unsigned int first = guard.from ? min(*guard.from, n_entries) : 0u;
 	const unsigned int n_warps = gridDim.x * (PM_FIX_THREADS / 32);
-	for (unsigned int e = blockIdx.x * (PM_FIX_THREADS / 32) + wid; e < n_entries; e += n_warps) {
+	for (unsigned int e = first + blockIdx.x * (PM_FIX_THREADS / 32) + wid; e < n_entries; e += n_warps) {
 		const unsigned long long ent = guard.entries[e];
 		const int gid = (int)(ent >> 48);
 		const long long n = (long long)(ent & 0xFFFFFFFFFFFFull);
@@ -850,6 +851,13 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, f
 	if (s == 12345.678f) out[0] = s;
 }
 
+// the guard count as of this point of the stream (a 4-byte cudaMemcpyAsync would queue on the copy engine behind the
+// chunks of the recording that are already submitted, and stall the launch stream until they are through)
+__global__ void guard_snapshot_kernel(const unsigned int *__restrict__ count, unsigned int *__restrict__ out)
+{
+	*out = *count;
+}
+
 // ---------------------------------------------------------------------------
 // host-side launchers (called from engine.cu)
 // ---------------------------------------------------------------------------
@@ -920,6 +928,12 @@ extern "C" cudaError_t pm_launch_guard_fixup(const Fp64Chain *chains, int warp_d
 	pm_kt_mark("guard_fixup_kernel", st);
 	guard_fixup_kernel<<<grid, PM_FIX_THREADS, smem, st>>>(chains, audio, n_audio, sign, sign_stride, soft,
 		soft_stride, guard, warp_doubles);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t pm_launch_guard_snapshot(const unsigned int *count, unsigned int *out, cudaStream_t st)
+{
+	guard_snapshot_kernel<<<1, 1, 0, st>>>(count, out);
 	return cudaGetLastError();
 }
 

@@ -142,6 +142,8 @@ struct GuardList {
 	unsigned int cap;
 	unsigned long long *stage_clk;     // optional tracing (option "stage_clocks"): per-CTA cycles of the AFSK front end's
 	                                   // stages summed over CTAs [stage, band-pass, correlators, low-pass+epilogue], [4] = CTAs
+	const unsigned int *from, *to;     // guard_fixup_kernel only: entries [*from, *to) (snapshots of count taken between the
+	                                   // front-end launches of a host-buffer run); null: [0, *count)
 };
 
 // ---- tables shared by the kernels and the host engine -------------------------
@@ -194,6 +196,10 @@ struct SlicerGeom {
 	                         // is left (every zero crossing multiplies the error by lock_rate) and the verify pass decides
 	int k_init;              // segment whose predecessor state is init[] (0 during the local pass; the first own
 	                         // segment when a hand-off repair starts there -- the segments before it are frozen)
+	int warm_far_f64;        // the far part crossing by crossing in float64 instead of FP32: an ulp or two off instead of
+	                         // 2^-24, so a 4096-sample exact tail suffices (tools/slicer_warm_sim.py)
+	int k_first;             // slicer_segments_kernel handles segments [k_first, k_first + k_count): the host-buffer
+	int k_count;             // path launches the segments of every chunk of audio as its sign words become final
 };
 
 // Per-chain placement of the local bitstream when the recording is sharded on

@@ -66,6 +66,8 @@ __device__ __forceinline__ void slicer_step(double &c, uint32_t &m, uint32_t z, 
 }
 
 // Advance the slicer over samples [w0*32, min(w1*32, nout)) of one chain.
+// The sign word of the next iteration is requested before the 32 dependent steps of this one (the loads were 1.2
+// stall cycles per issue, ncu r02k).
 template <bool WRITE, bool FAST, bool A0, bool F0>
 __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                             const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
@@ -76,14 +78,20 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 	const double thr = C.thr, sps = C.sps, lam = C.lock;
 	const double cs = __longlong_as_double(C.c_star_bits);
 	const double a_roll = FAST ? -C.sps_m1 : -C.sps, a_keep = FAST ? 1.0 : 0.0;
+	const long long w_last = (C.nout + 31) >> 5;           // words with at least one valid sample
+	if (w1 > w_last) w1 = w_last;
+	if (w0 >= w1) return;
+	uint32_t s_next = sg[w0], q_next = sgq ? sgq[w0] : 0u;
 	for (long long w = w0; w < w1; w++) {
 		const long long first = w << 5;
-		if (first >= C.nout) break;
-		const uint32_t s = sg[w];
+		const uint32_t s = s_next, q = q_next;
+		if (w + 1 < w1) {
+			s_next = sg[w + 1];
+			if (sgq) q_next = sgq[w + 1];
+		}
 		uint32_t z = s ^ ((s << 1) | last);          // zero crossings (slicer.py:99-102)
 		last = s >> 31;
 		if (sgq) {
-			const uint32_t q = sgq[w];
 			z |= q ^ ((q << 1) | last_q);
 			last_q = q >> 31;
 		}
@@ -103,7 +111,7 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 			}
 			// state after a partial word: last signs are those of sample cnt-1
 			last = (s >> (cnt - 1)) & 1u;
-			if (sgq) last_q = (sgq[w] >> (cnt - 1)) & 1u;
+			if (sgq) last_q = (q >> (cnt - 1)) & 1u;
 		}
 		if (WRITE) mk[w] = m;
 	}
@@ -112,30 +120,43 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 	st.last_q = last_q;
 }
 
-// The far end of a warm-up in FP32, crossing by crossing (no outputs, no claim of exactness: whatever error remains
-// is contracted by the float64 tail).  Between two crossings the loop only counts -- d steps of +1 with a roll-over
+// The far end of a warm-up crossing by crossing (no outputs, no claim of exactness: whatever error remains is
+// contracted by the exact tail).  Between two crossings the loop only counts -- d steps of +1 with a roll-over
 // whenever the clock reaches thr -- which has the closed form below, so a word costs one short iteration per zero
 // crossing (0-3 in a 32-sample word of 1200 Bd audio) instead of 32 unrolled steps.
+// T = float: round 1's form; 2^-24 of error needs ~75 crossings (16384 samples) of exact tail to vanish.
+// T = double [r2]: the closed form differs from the sample-by-sample loop only in how often it rounds (once per run
+// instead of once per binade the clock climbs through), i.e. by an ulp or two, which the exact tail loses within a
+// few crossings: tools/slicer_warm_sim.py measures 0.4 % of hand-offs not bit-identical with a 4096-sample tail
+// (0.2 % with 16384; 28 % for the FP32 form with 8192).
 // ONE_WRAP: at least 32 samples per symbol, so the clock rolls over at most once between two crossings of a word.
-template <bool ONE_WRAP>
-__device__ __forceinline__ void run_words_f32_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
+template <typename T, bool ONE_WRAP>
+__device__ __forceinline__ void run_words_far_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                                 const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
 {
-	float c = (float)st.clock;
+	T c = (T)st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
-	const float thr = (float)C.thr, sps = (float)C.sps, lam = (float)C.lock, inv_sps = 1.0f / sps;
+	const T thr = (T)C.thr, sps = (T)C.sps, lam = (T)C.lock, inv_sps = (T)1 / sps;
 	auto advance = [&](int d) {                      // d samples without a crossing
-		const float u = c + (float)d;
+		const T u = c + (T)d;
 		if (ONE_WRAP) c = u >= thr ? u - sps : u;
-		else c = u >= thr ? u - sps * (floorf((u - thr) * inv_sps) + 1.0f) : u;
+		else c = u >= thr ? u - sps * (floor((u - thr) * inv_sps) + (T)1) : u;
 	};
+	const long long w_full = C.nout >> 5;            // whole words only; the exact tail handles the rest
+	if (w1 > w_full) w1 = w_full;
+	if (w0 >= w1) return;
+	// (a flat loop -- one iteration per crossing or per word, lanes drifting apart -- was tried and is slower: 1.17 ms
+	// against 1.08 for the segments kernel, profiles/r02ae_slicer_split.txt)
+	uint32_t s_next = sg[w0], q_next = sgq ? sgq[w0] : 0u;
 	for (long long w = w0; w < w1; w++) {
-		if (((w + 1) << 5) > C.nout) break;            // whole words only; the float64 tail handles the rest
-		const uint32_t s = sg[w];
+		const uint32_t s = s_next, q = q_next;
+		if (w + 1 < w1) {
+			s_next = sg[w + 1];
+			if (sgq) q_next = sgq[w + 1];
+		}
 		uint32_t z = s ^ ((s << 1) | last);
 		last = s >> 31;
 		if (sgq) {
-			const uint32_t q = sgq[w];
 			z |= q ^ ((q << 1) | last_q);
 			last_q = q >> 31;
 		}
@@ -154,11 +175,18 @@ __device__ __forceinline__ void run_words_f32_t(const SlicerChain &C, const uint
 	st.last_q = last_q;
 }
 
-__device__ __forceinline__ void run_words_f32(const SlicerChain &C, const uint32_t *__restrict__ sg,
-                                              const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st)
+__device__ __forceinline__ void run_words_far(const SlicerChain &C, const uint32_t *__restrict__ sg,
+                                              const uint32_t *__restrict__ sgq, long long w0, long long w1, SegState &st,
+                                              bool f64)
 {
-	if (C.sps >= 32.0) run_words_f32_t<true>(C, sg, sgq, w0, w1, st);      // uniform per chain
-	else run_words_f32_t<false>(C, sg, sgq, w0, w1, st);
+	const bool one = C.sps >= 32.0;                  // uniform per chain
+	if (f64) {
+		if (one) run_words_far_t<double, true>(C, sg, sgq, w0, w1, st);
+		else run_words_far_t<double, false>(C, sg, sgq, w0, w1, st);
+	} else {
+		if (one) run_words_far_t<float, true>(C, sg, sgq, w0, w1, st);
+		else run_words_far_t<float, false>(C, sg, sgq, w0, w1, st);
+	}
 }
 
 template <bool WRITE>
@@ -182,7 +210,7 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
 	}
 }
 
-// grid: (ceil(n_seg / 128), n_chains); block 128
+// grid: (ceil(k_count / 128), n_chains); block 128: segments [k_first, k_first + k_count)
 // Segment k covers words [origin_w + k*seg_words, origin_w + (k+1)*seg_words).
 // true_start != 0: local sample 0 is the true start of the recording, so a
 // warm-up window clipped at 0 starts from init[] (no speculation).
@@ -192,9 +220,9 @@ slicer_segments_kernel(const SlicerChain *__restrict__ chains, const uint32_t *_
                        SegState *__restrict__ S, SegState *__restrict__ E, SegState *__restrict__ chk,
                        const SegState *__restrict__ init, SlicerGeom G)
 {
-	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = G.k_first + blockIdx.x * blockDim.x + threadIdx.x;
 	const int ch = blockIdx.y;
-	if (k >= G.n_seg) return;
+	if (k >= G.k_first + G.k_count || k >= G.n_seg) return;
 	const SlicerChain C = chains[ch];
 	const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
 	const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
@@ -212,7 +240,7 @@ slicer_segments_kernel(const SlicerChain *__restrict__ chains, const uint32_t *_
 	if (G.warm_f32_words > 0 && w_begin - w_warm > G.warm_f32_words / 4) {
 		const long long w_mid = min(w_begin, w_warm + G.warm_f32_words);
 		if (((w_mid) << 5) <= C.nout) {
-			run_words_f32(C, sg, sgq, w_warm, w_mid, st);
+			run_words_far(C, sg, sgq, w_warm, w_mid, st, G.warm_far_f64 != 0);
 			w_warm = w_mid;
 		}
 	}
@@ -373,7 +401,8 @@ extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int 
 	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, SegState *E, SegState *chk,
 	const SegState *init, SlicerGeom G, cudaStream_t st)
 {
-	dim3 grid((G.n_seg + 127) / 128, n_chains);
+	if (G.k_count <= 0) return cudaSuccess;
+	dim3 grid((G.k_count + 127) / 128, n_chains);
 	pm_kt_mark("slicer_segments_kernel", st);
 	slicer_segments_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E, chk, init, G);
 	return cudaGetLastError();

@@ -369,6 +369,13 @@ class Engine:
 			out.append((name, int(cnt), float(ms)))
 		return out
 
+	def trace(self):
+		"""Timeline of the last host-buffer run (option trace=1): [(label, ms since the start of the run)]."""
+		buf = ctypes.create_string_buffer(1 << 16)
+		if self._lib.pm_engine_trace(self._h, buf, len(buf)) < 0:
+			raise EngineError("pm_engine_trace failed")
+		return [(l.rsplit(" ", 1)[0], float(l.rsplit(" ", 1)[1])) for l in buf.value.decode().splitlines()]
+
 	def stage_clocks(self):
 		"""Cycles per front-end stage summed over CTAs since the last call (option stage_clocks=1); see the header."""
 		out = (ctypes.c_uint64 * 8)()

@@ -125,6 +125,38 @@ def test_pageable_and_pinned_input_agree(cuda_lib):
 		assert a == b == g.all_packets()
 
 
+@pytest.mark.parametrize("tag", ["afsk1200_superopt_48k", "afsk1200_ax25_44k1", "fsk9600_il2p_48k"])
+def test_early_tail_of_host_runs(cuda_lib, tag):
+	"""Host-buffer runs launch the guard fix-up chunk by chunk while the copy is still going (option early_tail = 1, the
+	default) and, with early_tail = 2, the slicer's segments too: same records as with the whole tail after the last chunk
+	(0), as the device-resident path and as the fixture -- with many small chunks, short segments (many batches), a guard
+	list that overflows and is grown, and with the tensor-core low-pass off."""
+	import torch
+	from pymodem_b200.engine import Engine
+	from pymodem_b200.modems_codecs import chain_builder
+	g = Golden(tag)
+	audio = g.audio()
+	stack = [chain_builder.build_chain(g.sample_rate, l) for l in g.chain_lines()]
+	want = g.all_packets()
+	dev = torch.from_numpy(audio).cuda()
+	for opts in ({"early_tail": 0}, {"early_tail": 1}, {"early_tail": 2}, {"h2d_chunk": 1 << 16}, {"h2d_chunk": 1 << 16, "early_tail": 2},
+			{"h2d_chunk": 1 << 17, "segment_len": 4096, "warmup_len": 16384, "early_tail": 2, "early_batches": 5},
+			{"h2d_chunk": 1 << 16, "tensor_lpf": 0}, {"h2d_chunk": 1 << 16, "tensor_lpf": 0, "early_tail": 2},
+			{"h2d_chunk": 1 << 16, "guard_cap": 1024, "guard_eps": 2.0 ** -9}, {"h2d_chunk": 1 << 16, "guard_cap": 1024, "guard_eps": 2.0 ** -9, "early_tail": 2}):
+		eng = Engine(stack, **opts)
+		try:
+			assert eng.pin(audio)
+			for _ in range(2):
+				assert as_tuples(eng.run(audio)) == want, opts
+			st = eng.stats()
+			eng.run_device_ptr(dev.data_ptr(), len(audio))
+			assert as_tuples(eng.packets(*eng.fetch())) == want, opts
+		finally:
+			eng.close()
+		if opts.get("guard_cap"):
+			assert st["guard_flagged"] > 1024      # the list did overflow and the run was repeated with a longer one
+
+
 @pytest.mark.parametrize("tag,count", [("bpsk300_il2p_8k", 5), ("qpsk2400_il2p_8k", 3), ("afsk1200_superopt_48k", 3), ("afsk300_full_8k", 2)])
 def test_batched_recordings_equal_single_runs(cuda_lib, oracle, tag, count):
 	"""pm_engine_run_batch: several recordings of different lengths x all chains in one call == one call per recording
