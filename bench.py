@@ -37,6 +37,7 @@ UNIT = "chain-samples/s"
 REF_FLOP_PER_CHAIN_SAMPLE = 956.0
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12       # 37.2: 64 FP64 lanes per SM
+SLICER_STEP_PEAK_G = 2544.5      # G exact slicer steps per second, measured: tools/ubench/slicer_step.cu variant 0, 24 warps per SM
 # profiles/r01g_verify_hour.txt: the oracle's packet set for the default hour (seeds 1000/1001), tools/verify_hour.py digest
 ORACLE_HOUR_DIGEST = "d794b4007f27f787"
 
@@ -280,6 +281,7 @@ def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3, tc
 	flagged = st["guard_flagged"]
 	# algorithmic bytes (or flops) per launch group, per step
 	sign_mask = n_chains * words * 4.0
+	st_seg, st_exact = 24576, 4096          # engine defaults (csrc/engine.cu opt_seg_words, opt_warm_exact_words)
 	work = {
 		"afsk_front_kernel": ("fp32", 2.0 * macs * n / 1e12, fp32_peak, "TFLOP/s"),
 		# tensor-core route: the front kernel stops at the magnitudes (band-pass + sliding correlators + piece split), the
@@ -288,7 +290,11 @@ def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3, tc
 		"afsk_front_kernel (magnitudes)": ("fp32", 2.0 * macs * n / 1e12, fp32_peak, "TFLOP/s"),
 		"lpf_tc_kernel": ("tensor", 2.0 * tc_macs * n / 1e12, peaks.get("bf16_tflops") or 1590.0, "TFLOP/s"),
 		"guard_fixup_kernel": ("fp64", flagged * 2.0 * (320 * 148 + 4 * 100 * 60 + 100) / 1e12, FP64_NOMINAL_TFLOPS, "TFLOP/s"),
-		"slicer_segments_kernel": ("alu-issue", (3.0 * sign_mask + sign_mask) / 1e9, hbm, "GB/s"),
+		# the slicer is bound by the issue of its exact step (DSETP, select, DADD, bit test, two selects, DMUL, funnel shift: the
+		# float64 and integer pipes of a scheduler take 15 cycles per warp and sample, whatever the occupancy --
+		# tools/ubench/slicer_step.cu, profiles/r02af_slicer_step.txt: 2.54e12 thread-steps/s with 24 warps per SM).
+		# Executed exact steps of a launch: every segment plus the exact tail of its warm-up, per chain.
+		"slicer_segments_kernel": ("fp64+alu issue", n_chains * (n / float(st_seg)) * (st_seg + st_exact) / 1e9, SLICER_STEP_PEAK_G, "G steps/s"),
 		"slicer_verify_kernel": ("latency", 0.0, hbm, "GB/s"),
 		"gather_count_kernel": ("hbm", sign_mask / 1e9, hbm, "GB/s"),
 		"memset bits": ("hbm", nbits / 8.0 / 1e9, hbm, "GB/s"),
@@ -311,8 +317,9 @@ def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3, tc
 		out.append(row)
 	return {"step_ms_under_events": total, "min_share_listed": 0.0,
 		"note": "timing pass with an event before every launch; shares, not absolute times, carry over to the timed region; "
-			"slicer_segments reads every sign word three times (32768 + 16384 samples of warm-up per 24576-sample segment) and is "
-			"bound by its dependent FP64/ALU instruction chain (profiles/: issue slots, not bytes); fp64 peak nominal 37.2 TFLOP/s",
+			"slicer_segments: achieved = exact float64 steps executed (segment + 4096-sample exact warm-up tail per segment) against "
+			"the step rate of tools/ubench/slicer_step.cu (profiles/r02af_slicer_step.txt); the crossing-by-crossing warm-up before "
+			"the tail (45056 samples per segment, 0.37 of the kernel's 1.08 ms) is not counted as work; fp64 peak nominal 37.2 TFLOP/s",
 		"kernels": out}
 
 

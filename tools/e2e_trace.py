@@ -11,7 +11,7 @@ lines = configs.demod_chains(configs.afsk_1200_ax25_super_opt())
 a = synth.afsk1200_ax25(duration_s=seconds, sample_rate=48000, frame_interval_s=3.1, noise_start=0.0, noise_end=1.6, seed=1000, noise_seed=1001)[0]
 audio = pinned_empty(len(a)); audio[:] = a
 stack = [chain_builder.build_chain(48000, l) for l in lines]
-for opts in [dict(early_tail=0), dict(early_tail=1), dict(early_tail=1, early_batches=6), dict(early_tail=1, early_batches=3)]:
+for opts in [dict(early_tail=0), dict(early_tail=1), dict(early_tail=2, early_batches=12), dict(early_tail=2, early_batches=3)]:
 	eng = Engine(stack, trace=1, **opts)
 	for i in range(4):
 		t0 = time.perf_counter()
