@@ -172,8 +172,10 @@ int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_c
 
 /* Tunables (results do not depend on any of them; they trade time against the amount of float64 re-evaluation):
  * "segment_len", "warmup_len", "checkpoint_len" (samples, multiples of 32; slicer geometry, defaults 24576 / 49152 / 1024),
- * "warmup_exact_len" (samples of float64 tail of every slicer warm-up; the part before it runs in FP32 -- a warm-up
- *   only has to get near the true state; 0 = all float64), "verify_passes", "slicer_fast" (0: always the plain clock update),
+ * "warmup_exact_len" (samples of exact, sample-by-sample tail of every slicer warm-up, default 4096; the part before it
+ *   runs crossing by crossing in closed form -- a warm-up only has to get near the true state; 0 = all exact),
+ *   "warmup_far_f64" (1, default: that part in float64; 0: in FP32, which needs an exact tail of 16384 samples),
+ *   "verify_passes", "slicer_fast" (0: always the plain clock update),
  * "guard_eps" (relative width of the FP32 front end's sign guard band, default 2^-18; samples inside it are
  *   re-evaluated in float64), "guard_abs" (the guard's raw-input term: multiples, default 0.25, of 2^-24 max|audio of the tile|
  *   sum|h_bpf| N_corr sum|h_lpf| (1 + space_gain) added to the band -- the band-pass rounds at the magnitude of the RAW
@@ -183,6 +185,9 @@ int pm_engine_load_chains(pm_engine *e, const pm_chain_desc *chains, int32_t n_c
  *   pipe, fused into the front kernel, even where the tensor-core route applies), "tile" (front-end outputs
  *   per CTA, 0 = cost model), "keep_soft" (1: keep the soft values for pm_engine_get_soft), "h2d_chunk" (samples per
  *   host-to-device copy of pm_engine_run), "copy_threads" (host threads that stage pageable input, default 4), "stage_clocks" (1: trace the front end's stages, pm_engine_stage_clocks),
+ * "early_tail" (host-buffer runs; 1, default: the float64 guard fix-up runs chunk by chunk beside the copy; 2: batches of
+ *   slicer segments too -- measured slower; 0: both after the last chunk), "early_batches" (about how many batches, default 12),
+ *   "trace" (1: timing events at the steps of a host-buffer run, pm_engine_trace), "kernel_times" (1: pm_engine_kernel_times),
  * "precise" (1: every AFSK chain takes the float64 pipeline; default: only chains whose tone pair is so
  *   close that |mark| - |space| cancels below FP32 resolution; set before pm_engine_load_chains). */
 int pm_engine_set_option(pm_engine *e, const char *key, double value);
