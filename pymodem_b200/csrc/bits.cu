@@ -161,7 +161,30 @@ gather_write_kernel(const BitChain *__restrict__ chains, const uint32_t *__restr
 	for (unsigned int i = threadIdx.x; i < stage_words; i += GB_THREADS) s_stage[i] = 0;
 	__syncthreads();
 
-	if (cnt) {
+	if (!C.quadrature && C.bps == 1) {
+		// binary slicer (uniform per block): one stream bit per symbol, everything in 32-bit arithmetic relative to the
+		// block's first symbol -- stream bit of block-local symbol k = bit_block + k
+		if (cnt) {
+			unsigned int k = ex;                                         // block-local index of this thread's next symbol
+			const unsigned int gl = (unsigned int)(bit_block & 7);        // where block-local symbol 0 sits in its stream byte
+			uint32_t *oa = oaddr + (bit_block >> 3);
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				uint32_t mm = m[q];
+				const uint32_t s = sv[q];
+				const uint32_t a0 = (uint32_t)((w0 + q) << 5) + 1u;        // 1-based address of the word's first sample (slicer.py:75)
+				while (mm) {
+					const int i = __ffs(mm) - 1;
+					mm &= mm - 1;
+					const unsigned int sp = k + stage_shift;
+					if ((s >> i) & 1u) atomicOr(&s_stage[sp >> 5], 1u << (sp & 31));
+					const unsigned int gb = k + gl;
+					if ((gb & 7u) == 7u) oa[gb >> 3] = a0 + i;
+					k++;
+				}
+			}
+		}
+	} else if (cnt) {
 		// quadrature: IQ signs of the symbol before this thread's first one
 		unsigned int prev_cur = 0;
 		if (C.quadrature && C.state_mask > 3u) {
@@ -789,25 +812,37 @@ packet_index_kernel(const ChainCounters *__restrict__ cc, int n_chains,
 	unsigned long long n_rec = s_base[0], n_bytes = s_base[1];
 	const int n = cc[ch].nflags;
 	const GapRec *g = gaps + (long long)ch * gap_stride;
-	for (int base = 0; base < n; base += 1024) {
-		const int j = base + threadIdx.x;
-		GapRec r;
-		r.emit = 0; r.len = 0; r.scratch_off = 0; r.addr = 0; r.corrected = 0;
-		if (j < n) r = g[j];
+	// four consecutive gaps per thread and round: a chain of noise has ~10^5 gaps and a round costs two block scans
+	for (int base = 0; base < n; base += 4096) {
+		const int j0 = base + 4 * threadIdx.x;
+		GapRec r[4];
+		unsigned int e_sum = 0, b_sum = 0;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			r[q].emit = 0; r[q].len = 0; r[q].scratch_off = 0; r[q].addr = 0; r[q].corrected = 0;
+			if (j0 + q < n) r[q] = g[j0 + q];
+			e_sum += r[q].emit ? 1u : 0u;
+			b_sum += r[q].emit ? r[q].len : 0u;
+		}
 		unsigned int tot_e, tot_b;
-		const unsigned int ex_e = block_excl_scan(r.emit, s_warp, tot_e);
-		const unsigned int ex_b = block_excl_scan(r.emit ? r.len : 0u, s_warp, tot_b);
-		if (r.emit) {
-			const unsigned long long ri = n_rec + ex_e;
-			if (ri < rec_cap) {
-				PacketRecDev p;
-				p.chain = ch; p.len = r.len; p.offset = n_bytes + ex_b;
-				p.streamaddress = sample_base + (long long)r.addr;
-				p.bytes_corrected = r.corrected; p.calculated_crc = 0; p.carried_crc = 0;
-				p.valid_crc = 0; p.valid_header = 0;
-				for (int q = 0; q < 6; q++) p.pad[q] = 0;
-				recs[ri] = p;
-				rec_src[ri] = r.scratch_off;
+		unsigned int ex_e = block_excl_scan(e_sum, s_warp, tot_e);
+		unsigned int ex_b = block_excl_scan(b_sum, s_warp, tot_b);
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if (r[q].emit) {
+				const unsigned long long ri = n_rec + ex_e;
+				if (ri < rec_cap) {
+					PacketRecDev p;
+					p.chain = ch; p.len = r[q].len; p.offset = n_bytes + ex_b;
+					p.streamaddress = sample_base + (long long)r[q].addr;
+					p.bytes_corrected = r[q].corrected; p.calculated_crc = 0; p.carried_crc = 0;
+					p.valid_crc = 0; p.valid_header = 0;
+					for (int t = 0; t < 6; t++) p.pad[t] = 0;
+					recs[ri] = p;
+					rec_src[ri] = r[q].scratch_off;
+				}
+				ex_e += 1u;
+				ex_b += r[q].len;
 			}
 		}
 		n_rec += tot_e;

@@ -41,7 +41,8 @@ __device__ __forceinline__ bool seg_state_equal(const SegState &a, const SegStat
 // lock_rate is zero (40 or 36.75 samples per symbol, lock_rate 0.75 ...): one 32-bit select of the high word makes
 // the operand instead of two.  The roll-over mask is collected from the SIGN of the addend (negative <=> roll) with
 // one funnel shift per sample, most recent sample in bit 0: the caller bit-reverses the finished word.
-template <bool WRITE, bool FAST, bool A0, bool F0>
+// QUIET: a step of a word without zero crossings (the multiply by 1.0 left out).
+template <bool WRITE, bool FAST, bool A0, bool F0, bool QUIET = false>
 __device__ __forceinline__ void slicer_step(double &c, uint32_t &m, uint32_t z, uint32_t bit, const SlicerChain &C,
                                             double cs, double a_roll, double a_keep)
 {
@@ -59,16 +60,24 @@ __device__ __forceinline__ void slicer_step(double &c, uint32_t &m, uint32_t z, 
 	const double add = A0 ? __hiloint2double(roll ? __double2hiint(a_roll) : __double2hiint(a_keep), 0)
 	                      : (roll ? a_roll : a_keep);
 	const double t = __dadd_rn(base, add);
-	const bool cross = (z & bit) != 0;                   // slicer.py:99-104
-	const double f = F0 ? __hiloint2double(cross ? __double2hiint(C.lock) : 0x3FF00000, 0) : (cross ? C.lock : 1.0);
-	c = __dmul_rn(t, f);
+	if (QUIET) {
+		c = t;                                           // no crossing in this word: t * 1.0 == t, bit for bit
+	} else {
+		const bool cross = (z & bit) != 0;               // slicer.py:99-104
+		const double f = F0 ? __hiloint2double(cross ? __double2hiint(C.lock) : 0x3FF00000, 0) : (cross ? C.lock : 1.0);
+		c = __dmul_rn(t, f);
+	}
 	if (WRITE) m = __funnelshift_l((uint32_t)__double2hiint(add), m, 1);
 }
 
 // Advance the slicer over samples [w0*32, min(w1*32, nout)) of one chain.
 // The sign word of the next iteration is requested before the 32 dependent steps of this one (the loads were 1.2
 // stall cycles per issue, ncu r02k).
-template <bool WRITE, bool FAST, bool A0, bool F0>
+// SPARSE: the caller runs with few threads of a warp active (verify / sweep: a repair is one thread re-running up to a
+// whole segment, and the repairs that do not merge early sit in stretches WITHOUT zero crossings): words without a
+// crossing take steps without the lock multiply, a quarter off the dependent chain.  Not for the segments kernel, where
+// all lanes are active and would run both forms.
+template <bool WRITE, bool FAST, bool A0, bool F0, bool SPARSE>
 __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                             const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
                                             long long w0, long long w1, SegState &st)
@@ -99,8 +108,13 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 		const long long remain = C.nout - first;
 		const int cnt = remain >= 32 ? 32 : (int)remain;
 		if (cnt == 32) {
+			if (SPARSE && z == 0u) {
 #pragma unroll
-			for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+				for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0, true>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+			} else {
+#pragma unroll
+				for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+			}
 			if (WRITE) m = __brev(m);
 		} else {
 			for (int i = 0; i < cnt; i++) {
@@ -189,7 +203,7 @@ __device__ __forceinline__ void run_words_far(const SlicerChain &C, const uint32
 	}
 }
 
-template <bool WRITE>
+template <bool WRITE, bool SPARSE = false>
 __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                           const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
                                           long long w0, long long w1, SegState &st)
@@ -198,15 +212,15 @@ __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *
 	const bool a0 = __double2loint(C.fast ? C.sps_m1 : C.sps) == 0, f0 = __double2loint(C.lock) == 0;
 	if (C.fast) {
 		if (a0) {
-			if (f0) run_words_t<WRITE, true, true, true>(C, sg, sgq, mk, w0, w1, st);
-			else run_words_t<WRITE, true, true, false>(C, sg, sgq, mk, w0, w1, st);
+			if (f0) run_words_t<WRITE, true, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+			else run_words_t<WRITE, true, true, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
 		} else {
-			if (f0) run_words_t<WRITE, true, false, true>(C, sg, sgq, mk, w0, w1, st);
-			else run_words_t<WRITE, true, false, false>(C, sg, sgq, mk, w0, w1, st);
+			if (f0) run_words_t<WRITE, true, false, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+			else run_words_t<WRITE, true, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
 		}
 	} else {
-		if (a0 && f0) run_words_t<WRITE, false, true, true>(C, sg, sgq, mk, w0, w1, st);
-		else run_words_t<WRITE, false, false, false>(C, sg, sgq, mk, w0, w1, st);
+		if (a0 && f0) run_words_t<WRITE, false, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+		else run_words_t<WRITE, false, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
 	}
 }
 
@@ -300,7 +314,7 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
 	SegState *ck = chk + idx * G.n_chk;
 	for (int j = 0; j < G.n_chk; j++) {
 		const long long a = w_begin + (long long)j * G.chk_words;
-		run_words<true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+		run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st);
 		if (seg_state_equal(ck[j], st)) {          // merged with the first run: the rest is already right
 			E_out[idx] = E_in[idx];
 			return;
@@ -341,7 +355,7 @@ __global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, cons
 				bool merged = false;
 				for (int j = 0; j < G.n_chk && !merged; j++) {
 					const long long a = w_begin + (long long)j * G.chk_words;
-					run_words<true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+					run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st);
 					if (seg_state_equal(ck[j], st)) merged = true; else ck[j] = st;
 				}
 				if (!merged) E[idx] = st;
