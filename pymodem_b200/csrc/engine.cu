@@ -76,7 +76,10 @@ cudaError_t pm_link_preload(void);
 cudaError_t pm_link_push_states(LinkGeom, LinkPeers, int, unsigned int, const SegState *, const SegState *, int, int,
 	const unsigned long long *, const unsigned int *, int, unsigned int, cudaStream_t);
 cudaError_t pm_link_wait_states(LinkGeom, unsigned char *, int, unsigned int, const BitChain *, int, int, int, ShardBits *,
-	int *, cudaStream_t);
+	int *, long long *, cudaStream_t);
+cudaError_t pm_link_il2p_in(LinkGeom, unsigned char *, int, unsigned int, int, const BitChain *, const ShardBits *, const long long *,
+	Il2pHand *, ChainCounters *, int *, cudaStream_t);
+cudaError_t pm_link_il2p_out(LinkGeom, LinkPeers, int, unsigned int, const Il2pHand *, const long long *, cudaStream_t);
 cudaError_t pm_link_set_flag(unsigned int *, unsigned int, cudaStream_t);
 cudaError_t pm_link_wait_flag(const unsigned int *, unsigned int, int *, cudaStream_t);
 cudaError_t pm_link_push_records(LinkGeom, LinkPeers, int, unsigned int, const PacketRecDev *, const uint8_t *,
@@ -270,6 +273,7 @@ struct pm_engine {
 	unsigned int link_epoch = 0;
 	int link_tail_bits = 0;
 	DevBuf<int> d_link_status;
+	DevBuf<long long> d_link_A0;          // global index of local stream bit 0, per chain (written by the link's wait kernel)
 	DevBuf<unsigned int> d_link_lb;
 	DevBuf<unsigned long long> d_link_obase;
 	DevBuf<pm_packet_rec> d_mrecs;
@@ -814,7 +818,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	for (auto &ev : e->ev_chunks) cudaEventDestroy(ev);
 	for (auto &ev : e->ev_trace) cudaEventDestroy(ev);
 	for (void *p : e->link_opened) cudaIpcCloseMemHandle(p);
-	e->d_link.release(); e->d_link_status.release(); e->d_link_lb.release(); e->d_link_obase.release();
+	e->d_link.release(); e->d_link_status.release(); e->d_link_A0.release(); e->d_link_lb.release(); e->d_link_obase.release();
 	e->d_mrecs.release(); e->d_marena.release(); e->d_mtotals.release();
 	if (e->h_link_status) cudaFreeHost(e->h_link_status);
 	if (e->h_mtotals) cudaFreeHost(e->h_mtotals);
@@ -2378,12 +2382,13 @@ extern "C" int pm_engine_link_create(pm_engine *e, int32_t rank, int32_t world, 
 	// worst-case records + packet bytes of one rank (the bounds prepare_run uses)
 	long long rec_cap = 16, arena_cap = 64;
 	for (auto &hc : e->chains) {
-		if (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK) || hc.d.codec_kind != PM_CODEC_AX25)
-			return fail(e, PM_ERR_UNSUPPORTED, "only binary-slicer AX.25 chains without a carrier loop can be sharded");
+		if (hc.d.slicer_kind != PM_SLICER_BINARY || (hc.p64 && hc.d.modem_kind != PM_MODEM_AFSK) ||
+		    (hc.d.codec_kind != PM_CODEC_AX25 && hc.d.codec_kind != PM_CODEC_IL2P))
+			return fail(e, PM_ERR_UNSUPPORTED, "only binary-slicer AX.25 / IL2P chains without a carrier loop can be sharded");
 		const double thr = hc.d.slicer_sample_rate / hc.d.symbol_rate / 2.0 - 0.5;
 		const long long min_gap = std::max<long long>(1, (long long)std::ceil(thr));
 		const long long mb = (max_samples / min_gap + 8) + 64 + tail_bits;
-		rec_cap += mb / 152 + 4;
+		rec_cap += mb / (hc.d.codec_kind == PM_CODEC_IL2P ? 144 : 152) + 4;
 		arena_cap += mb / 8 + 64;
 	}
 	LinkGeom &G = e->lg;
@@ -2397,11 +2402,14 @@ extern "C" int pm_engine_link_create(pm_engine *e, int32_t rank, int32_t world, 
 	G.off_tflag = off; off += 256;
 	G.off_rflag = off; off = align_up(off + 4ll * world, 256);
 	G.off_rhdr = off; off = align_up(off + 16ll * world, 256);
+	G.off_il2p = off; off = align_up(off + (long long)nc * sizeof(pm_il2p_state), 256);
+	G.off_iflag = off; off += 256;
 	G.off_rdata = off; off += (long long)world * G.rec_region;
 	G.slot_bytes = align_up(off, 4096);
 	CK(e->d_link.ensure((size_t)(2 * G.slot_bytes)));
 	CK(cudaMemset(e->d_link.p, 0, (size_t)(2 * G.slot_bytes)));
 	CK(e->d_link_status.ensure(8));
+	CK(e->d_link_A0.ensure((size_t)nc));
 	CK(e->d_link_lb.ensure((size_t)world * (nc + 1)));
 	CK(e->d_link_obase.ensure((size_t)world * (nc + 1) + world));
 	CK(e->d_mrecs.ensure((size_t)(rec_cap * world)));
@@ -2475,7 +2483,7 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_link_push_states(G, e->lp, parity, epoch, e->d_S.p + e->k0, e->E_cur, e->geom.n_seg, e->k_end, e->d_symcount.p,
 		e->d_counters.p, e->fast_passes, e->guard_cap, st));
 	CKL(pm_link_wait_states(G, own, parity, epoch, e->d_bitchain.p, plan->first, plan->last, plan->tail_bits,
-		e->d_shardbits.p, status, st));
+		e->d_shardbits.p, status, e->d_link_A0.p, st));
 	e->up_sb.clear();                       // the placement was written on the device
 	CKL(pm_launch_gather(e->d_bitchain.p, nc, e->d_cc.p, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride, e->own_w0,
 		std::max<long long>(1, e->end_w - e->own_w0), e->d_blk_count.p, e->d_blk_base.p, e->d_sym_totals.p, e->d_bits_raw.p,
@@ -2499,6 +2507,19 @@ extern "C" int pm_engine_run_linked_begin(pm_engine *e, const int16_t *audio, in
 	CKL(pm_launch_ax25(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_blk_count.p, e->d_blk_base.p,
 		e->d_flag_totals.p, e->d_flag_pos.p, e->flag_stride, e->d_byte_addr.p, e->addr_stride, e->d_scratch.p,
 		e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, 0, e->d_gap_cand.p, e->d_gap_ncand.p, st));
+	if (e->has_il2p) {
+		// the IL2P walk crosses the boundary rank after rank: wait for where the previous rank's walk stands, decode,
+		// tell the next rank (csrc/link.cu) -- no host in between
+		CKL(pm_link_il2p_in(G, own, parity, epoch, plan->first, e->d_bitchain.p, e->d_shardbits.p, e->d_link_A0.p,
+			e->d_il2p_hand.p, e->d_cc.p, status, st));
+		CKL(pm_launch_il2p(e->d_bitchain.p, nc, e->d_cc.p, e->d_bits_lfsr.p, e->bits_stride, e->d_flag_pos.p,
+			e->flag_stride, e->d_flag_totals.p, e->il2p_cand_cap, e->d_il2p_slots.p,
+			(long long)(e->il2p_cand_cap + 1) * IL2P_SLOT, e->d_il2p_res.p, e->d_byte_addr.p, e->addr_stride,
+			e->d_scratch.p, e->scratch_stride, e->d_gaps.p, e->flag_stride, e->d_shardbits.p, e->d_il2p_hand.p,
+			e->d_il2p_hand.p + nc, st));
+		if (!plan->last) CKL(pm_link_il2p_out(G, e->lp, parity, epoch, e->d_il2p_hand.p + nc, e->d_link_A0.p, st));
+		e->stats.kernel_launches += plan->last ? 3 : 4;
+	}
 	CKL(pm_launch_packets(nc, e->d_cc.p, e->d_gaps.p, e->flag_stride, e->d_recs.p, e->d_rec_src.p, e->d_recs.n,
 		e->d_totals.p, e->d_scratch.p, e->scratch_stride, e->d_arena.p, e->d_arena.n, e->sample_base, st));
 	CK(cudaEventRecord(e->ev[4], st));

@@ -95,7 +95,7 @@ link_push_states_kernel(LinkGeom G, LinkPeers peers, int parity, unsigned int ep
 __global__ void __launch_bounds__(256)
 link_wait_states_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int epoch,
                         const BitChain *__restrict__ chains, int first, int last, int tail_bits,
-                        ShardBits *__restrict__ sb, int *__restrict__ status)
+                        ShardBits *__restrict__ sb, int *__restrict__ status, long long *__restrict__ A0_out)
 {
 	__shared__ int s_ok, s_bad, s_err;
 	unsigned char *slot = slot_of(own, G, parity);
@@ -111,6 +111,7 @@ link_wait_states_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int
 			ShardBits b;
 			b.bit_off = 0; b.own_lo = 0; b.own_hi = 0; b.valid_from = 0; b.first = 1; b.pad = 0;
 			sb[c] = b;
+			A0_out[c] = 0;
 		}
 		if (threadIdx.x == 0) { status[0] = 0; status[1] = PM_ERR_STATE; status[2] = 1; }
 		return;
@@ -137,10 +138,11 @@ link_wait_states_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int
 		if (n_own < 0) n_own = 0;
 		ShardBits b;
 		b.first = first; b.pad = 0; b.valid_from = 0;
-		if (first) { b.bit_off = 0; b.own_lo = 0; }
+		if (first) { b.bit_off = 0; b.own_lo = 0; A0_out[c] = 0; }
 		else {
 			if (P < tail_bits && !s_bad) atomicExch(&s_err, 1);
 			const long long A0 = ((P - tail_bits) >> 3) << 3;          // global bit index of local bit 0
+			A0_out[c] = A0;
 			b.bit_off = P - A0;
 			b.own_lo = b.bit_off;
 			int deg = 0;
@@ -173,6 +175,68 @@ __global__ void link_wait_flag_kernel(const unsigned int *flag, unsigned int epo
 {
 	if (!link_spin(flag, epoch)) { status[1] = PM_ERR_STATE; status[2] = 2; }
 	__threadfence_system();
+}
+
+// ---- IL2P decoder state ---------------------------------------------------------------------------------
+// The IL2P walk of a chain (il2p.cu: sync search, frame by frame) crosses the shard boundary with three numbers: where
+// the search resumes (a GLOBAL stream bit), in which mode, and the corrected-byte count of failed frames not yet
+// attributed (il2p.py:200-211).  Rank r - 1 stores them into rank r's slot when its own walk is done; rank r waits,
+// rebases the position onto its local stream (A0 = global index of its local bit 0) and checks that everything the
+// walk will look at lies in the hand-off tail -- the same test the host protocol makes (engine.cu shard_finish_impl);
+// a frame that reaches back further marks the chain (tail_short) and the run recovers from the gathered bitstream.
+// The walks of the ranks are serial by nature; what the link removes is the host round trip between them.
+__global__ void link_il2p_in_kernel(LinkGeom G, unsigned char *own, int parity, unsigned int epoch, int first,
+                                    const BitChain *__restrict__ chains, const ShardBits *__restrict__ sb,
+                                    const long long *__restrict__ A0, Il2pHand *__restrict__ hand,
+                                    ChainCounters *__restrict__ cc, int *__restrict__ status)
+{
+	__shared__ int s_ok;
+	unsigned char *slot = slot_of(own, G, parity);
+	if (threadIdx.x == 0) {
+		s_ok = 1;
+		if (!first && !link_spin(reinterpret_cast<const unsigned int *>(slot + G.off_iflag), epoch)) {
+			s_ok = 0;
+			status[1] = PM_ERR_STATE; status[2] = 2;
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+	const pm_il2p_state *prev = reinterpret_cast<const pm_il2p_state *>(slot + G.off_il2p);
+	for (int c = threadIdx.x; c < G.nc; c += blockDim.x) {
+		Il2pHand h;
+		h.pos = 0; h.mode = 0; h.leak = 0;
+		if (!first && chains[c].codec == PM_CODEC_IL2P) {
+			if (s_ok) {
+				h.pos = prev[c].pos - A0[c];
+				h.mode = prev[c].mode;
+				h.leak = prev[c].leak;
+			}
+			const long long need = h.mode == 1 ? h.pos - 8 : h.pos - 63;
+			if (!s_ok || h.mode > 2 || h.mode == 0 || need < sb[c].valid_from) {
+				// the walk would restart outside what this shard holds: plain search from the first own bit, and say so
+				h.pos = sb[c].own_lo; h.mode = 2; h.leak = 0;
+				cc[c].tail_short = 1;
+			}
+		}
+		hand[c] = h;
+	}
+}
+
+__global__ void link_il2p_out_kernel(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch,
+                                     const Il2pHand *__restrict__ hand_out, const long long *__restrict__ A0)
+{
+	unsigned char *slot = slot_of(peers.base[G.rank + 1], G, parity);
+	pm_il2p_state *dst = reinterpret_cast<pm_il2p_state *>(slot + G.off_il2p);
+	for (int c = threadIdx.x; c < G.nc; c += blockDim.x) {
+		pm_il2p_state o;
+		o.pos = hand_out[c].pos + A0[c];
+		o.mode = hand_out[c].mode;
+		o.leak = hand_out[c].leak;
+		dst[c] = o;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) st_flag(reinterpret_cast<unsigned int *>(slot + G.off_iflag), epoch);
 }
 
 // ---- 2. records -----------------------------------------------------------------------------------------
@@ -321,6 +385,8 @@ cudaError_t pm_link_preload(void)
 	if ((e = cudaFuncGetAttributes(&a, link_push_records_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_check_decode_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_publish_records_kernel)) != cudaSuccess) return e;
+	if ((e = cudaFuncGetAttributes(&a, link_il2p_in_kernel)) != cudaSuccess) return e;
+	if ((e = cudaFuncGetAttributes(&a, link_il2p_out_kernel)) != cudaSuccess) return e;
 	if ((e = cudaFuncGetAttributes(&a, link_merge_plan_kernel)) != cudaSuccess) return e;
 	return cudaFuncGetAttributes(&a, link_merge_write_kernel);
 }
@@ -336,10 +402,26 @@ cudaError_t pm_link_push_states(LinkGeom G, LinkPeers peers, int parity, unsigne
 }
 
 cudaError_t pm_link_wait_states(LinkGeom G, unsigned char *own, int parity, unsigned int epoch, const BitChain *chains,
-	int first, int last, int tail_bits, ShardBits *sb, int *status, cudaStream_t st)
+	int first, int last, int tail_bits, ShardBits *sb, int *status, long long *A0_out, cudaStream_t st)
 {
 	pm_kt_mark("link_wait_states_kernel", st);
-	link_wait_states_kernel<<<1, 256, 0, st>>>(G, own, parity, epoch, chains, first, last, tail_bits, sb, status);
+	link_wait_states_kernel<<<1, 256, 0, st>>>(G, own, parity, epoch, chains, first, last, tail_bits, sb, status, A0_out);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_link_il2p_in(LinkGeom G, unsigned char *own, int parity, unsigned int epoch, int first, const BitChain *chains,
+	const ShardBits *sb, const long long *A0, Il2pHand *hand, ChainCounters *cc, int *status, cudaStream_t st)
+{
+	pm_kt_mark("link_il2p_in_kernel", st);
+	link_il2p_in_kernel<<<1, 128, 0, st>>>(G, own, parity, epoch, first, chains, sb, A0, hand, cc, status);
+	return cudaGetLastError();
+}
+
+cudaError_t pm_link_il2p_out(LinkGeom G, LinkPeers peers, int parity, unsigned int epoch, const Il2pHand *hand_out,
+	const long long *A0, cudaStream_t st)
+{
+	pm_kt_mark("link_il2p_out_kernel", st);
+	link_il2p_out_kernel<<<1, 128, 0, st>>>(G, peers, parity, epoch, hand_out, A0);
 	return cudaGetLastError();
 }
 

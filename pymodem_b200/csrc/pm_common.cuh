@@ -292,6 +292,8 @@ struct LinkGeom {
 	long long off_rhdr;        // u64[world][2]: records, arena bytes
 	long long off_rdata;       // world regions of rec_region bytes: records then arena
 	long long rec_region;
+	long long off_il2p;        // pm_il2p_state[nc]: where the previous rank's IL2P walk stands (written by rank - 1)
+	long long off_iflag;       // unsigned
 };
 struct LinkPeers {
 	unsigned char *base[LINK_MAX_WORLD];

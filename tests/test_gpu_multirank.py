@@ -26,11 +26,19 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = {}
-for case, kw in (("noise_ramp", dict(duration_s=240.0, frame_interval_s=1.7, noise_start=0.0, noise_end=1.5, seed=81, noise_seed=82)),
-		("long_frames", dict(duration_s=120.0, frame_interval_s=9.0, noise_start=0.0, noise_end=0.3, seed=83, noise_seed=84,
-			payload_len=[1100, 60, 1300, 40, 1500]))):
-	audio = synth.afsk1200_ax25(sample_rate=48000, **kw)[0]
-	stack = [chain_builder.build_chain(48000, l) for l in configs.demod_chains(configs.afsk_1200_ax25_super_opt())]
+superopt = configs.demod_chains(configs.afsk_1200_ax25_super_opt())
+sys.path.insert(0, os.path.join(%(repo)r, "tests"))
+from util import Golden
+mixed = Golden("afsk1200_il2p_48k").chain_lines()      # afsk_1200.json as shipped: two AX.25 and two IL2P chains
+cases = [("noise_ramp", superopt, synth.afsk1200_ax25(sample_rate=48000, duration_s=240.0, frame_interval_s=1.7, noise_start=0.0,
+		noise_end=1.5, seed=81, noise_seed=82)[0]),
+	("long_frames", superopt, synth.afsk1200_ax25(sample_rate=48000, duration_s=120.0, frame_interval_s=9.0, noise_start=0.0,
+		noise_end=0.3, seed=83, noise_seed=84, payload_len=[1100, 60, 1300, 40, 1500])[0]),
+	# the IL2P decoder state crosses the rank boundaries inside the link buffer (csrc/link.cu link_il2p_*)
+	("il2p_mixed", mixed, synth.afsk1200_il2p(sample_rate=48000, duration_s=120.0, frame_interval_s=0.8, noise_start=0.1,
+		noise_end=1.0, seed=85, noise_seed=86, first_frame_s=0.3, payload_len=[None, 300, 10, 0, 240, 60])[0])]
+for case, lines, audio in cases:
+	stack = [chain_builder.build_chain(48000, l) for l in lines]
 	plans = plan_shards(len(audio), world, trim_max=305, samples_per_symbol=40.0)
 	plan = plans[rank]
 	local_audio = np.ascontiguousarray(audio[plan['audio_begin']:plan['audio_end']])
@@ -81,3 +89,5 @@ def test_torchrun_ranks_equal_unsharded(cuda_lib, tmp_path, world):
 	# bitstream recovery (recoveries), or through the host-driven protocol when the quiet stretches between the frames
 	# also left the slicer passes unsettled (fallbacks), which then recovers the same way
 	assert all(r[2] + r[3] == 2 for r in res["long_frames"]["ranks"]), res["long_frames"]
+	# the mixed AX.25 / IL2P config decodes through the link itself: no fall-back to the host protocol, no recovery
+	assert all(r[2] + r[3] == 0 for r in res["il2p_mixed"]["ranks"]), res["il2p_mixed"]

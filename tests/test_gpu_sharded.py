@@ -198,3 +198,41 @@ def test_sharded_il2p_noisy_many_boundaries(cuda_lib, oracle):
 	for world in (2, 3, 5, 6):
 		got, info = run_sharded_local(stack, audio, world, tail_bits=12288, segment_len=4096, warmup_len=8192)
 		assert as_tuples(got) == want, f"world {world}"
+
+
+# ---- IL2P chains over the shard link: the decoder state travels from GPU to GPU (csrc/link.cu link_il2p_*) ------
+@pytest.mark.parametrize("tag,world,tail", [("afsk1200_il2p_48k", 2, 4096), ("afsk1200_il2p_48k", 3, 4096),
+	("fsk9600_il2p_48k", 2, 4096), ("fsk9600_il2p_48k", 4, 4096), ("afsk1200_il2p_48k", 1, 4096)])
+def test_linked_il2p_equals_reference(cuda_lib, tag, world, tail):
+	"""Mixed AX.25 / IL2P configs through run_linked_begin: where the previous rank's IL2P walk stands arrives through
+	the link buffer, not through the host.  Every rank ends with the fixture's packet set (either straight from the
+	link, or -- a frame longer than the tail -- from the gathered bitstream)."""
+	from pymodem_b200.sharded import run_linked_local
+	g = Golden(tag)
+	got, info = run_linked_local(build_stack(g.sample_rate, g.lines), g.audio(), world, tail_bits=tail,
+		segment_len=4096, warmup_len=16384)
+	assert as_tuples(got) == g.all_packets()
+	if all(v == 1 for v in info['verified']):
+		assert info['all_ranks_equal']
+
+
+def test_linked_il2p_noisy_many_boundaries(cuda_lib, oracle):
+	"""The noisy many-frame recording of test_sharded_il2p_noisy_many_boundaries through the link: leaked corrected-byte
+	counts, frames straddling boundaries and false syncs ending right before them all cross inside the link buffer."""
+	import json
+	from pymodem_b200 import synth
+	from pymodem_b200.sharded import run_linked_local
+	audio = synth.fsk9600_il2p(duration_s=12.0, sample_rate=48000, frame_interval_s=0.1, noise_start=0.4, noise_end=1.0,
+		seed=91, noise_seed=92, first_frame_s=0.02, payload_len=[None, 500, 3, 0, 239, 240, 1023])[0]
+	lines = [json.loads(json.dumps(l)) for l in Golden("fsk9600_il2p_48k").chain_lines()]
+	for l in lines:
+		if l["codec"]["type"] == "il2p":
+			l["codec"]["options"]["sync_tol"] = "3"
+	want = oracle.run_config(48000, lines, audio)
+	stack = build_stack(48000, lines)
+	straight = 0
+	for world in (2, 3, 5):
+		got, info = run_linked_local(stack, audio, world, tail_bits=12288, segment_len=4096, warmup_len=16384)
+		assert as_tuples(got) == want, f"world {world}"
+		straight += all(v == 1 for v in info['verified'])
+	assert straight >= 1          # at least one split decodes through the link itself, without recovery or fall-back
