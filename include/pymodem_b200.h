@@ -286,7 +286,8 @@ typedef struct pm_il2p_state {      /* one per chain (ignored for AX.25 chains) 
 int pm_engine_shard_finish_il2p(pm_engine *e, const uint32_t *tail_in, const pm_il2p_state *prev, pm_il2p_state *out);
 
 /*
- * Shard link: the same hand-off carried out by the GPUs themselves over NVLink peer memory (csrc/link.cu).
+ * Shard link: the same hand-off carried out by the GPUs themselves over NVLink peer memory (csrc/link.cu); IL2P chains
+ * included: the pm_il2p_state of the previous rank arrives through the link buffer instead of pm_engine_shard_finish_il2p.
  * Every rank creates a link buffer, the ranks exchange the 64-byte CUDA IPC handles once (any transport) and
  * map each other's buffers.  run_linked_begin then enqueues the whole sharded run -- front end, slicer, state
  * push, bit placement, tail push/wait, decode, record push, merge -- on the engine's stream with no host round
