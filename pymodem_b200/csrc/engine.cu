@@ -55,7 +55,7 @@ cudaError_t pm_launch_slicer_segments(const SlicerChain *, int, const uint32_t *
 	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, cudaStream_t);
 cudaError_t pm_launch_slicer_verify(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
 	SegState *, const SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *,
-	const unsigned int *, cudaStream_t);
+	const unsigned int *, unsigned int *, cudaStream_t);
 cudaError_t pm_launch_slicer_sweep(const SlicerChain *, int, const uint32_t *, long long, uint32_t *, long long,
 	SegState *, SegState *, SegState *, const SegState *, SlicerGeom, unsigned int *, cudaStream_t);
 cudaError_t pm_launch_slicer_count(const SlicerChain *, int, const uint32_t *, long long, long long, long long,
@@ -182,6 +182,7 @@ struct pm_engine {
 	cudaStream_t st_tail[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev_tail[3] = {nullptr, nullptr, nullptr};
 	std::vector<cudaEvent_t> ev_steps;               // front end of a chunk done / its fix-up done
+	DevBuf<unsigned int> d_repair_list;              // segments a verify pass found to re-run (slicer_repair_kernel)
 	DevBuf<unsigned int> d_snap;                     // guard count after the front-end launches of chunk i: d_snap[i + 1]
 	int opt_early_tail = 1;                          // host-buffer runs: 1 guard fix-up chunk by chunk beside the copy, 2 slicer segments too, 0 neither
 	int opt_trace = 0;                               // option "trace": timing events at the steps of a host-buffer run (pm_engine_trace)
@@ -199,6 +200,7 @@ struct pm_engine {
 	int opt_chk_words = 32;       // checkpoint every 1024 samples
 	int opt_verify_passes = 6;    // parallel verify passes before the sequential sweep
 	int opt_warm_exact_words = 128; // exact sample-by-sample tail of a warm-up (4096 samples; 16384 before the float64 far part); the part before it runs crossing by crossing (0: all exact)
+	int opt_quiet_skip = 1;       // repairs copy the exactly repeating clock/mask of stretches without zero crossings (SlicerChain::quiet_words)
 	int opt_warm_far_f64 = 1;     // the crossing-by-crossing part in float64 (0: FP32, round 1's form, needs a 16384-sample tail)
 	double opt_guard_eps = 3.814697265625e-06;  // 2^-18 of the in-band magnitude scale: 4x the largest error seen (tools/guard_sweep.py, guard_bound.py)
 	double opt_guard_abs = 0.25;                // c_abs of the raw-input term: 4x the largest error seen in units of
@@ -807,7 +809,7 @@ extern "C" void pm_engine_destroy(pm_engine *e)
 	e->d_chk.release(); e->d_shardbits.release(); e->d_symcount.release(); e->d_tail.release();
 	e->d_mag.release(); e->d_amax.release();
 	for (auto &b : e->d_btaps) b.release();
-	e->d_guard_entries.release(); e->d_counters.release(); e->d_stage_clk.release(); e->d_S.release(); e->d_E0.release();
+	e->d_guard_entries.release(); e->d_repair_list.release(); e->d_counters.release(); e->d_stage_clk.release(); e->d_S.release(); e->d_E0.release();
 	e->d_E1.release(); e->d_blk_count.release(); e->d_blk_base.release(); e->d_sym_totals.release();
 	e->d_flag_totals.release(); e->d_flag_pos.release(); e->d_rec_src.release(); e->d_scratch.release();
 	e->d_gap_cand.release(); e->d_gap_ncand.release();
@@ -1043,6 +1045,7 @@ extern "C" int pm_engine_set_option(pm_engine *e, const char *key, double value)
 	else if (k == "verify_passes") e->opt_verify_passes = std::max(0, (int)value);
 	else if (k == "warmup_exact_len") e->opt_warm_exact_words = std::max(0, (int)((value + 31) / 32));
 	else if (k == "warmup_far_f64") e->opt_warm_far_f64 = value != 0;
+	else if (k == "quiet_skip") e->opt_quiet_skip = value != 0;
 	else if (k == "guard_eps") { e->opt_guard_eps = value; replan = true; }
 	else if (k == "guard_abs") { e->opt_guard_abs = value; replan = true; }
 	else if (k == "tile") { e->opt_tile = (int)value; replan = true; }
@@ -1159,6 +1162,20 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 			s.fast = fast ? 1 : 0;
 			memcpy(&s.c_star_bits, &cs, sizeof(double));
 			s.sps_m1 = s.sps - 1.0;
+			// exact repetition of the clock in stretches without crossings (SlicerChain::quiet_words): sps a dyadic
+			// rational, P = its smallest integer multiple, the repetition lcm(32, P) / 32 words long
+			s.quiet_words = 0; s.quiet_lead = 0;
+			if (e->opt_quiet_skip && s.sps >= 2.0 && s.sps * 65536.0 == std::floor(s.sps * 65536.0)) {
+				long long P = 0;
+				for (int k = 1; k <= 64 && !P; k++)
+					if (s.sps * k == std::floor(s.sps * k)) P = (long long)(s.sps * k);
+				if (P > 0 && P <= 4096) {
+					long long a = 32, b = P;
+					while (b) { const long long t = a % b; a = b; b = t; }       // a = gcd(32, P)
+					const long long lw = P / a;
+					if (lw <= PM_QUIET_MAX) { s.quiet_words = (int)lw; s.quiet_lead = (int)((P + 31) / 32) + 1; }
+				}
+			}
 		}
 		BitChain &b = bc[c];
 		memset(&b, 0, sizeof(b));
@@ -1217,6 +1234,7 @@ static int prepare_run(pm_engine *e, long long n, const pm_shard_plan &plan, boo
 	CK(e->d_E0.ensure((size_t)nc * G.n_seg));
 	CK(e->d_E1.ensure((size_t)nc * G.n_seg));
 	CK(e->d_chk.ensure((size_t)nc * G.n_seg * G.n_chk));
+	CK(e->d_repair_list.ensure((size_t)nc * G.n_seg));
 	CK(e->d_shardbits.ensure(nc));
 	CK(e->d_symcount.ensure(nc));
 	CK(e->d_tail.ensure((size_t)nc * std::max(1, plan.tail_bits / 32)));
@@ -1417,14 +1435,14 @@ static int slicer_converge(pm_engine *e)
 		CK(cudaMemsetAsync(e->d_counters.p + 1, 0, sizeof(unsigned int), e->st));
 		if (pass < e->opt_verify_passes) {
 			ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
-				e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, nullptr, e->st);
+				e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, nullptr, e->d_repair_list.p, e->st);
 			std::swap(e->E_cur, e->E_alt);
 		} else {
 			ce = pm_launch_slicer_sweep(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
 				e->d_S.p, e->E_cur, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 1, e->st);
 		}
 		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
-		e->stats.kernel_launches++;
+		e->stats.kernel_launches += 2;
 		pm_kt_mark("d2h counters + host sync", e->st);
 		CK(cudaMemcpyAsync(e->h_counters, e->d_counters.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->st));
 		CK(cudaStreamSynchronize(e->st));
@@ -1448,10 +1466,10 @@ static int slicer_enqueue_fast(pm_engine *e)
 	for (int p = 0; p < e->fast_passes; p++) {
 		cudaError_t ce = pm_launch_slicer_verify(e->d_slicer.p, nc, e->d_sign.p, e->sign_stride, e->d_mask.p, e->sign_stride,
 			e->d_S.p, e->E_cur, e->E_alt, e->d_chk.p, e->d_init.p, e->geom, e->d_counters.p + 2 + p,
-			p ? e->d_counters.p + 2 + p - 1 : nullptr, e->st);
+			p ? e->d_counters.p + 2 + p - 1 : nullptr, e->d_repair_list.p, e->st);
 		if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "slicer verify launch failed: %s", cudaGetErrorString(ce));
 		std::swap(e->E_cur, e->E_alt);
-		e->stats.kernel_launches++;
+		e->stats.kernel_launches += 2;
 	}
 	e->fast_pending = true;
 	return PM_OK;

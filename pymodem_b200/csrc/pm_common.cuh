@@ -174,6 +174,21 @@ struct SlicerChain {
 	// of the next clock come straight from the old one, one double operation deep instead of two plus a compare.
 	long long c_star_bits;
 	double sps_m1;           // sps - 1.0 (exact for sps >= 1)
+	// Stretches without zero crossings (digital silence: a squelched receiver, the gaps of clean synthetic audio).  The
+	// clock then only counts and rolls over, and when sps is a dyadic rational it becomes EXACTLY periodic within one
+	// period: the first pass through the top binade rounds it onto that binade's grid, after which every +1.0 and -sps
+	// is exact (tools/slicer_quiet_check.py: every start state periodic from sample < P on, P = smallest integer
+	// multiple of sps).  Mask words and word-end clocks then repeat every quiet_words = lcm(32, P) / 32 words: a repair
+	// (slicer_verify / slicer_sweep) copies them instead of stepping.  0: not available for this chain.
+	int quiet_words;
+	int quiet_lead;          // quiet words to step exactly before the repetition may be trusted: ceil(P / 32) + 1
+};
+
+#define PM_QUIET_MAX 8       // longest repetition (in words) the repairs keep
+struct QuietState {           // carried by a repairing thread across its run_words calls
+	int run;                 // whole quiet words processed since the last word with a crossing
+	double c[PM_QUIET_MAX];  // clock after the most recent quiet word w with w % quiet_words == slot
+	uint32_t m[PM_QUIET_MAX];// its mask word
 };
 
 struct SegState {

@@ -80,8 +80,9 @@ __device__ __forceinline__ void slicer_step(double &c, uint32_t &m, uint32_t z, 
 template <bool WRITE, bool FAST, bool A0, bool F0, bool SPARSE>
 __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                             const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
-                                            long long w0, long long w1, SegState &st)
+                                            long long w0, long long w1, SegState &st, QuietState *Q)
 {
+	const int q_words = (SPARSE && Q) ? C.quiet_words : 0, q_lead = C.quiet_lead;
 	double c = st.clock;
 	unsigned int last = st.last, last_q = st.last_q;
 	const double thr = C.thr, sps = C.sps, lam = C.lock;
@@ -109,14 +110,27 @@ __device__ __forceinline__ void run_words_t(const SlicerChain &C, const uint32_t
 		const int cnt = remain >= 32 ? 32 : (int)remain;
 		if (cnt == 32) {
 			if (SPARSE && z == 0u) {
+				const int slot = q_words ? (int)(w % q_words) : 0;
+				if (q_words && Q->run >= q_lead + q_words) {
+					// deep inside a stretch without crossings: this word repeats the one quiet_words earlier, clock and mask
+					// (SlicerChain::quiet_words)
+					c = Q->c[slot];
+					m = Q->m[slot];
+				} else {
 #pragma unroll
-				for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0, true>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+					for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0, true>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+					if (WRITE) m = __brev(m);
+					if (q_words) { Q->c[slot] = c; Q->m[slot] = m; }
+				}
+				if (q_words) Q->run++;
 			} else {
 #pragma unroll
 				for (int i = 0; i < 32; i++) slicer_step<WRITE, FAST, A0, F0>(c, m, z, 1u << i, C, cs, a_roll, a_keep);
+				if (WRITE) m = __brev(m);
+				if (q_words) Q->run = 0;
 			}
-			if (WRITE) m = __brev(m);
 		} else {
+			if (q_words) Q->run = 0;
 			for (int i = 0; i < cnt; i++) {
 				// one rounding per operation, as in CPython: the compiler must not contract c * lam with the next + 1.0 (--fmad)
 				c = __dadd_rn(c, 1.0);                                    // slicer.py:77
@@ -206,21 +220,21 @@ __device__ __forceinline__ void run_words_far(const SlicerChain &C, const uint32
 template <bool WRITE, bool SPARSE = false>
 __device__ __forceinline__ void run_words(const SlicerChain &C, const uint32_t *__restrict__ sg,
                                           const uint32_t *__restrict__ sgq, uint32_t *__restrict__ mk,
-                                          long long w0, long long w1, SegState &st)
+                                          long long w0, long long w1, SegState &st, QuietState *Q = nullptr)
 {
 	// uniform per chain (blockIdx.y)
 	const bool a0 = __double2loint(C.fast ? C.sps_m1 : C.sps) == 0, f0 = __double2loint(C.lock) == 0;
 	if (C.fast) {
 		if (a0) {
-			if (f0) run_words_t<WRITE, true, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
-			else run_words_t<WRITE, true, true, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+			if (f0) run_words_t<WRITE, true, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
+			else run_words_t<WRITE, true, true, false, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
 		} else {
-			if (f0) run_words_t<WRITE, true, false, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
-			else run_words_t<WRITE, true, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+			if (f0) run_words_t<WRITE, true, false, true, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
+			else run_words_t<WRITE, true, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
 		}
 	} else {
-		if (a0 && f0) run_words_t<WRITE, false, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st);
-		else run_words_t<WRITE, false, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st);
+		if (a0 && f0) run_words_t<WRITE, false, true, true, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
+		else run_words_t<WRITE, false, false, false, SPARSE>(C, sg, sgq, mk, w0, w1, st, Q);
 	}
 }
 
@@ -270,14 +284,18 @@ slicer_segments_kernel(const SlicerChain *__restrict__ chains, const uint32_t *_
 	E[idx] = st;
 }
 
-// One verification / repair pass.  E_in -> E_out (double buffered so that a
-// thread never reads a neighbour's half-written state).
+// One verification / repair pass.  E_in -> E_out (double buffered so that a thread never reads a neighbour's
+// half-written state), in two kernels: slicer_verify_kernel compares every hand-off (one thread per segment) and lists
+// the segments that have to be re-run; slicer_repair_kernel re-runs them, ONE WARP per listed segment with lane 0
+// working.  A repair is a long sequential chain: 32 of them in one warp would execute each other's paths, and the cheap
+// paths of a repair (words without crossings, SlicerChain::quiet_words) only pay when no neighbour is stepping -- a
+// recording whose quiet gaps defeat the warm-up (a chain with a large space gain sees hardly a zero crossing in noise)
+// has hundreds of repairs per pass in runs of consecutive segments (profiles/r02al_*: verify passes 3.0 -> 2.0 ms on
+// afsk_1200.json / IL2P audio).
 __global__ void __launch_bounds__(128)
-slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ sign,
-                     long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
-                     SegState *__restrict__ S, const SegState *__restrict__ E_in, SegState *__restrict__ E_out,
-                     SegState *__restrict__ chk, const SegState *__restrict__ init, SlicerGeom G,
-                     unsigned int *repairs, const unsigned int *__restrict__ skip_if_zero)
+slicer_verify_kernel(const SlicerChain *__restrict__ chains, SegState *__restrict__ S, const SegState *__restrict__ E_in,
+                     SegState *__restrict__ E_out, const SegState *__restrict__ init, SlicerGeom G,
+                     unsigned int *repairs, const unsigned int *__restrict__ skip_if_zero, unsigned int *__restrict__ list)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int ch = blockIdx.y;
@@ -299,29 +317,46 @@ slicer_verify_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__r
 		E_out[idx] = E_in[idx];
 		return;
 	}
-	const SlicerChain C = chains[ch];
 	const long long w_begin = G.origin_w + (long long)k * G.seg_words;
 	S[idx] = prev;
-	if ((w_begin << 5) >= C.nout) {     // empty segment past the end
+	if ((w_begin << 5) >= chains[ch].nout) {     // empty segment past the end
 		E_out[idx] = prev;
 		return;
 	}
-	atomicAdd(repairs, 1u);
-	const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
-	const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
-	uint32_t *mk = mask + (long long)ch * mask_stride;
-	SegState st = prev;
-	SegState *ck = chk + idx * G.n_chk;
-	for (int j = 0; j < G.n_chk; j++) {
-		const long long a = w_begin + (long long)j * G.chk_words;
-		run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st);
-		if (seg_state_equal(ck[j], st)) {          // merged with the first run: the rest is already right
-			E_out[idx] = E_in[idx];
-			return;
+	list[atomicAdd(repairs, 1u)] = (unsigned int)idx;      // at most one entry per segment: the list holds n_chains * n_seg
+}
+
+__global__ void __launch_bounds__(128)
+slicer_repair_kernel(const SlicerChain *__restrict__ chains, const uint32_t *__restrict__ sign,
+                     long long sign_stride, uint32_t *__restrict__ mask, long long mask_stride,
+                     const SegState *__restrict__ S, const SegState *__restrict__ E_in, SegState *__restrict__ E_out,
+                     SegState *__restrict__ chk, SlicerGeom G, const unsigned int *__restrict__ repairs,
+                     const unsigned int *__restrict__ list)
+{
+	if ((threadIdx.x & 31) != 0) return;
+	const unsigned int n = *repairs;
+	const unsigned int n_warps = gridDim.x * (blockDim.x >> 5);
+	for (unsigned int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += n_warps) {
+		const long long idx = list[e];
+		const int ch = (int)(idx / G.n_seg), k = (int)(idx - (long long)ch * G.n_seg);
+		const SlicerChain C = chains[ch];
+		const long long w_begin = G.origin_w + (long long)k * G.seg_words;
+		const uint32_t *sg = sign + (long long)C.sign_row * sign_stride;
+		const uint32_t *sgq = C.quadrature ? sign + (long long)C.sign_q_row * sign_stride : nullptr;
+		uint32_t *mk = mask + (long long)ch * mask_stride;
+		SegState st = S[idx];                        // the true start state (slicer_verify_kernel put it there)
+		SegState *ck = chk + idx * G.n_chk;
+		QuietState Q;
+		Q.run = 0;
+		bool merged = false;
+		for (int j = 0; j < G.n_chk && !merged; j++) {
+			const long long a = w_begin + (long long)j * G.chk_words;
+			run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st, &Q);
+			if (seg_state_equal(ck[j], st)) merged = true;     // merged with the first run: the rest is already right
+			else ck[j] = st;
 		}
-		ck[j] = st;
+		E_out[idx] = merged ? E_in[idx] : st;
 	}
-	E_out[idx] = st;
 }
 
 // Sequential fallback: one thread per chain walks its segments in order and repairs
@@ -341,6 +376,8 @@ __global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, cons
 	uint32_t *mk = mask + (long long)ch * mask_stride;
 	SegState prev = init[ch];
 	unsigned int fixed = 0;
+	QuietState Q;                          // (segments that verify are skipped: their words were not seen)
+	Q.run = 0;
 	for (int k = G.k_init; k < G.n_seg; k++) {
 		const long long idx = (long long)ch * G.n_seg + k;
 		const long long w_begin = G.origin_w + (long long)k * G.seg_words;
@@ -355,11 +392,14 @@ __global__ void slicer_sweep_kernel(const SlicerChain *__restrict__ chains, cons
 				bool merged = false;
 				for (int j = 0; j < G.n_chk && !merged; j++) {
 					const long long a = w_begin + (long long)j * G.chk_words;
-					run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st);
+					run_words<true, true>(C, sg, sgq, mk, a, a + G.chk_words, st, &Q);
 					if (seg_state_equal(ck[j], st)) merged = true; else ck[j] = st;
 				}
 				if (!merged) E[idx] = st;
+				else Q.run = 0;                    // the rest of the segment was not walked
 			}
+		} else {
+			Q.run = 0;                             // nor was this segment
 		}
 		prev = E[idx];
 	}
@@ -425,12 +465,16 @@ extern "C" cudaError_t pm_launch_slicer_segments(const SlicerChain *chains, int 
 extern "C" cudaError_t pm_launch_slicer_verify(const SlicerChain *chains, int n_chains, const uint32_t *sign,
 	long long sign_stride, uint32_t *mask, long long mask_stride, SegState *S, const SegState *E_in,
 	SegState *E_out, SegState *chk, const SegState *init, SlicerGeom G, unsigned int *repairs,
-	const unsigned int *skip_if_zero, cudaStream_t st)
+	const unsigned int *skip_if_zero, unsigned int *list, cudaStream_t st)
 {
 	dim3 grid((G.n_seg + 127) / 128, n_chains);
 	pm_kt_mark("slicer_verify_kernel", st);
-	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, chk,
-		init, G, repairs, skip_if_zero);
+	slicer_verify_kernel<<<grid, 128, 0, st>>>(chains, S, E_in, E_out, init, G, repairs, skip_if_zero, list);
+	cudaError_t ce = cudaGetLastError();
+	if (ce != cudaSuccess) return ce;
+	pm_kt_mark("slicer_repair_kernel", st);
+	slicer_repair_kernel<<<148 * 4, 128, 0, st>>>(chains, sign, sign_stride, mask, mask_stride, S, E_in, E_out, chk, G,
+		repairs, list);
 	return cudaGetLastError();
 }
 

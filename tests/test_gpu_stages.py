@@ -176,3 +176,22 @@ def test_batched_recordings_equal_single_runs(cuda_lib, oracle, tag, count):
 	assert as_tuples(got[0]) == g.all_packets()
 	for r in range(1, count):
 		assert as_tuples(got[r]) == oracle.run_config(g.sample_rate, g.chain_lines(), recs[r]), r
+
+
+@pytest.mark.parametrize("rate,config", [(48000, '1200'), (44100, '1200'), (48000, '9600'), (48000, '300'), (48000, '4800'), (22050, '1200')])
+def test_slicer_long_stretches_without_crossings(cuda_lib, oracle, rate, config):
+	"""Digital silence / a steady tone: stretches of 10^5 samples without a zero crossing.  No speculated start state
+	converges there, every segment in them is repaired from its predecessor -- and where samples per symbol is a dyadic
+	rational (40, 5, 160, 10; not 36.75 within eight words, not 18.375) the repair copies the exactly repeating clock
+	and mask words instead of stepping (SlicerChain::quiet_words).  Bytes and addresses equal the oracle's loop."""
+	from pymodem_b200.modems_codecs import slicer as slicer_mod
+	rng = np.random.default_rng(rate + len(config))
+	parts = []
+	for k in range(7):
+		parts.append(rng.normal(0.0, 1.0, int(rng.integers(3000, 60000))))                 # crossings at every scale
+		level = [1.0, -1.0, 0.0, -0.25][k % 4]
+		parts.append(np.full(int(rng.integers(40000, 260000)), level))                      # none at all (0.0 counts as >= 0)
+	soft = np.concatenate(parts + [rng.normal(0.0, 1.0, 5000)])
+	want = oracle.BinarySlicer(rate, config, {}).slice(soft)
+	got = slicer_mod.BinarySlicer(sample_rate=rate, config=config).slice(soft)
+	assert _pairs(got) == _zip(*want) and len(got) > 100
