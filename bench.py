@@ -296,6 +296,7 @@ def kernel_rooflines(eng, n, n_chains, macs, fp32_peak, peaks, stats, runs=3, tc
 		# Executed exact steps of a launch: every segment plus the exact tail of its warm-up, per chain.
 		"slicer_segments_kernel": ("fp64+alu issue", n_chains * (n / float(st_seg)) * (st_seg + st_exact) / 1e9, SLICER_STEP_PEAK_G, "G steps/s"),
 		"slicer_verify_kernel": ("latency", 0.0, hbm, "GB/s"),
+		"slicer_repair_kernel": ("latency", 0.0, hbm, "GB/s"),      # a repair is one thread's chain of up to a segment of exact steps
 		"gather_count_kernel": ("hbm", sign_mask / 1e9, hbm, "GB/s"),
 		"memset bits": ("hbm", nbits / 8.0 / 1e9, hbm, "GB/s"),
 		"gather_write_kernel": ("hbm", (2.0 * sign_mask + nbits / 8.0 + nbits / 8.0 * 4.0) / 1e9, hbm, "GB/s"),

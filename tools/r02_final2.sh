@@ -2,9 +2,7 @@
 # final single-GPU evidence of round 2, second session: all GPU tests, the bench line (driver flags; it carries the
 # full-hour packet-set digest), front-end tile sweep, run timelines, ncu launch list + full capture (tools/gpu_profile_r02.sh)
 mkdir -p gpurun_out
-tag=${1:-r02ag}
+tag=${1:-r02am}
 ( timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 ) > gpurun_out/${tag}_pytest_gpu.txt; tail -3 gpurun_out/${tag}_pytest_gpu.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err; head -c 200 gpurun_out/${tag}_bench_n1.json; echo
-( timeout 200 python tools/tile_sweep.py 4096 5120 6144 6656 7168 7360 7616 7872 8128 8640 9152 10240 ) > gpurun_out/${tag}_tile_sweep.txt 2>&1; cat gpurun_out/${tag}_tile_sweep.txt
-( timeout 100 python tools/e2e_trace.py ) > gpurun_out/${tag}_e2e_trace.txt 2>&1; grep "early_tail" gpurun_out/${tag}_e2e_trace.txt
 timeout 500 bash tools/gpu_profile_r02.sh ${tag}
