@@ -19,10 +19,12 @@
 //      failed frames leak into the next emitted frame (il2p.py:200-211).
 #include "pm_common.cuh"
 
-__constant__ unsigned char c_gf_exp[256];   // gf_functions.py table[] (255 entries)
-__constant__ unsigned char c_gf_log[256];   // gf_functions.py index[] (index[0] = 0)
-__constant__ unsigned char c_gf_inv[256];   // gf_functions.py inverse[]
 __constant__ unsigned char c_hamming[128];  // il2p.py:19-42
+// GF(2^8) tables back to back in global memory: exp (gf_functions.py table[], 255 entries) | log (index[], index[0] = 0)
+// | inverse[].  Not __constant__: the speculative decode runs one thread per candidate, every lane looks up a different
+// entry, and the constant cache serialises that -- il2p_decode_kernel copies them into shared memory, the resolve walk
+// (one lane) reads them through L1; both pass the base pointer down (T below).
+__device__ unsigned char d_gf_tab[768];
 
 // GF(2^8) tables exactly as gf_functions.py:47-74 builds them (Galois LFSR over genpoly 0x11D walking
 // the exponents downwards, inverse by definition) and the Hamming(7,4) table of il2p.py:19-42.
@@ -48,32 +50,33 @@ extern "C" cudaError_t pm_il2p_init_tables(void)
 	}
 	for (int a = 1; a < 256; a++) inv_t[a] = exp_t[(255 - log_t[a]) % 255];
 	cudaError_t e;
-	if ((e = cudaMemcpyToSymbol(c_gf_exp, exp_t, 256)) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_gf_log, log_t, 256)) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_gf_inv, inv_t, 256)) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(d_gf_tab, exp_t, 256, 0)) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(d_gf_tab, log_t, 256, 256)) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(d_gf_tab, inv_t, 256, 512)) != cudaSuccess) return e;
 	return cudaMemcpyToSymbol(c_hamming, hamming, 128);
 }
 
-__device__ __forceinline__ int gf_mul(int a, int b)                 // gf_functions.py:18-24
+// T: exp[256] | log[256] | inverse[256] (shared or global memory)
+__device__ __forceinline__ int gf_mul(const unsigned char *__restrict__ T, int a, int b)   // gf_functions.py:18-24
 {
 	if (a == 0 || b == 0) return 0;
-	int r = c_gf_log[a] + c_gf_log[b];
+	int r = T[256 + a] + T[256 + b];
 	if (r > 254) r -= 255;
-	return c_gf_exp[r];
+	return T[r];
 }
 
 // rs_functions.py:33-150, first_root 0.  NR = number of roots (2 header, 16 blocks).
 // Returns the number of corrected bytes or -1; corrects data in place.
 template <int NR>
-__device__ int rs_decode_dev(unsigned char *data, int block_size, int min_distance)
+__device__ int rs_decode_dev(const unsigned char *__restrict__ T, unsigned char *data, int block_size, int min_distance)
 {
 	int syn[NR], loc[NR], nxt[NR], where[NR];
 	int cor[NR + 1];
 	int error_count = 0;
 	for (int i = 0; i < NR; i++) {                                  // :36-42
 		int s = 0;
-		const int x = c_gf_exp[i];
-		for (int j = 0; j < block_size - 1; j++) s = gf_mul(s ^ data[j], x);
+		const int x = T[i];
+		for (int j = 0; j < block_size - 1; j++) s = gf_mul(T, s ^ data[j], x);
 		syn[i] = s ^ data[block_size - 1];
 		loc[i] = 0; nxt[i] = 0; where[i] = 0;
 	}
@@ -84,11 +87,11 @@ __device__ int rs_decode_dev(unsigned char *data, int block_size, int min_distan
 	for (int step = 1; step <= NR; step++) {                        // :60-82
 		const int y = step - 1;
 		int e = syn[y];
-		for (int i = 1; i <= order; i++) e ^= gf_mul(loc[i], syn[y - i]);
+		for (int i = 1; i <= order; i++) e ^= gf_mul(T, loc[i], syn[y - i]);
 		if (e != 0) {
-			for (int i = 0; i <= order; i++) nxt[i] = loc[i] ^ gf_mul(e, cor[i]);
-			e = c_gf_inv[e];
-			for (int i = 0; i < NR / 2 + 1; i++) cor[i] = gf_mul(loc[i], e);
+			for (int i = 0; i <= order; i++) nxt[i] = loc[i] ^ gf_mul(T, e, cor[i]);
+			e = T[512 + e];
+			for (int i = 0; i < NR / 2 + 1; i++) cor[i] = gf_mul(T, loc[i], e);
 			for (int i = 0; i < NR / 2 + 1; i++) loc[i] = nxt[i];
 		}
 		if (2 * order < step) order = step - order;
@@ -99,14 +102,14 @@ __device__ int rs_decode_dev(unsigned char *data, int block_size, int min_distan
 		int x = 0;
 		const int y = j + 256 - block_size;
 		for (int i = 1; i < NR / 2 + 1; i++)
-			if (loc[i]) x ^= c_gf_exp[(y * i + c_gf_log[loc[i]]) % 255];
+			if (loc[i]) x ^= T[(y * i + T[256 + loc[i]]) % 255];
 		x ^= loc[0];
 		if (x == 0) where[error_count++] = j;
 	}
 	if (error_count <= NR / 2 - min_distance) {                     // :99-140 Forney
 		for (int i = 0; i < error_count; i++) {
 			cor[i] = syn[i];
-			for (int j = 1; j <= i; j++) cor[i] ^= gf_mul(syn[i - j], loc[j]);
+			for (int j = 1; j <= i; j++) cor[i] ^= gf_mul(T, syn[i - j], loc[j]);
 		}
 		for (int i = 0; i < error_count; i++) {
 			const int e = block_size - where[i] - 1;
@@ -114,26 +117,26 @@ __device__ int rs_decode_dev(unsigned char *data, int block_size, int min_distan
 			for (int j = 1; j < error_count; j++) {
 				int x = (e * j) % 255;
 				x = (255 - x) % 255;
-				z ^= gf_mul(cor[j], c_gf_exp[x]);
+				z ^= gf_mul(T, cor[j], T[x]);
 			}
-			z = gf_mul(z, c_gf_exp[e]);
+			z = gf_mul(T, z, T[e]);
 			int y = loc[1];
 			for (int j = 3; j < NR / 2 + 1; j += 2) {
 				int x = (e * (j - 1)) % 255;
 				x = (255 - x) % 255;
-				y ^= gf_mul(loc[j], c_gf_exp[x]);
+				y ^= gf_mul(T, loc[j], T[x]);
 			}
-			y = c_gf_log[y];
+			y = T[256 + y];
 			y = 256 - y - 1;
 			if (y == 255) y = 0;
-			y = c_gf_exp[y];
-			data[where[i]] ^= (unsigned char)gf_mul(y, z);
+			y = T[y];
+			data[where[i]] ^= (unsigned char)gf_mul(T, y, z);
 		}
 	}
 	for (int i = 0; i < NR; i++) {                                  // :142-149
 		int s = 0;
-		const int x = c_gf_exp[i];
-		for (int j = 0; j < block_size - 1; j++) s = gf_mul(s ^ data[j], x);
+		const int x = T[i];
+		for (int j = 0; j < block_size - 1; j++) s = gf_mul(T, s ^ data[j], x);
 		if ((s ^ data[block_size - 1]) != 0) return -1;
 	}
 	return error_count;
@@ -179,8 +182,8 @@ __device__ unsigned int crc16_x25_il2p(const unsigned char *p, unsigned int n)  
 
 // Decode the frame that follows a sync word whose last bit is stream bit g.
 // out: packet bytes (the rebuilt AX.25 frame + FCS).  nb = stream length in bits.
-__device__ void il2p_try(const uint32_t *__restrict__ d, long long nb, long long g, const BitChain &C,
-                         unsigned char *out, Il2pRes &res)
+__device__ void il2p_try(const unsigned char *__restrict__ T, const uint32_t *__restrict__ d, long long nb, long long g,
+                         const BitChain &C, unsigned char *out, Il2pRes &res)
 {
 	unsigned char buf[256];
 	long long p = g + 1;
@@ -192,7 +195,7 @@ __device__ void il2p_try(const uint32_t *__restrict__ d, long long nb, long long
 	p += 120;
 	bool fail = false;
 	{
-		const int r = C.il2p_disable_rs ? 0 : rs_decode_dev<2>(buf, 15, C.il2p_min_dist);      // il2p.py:188-207
+		const int r = C.il2p_disable_rs ? 0 : rs_decode_dev<2>(T, buf, 15, C.il2p_min_dist);      // il2p.py:188-207
 		if (r < 0) fail = true; else corrected += r;
 	}
 	il2p_unscramble(buf, 13);
@@ -242,7 +245,7 @@ __device__ void il2p_try(const uint32_t *__restrict__ d, long long nb, long long
 			if (p + 8ll * total > nb) { res.corrected = (unsigned int)corrected; return; }    // stream ends inside the frame
 			for (int i = 0; i < total; i++) buf[i] = (unsigned char)il2p_byte(d, p + 8 * i);
 			p += 8ll * total;
-			const int r = C.il2p_disable_rs ? 0 : rs_decode_dev<16>(buf, total, C.il2p_min_dist);
+			const int r = C.il2p_disable_rs ? 0 : rs_decode_dev<16>(T, buf, total, C.il2p_min_dist);
 			if (r < 0) fail = true; else corrected += r;
 			il2p_unscramble(buf, total);
 			for (int i = 0; i < size; i++) out[len++] = buf[i];
@@ -276,15 +279,19 @@ il2p_decode_kernel(const BitChain *__restrict__ chains, const ChainCounters *__r
                    unsigned char *__restrict__ cand_scratch, long long cand_scratch_stride,
                    Il2pRes *__restrict__ results)
 {
+	__shared__ unsigned char s_tab[768];
 	const int ch = blockIdx.y;
 	const BitChain C = chains[ch];
 	if (C.codec != 2) return;
 	const unsigned int n = min(cand_totals[ch], (unsigned int)cand_cap);
+	if (blockIdx.x * blockDim.x >= n) return;                  // (uniform per block: nobody waits at the barrier below)
+	for (int i = threadIdx.x; i < 768; i += blockDim.x) s_tab[i] = d_gf_tab[i];
+	__syncthreads();
 	const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	const long long nb = cc[ch].nbytes * 8;
 	Il2pRes r;
-	il2p_try(d + (long long)ch * bits_stride, nb, cand_pos[(long long)ch * cand_stride + j], C,
+	il2p_try(s_tab, d + (long long)ch * bits_stride, nb, cand_pos[(long long)ch * cand_stride + j], C,
 		cand_scratch + (long long)ch * cand_scratch_stride + (long long)j * IL2P_SLOT, r);
 	results[(long long)ch * cand_cap + j] = r;
 }
@@ -353,30 +360,34 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 		Il2pRes r;
 		const unsigned char *src = nullptr;
 		r.status = IL2P_INCOMPLETE; r.len = 0; r.corrected = 0; r.end_bit = nb - 1;
+		// right after a frame (mode 1, the state of nearly every iteration): the 32 windows ending at pos .. pos+31 all lie
+		// inside stream bits [pos-31, pos+31] -- fetched once (bit j of span = stream bit pos-31+j), what the reference's
+		// register no longer holds (everything before the last collected byte, i.e. before pos-8) blanked; lane l tests the
+		// window ending at pos+l (pos and mode are the same on every lane)
+		long long found1 = -1;
+		if (mode == 1 && pos < nb) {
+			unsigned long long span = 0;
+			const long long b0 = pos - 31;
+			for (int q = 0; q < 3; q++) {
+				const long long w = (b0 >> 5) + q;               // floor division: b0 may be negative
+				if (w < 0 || (w << 5) >= nb) continue;
+				const unsigned long long word = d[w];
+				const long long sh = (w << 5) - b0;              // position of the word's bit 0 inside span
+				if (sh >= 64) continue;
+				span |= sh >= 0 ? (word << sh) : (word >> (-sh));
+			}
+			span &= ~((1ull << 23) - 1ull);                      // indices below pos-8 read as 0
+			const bool hit = pos + lane < nb && il2p_sync_match(__brev((unsigned int)(span >> lane)), C.il2p_sync_tol);
+			const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+			if (hits) found1 = pos + (__ffs(hits) - 1);
+		}
 		if (lane == 0 && pos < nb) {
 			const long long lim = min(pos + 32, nb);
 			if (mode == 0) {
 				for (long long g = pos; g < lim; g++)
 					if (il2p_sync_match(il2p_window(d, g, pos, true), C.il2p_sync_tol)) { found = g; break; }
 			} else if (mode == 1) {
-				// the 32 windows ending at pos .. pos+31 all lie inside stream bits [pos-31, pos+31]: fetch them once
-				// (bit j of span = stream bit pos-31+j), blank what the reference's register no longer holds (everything
-				// before the last collected byte, i.e. before pos-8) and slide
-				unsigned long long span = 0;
-				const long long b0 = pos - 31;
-				for (int q = 0; q < 3; q++) {
-					const long long w = (b0 >> 5) + q;               // floor division: b0 may be negative
-					if (w < 0 || (w << 5) >= nb) continue;
-					const unsigned long long word = d[w];
-					const long long sh = (w << 5) - b0;              // position of the word's bit 0 inside span
-					if (sh >= 64) continue;
-					span |= sh >= 0 ? (word << sh) : (word >> (-sh));
-				}
-				span &= ~((1ull << 23) - 1ull);                      // indices below pos-8 read as 0
-				for (long long g = pos; g < lim; g++) {
-					const unsigned int ww = __brev((unsigned int)(span >> (int)(g - pos)));
-					if (il2p_sync_match(ww, C.il2p_sync_tol)) { found = g; break; }
-				}
+				found = found1;
 			}
 			if (found < 0) {
 				const long long from = (mode == 2) ? pos : pos + 32;
@@ -390,7 +401,7 @@ il2p_resolve_kernel(const BitChain *__restrict__ chains, ChainCounters *__restri
 					r = results[(long long)ch * cand_cap + ci];
 					src = slots + (long long)ci * IL2P_SLOT;
 				} else {
-					il2p_try(d, nb, found, C, tmp, r);
+					il2p_try(d_gf_tab, d, nb, found, C, tmp, r);
 					src = tmp;
 				}
 			}
