@@ -157,7 +157,8 @@ def test_early_tail_of_host_runs(cuda_lib, tag):
 			assert st["guard_flagged"] > 1024      # the list did overflow and the run was repeated with a longer one
 
 
-@pytest.mark.parametrize("tag,count", [("bpsk300_il2p_8k", 5), ("qpsk2400_il2p_8k", 3), ("afsk1200_superopt_48k", 3), ("afsk300_full_8k", 2)])
+@pytest.mark.parametrize("tag,count", [("bpsk300_il2p_8k", 5), ("qpsk2400_il2p_8k", 3), ("afsk1200_superopt_48k", 3), ("afsk300_full_8k", 2),
+	("afsk1200_il2p_48k", 1), ("bpsk1200_il2p_12k", 1)])
 def test_batched_recordings_equal_single_runs(cuda_lib, oracle, tag, count):
 	"""pm_engine_run_batch: several recordings of different lengths x all chains in one call == one call per recording
 	(and == the fixture for the unmodified one)."""
