@@ -1,3 +1,5 @@
+"""pm_engine_slice_soft on soft values with long constant stretches (no zero crossings) against the oracle's slicer, with the
+exact-repetition shortcut of the repairs (engine option quiet_skip) on and off, two segment lengths, six rate/preset pairs."""
 import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)

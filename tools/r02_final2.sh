@@ -1,6 +1,7 @@
 #!/bin/bash
 # final single-GPU evidence of round 2, second session: all GPU tests, the bench line (driver flags; it carries the
-# full-hour packet-set digest), front-end tile sweep, run timelines, ncu launch list + full capture (tools/gpu_profile_r02.sh)
+# full-hour packet-set digest), ncu launch list + full capture (tools/gpu_profile_r02.sh).  (The r02ag run also had
+# tools/tile_sweep.py and tools/e2e_trace.py in it.)
 mkdir -p gpurun_out
 tag=${1:-r02am}
 ( timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 ) > gpurun_out/${tag}_pytest_gpu.txt; tail -3 gpurun_out/${tag}_pytest_gpu.txt
